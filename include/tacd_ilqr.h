@@ -1,0 +1,200 @@
+/*
+ * tacd_ilqr.h — C ABI of the B200-native batched differentiable iLQR solve.
+ *
+ * This is the drop-in boundary for ONE hot path of TACDMPC/TACDMPC: the solve
+ * behind DifferentialMPC.ILQRSolve / DifferentiableMPCController.  Every entry
+ * point takes plain device pointers and sizes (no torch types); the Python host
+ * mirror in tacdmpc_b200/DifferentialMPC binds them with ctypes.
+ *
+ * Reference interface replaced (paths relative to the reference checkout):
+ *   tacd_ilqr_forward   <- ILQRSolve.forward / solve_step   DifferentialMPC/controller.py:27-60, 275-315
+ *   tacd_ilqr_backward  <- ILQRSolve.backward + _zero_constrained_lqr  controller.py:63-115, 707-788
+ *   tacd_linearize      <- linearize_dynamics                controller.py:448-471
+ *   tacd_riccati        <- backward_lqr (live fallback loop) controller.py:546-578
+ *   tacd_linesearch     <- evaluate_alphas                   controller.py:589-620
+ *   tacd_rollout        <- rollout_trajectory                controller.py:361-398
+ *   tacd_objective      <- GeneralQuadCost.objective         DifferentialMPC/cost.py:37-62
+ *   tacd_pnqp           <- pnqp                              DifferentialMPC/utils.py:66-124
+ *
+ * Conventions
+ *   - All tensors are dense, row-major, in the scalar type named by
+ *     tacd_problem.dtype (TACD_F32 / TACD_F64); n = nx + nu.
+ *   - Every function returns 0 on success or a negative TACD_E* code; nothing
+ *     throws or exits.  tacd_last_error() returns a thread-local message.
+ *   - Kernels are enqueued on `stream` (a cudaStream_t passed as void*); no
+ *     entry point synchronises the host.  No entry point allocates or frees
+ *     user-visible memory; scratch comes from the caller (`workspace`).
+ *   - The oracle (oracle/ilqr_oracle.c, test infrastructure only) exports the
+ *     same signatures with the prefix tacd_oracle_ and HOST pointers.
+ */
+#ifndef TACD_ILQR_H
+#define TACD_ILQR_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TACD_ABI_VERSION 1
+
+#define TACD_MAX_ALPHA 8
+#define TACD_MAX_NU 16
+#define TACD_MAX_NX 64
+
+/* error codes */
+#define TACD_OK 0
+#define TACD_EINVAL (-1)      /* bad argument / unsupported shape */
+#define TACD_EUNSUPPORTED (-2)/* valid request this build has no kernel for */
+#define TACD_ECUDA (-3)       /* CUDA launch / runtime error (see tacd_last_error) */
+#define TACD_EWORKSPACE (-4)  /* workspace too small */
+
+enum tacd_dtype { TACD_F32 = 0, TACD_F64 = 1 };
+
+/* Shipped dynamics.  f(x,u,dt) -> x+ and its Jacobians are
+ * embedded in device code; EXTERNAL means "A_t,B_t are supplied as tensors"
+ * (stand-alone Riccati / backward only). */
+enum tacd_dyn {
+  TACD_DYN_LTI = 0,               /* x+ = A x + B u, A[nx,nx], B[nx,nu] device ptrs (double integrator: examples/01_demo_linear.py:12-26) */
+  TACD_DYN_CARTPOLE = 1,          /* explicit-Euler gym cart-pole, params {m_c,m_p,l,g} (examples/02_demo_cartpole_regulation.py:29-80) */
+  TACD_DYN_UNICYCLE = 2,          /* explicit-Euler unicycle (examples/03_demo_unicycle_tracking.py:8-49) */
+  TACD_DYN_UNICYCLE_WRAPPED = 3,  /* same with theta wrapped to [-pi,pi) (examples/03_demo_unicycle_AC.py:107-125) */
+  TACD_DYN_EXTERNAL = 4
+};
+
+/* GradMethod (controller.py:119-129) */
+enum tacd_jac { TACD_JAC_ANALYTIC = 0, TACD_JAC_AUTO_DIFF = 1, TACD_JAC_FINITE_DIFF = 2 };
+
+/* flags[b] bits written by the solve */
+#define TACD_FLAG_NONPD 1u    /* some Q_uu + reg*I was not positive definite; LU fallback used (quirk Q8) */
+#define TACD_FLAG_MAXITER 2u  /* stopped by max_iter while still improving */
+
+typedef struct tacd_problem {
+  int32_t B, T, nx, nu;
+  int32_t dtype;            /* enum tacd_dtype */
+  /* broadcast flags (cost.py:29-35): 1 = per-element leading batch dim, 0 = shared */
+  int32_t C_batched;        /* C[B,T,n,n], c[B,T,n]   vs  C[T,n,n], c[T,n] */
+  int32_t Cf_batched;       /* C_final[B,n,n], c_final[B,n]  vs  [n,n],[n] */
+  int32_t xref_batched;     /* x_ref[B,T+1,nx] vs [1,T+1,nx] */
+  int32_t uref_batched;     /* u_ref[B,T,nu]   vs [1,T,nu] */
+  /* line-search cost (quirk Q4): 1 = candidate costs use the separate, shared
+   * (C_ls,c_ls,Cf_ls,cf_ls) of shapes [T,n,n],[T,n],[n,n],[n]; 0 = same cost as acceptance */
+  int32_t ls_cost_shared;
+  int32_t dyn_id;           /* enum tacd_dyn */
+  int32_t jac_mode;         /* enum tacd_jac */
+  double dyn_params[8];
+  const void* dyn_A;        /* LTI only: [nx,nx], dtype as above */
+  const void* dyn_B;        /* LTI only: [nx,nu] */
+  double dt;
+  double reg_eps;
+  double fd_eps;            /* finite-difference step actually used (reference: always 1e-4, quirk Q9) */
+  int32_t max_iter;
+  int32_t n_alpha;
+  double alphas[TACD_MAX_ALPHA];
+  int32_t has_umin, has_umax;
+  double umin[TACD_MAX_NU], umax[TACD_MAX_NU];
+} tacd_problem;
+
+/* ---- whole solve ------------------------------------------------------- */
+typedef struct tacd_forward_io {
+  /* inputs */
+  const void* x0;     /* [B,nx] */
+  const void* C;      /* see C_batched */
+  const void* c;
+  const void* Cf;
+  const void* cf;
+  const void* C_ls;   /* only read when ls_cost_shared */
+  const void* c_ls;
+  const void* Cf_ls;
+  const void* cf_ls;
+  const void* xref;
+  const void* uref;
+  const void* Uinit;  /* [B,T,nu] */
+  /* lock-step replay of a recorded decision trace (tests only): when
+   * replay_iters != NULL the argmin / improved decisions are taken from the
+   * trace instead of being computed. */
+  const int32_t* replay_iters;   /* [B] executed iterations */
+  const uint8_t* replay_alpha;   /* [B,max_iter] */
+  const uint8_t* replay_flags;   /* [B] (TACD_FLAG_MAXITER decides whether the last iteration improved) */
+  /* outputs */
+  void* X;            /* [B,T+1,nx] */
+  void* U;            /* [B,T,nu] */
+  void* A;            /* [B,T,nx,nx] Jacobians at the solution, nullable */
+  void* Bm;           /* [B,T,nx,nu] nullable */
+  uint8_t* tight;     /* [B,T,nu] active-set mask (controller.py:636-642) */
+  int32_t* iters;     /* [B] executed iLQR iterations (= improving + 1, capped by max_iter) */
+  uint8_t* alpha_trace; /* [B,max_iter] argmin alpha index per executed iteration, 0xFF after; nullable */
+  uint8_t* flags;     /* [B] TACD_FLAG_* */
+  void* cost;         /* [B] final objective; nullable */
+  void* cost_trace;   /* [B,max_iter,n_alpha+2] candidate costs, new cost, best cost before; nullable (debug) */
+} tacd_forward_io;
+
+typedef struct tacd_backward_io {
+  /* inputs (saved by forward) */
+  const void* X;       /* [B,T+1,nx] */
+  const void* U;       /* [B,T,nu] */
+  const void* C;       /* Hessian blocks are views of C (cost.py:95-97) */
+  const void* Cf;      /* unused by the reference backward (quirk Q1); kept for the ABI */
+  const void* xref;
+  const void* uref;
+  const uint8_t* tight;/* [B,T,nu] */
+  const void* A;       /* [B,T,nx,nx], required iff dyn_id == EXTERNAL */
+  const void* Bm;      /* [B,T,nx,nu] */
+  const void* gX;      /* upstream grad wrt X* [B,T+1,nx] */
+  const void* gU;      /* upstream grad wrt U* [B,T,nu] */
+  /* outputs, each nullable = not needed.  When C_batched==0 grad_C/grad_c are
+   * the SUM over the batch ([T,n,n]/[T,n]); same for Cf_batched / xref / uref. */
+  void* grad_C;
+  void* grad_c;
+  void* grad_Cf;
+  void* grad_cf;
+  void* grad_x0;       /* [B,nx]; identically zero in the reference (quirk Q3) */
+  void* grad_xref;
+  void* grad_uref;
+  void* dX;            /* [B,T+1,nx] KKT sensitivities, nullable (debug / tests) */
+  void* dU;            /* [B,T,nu] */
+} tacd_backward_io;
+
+int tacd_abi_version(void);
+const char* tacd_last_error(void);
+
+/* bytes of device scratch tacd_ilqr_forward / tacd_ilqr_backward need */
+size_t tacd_forward_workspace_bytes(const tacd_problem* p);
+size_t tacd_backward_workspace_bytes(const tacd_problem* p);
+
+int tacd_ilqr_forward(const tacd_problem* p, const tacd_forward_io* io,
+                      void* workspace, size_t workspace_bytes, void* stream);
+int tacd_ilqr_backward(const tacd_problem* p, const tacd_backward_io* io,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- stand-alone stages (unit parity + generic-callable path) ---------- */
+/* X[B,T+1,nx] from x0[B,nx], U[B,T,nu]; no clamping (controller.py:361-398) */
+int tacd_rollout(const tacd_problem* p, const void* x0, const void* U, void* X, void* stream);
+/* A[B,T,nx,nx], Bm[B,T,nx,nu] at (X[:, :-1], U) (controller.py:448-471) */
+int tacd_linearize(const tacd_problem* p, const void* X, const void* U, void* A, void* Bm, void* stream);
+/* cost[B] (cost.py:37-62) */
+int tacd_objective(const tacd_problem* p, const void* X, const void* U,
+                   const void* C, const void* c, const void* Cf, const void* cf,
+                   const void* xref, const void* uref, void* cost, void* stream);
+/* backward_lqr inputs in the reference's layout: A[B,T,nx,nx] B[B,T,nx,nu]
+ * lx[B,T,nx] lu[B,T,nu] lxx[B,T,nx,nx] lxu[B,T,nx,nu] luu[B,T,nu,nu] lxN[B,nx] lxxN[B,nx,nx]
+ * -> K[B,T,nu,nx], k[B,T,nu], flags[B] (nullable) */
+int tacd_riccati(const tacd_problem* p, const void* A, const void* Bm,
+                 const void* lx, const void* lu, const void* lxx, const void* lxu, const void* luu,
+                 const void* lxN, const void* lxxN, void* K, void* k, uint8_t* flags, void* stream);
+/* evaluate_alphas: Xc[B,n_alpha,T+1,nx], Uc[B,n_alpha,T,nu], costs[B,n_alpha];
+ * cost tensors follow C_batched/Cf_batched (NOT the ls_* split). */
+int tacd_linesearch(const tacd_problem* p, const void* x0, const void* X, const void* U,
+                    const void* K, const void* k,
+                    const void* C, const void* c, const void* Cf, const void* cf,
+                    const void* xref, const void* uref,
+                    void* Xc, void* Uc, void* costs, void* stream);
+/* batched projected-Newton box QP: H[N,m,m] q[N,m] lo[N,m] hi[N,m] -> x[N,m], iters[N] (nullable) */
+int tacd_pnqp(int32_t dtype, int32_t N, int32_t m, const void* H, const void* q,
+              const void* lo, const void* hi, void* x, int32_t* iters, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TACD_ILQR_H */

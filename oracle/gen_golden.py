@@ -1,0 +1,551 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference):
+
+    python oracle/gen_golden.py            # writes tests/golden/*.npz
+
+The reference ships no golden vectors for the DMPC path and its own tests are
+stale, so parity is pinned by executing the reference's
+DifferentialMPC package (torch, CPU) on seeded inputs and recording
+  * the solve outputs X*, U*, the active-set mask and the final Jacobians,
+  * a lock-step decision trace (argmin alpha index, improved flag, candidate /
+    new / best costs per iteration and element) obtained by re-driving
+    solve_step with the controller's OWN methods (asserted bit-identical to
+    solve_step itself),
+  * first-iteration intermediates (A, B, l_*, K, k, candidates) for stage parity,
+  * the seven gradients for three losses,
+  * pnqp known answers.
+The dynamics plugins are the shipped example functions, imported from
+/root/reference/examples with matplotlib/gym stubbed.
+"""
+from __future__ import annotations
+
+import importlib.util
+import os
+import sys
+import warnings
+from unittest.mock import MagicMock
+
+import numpy as np
+import torch
+
+REF = os.environ.get("TACD_REFERENCE", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+for _m in ["matplotlib", "matplotlib.pyplot", "gym", "gymnasium", "gym.spaces", "gymnasium.spaces"]:
+    sys.modules.setdefault(_m, MagicMock())
+sys.path.insert(0, REF)
+warnings.filterwarnings("ignore")
+
+from DifferentialMPC import DifferentiableMPCController, GeneralQuadCost, pnqp  # noqa: E402
+from DifferentialMPC.controller import _vmap  # noqa: E402
+
+
+def _load(name):
+    spec = importlib.util.spec_from_file_location("ex_" + name, f"{REF}/examples/{name}.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+EX1 = _load("01_demo_linear")
+EX2 = _load("02_demo_cartpole_regulation")
+EX3 = _load("03_demo_unicycle_tracking")
+EX3AC = _load("03_demo_unicycle_AC")
+CP_PARAMS = EX2.CartPoleParams(m_c=1.0, m_p=0.1, l=0.5, g=9.8)  # gym CartPole-v1 constants
+
+
+# ----------------------------------------------------------------------------
+# lock-step tracer: solve_step (controller.py:275-315) re-driven with the
+# controller's own methods
+# ----------------------------------------------------------------------------
+def traced_solve(ctrl, x0, U_init, first_iter_n=4, force=None):
+    """force=(alpha[B,G], improved[B,G]) replays a recorded decision sequence instead of deciding."""
+    B = x0.shape[0]
+    cm = ctrl.cost_module
+    U, X = U_init.clone(), ctrl.rollout_trajectory(x0, U_init)
+    xr, ur = cm.x_ref, cm.u_ref
+    best = cm.objective(X, U, x_ref_override=xr, u_ref_override=ur)
+    tr = dict(alpha=[], improved=[], cand=[], newc=[], best=[])
+    first = None
+    active = torch.ones(B, dtype=torch.bool)
+    for i in range(ctrl.max_iter):
+        l = cm.quadraticize(X, U)
+        A, Bm = ctrl.linearize_dynamics(X, U)
+        K, k = _vmap(ctrl.backward_lqr)(A, Bm, *l)
+        Xc, Uc, costs = _vmap(ctrl.evaluate_alphas, in_dims=(0, 0, 0, 0, 0, 0, 0))(x0, X, U, K, k, xr, ur)
+        ai = torch.argmin(costs, dim=1)
+        if force is not None:
+            if i >= force[0].shape[1]:
+                break
+            ai = force[0][:, i].long()
+        Xn = torch.gather(Xc, 1, ai.view(B, 1, 1, 1).expand(-1, 1, X.shape[1], X.shape[2])).squeeze(1)
+        Un = torch.gather(Uc, 1, ai.view(B, 1, 1, 1).expand(-1, 1, U.shape[1], U.shape[2])).squeeze(1)
+        newc = cm.objective(Xn, Un, x_ref_override=xr, u_ref_override=ur)
+        imp = newc < best
+        if force is not None:
+            imp = force[1][:, i].bool()
+        if first is None:
+            n = min(first_iter_n, B)
+            first = dict(A=A[:n], Bm=Bm[:n], lx=l[0][:n], lu=l[1][:n],
+                         lxx=l[2].expand(B, *l[2].shape[-3:])[:n] if l[2].ndim == 4 else l[2][:n],
+                         lxu=l[3].expand(B, *l[3].shape[-3:])[:n], luu=l[4].expand(B, *l[4].shape[-3:])[:n],
+                         lxN=l[5][:n], lxxN=l[6].expand(B, *l[6].shape[-2:])[:n],
+                         K=K[:n], k=k[:n], Xc=Xc[:n], Uc=Uc[:n], costs=costs[:n], X=X[:n], U=U[:n])
+        tr["alpha"].append(ai.clone()); tr["improved"].append(imp.clone() & active)
+        tr["cand"].append(costs.clone()); tr["newc"].append(newc.clone()); tr["best"].append(best.clone())
+        tr["active"] = tr.get("active", []) + [active.clone()]
+        if not imp.any():
+            break
+        # an element that fails to improve is frozen for good (quirk Q11)
+        active = active & imp
+        best = torch.where(imp, newc, best)
+        X = torch.where(imp.view(B, 1, 1), Xn, X)
+        U = torch.where(imp.view(B, 1, 1), Un, U)
+    out = {k_: torch.stack(v, dim=1) for k_, v in tr.items()}
+    return X, U, out, first
+
+
+def per_element_trace(tr, max_iter):
+    """Convert the batch-global trace to the per-element format of the C ABI."""
+    act = tr["active"].numpy()            # [B, G] element still live at global iteration g
+    imp = tr["improved"].numpy()
+    alpha = tr["alpha"].numpy().astype(np.uint8)
+    B, G = act.shape
+    iters = act.sum(1).astype(np.int32)   # executed iterations while live
+    at = np.full((B, max_iter), 255, np.uint8)
+    flags = np.zeros(B, np.uint8)
+    for b in range(B):
+        at[b, :iters[b]] = alpha[b, :iters[b]]
+        if iters[b] == max_iter and imp[b, iters[b] - 1]:
+            flags[b] |= 2  # TACD_FLAG_MAXITER
+    return iters, at, flags
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def run_case(name, *, nx, nu, T, dt, f_dyn, f_dyn_jac, grad_method, dtype, x0, C, c, Cf, cf, xref, uref, Uinit,
+             u_min=None, u_max=None, reg_eps=1e-6, max_iter=40, spec_extra=None, grads=True):
+    torch.set_default_dtype(dtype)
+    leaves = [t.clone().detach().to(dtype) for t in (x0, C, c, Cf, cf, xref, uref)]
+    x0, C, c, Cf, cf, xref, uref = leaves
+    Uinit = Uinit.to(dtype)
+    if u_min is not None:
+        u_min, u_max = u_min.to(dtype), u_max.to(dtype)
+
+    def make():
+        cm = GeneralQuadCost(nx, nu, C, c, Cf, cf, device="cpu", x_ref=xref, u_ref=uref)
+        ctrl = DifferentiableMPCController(f_dyn, T * dt, dt, T, cm, u_min=u_min, u_max=u_max, reg_eps=reg_eps,
+                                           device="cpu", grad_method=grad_method, f_dyn_jac=f_dyn_jac,
+                                           max_iter=max_iter)
+        return cm, ctrl
+
+    cm, ctrl = make()
+    with torch.no_grad():
+        Xt, Ut, tr, first = traced_solve(ctrl, x0, Uinit)
+        cm2, ctrl2 = make()
+        Xs, Us = ctrl2.solve_step(x0, Uinit)
+        assert torch.equal(Xs, Xt) and torch.equal(Us, Ut), f"{name}: tracer is not bit-identical to solve_step"
+        A_fin, B_fin = ctrl2.F_last
+        tight = ctrl2.tight_mask_last
+        final_cost = cm2.objective(Xs, Us, x_ref_override=cm2.x_ref, u_ref_override=cm2.u_ref)
+    iters, at, flags = per_element_trace(tr, max_iter)
+    force = (tr["alpha"], tr["improved"])
+
+    def rel(a, b):
+        a = a.double().reshape(a.shape[0], -1)
+        b = b.double().reshape(b.shape[0], -1)
+        return ((a - b).abs().amax(1) / b.abs().amax(1).clamp_min(1.0)).numpy()
+
+    # (1) the reference's own sensitivity: x0 moved by one ulp, decisions held fixed
+    noise_X = np.zeros(x0.shape[0])
+    noise_U = np.zeros(x0.shape[0])
+    gp = torch.Generator().manual_seed(99)
+    with torch.no_grad():
+        for trial in range(3):
+            sgn = torch.where(torch.rand(x0.shape, generator=gp) < 0.5, -1.0, 1.0).to(dtype)
+            x0p = torch.nextafter(x0, x0 + sgn)
+            _, ctrlp = make()
+            Xp, Up, _, _ = traced_solve(ctrlp, x0p, Uinit, force=force)
+            noise_X = np.maximum(noise_X, rel(Xp, Xs))
+            noise_U = np.maximum(noise_U, rel(Up, Us))
+    # (2) the same decision sequence carried out in fp64 (the "exact" answer the fp32 run approximates)
+    X64 = U64 = None
+    if dtype == torch.float32:
+        torch.set_default_dtype(torch.float64)
+        with torch.no_grad():
+            cm64 = GeneralQuadCost(nx, nu, C.double(), c.double(), Cf.double(), cf.double(), device="cpu",
+                                   x_ref=xref.double(), u_ref=uref.double())
+            ctrl64 = DifferentiableMPCController(
+                f_dyn, T * dt, dt, T, cm64, u_min=None if u_min is None else u_min.double(),
+                u_max=None if u_max is None else u_max.double(), reg_eps=reg_eps, device="cpu",
+                grad_method=grad_method, f_dyn_jac=f_dyn_jac, max_iter=max_iter)
+            X64, U64, _, first64 = traced_solve(ctrl64, x0.double(), Uinit.double(), force=force)
+        torch.set_default_dtype(dtype)
+    d = dict(
+        meta_nx=nx, meta_nu=nu, meta_T=T, meta_dt=dt, meta_reg_eps=reg_eps, meta_max_iter=max_iter,
+        meta_grad_method=grad_method, meta_dtype=str(dtype).replace("torch.", ""),
+        x0=_np(x0), C=_np(C), c=_np(c), Cf=_np(Cf), cf=_np(cf), xref=_np(xref), uref=_np(uref), Uinit=_np(Uinit),
+        X=_np(Xs), U=_np(Us), A=_np(A_fin), Bm=_np(B_fin), tight=_np(tight).astype(np.uint8), cost=_np(final_cost),
+        iters=iters, alpha_trace=at, flags=flags, global_iters=np.int32(tr["alpha"].shape[1]),
+        tr_cand=_np(tr["cand"]), tr_newc=_np(tr["newc"]), tr_best=_np(tr["best"]),
+        tr_improved=_np(tr["improved"]).astype(np.uint8), tr_active=_np(tr["active"]).astype(np.uint8),
+    )
+    d["noise_X"], d["noise_U"] = noise_X, noise_U
+    if X64 is not None:
+        d["X64"], d["U64"] = _np(X64), _np(U64)
+        d["it0_K64"], d["it0_k64"] = _np(first64["K"]), _np(first64["k"])
+    if u_min is not None:
+        d["u_min"] = _np(u_min)
+        d["u_max"] = _np(u_max)
+    for k_, v in (spec_extra or {}).items():
+        d["meta_" + k_] = v
+    for k_, v in first.items():
+        d["it0_" + k_] = _np(v.contiguous())
+    if grads:
+        g = torch.Generator().manual_seed(1234)
+        wX = torch.randn(Xs.shape, generator=g, dtype=dtype)
+        wU = torch.randn(Us.shape, generator=g, dtype=dtype)
+        d["wX"], d["wU"] = _np(wX), _np(wU)
+        losses = {
+            "Usum": lambda X_, U_: U_.sum(),
+            "U0sum": lambda X_, U_: U_[:, 0].sum(),
+            "weighted": lambda X_, U_: (X_ * wX).sum() + (U_ * wU).sum(),
+        }
+        for ln, lf in losses.items():
+            lv = [t.clone().detach().requires_grad_(True) for t in leaves]
+            cm3 = GeneralQuadCost(nx, nu, lv[1], lv[2], lv[3], lv[4], device="cpu", x_ref=lv[5], u_ref=lv[6])
+            # registered buffers are not leaves any more; route the leaf tensors in again
+            cm3.x_ref, cm3.u_ref = lv[5], lv[6]
+            ctrl3 = DifferentiableMPCController(f_dyn, T * dt, dt, T, cm3, u_min=u_min, u_max=u_max, reg_eps=reg_eps,
+                                                device="cpu", grad_method=grad_method, f_dyn_jac=f_dyn_jac,
+                                                max_iter=max_iter)
+            Xo, Uo = ctrl3(lv[0], Uinit)
+            assert torch.equal(Xo.detach(), Xs) and torch.equal(Uo.detach(), Us)
+            lf(Xo, Uo).backward()
+            for nm, t in zip(("x0", "C", "c", "Cf", "cf", "xref", "uref"), lv):
+                d[f"grad_{ln}_{nm}"] = _np(t.grad if t.grad is not None else torch.zeros_like(t))
+            if dtype == torch.float32:
+                # the same backward (ILQRSolve.backward, controller.py:63-115) carried out in fp64 on the
+                # SAME saved tensors: how far the reference's fp32 gradients are from exact arithmetic
+                from types import SimpleNamespace
+                from DifferentialMPC import ILQRSolve
+                torch.set_default_dtype(torch.float64)
+                H = ctrl3.H_last
+                ctrl3.u_min = None if u_min is None else u_min.double()
+                ctrl3.u_max = None if u_max is None else u_max.double()
+                ctx = SimpleNamespace(controller=ctrl3, saved_tensors=tuple(
+                    t.detach().double() if t.dtype.is_floating_point else t.detach() for t in
+                    (Xo, Uo, H[0], H[1], H[2], ctrl3.F_last[0], ctrl3.F_last[1], ctrl3.tight_mask_last, lv[5], lv[6])))
+                gXo = torch.autograd.grad(lf(Xo.detach().requires_grad_(True), Uo.detach()), [], allow_unused=True) \
+                    if False else None
+                Xd, Ud = Xo.detach().double().requires_grad_(True), Uo.detach().double().requires_grad_(True)
+                lval = (Ud.sum() if ln == "Usum" else Ud[:, 0].sum() if ln == "U0sum"
+                        else (Xd * wX.double()).sum() + (Ud * wU.double()).sum())
+                gXd, gUd = torch.autograd.grad(lval, [Xd, Ud], allow_unused=True)
+                gXd = torch.zeros_like(Xd) if gXd is None else gXd
+                gUd = torch.zeros_like(Ud) if gUd is None else gUd
+                with torch.no_grad():
+                    g64 = ILQRSolve.backward(ctx, gXd, gUd)
+                shapes = [t.shape for t in lv]
+                for nm, t, sh in zip(("x0", "C", "c", "Cf", "cf", "xref", "uref"), g64[:7], shapes):
+                    d[f"grad64_{ln}_{nm}"] = _np(t.sum_to_size(sh) if t.shape != sh else t)
+                torch.set_default_dtype(dtype)
+    os.makedirs(OUT, exist_ok=True)
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **d)
+    print(f"{name:32s} B={x0.shape[0]:3d} global_iters={int(d['global_iters']):2d} "
+          f"iters[min,max]=[{iters.min()},{iters.max()}] tight={d['tight'].mean():.2f} noiseU={noise_U.max():.1e} "
+          + (f"ref32-vs-64={rel(Us, U64).max():.1e} " if X64 is not None else "") +
+          f"{os.path.getsize(path) / 1024:.0f} KB")
+    return d
+
+
+# ----------------------------------------------------------------------------
+# configurations
+# ----------------------------------------------------------------------------
+def quad_cost(Q, R, T, final_scale=10.0, final_full=True):
+    nx, nu = Q.shape[0], R.shape[0]
+    n = nx + nu
+    C = torch.zeros(T, n, n)
+    C[:, :nx, :nx] = Q
+    C[:, nx:, nx:] = R
+    c = torch.zeros(T, n)
+    if final_full:
+        Cf = C[0].clone() * final_scale
+    else:
+        Cf = torch.zeros(n, n)
+        Cf[:nx, :nx] = Q * final_scale
+    cf = torch.zeros(n)
+    return C, c, Cf, cf
+
+
+def case_di(dtype, B=6, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    nx, nu, T, dt = 2, 1, 20, 0.05
+    C, c, Cf, cf = quad_cost(torch.diag(torch.tensor([100.0, 1.0])), torch.diag(torch.tensor([0.01])), T)
+    t = torch.arange(T + 1) * dt
+    amp = 5.0 + torch.rand(B, 1, generator=g) * 5.0
+    om = 1.0 + torch.rand(B, 1, generator=g)
+    ph = torch.rand(B, 1, generator=g) * 3.0
+    xref = torch.stack([amp * torch.sin(om * t + ph), amp * om * torch.cos(om * t + ph)], dim=2)
+    uref = torch.zeros(B, T, nu)
+    x0 = torch.randn(B, nx, generator=g) * torch.tensor([2.0, 1.0])
+    return dict(nx=nx, nu=nu, T=T, dt=dt, f_dyn=EX1.f_dyn_linear, f_dyn_jac=EX1.f_dyn_jac_linear_batched,
+                grad_method="analytic", dtype=dtype, x0=x0, C=C, c=c, Cf=Cf, cf=cf, xref=xref, uref=uref,
+                Uinit=torch.zeros(B, T, nu), u_min=torch.tensor([-50.0]), u_max=torch.tensor([50.0]),
+                spec_extra=dict(dyn="lti", lti_A=np.array([[1.0, dt], [0.0, 1.0]]), lti_B=np.array([[0.0], [dt]])))
+
+
+def cartpole_fns():
+    return (lambda x, u, dt: EX2.f_cartpole(x, u, dt, CP_PARAMS),
+            lambda x, u, dt: EX2.f_cartpole_jac_batched(x, u, dt, CP_PARAMS))
+
+
+def case_cartpole_shared(dtype, B=32, seed=0, grad_method="analytic", T=20):
+    g = torch.Generator().manual_seed(seed)
+    nx, nu, dt = 4, 1, 0.05
+    C, c, Cf, cf = quad_cost(torch.diag(torch.tensor([10.0, 1.0, 100.0, 1.0])), torch.diag(torch.tensor([0.1])), T,
+                             final_full=False)
+    x0 = torch.tensor([0.0, 0.0, 0.2, 0.0]) + torch.randn(B, nx, generator=g) * torch.tensor([0.5, 0.5, 0.2, 0.2])
+    f, fj = cartpole_fns()
+    return dict(nx=nx, nu=nu, T=T, dt=dt, f_dyn=f, f_dyn_jac=fj if grad_method == "analytic" else None,
+                grad_method=grad_method, dtype=dtype, x0=x0, C=C, c=c, Cf=Cf, cf=cf,
+                xref=torch.zeros(B, T + 1, nx), uref=torch.zeros(B, T, nu), Uinit=torch.zeros(B, T, nu),
+                u_min=torch.tensor([-20.0]), u_max=torch.tensor([20.0]),
+                spec_extra=dict(dyn="cartpole", dyn_params=np.array([1.0, 0.1, 0.5, 9.8])))
+
+
+def case_cartpole_actor(dtype, B=16, seed=1, T=20):
+    """ActorMPC-shaped problem (ACMPC/actor.py:58-81): per-element diagonal C, c; C_final=C[:,-1];
+    reg_eps=1e-2; no bounds; U_init = 0.01 randn.  Exercises quirk Q4."""
+    g = torch.Generator().manual_seed(seed)
+    nx, nu, dt = 4, 1, 0.05
+    n = nx + nu
+    q = torch.nn.functional.softplus(torch.randn(B, T, n, generator=g)) + 1e-2
+    C = torch.diag_embed(q)
+    c = 0.3 * torch.randn(B, T, n, generator=g)
+    Cf, cf = C[:, -1].clone(), c[:, -1].clone()
+    x0 = torch.rand(B, nx, generator=g) * 0.45 - 0.2
+    f, fj = cartpole_fns()
+    return dict(nx=nx, nu=nu, T=T, dt=dt, f_dyn=f, f_dyn_jac=fj, grad_method="analytic", dtype=dtype,
+                x0=x0, C=C, c=c, Cf=Cf, cf=cf, xref=torch.zeros(B, T + 1, nx), uref=torch.zeros(B, T, nu),
+                Uinit=0.01 * torch.randn(B, T, nu, generator=g), reg_eps=1e-2,
+                spec_extra=dict(dyn="cartpole", dyn_params=np.array([1.0, 0.1, 0.5, 9.8])))
+
+
+def case_unicycle(dtype, B=8, seed=2, tight=True, wrapped=False, T=30):
+    g = torch.Generator().manual_seed(seed)
+    nx, nu, dt = 3, 2, 0.1
+    C, c, Cf, cf = quad_cost(torch.diag(torch.tensor([20.0, 20.0, 5.0])), torch.diag(torch.tensor([0.1, 0.1])), T)
+    ph = torch.rand(B, 1, generator=g) * 2 * torch.pi
+    amp = 3.0 + 2.0 * torch.rand(B, 1, generator=g)
+    tt = ph + torch.arange(T + 1) * dt * 0.5
+    xr = amp * torch.sin(tt)
+    yr = amp * torch.sin(tt) * torch.cos(tt)
+    dxr = amp * torch.cos(tt)
+    dyr = amp * torch.cos(2 * tt)
+    th = torch.atan2(dyr, dxr)
+    xref = torch.stack([xr, yr, th], dim=2)
+    uref = torch.zeros(B, T, nu)
+    x0 = xref[:, 0] + torch.randn(B, nx, generator=g) * torch.tensor([1.0, 1.0, 0.5])
+    if tight:
+        umin, umax = torch.tensor([-2.0, -1.0]), torch.tensor([2.0, 1.0])
+    else:
+        umin, umax = torch.tensor([-10.0, -2 * np.pi]), torch.tensor([10.0, 2 * np.pi])
+    f = EX3AC.f_dyn_torch if wrapped else EX3.f_dyn_unicycle
+    fj = EX3AC.f_dyn_jac_torch if wrapped else EX3.f_dyn_jac_unicycle
+    return dict(nx=nx, nu=nu, T=T, dt=dt, f_dyn=f, f_dyn_jac=fj, grad_method="analytic", dtype=dtype,
+                x0=x0, C=C, c=c, Cf=Cf, cf=cf, xref=xref, uref=uref, Uinit=torch.zeros(B, T, nu),
+                u_min=umin, u_max=umax, spec_extra=dict(dyn="unicycle_wrapped" if wrapped else "unicycle"))
+
+
+def case_lti(dtype, nx=8, nu=4, T=50, B=4, seed=0, mixed=False):
+    """config 5: shared LTI dynamics, per-element diagonal costs."""
+    g = torch.Generator().manual_seed(seed)
+    n = nx + nu
+    A = torch.eye(nx) + 0.1 * torch.randn(nx, nx, generator=g) / np.sqrt(nx)
+    Bm = 0.1 * torch.randn(nx, nu, generator=g)
+    d = 0.5 + torch.rand(B, T, n, generator=g)
+    d[..., nx:] *= 0.1
+    C = torch.diag_embed(d)
+    c = 0.1 * torch.randn(B, T, n, generator=g)
+    Cf, cf = C[:, -1].clone(), c[:, -1].clone()
+    if mixed:  # shared running cost, per-element terminal cost
+        C, c = C[0].clone(), c[0].clone()
+    x0 = torch.randn(B, nx, generator=g)
+
+    def f(x, u, dt, A=A, Bm=Bm):
+        return x @ A.to(x.dtype).T + u @ Bm.to(x.dtype).T
+
+    def fj(x, u, dt, A=A, Bm=Bm):
+        N = x.shape[0]
+        return A.to(x.dtype).unsqueeze(0).expand(N, -1, -1), Bm.to(x.dtype).unsqueeze(0).expand(N, -1, -1)
+
+    return dict(nx=nx, nu=nu, T=T, dt=0.1, f_dyn=f, f_dyn_jac=fj, grad_method="analytic", dtype=dtype,
+                x0=x0, C=C, c=c, Cf=Cf, cf=cf, xref=torch.zeros(B, T + 1, nx), uref=torch.zeros(B, T, nu),
+                Uinit=torch.zeros(B, T, nu), spec_extra=dict(dyn="lti", lti_A=A.numpy().astype(np.float64),
+                                                             lti_B=Bm.numpy().astype(np.float64)))
+
+
+def case_gradcheck():
+    """tests/test_gradcheck.py:7-51 adapted to the current API: nx=nu=1, H=4, all-zero cost, f = x + dt u."""
+    nx = nu = 1
+    T, dt = 4, 0.1
+    torch.manual_seed(0)
+    x0 = torch.randn(1, nx, dtype=torch.float64)
+    n = nx + nu
+
+    def f(x, u, dt):
+        return x + dt * u
+
+    return dict(nx=nx, nu=nu, T=T, dt=dt, f_dyn=f, f_dyn_jac=None, grad_method="auto_diff", dtype=torch.float64,
+                x0=x0, C=torch.zeros(T, n, n), c=torch.zeros(T, n), Cf=torch.zeros(n, n), cf=torch.zeros(n),
+                xref=torch.zeros(1, T + 1, nx), uref=torch.zeros(1, T, nu), Uinit=torch.zeros(1, T, nu),
+                spec_extra=dict(dyn="lti", lti_A=np.array([[1.0]]), lti_B=np.array([[dt]])))
+
+
+def closed_loop_batch_tracking():
+    """tests/test_batch_tracking.py:25-90 adapted to the current API (per-step set_reference + forward,
+    as examples/01_demo_linear.py:114-125 does): B=2 double integrator, T=5, N_sim=20."""
+    torch.set_default_dtype(torch.float64)
+    nx, nu, T, N_sim, dt, B = 2, 1, 5, 20, 0.1, 2
+    C, c, Cf, cf = quad_cost(torch.diag(torch.tensor([1.0, 0.1])), torch.diag(torch.tensor([0.01])), T)
+    C, c, Cf, cf = (t.double() for t in (C, c, Cf, cf))
+    cm = GeneralQuadCost(nx, nu, C, c, Cf, cf, device="cpu")
+    Tm = __import__("importlib").import_module  # noqa: F841
+
+    def f(x, u, dt):
+        A = torch.tensor([[1.0, dt], [0.0, 1.0]], dtype=x.dtype)
+        Bm = torch.tensor([[0.0], [dt]], dtype=x.dtype)
+        return torch.einsum("...ij,...j->...i", A, x) + torch.einsum("...ij,...j->...i", Bm, u)
+
+    def fj(x, u, dt):
+        N = x.shape[0]
+        A = torch.tensor([[1.0, dt], [0.0, 1.0]], dtype=x.dtype)
+        Bm = torch.tensor([[0.0], [dt]], dtype=x.dtype)
+        return A.expand(N, -1, -1), Bm.expand(N, -1, -1)
+
+    mpc = DifferentiableMPCController(f, T * dt, dt, T, cm, grad_method="analytic", f_dyn_jac=fj, device="cpu",
+                                      N_sim=N_sim)
+    x0 = torch.tensor([[4.0, 0.0], [-4.0, 0.0]])
+    ref_len = N_sim + T + 1
+    ts = torch.linspace(0, 10, ref_len)
+    xrA = torch.stack([torch.sin(ts), torch.cos(ts)], dim=1)
+    xrB = torch.stack([0.5 * torch.cos(ts), -0.5 * torch.sin(ts)], dim=1)
+    xref_full = torch.stack([xrA, xrB], dim=0)
+    uref_full = torch.zeros(B, ref_len - 1, nu)
+    Xs = [x0]
+    Us = []
+    x = x0
+    with torch.no_grad():
+        for k in range(N_sim):
+            cm.set_reference(xref_full[:, k:k + T + 1], uref_full[:, k:k + T])
+            _, U = mpc.forward(x)
+            u = U[:, 0]
+            x = f(x, u, dt)
+            Xs.append(x)
+            Us.append(u)
+    d = dict(x0=_np(x0), xref_full=_np(xref_full), uref_full=_np(uref_full), C=_np(C), c=_np(c), Cf=_np(Cf), cf=_np(cf),
+             Xs=_np(torch.stack(Xs, 1)), Us=_np(torch.stack(Us, 1)), meta_T=T, meta_N_sim=N_sim, meta_dt=dt)
+    np.savez_compressed(os.path.join(OUT, "closed_loop_batch_tracking.npz"), **d)
+    print("closed_loop_batch_tracking       Xs", d["Xs"].shape)
+
+
+def pnqp_kats():
+    d = {}
+    for dtype, tag in ((torch.float64, "f64"), (torch.float32, "f32")):
+        g = torch.Generator().manual_seed(7)
+        for m in (1, 2, 3, 4):
+            N = 48
+            M = torch.randn(N, m, m, generator=g, dtype=torch.float64)
+            H = (M @ M.mT + 0.3 * torch.eye(m)).to(dtype)
+            q = (3.0 * torch.randn(N, m, generator=g, dtype=torch.float64)).to(dtype)
+            lo = (-torch.rand(N, m, generator=g, dtype=torch.float64) * 1.5).to(dtype)
+            hi = (torch.rand(N, m, generator=g, dtype=torch.float64) * 1.5).to(dtype)
+            # a third of the problems unbounded, as in the un-constrained backward (controller.py:739-740)
+            lo[::3] = -float("inf")
+            hi[::3] = float("inf")
+            xs, its = [], []
+            for i in range(N):
+                x, info = pnqp(H[i:i + 1], q[i:i + 1], lo[i:i + 1], hi[i:i + 1])
+                xs.append(x[0])
+                its.append(info["iters"])
+            d[f"{tag}_m{m}_H"], d[f"{tag}_m{m}_q"] = _np(H), _np(q)
+            d[f"{tag}_m{m}_lo"], d[f"{tag}_m{m}_hi"] = _np(lo), _np(hi)
+            d[f"{tag}_m{m}_x"] = _np(torch.stack(xs))
+            d[f"{tag}_m{m}_iters"] = np.array(its, np.int32)
+    np.savez_compressed(os.path.join(OUT, "pnqp_kat.npz"), **d)
+    print("pnqp_kat                         ", len(d), "arrays")
+
+
+def fd_jacobian_kats():
+    """grad_method="finite_diff" cannot be run end to end at reference HEAD: linearize_dynamics
+    shadows the batch size B with the returned Jacobian (controller.py:468-471) and raises TypeError.
+    The stage it calls, jacobian_finite_diff_batched (utils.py:48-64, eps=1e-4), works and is pinned here."""
+    from DifferentialMPC import jacobian_finite_diff_batched
+    d = {}
+    f_cp, _ = cartpole_fns()
+    for dtype, tag in ((torch.float64, "f64"), (torch.float32, "f32")):
+        g = torch.Generator().manual_seed(11)
+        x = torch.randn(32, 4, generator=g, dtype=torch.float64).to(dtype)
+        u = (3 * torch.randn(32, 1, generator=g, dtype=torch.float64)).to(dtype)
+        A, Bm = jacobian_finite_diff_batched(f_cp, x, u, dt=0.05)
+        d[f"cartpole_{tag}_x"], d[f"cartpole_{tag}_u"] = _np(x), _np(u)
+        d[f"cartpole_{tag}_A"], d[f"cartpole_{tag}_B"] = _np(A), _np(Bm)
+        x = torch.randn(32, 3, generator=g, dtype=torch.float64).to(dtype)
+        u = torch.randn(32, 2, generator=g, dtype=torch.float64).to(dtype)
+        A, Bm = jacobian_finite_diff_batched(EX3.f_dyn_unicycle, x, u, dt=0.1)
+        d[f"unicycle_{tag}_x"], d[f"unicycle_{tag}_u"] = _np(x), _np(u)
+        d[f"unicycle_{tag}_A"], d[f"unicycle_{tag}_B"] = _np(A), _np(Bm)
+    np.savez_compressed(os.path.join(OUT, "fd_jacobian_kat.npz"), **d)
+    print("fd_jacobian_kat                  ", len(d), "arrays")
+
+
+def check_shipped_dynamics_match_example_variants():
+    """The three cart-pole f's shipped in the reference (examples/02_demo_cartpole_regulation.py,
+    02_demo_cartpole_AC.py, tests/test_forward.py) are the same function; record that."""
+    ac = _load("02_demo_cartpole_AC")
+    x = torch.randn(64, 4, dtype=torch.float64)
+    u = torch.randn(64, 1, dtype=torch.float64)
+    p2 = ac.CartPoleParams(m_c=1.0, m_p=0.1, l=0.5, g=9.8)
+    a = EX2.f_cartpole(x, u, 0.05, CP_PARAMS)
+    b = ac.f_cartpole_torch(x, u, 0.05, p2)
+    assert torch.allclose(a, b, rtol=0, atol=1e-15), (a - b).abs().max()
+
+
+def main():
+    torch.manual_seed(0)
+    torch.set_num_threads(4)
+    os.makedirs(OUT, exist_ok=True)
+    check_shipped_dynamics_match_example_variants()
+    F32, F64 = torch.float32, torch.float64
+    run_case("di_f64", **case_di(F64))
+    run_case("di_f32", **case_di(F32))
+    run_case("cartpole_shared_f32", **case_cartpole_shared(F32))
+    run_case("cartpole_shared_f64", **case_cartpole_shared(F64, B=16))
+    run_case("cartpole_actor_f32", **case_cartpole_actor(F32))
+    run_case("cartpole_actor_f64", **case_cartpole_actor(F64, B=8))
+    fd_jacobian_kats()
+    run_case("cartpole_ad_f64", **case_cartpole_shared(F64, B=4, grad_method="auto_diff"))
+    run_case("unicycle_tight_f32", **case_unicycle(F32))
+    run_case("unicycle_tight_f64", **case_unicycle(F64))
+    run_case("unicycle_loose_f64", **case_unicycle(F64, B=4, tight=False))
+    run_case("unicycle_loose_f32", **case_unicycle(F32, B=8, tight=False, seed=5, T=20))
+    run_case("unicycle_wrapped_f64", **case_unicycle(F64, B=4, tight=True, wrapped=True, T=15))
+    run_case("lti8_f32", **case_lti(F32))
+    run_case("lti8_T20_f32", **case_lti(F32, T=20, B=4, seed=3))
+    run_case("lti8_f64", **case_lti(F64, T=20))
+    run_case("lti8_mixed_f64", **case_lti(F64, T=12, mixed=True))
+    run_case("lti16_f32", **case_lti(F32, nx=16, nu=4, T=20, B=2))
+    run_case("lti32_f32", **case_lti(F32, nx=32, nu=8, T=10, B=2))
+    run_case("gradcheck_f64", **case_gradcheck())
+    closed_loop_batch_tracking()
+    pnqp_kats()
+
+
+if __name__ == "__main__":
+    main()
