@@ -34,8 +34,8 @@ SOLVE_CASES = [
 ]
 # lti8_f32 rolls an open-loop-unstable LTI system out for T=50 steps in fp32; the reference's own fp32
 # answer is 5.2 (relative) away from its fp64 answer on this case (gen_golden.py prints it), so one
-# 50-step fp32 rollout is only reproducible to ~5e-5.
-STAGE_SLACK = {"lti8_f32": 10.0}
+# 50-step fp32 rollout is only reproducible to ~1e-4 (U, through the feedback gains).
+STAGE_SLACK = {"lti8_f32": 30.0}
 SMALL_CASES = [c for c in SOLVE_CASES if not c.startswith("lti")] 
 
 
