@@ -1,0 +1,18 @@
+"""Drop-in for the reference package ``DifferentialMPC`` (DifferentialMPC/__init__.py:1-16): same names,
+same constructor arguments, same side effects — the solve itself runs in hand-written sm_100a kernels.
+
+    import tacdmpc_b200.DifferentialMPC as DifferentialMPC
+"""
+from .cost import GeneralQuadCost
+from .controller import DifferentiableMPCController, GradMethod, ILQRSolve
+from .utils import pnqp, batched_jacobian, jacobian_finite_diff_batched
+
+__all__ = [
+    "GeneralQuadCost",
+    "ILQRSolve",
+    "DifferentiableMPCController",
+    "GradMethod",
+    "pnqp",
+    "batched_jacobian",
+    "jacobian_finite_diff_batched",
+]

@@ -1,0 +1,104 @@
+// capi.cu — the C ABI of include/tacd_ilqr.h: argument validation, dispatch
+// between the thread-per-element kernels (shipped small plugins) and the generic
+// CTA-per-element kernels, error reporting.  Nothing here synchronises the host.
+#include <string.h>
+
+#include "host_common.h"
+
+namespace tacd {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return TACD_OK;
+  set_error("%s: %s", what, cudaGetErrorString(e));
+  return TACD_ECUDA;
+}
+
+DeviceInfo device_info() {
+  static thread_local int cached_dev = -1;
+  static thread_local DeviceInfo di;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev != cached_dev) {
+    cudaDeviceGetAttribute(&di.sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&di.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cached_dev = dev;
+  }
+  return di;
+}
+
+static int validate(const tacd_problem* p) {
+  if (!p) { set_error("null problem"); return TACD_EINVAL; }
+  if (p->B < 0 || p->T < 1 || p->nx < 1 || p->nu < 1) { set_error("bad sizes B=%d T=%d nx=%d nu=%d", p->B, p->T, p->nx, p->nu); return TACD_EINVAL; }
+  if (p->nx > TACD_MAX_NX || p->nu > TACD_MAX_NU) { set_error("nx<=%d, nu<=%d supported", TACD_MAX_NX, TACD_MAX_NU); return TACD_EINVAL; }
+  if (p->n_alpha < 1 || p->n_alpha > TACD_MAX_ALPHA) { set_error("n_alpha must be in 1..%d", TACD_MAX_ALPHA); return TACD_EINVAL; }
+  if (p->dtype != TACD_F32 && p->dtype != TACD_F64) { set_error("dtype must be TACD_F32 or TACD_F64"); return TACD_EINVAL; }
+  if (p->max_iter < 0) { set_error("max_iter < 0"); return TACD_EINVAL; }
+  if (p->dyn_id == TACD_DYN_LTI && (!p->dyn_A || !p->dyn_B)) { set_error("LTI dynamics need dyn_A, dyn_B"); return TACD_EINVAL; }
+  if (p->dyn_id == TACD_DYN_CARTPOLE && !(p->nx == 4 && p->nu == 1)) { set_error("cartpole is nx=4, nu=1"); return TACD_EINVAL; }
+  if ((p->dyn_id == TACD_DYN_UNICYCLE || p->dyn_id == TACD_DYN_UNICYCLE_WRAPPED) && !(p->nx == 3 && p->nu == 2)) { set_error("unicycle is nx=3, nu=2"); return TACD_EINVAL; }
+  if (p->dyn_id < 0 || p->dyn_id > TACD_DYN_EXTERNAL) { set_error("unknown dyn_id %d", p->dyn_id); return TACD_EINVAL; }
+  return TACD_OK;
+}
+
+}  // namespace tacd
+
+using namespace tacd;
+
+extern "C" {
+
+int tacd_abi_version(void) { return TACD_ABI_VERSION; }
+const char* tacd_last_error(void) { return g_err; }
+
+size_t tacd_forward_workspace_bytes(const tacd_problem* p) {
+  if (validate(p)) return 0;
+  return 256 + generic_forward_ws_bytes(p);
+}
+size_t tacd_backward_workspace_bytes(const tacd_problem* p) {
+  if (validate(p)) return 0;
+  return 256 + generic_backward_ws_bytes(p);
+}
+
+int tacd_ilqr_forward(const tacd_problem* p, const tacd_forward_io* io, void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = validate(p)) return rc;
+  if (!io || !io->x0 || !io->C || !io->c || !io->Cf || !io->cf || !io->xref || !io->uref || !io->Uinit || !io->X || !io->U ||
+      !io->tight || !io->iters || !io->flags) { set_error("tacd_ilqr_forward: required pointer is null"); return TACD_EINVAL; }
+  if (p->ls_cost_shared && (!io->C_ls || !io->c_ls || !io->Cf_ls || !io->cf_ls)) { set_error("ls_cost_shared needs C_ls/c_ls/Cf_ls/cf_ls"); return TACD_EINVAL; }
+  if (p->dyn_id == TACD_DYN_EXTERNAL) { set_error("the whole solve needs embedded dynamics (dyn_id != EXTERNAL)"); return TACD_EINVAL; }
+  if (io->replay_iters && (!io->replay_alpha || !io->replay_flags)) { set_error("replay needs iters, alpha and flags"); return TACD_EINVAL; }
+  if (!workspace || workspace_bytes < 256) { set_error("workspace too small (need tacd_forward_workspace_bytes)"); return TACD_EWORKSPACE; }
+  if (p->B == 0) return TACD_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = (p->dtype == TACD_F32) ? launch_forward_small<float>(p, io, workspace, s) : launch_forward_small<double>(p, io, workspace, s);
+  if (rc != TACD_EUNSUPPORTED) return rc;
+  char* ws = (char*)workspace + 256;
+  rc = (p->dtype == TACD_F32) ? launch_forward_generic<float>(p, io, ws, workspace_bytes - 256, s)
+                              : launch_forward_generic<double>(p, io, ws, workspace_bytes - 256, s);
+  return rc;
+}
+
+int tacd_ilqr_backward(const tacd_problem* p, const tacd_backward_io* io, void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = validate(p)) return rc;
+  if (!io || !io->X || !io->U || !io->C || !io->xref || !io->uref || !io->tight || !io->gX || !io->gU) { set_error("tacd_ilqr_backward: required pointer is null"); return TACD_EINVAL; }
+  if (p->dyn_id == TACD_DYN_EXTERNAL && (!io->A || !io->Bm)) { set_error("EXTERNAL dynamics need A and Bm"); return TACD_EINVAL; }
+  if (p->has_umin && !p->has_umax) { set_error("backward assumes u_max whenever u_min is set (reference quirk Q10)"); return TACD_EINVAL; }
+  if (p->B == 0) return TACD_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = (p->dtype == TACD_F32) ? launch_backward_small<float>(p, io, s) : launch_backward_small<double>(p, io, s);
+  if (rc != TACD_EUNSUPPORTED) return rc;
+  if (!workspace || workspace_bytes < 256) { set_error("workspace too small (need tacd_backward_workspace_bytes)"); return TACD_EWORKSPACE; }
+  char* ws = (char*)workspace + 256;
+  rc = (p->dtype == TACD_F32) ? launch_backward_generic<float>(p, io, ws, workspace_bytes - 256, s)
+                              : launch_backward_generic<double>(p, io, ws, workspace_bytes - 256, s);
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,45 @@
+// host_common.h — host-side helpers shared by the C-ABI translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "tacd_dev.cuh"
+#include "ilqr_small.cuh"
+
+namespace tacd {
+
+void set_error(const char* fmt, ...);
+int check_cuda(cudaError_t e, const char* what);
+
+struct DeviceInfo { int sms; int smem_optin; };
+DeviceInfo device_info();
+
+template <typename R>
+inline DevProblem<R> to_dev(const tacd_problem* p) {
+  DevProblem<R> d;
+  d.B = p->B; d.T = p->T; d.max_iter = p->max_iter; d.n_alpha = p->n_alpha;
+  d.C_batched = p->C_batched; d.Cf_batched = p->Cf_batched;
+  d.xref_batched = p->xref_batched; d.uref_batched = p->uref_batched;
+  d.ls_cost_shared = p->ls_cost_shared;
+  d.jac_mode = p->jac_mode; d.has_umin = p->has_umin; d.has_umax = p->has_umax;
+  d.dt = (R)p->dt; d.reg = (R)p->reg_eps; d.fd_eps = (R)p->fd_eps;
+  for (int i = 0; i < TACD_MAX_ALPHA; ++i) d.alphas[i] = (R)p->alphas[i];
+  for (int i = 0; i < TACD_MAX_NU; ++i) { d.umin[i] = (R)p->umin[i]; d.umax[i] = (R)p->umax[i]; }
+  for (int i = 0; i < 8; ++i) d.dynp[i] = (R)p->dyn_params[i];
+  d.dyn_A = (const R*)p->dyn_A; d.dyn_B = (const R*)p->dyn_B;
+  return d;
+}
+
+// small-system (thread-per-element) launchers; return TACD_EUNSUPPORTED when
+// (nx, nu, dyn) has no instantiation or the per-thread state does not fit shared memory
+template <typename R> int launch_forward_small(const tacd_problem* p, const tacd_forward_io* io, void* ws, cudaStream_t s);
+template <typename R> int launch_backward_small(const tacd_problem* p, const tacd_backward_io* io, cudaStream_t s);
+
+// generic (CTA-per-element, run-time dimensions) launchers
+template <typename R> int launch_forward_generic(const tacd_problem* p, const tacd_forward_io* io, void* ws, size_t ws_bytes, cudaStream_t s);
+template <typename R> int launch_backward_generic(const tacd_problem* p, const tacd_backward_io* io, void* ws, size_t ws_bytes, cudaStream_t s);
+size_t generic_forward_ws_bytes(const tacd_problem* p);
+size_t generic_backward_ws_bytes(const tacd_problem* p);
+
+}  // namespace tacd

@@ -1,0 +1,695 @@
+// ilqr_generic.cu — CTA-per-element whole-solve kernels for run-time dimensions,
+// plus the stand-alone stage entry points of the C ABI (rollout, linearize,
+// objective, riccati, linesearch, pnqp).  See ilqr_generic.cuh for the layout.
+#include "host_common.h"
+#include "ilqr_generic.cuh"
+
+namespace tacd {
+
+// per-CTA slice of the workspace: X[(T+1)nx] U[T nu] K[T nu nx] k[T nu]
+static inline size_t gen_slice_scalars(const tacd_problem* p) {
+  const size_t nx = p->nx, nu = p->nu, T = p->T;
+  return (T + 1) * nx + T * nu + T * nu * nx + T * nu;
+}
+static int gen_grid(const tacd_problem* p) {
+  const DeviceInfo di = device_info();
+  int g = di.sms * 4;
+  if (g > p->B) g = p->B;
+  return g < 1 ? 1 : g;
+}
+size_t generic_forward_ws_bytes(const tacd_problem* p) {
+  const size_t es = (p->dtype == TACD_F32) ? 4 : 8;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  size_t g = (size_t)sms * 4;
+  return g * gen_slice_scalars(p) * es + 256;
+}
+size_t generic_backward_ws_bytes(const tacd_problem* p) { return generic_forward_ws_bytes(p); }
+
+template <typename R>
+static GenDims<R> dims_of(const tacd_problem* p) {
+  GenDims<R> d;
+  d.nx = p->nx; d.nu = p->nu; d.n = p->nx + p->nu; d.T = p->T; d.dyn = p->dyn_id;
+  return d;
+}
+
+// ---------------------------------------------------------------------------
+// forward solve (solve_step, controller.py:275-315)
+template <typename R>
+__global__ void __launch_bounds__(kGenThreads) ilqr_forward_generic(const DevProblem<R> P, const GenDims<R> d, const FwdPtrs<R> io, R* ws, size_t slice) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  GenSmem<R> s = gen_carve<R>(smem_raw, d.nx, d.nu);
+  const int tid = threadIdx.x, nx = d.nx, nu = d.nu, n = d.n, T = d.T;
+  const size_t szX = (size_t)(T + 1) * nx, szU = (size_t)T * nu;
+  R* gXs = ws + (size_t)blockIdx.x * slice;
+  R* gUs = gXs + szX;
+  R* gK = gUs + szU;
+  R* gk = gK + (size_t)T * nu * nx;
+  if (d.dyn == TACD_DYN_LTI) {
+    for (int i = tid; i < nx * nx; i += kGenThreads) s.A[i] = P.dyn_A[i];
+    for (int i = tid; i < nx * nu; i += kGenThreads) s.Bm[i] = P.dyn_B[i];
+  }
+  __syncthreads();
+  const bool lssep = P.ls_cost_shared != 0;
+  for (int b = blockIdx.x; b < P.B; b += gridDim.x) {
+    const R* Cp = io.C + (P.C_batched ? (size_t)b * T * n * n : 0);
+    const R* cp = io.c + (P.C_batched ? (size_t)b * T * n : 0);
+    const R* Cfp = io.Cf + (P.Cf_batched ? (size_t)b * n * n : 0);
+    const R* cfp = io.cf + (P.Cf_batched ? (size_t)b * n : 0);
+    const R* Cl = lssep ? io.C_ls : Cp;
+    const R* cl = lssep ? io.c_ls : cp;
+    const R* Cfl = lssep ? io.Cf_ls : Cfp;
+    const R* cfl = lssep ? io.cf_ls : cfp;
+    const R* xr = io.xref + (P.xref_batched ? (size_t)b * szX : 0);
+    const R* ur = io.uref + (P.uref_batched ? (size_t)b * szU : 0);
+    // ---- init: U = U_init, X = rollout (no clamping), best = objective
+    for (int i = tid; i < (int)szU; i += kGenThreads) gUs[i] = io.Uinit[(size_t)b * szU + i];
+    for (int i = tid; i < nx; i += kGenThreads) gXs[i] = io.x0[(size_t)b * nx + i];
+    if (io.alpha_trace) for (int j = tid; j < P.max_iter; j += kGenThreads) io.alpha_trace[(size_t)b * P.max_iter + j] = 0xFF;
+    __syncthreads();
+    for (int t = 0; t < T; ++t) {
+      gen_dyn_step<R>(P, d, s.A, s.Bm, 1, gXs + (size_t)t * nx, gUs + (size_t)t * nu, gXs + (size_t)(t + 1) * nx);
+      __syncthreads();
+    }
+    R best = gen_objective<R>(d, s, gXs, gUs, Cp, cp, Cfp, cfp, xr, ur);
+    unsigned flg = 0;
+    int it = 0;
+    const bool replay = io.replay_iters != nullptr;
+    while (it < P.max_iter && !(replay && it >= io.replay_iters[b])) {
+      // ---- reverse Riccati pass
+      for (int i = tid; i < nx; i += kGenThreads) s.tau[i] = gXs[(size_t)T * nx + i] - xr[T * nx + i];
+      __syncthreads();
+      for (int idx = tid; idx < nx * nx; idx += kGenThreads) s.V[idx] = Cfp[(idx / nx) * n + (idx % nx)];
+      for (int i = tid; i < nx; i += kGenThreads) {
+        R a = 0;
+        for (int j = 0; j < nx; ++j) a += Cfp[i * n + j] * s.tau[j];
+        s.v[i] = a + cfp[i];
+      }
+      __syncthreads();
+      for (int t = T - 1; t >= 0; --t) {
+        for (int i = tid; i < nx; i += kGenThreads) { s.x[i] = gXs[(size_t)t * nx + i]; s.tau[i] = s.x[i] - xr[t * nx + i]; }
+        for (int i = tid; i < nu; i += kGenThreads) { s.u[i] = gUs[(size_t)t * nu + i]; s.tau[nx + i] = s.u[i] - ur[t * nu + i]; }
+        for (int idx = tid; idx < n * n; idx += kGenThreads) s.Ct[idx] = Cp[(size_t)t * n * n + idx];
+        __syncthreads();
+        for (int i = tid; i < n; i += kGenThreads) {
+          R a = 0;
+          for (int j = 0; j < n; ++j) a += s.Ct[i * n + j] * s.tau[j];
+          a += cp[(size_t)t * n + i];
+          if (i < nx) s.qx[i] = a; else s.qu[i - nx] = a;
+        }
+        for (int idx = tid; idx < nx * nx; idx += kGenThreads) s.Qxx[idx] = s.Ct[(idx / nx) * n + (idx % nx)];
+        for (int idx = tid; idx < nx * nu; idx += kGenThreads) s.Qxu[idx] = s.Ct[(idx / nu) * n + nx + (idx % nu)];
+        for (int idx = tid; idx < nu * nu; idx += kGenThreads) s.Quu[idx] = s.Ct[(nx + idx / nu) * n + nx + (idx % nu)];
+        gen_dyn_jac<R>(P, d, s.x, s.u, s.A, s.Bm);
+        __syncthreads();
+        if (gen_value_step<R>(P, d, s, false, nullptr, nullptr)) flg |= TACD_FLAG_NONPD;
+        for (int idx = tid; idx < nu * nx; idx += kGenThreads) gK[(size_t)t * nu * nx + idx] = s.Kt[idx];
+        for (int i = tid; i < nu; i += kGenThreads) gk[(size_t)t * nu + i] = s.kt[i];
+        __syncthreads();
+      }
+      // ---- all line-search candidates (evaluate_alphas, controller.py:589-620)
+      const int na = P.n_alpha;
+      for (int idx = tid; idx < na * nx; idx += kGenThreads) s.xa[idx] = gXs[idx % nx];
+      for (int idx = tid; idx < na * n; idx += kGenThreads) { s.part1[idx] = 0; s.part2[idx] = 0; }
+      __syncthreads();
+      for (int t = 0; t < T; ++t) {
+        for (int idx = tid; idx < na * nu; idx += kGenThreads) {
+          const int a = idx / nu, i = idx % nu;
+          R acc = 0;
+          for (int j = 0; j < nx; ++j) acc += gK[(size_t)t * nu * nx + i * nx + j] * (s.xa[a * nx + j] - gXs[(size_t)t * nx + j]);
+          R ui = gUs[(size_t)t * nu + i] + (P.alphas[a] * gk[(size_t)t * nu + i] + acc);
+          if (P.has_umin) ui = tmax<R>(ui, P.umin[i]);
+          if (P.has_umax) ui = tmin<R>(ui, P.umax[i]);
+          s.ua[idx] = ui;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < na * n; idx += kGenThreads) {
+          const int a = idx / n, i = idx % n;
+          const R* Ct = Cl + (size_t)t * n * n + (size_t)i * n;
+          R sd = 0;
+          for (int j = 0; j < nx; ++j) sd += Ct[j] * (s.xa[a * nx + j] - xr[t * nx + j]);
+          for (int j = 0; j < nu; ++j) sd += Ct[nx + j] * (s.ua[a * nu + j] - ur[t * nu + j]);
+          const R ti = (i < nx) ? (s.xa[a * nx + i] - xr[t * nx + i]) : (s.ua[a * nu + (i - nx)] - ur[t * nu + (i - nx)]);
+          s.part1[idx] += (R)0.5 * (ti * sd) + cl[(size_t)t * n + i] * ti;
+          if (lssep) {
+            const R* Co = Cp + (size_t)t * n * n + (size_t)i * n;
+            R so = 0;
+            for (int j = 0; j < nx; ++j) so += Co[j] * (s.xa[a * nx + j] - xr[t * nx + j]);
+            for (int j = 0; j < nu; ++j) so += Co[nx + j] * (s.ua[a * nu + j] - ur[t * nu + j]);
+            s.part2[idx] += (R)0.5 * (ti * so) + cp[(size_t)t * n + i] * ti;
+          }
+        }
+        gen_dyn_step<R>(P, d, s.A, s.Bm, na, s.xa, s.ua, s.xan);
+        __syncthreads();
+        for (int idx = tid; idx < na * nx; idx += kGenThreads) s.xa[idx] = s.xan[idx];
+        __syncthreads();
+      }
+      // terminal terms + per-candidate totals (thread a sums its candidate)
+      if (tid < na) {
+        const int a = tid;
+        R tot = 0, tot2 = 0;
+        for (int i = 0; i < n; ++i) { tot += s.part1[a * n + i]; tot2 += s.part2[a * n + i]; }
+        R qN = 0, lN = 0, qN2 = 0, lN2 = 0;
+        for (int i = 0; i < nx; ++i) {
+          const R ti = s.xa[a * nx + i] - xr[T * nx + i];
+          R sd = 0, so = 0;
+          for (int j = 0; j < nx; ++j) {
+            const R tj = s.xa[a * nx + j] - xr[T * nx + j];
+            sd += Cfl[i * n + j] * tj;
+            if (lssep) so += Cfp[i * n + j] * tj;
+          }
+          qN += ti * sd; lN += cfl[i] * ti;
+          if (lssep) { qN2 += ti * so; lN2 += cfp[i] * ti; }
+        }
+        s.red[a] = tot + ((R)0.5 * qN + lN);
+        s.red[TACD_MAX_ALPHA + a] = lssep ? tot2 + ((R)0.5 * qN2 + lN2) : s.red[a];
+      }
+      __syncthreads();
+      int ai = 0;
+      for (int a = 1; a < na; ++a) {
+        if (s.red[ai] != s.red[ai]) break;
+        if (s.red[a] < s.red[ai] || s.red[a] != s.red[a]) ai = a;
+      }
+      if (replay) ai = io.replay_alpha[(size_t)b * P.max_iter + it];
+      const R newc = s.red[TACD_MAX_ALPHA + ai];
+      bool improved = newc < best;
+      if (replay) improved = (it < io.replay_iters[b] - 1) || ((io.replay_flags[b] & TACD_FLAG_MAXITER) != 0);
+      if (tid == 0) {
+        if (io.alpha_trace) io.alpha_trace[(size_t)b * P.max_iter + it] = (uint8_t)ai;
+        if (io.cost_trace) {
+          R* ctr = io.cost_trace + ((size_t)b * P.max_iter + it) * (na + 2);
+          for (int a = 0; a < na; ++a) ctr[a] = s.red[a];
+          ctr[na] = newc;
+          ctr[na + 1] = best;
+        }
+      }
+      __syncthreads();
+      it += 1;
+      if (!improved) break;
+      best = newc;
+      // ---- re-rollout of the accepted candidate in place
+      const R alpha = P.alphas[ai];
+      for (int i = tid; i < nx; i += kGenThreads) { s.xa[i] = gXs[i]; s.xan[nx + i] = gXs[i]; }  // xan[nx..] = old X_t
+      __syncthreads();
+      for (int t = 0; t < T; ++t) {
+        for (int i = tid; i < nu; i += kGenThreads) {
+          R acc = 0;
+          for (int j = 0; j < nx; ++j) acc += gK[(size_t)t * nu * nx + i * nx + j] * (s.xa[j] - s.xan[nx + j]);
+          R ui = gUs[(size_t)t * nu + i] + (alpha * gk[(size_t)t * nu + i] + acc);
+          if (P.has_umin) ui = tmax<R>(ui, P.umin[i]);
+          if (P.has_umax) ui = tmin<R>(ui, P.umax[i]);
+          s.ua[i] = ui;
+        }
+        __syncthreads();
+        for (int i = tid; i < nu; i += kGenThreads) gUs[(size_t)t * nu + i] = s.ua[i];
+        gen_dyn_step<R>(P, d, s.A, s.Bm, 1, s.xa, s.ua, s.xan);
+        __syncthreads();
+        for (int i = tid; i < nx; i += kGenThreads) {
+          s.xan[nx + i] = gXs[(size_t)(t + 1) * nx + i];
+          s.xa[i] = s.xan[i];
+          gXs[(size_t)(t + 1) * nx + i] = s.xan[i];
+        }
+        __syncthreads();
+      }
+      if (it >= P.max_iter) flg |= TACD_FLAG_MAXITER;
+    }
+    // ---- finalise
+    for (int i = tid; i < (int)szX; i += kGenThreads) io.X[(size_t)b * szX + i] = gXs[i];
+    for (int i = tid; i < (int)szU; i += kGenThreads) {
+      const R ui = gUs[i];
+      io.U[(size_t)b * szU + i] = ui;
+      bool m = false;
+      if (P.has_umin) m = m || isclose_<R>(ui, P.umin[i % nu]);
+      if (P.has_umax) m = m || isclose_<R>(ui, P.umax[i % nu]);
+      io.tight[(size_t)b * szU + i] = m ? 1 : 0;
+    }
+    if (io.A != nullptr || io.Bm != nullptr) {
+      for (int t = 0; t < T; ++t) {
+        __syncthreads();
+        for (int i = tid; i < nx; i += kGenThreads) s.x[i] = gXs[(size_t)t * nx + i];
+        for (int i = tid; i < nu; i += kGenThreads) s.u[i] = gUs[(size_t)t * nu + i];
+        __syncthreads();
+        gen_dyn_jac<R>(P, d, s.x, s.u, s.A, s.Bm);
+        __syncthreads();
+        if (io.A) for (int i = tid; i < nx * nx; i += kGenThreads) io.A[((size_t)b * T + t) * nx * nx + i] = s.A[i];
+        if (io.Bm) for (int i = tid; i < nx * nu; i += kGenThreads) io.Bm[((size_t)b * T + t) * nx * nu + i] = s.Bm[i];
+      }
+    }
+    if (tid == 0) {
+      io.iters[b] = it;
+      io.flags[b] = (uint8_t)flg;
+      if (io.cost) io.cost[b] = best;
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// backward (ILQRSolve.backward + _zero_constrained_lqr, controller.py:63-115, 707-788)
+template <typename R>
+__global__ void __launch_bounds__(kGenThreads) ilqr_backward_generic(const DevProblem<R> P, const GenDims<R> d, const BwdPtrs<R> io, R* ws, size_t slice) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  GenSmem<R> s = gen_carve<R>(smem_raw, d.nx, d.nu);
+  const int tid = threadIdx.x, nx = d.nx, nu = d.nu, n = d.n, T = d.T;
+  const size_t szX = (size_t)(T + 1) * nx, szU = (size_t)T * nu;
+  R* gK = ws + (size_t)blockIdx.x * slice;
+  R* gk = gK + (size_t)T * nu * nx;
+  if (d.dyn == TACD_DYN_LTI) {
+    for (int i = tid; i < nx * nx; i += kGenThreads) s.A[i] = P.dyn_A[i];
+    for (int i = tid; i < nx * nu; i += kGenThreads) s.Bm[i] = P.dyn_B[i];
+  }
+  __syncthreads();
+  for (int b = blockIdx.x; b < P.B; b += gridDim.x) {
+    const R* X = io.X + (size_t)b * szX;
+    const R* U = io.U + (size_t)b * szU;
+    const R* Cp = io.C + (P.C_batched ? (size_t)b * T * n * n : 0);
+    const R* xr = io.xref + (P.xref_batched ? (size_t)b * szX : 0);
+    const R* ur = io.uref + (P.uref_batched ? (size_t)b * szU : 0);
+    const R* gX = io.gX + (size_t)b * szX;
+    const R* gU = io.gU + (size_t)b * szU;
+    const uint8_t* tg = io.tight + (size_t)b * szU;
+    auto load_AB = [&](int t) {
+      if (d.dyn == TACD_DYN_EXTERNAL) {
+        for (int i = tid; i < nx * nx; i += kGenThreads) s.A[i] = io.A[((size_t)b * T + t) * nx * nx + i];
+        for (int i = tid; i < nx * nu; i += kGenThreads) s.Bm[i] = io.Bm[((size_t)b * T + t) * nx * nu + i];
+      } else if (d.dyn != TACD_DYN_LTI) {
+        for (int i = tid; i < nx; i += kGenThreads) s.x[i] = X[t * nx + i];
+        for (int i = tid; i < nu; i += kGenThreads) s.u[i] = U[t * nu + i];
+        __syncthreads();
+        gen_dyn_jac<R>(P, d, s.x, s.u, s.A, s.Bm);
+      }
+      __syncthreads();
+    };
+    for (int idx = tid; idx < nx * nx; idx += kGenThreads) s.V[idx] = Cp[(size_t)(T - 1) * n * n + (idx / nx) * n + (idx % nx)];
+    for (int i = tid; i < nx; i += kGenThreads) s.v[i] = -gX[(T - 1) * nx + i];
+    __syncthreads();
+    for (int t = T - 1; t >= 0; --t) {
+      const R* Ct = Cp + (size_t)t * n * n;
+      for (int idx = tid; idx < nx * nx; idx += kGenThreads) s.Qxx[idx] = Ct[(idx / nx) * n + (idx % nx)];
+      for (int idx = tid; idx < nx * nu; idx += kGenThreads) s.Qxu[idx] = Ct[(idx / nu) * n + nx + (idx % nu)];
+      for (int idx = tid; idx < nu * nu; idx += kGenThreads) s.Quu[idx] = Ct[(nx + idx / nu) * n + nx + (idx % nu)];
+      for (int i = tid; i < nx; i += kGenThreads) s.qx[i] = -gX[t * nx + i];
+      for (int i = tid; i < nu; i += kGenThreads) s.qu[i] = -gU[t * nu + i];
+      load_AB(t);
+      gen_value_step<R>(P, d, s, true, tg + (size_t)t * nu, U + (size_t)t * nu);
+      for (int idx = tid; idx < nu * nx; idx += kGenThreads) gK[(size_t)t * nu * nx + idx] = s.Kt[idx];
+      for (int i = tid; i < nu; i += kGenThreads) gk[(size_t)t * nu + i] = s.kt[i];
+      __syncthreads();
+    }
+    // forward sweep + gradients; s.x = dx_t, s.u = du_t, s.tau = tau_t, s.qx (n entries via ct) = dtau_t
+    R* dtau = s.ct;
+    for (int i = tid; i < nx; i += kGenThreads) s.x[i] = 0;
+    if (io.grad_x0) for (int i = tid; i < nx; i += kGenThreads) io.grad_x0[(size_t)b * nx + i] = 0;
+    __syncthreads();
+    for (int t = 0; t <= T; ++t) {
+      if (t < T) {
+        for (int i = tid; i < nu; i += kGenThreads) {
+          R a = 0;
+          for (int j = 0; j < nx; ++j) a += gK[(size_t)t * nu * nx + i * nx + j] * s.x[j];
+          s.u[i] = a + gk[(size_t)t * nu + i];
+        }
+      }
+      __syncthreads();
+      for (int i = tid; i < nx; i += kGenThreads) { s.tau[i] = X[t * nx + i] - xr[t * nx + i]; dtau[i] = s.x[i]; }
+      if (t < T) for (int i = tid; i < nu; i += kGenThreads) { s.tau[nx + i] = U[t * nu + i] - ur[t * nu + i]; dtau[nx + i] = s.u[i]; }
+      __syncthreads();
+      if (t < T) {
+        if (io.grad_C)
+          for (int idx = tid; idx < n * n; idx += kGenThreads) {
+            const int i = idx / n, j = idx % n;
+            const R g = (R)-0.5 * (dtau[i] * s.tau[j] + s.tau[i] * dtau[j]);
+            if (P.C_batched) io.grad_C[((size_t)b * T + t) * n * n + idx] = g; else atomicAdd(&io.grad_C[(size_t)t * n * n + idx], g);
+          }
+        if (io.grad_c)
+          for (int i = tid; i < n; i += kGenThreads) {
+            if (P.C_batched) io.grad_c[((size_t)b * T + t) * n + i] = -dtau[i]; else atomicAdd(&io.grad_c[(size_t)t * n + i], -dtau[i]);
+          }
+        if (io.grad_uref)
+          for (int i = tid; i < nu; i += kGenThreads) {
+            if (P.uref_batched) io.grad_uref[(size_t)b * szU + t * nu + i] = s.u[i]; else atomicAdd(&io.grad_uref[t * nu + i], s.u[i]);
+          }
+        if (io.dU) for (int i = tid; i < nu; i += kGenThreads) io.dU[(size_t)b * szU + t * nu + i] = s.u[i];
+      } else {
+        if (io.grad_Cf)
+          for (int idx = tid; idx < n * n; idx += kGenThreads) {
+            const int i = idx / n, j = idx % n;
+            const bool in = (i < nx && j < nx);
+            const R g = in ? (R)-0.5 * (dtau[i] * s.tau[j] + s.tau[i] * dtau[j]) : (R)0;
+            if (P.Cf_batched) io.grad_Cf[(size_t)b * n * n + idx] = g; else if (in) atomicAdd(&io.grad_Cf[idx], g);
+          }
+        if (io.grad_cf)
+          for (int i = tid; i < n; i += kGenThreads) {
+            const R g = (i < nx) ? -dtau[i] : (R)0;
+            if (P.Cf_batched) io.grad_cf[(size_t)b * n + i] = g; else if (i < nx) atomicAdd(&io.grad_cf[i], g);
+          }
+      }
+      if (io.grad_xref)
+        for (int i = tid; i < nx; i += kGenThreads) {
+          if (P.xref_batched) io.grad_xref[(size_t)b * szX + t * nx + i] = s.x[i]; else atomicAdd(&io.grad_xref[t * nx + i], s.x[i]);
+        }
+      if (io.dX) for (int i = tid; i < nx; i += kGenThreads) io.dX[(size_t)b * szX + t * nx + i] = s.x[i];
+      if (t < T) {
+        __syncthreads();
+        // dx+ = A dx + B du; the jacobian load clobbers s.x/s.u for non-LTI embedded dynamics, so stash them
+        for (int i = tid; i < nx; i += kGenThreads) s.xa[i] = s.x[i];
+        for (int i = tid; i < nu; i += kGenThreads) s.ua[i] = s.u[i];
+        __syncthreads();
+        load_AB(t);
+        for (int i = tid; i < nx; i += kGenThreads) {
+          R a = 0, a2 = 0;
+          for (int j = 0; j < nx; ++j) a += s.A[i * nx + j] * s.xa[j];
+          for (int j = 0; j < nu; ++j) a2 += s.Bm[i * nu + j] * s.ua[j];
+          s.xan[i] = a + a2;
+        }
+        __syncthreads();
+        for (int i = tid; i < nx; i += kGenThreads) s.x[i] = s.xan[i];
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// stand-alone stages (one CTA per element)
+template <typename R>
+__global__ void __launch_bounds__(kGenThreads) stage_rollout(const DevProblem<R> P, const GenDims<R> d, const R* x0, const R* U, R* X) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  GenSmem<R> s = gen_carve<R>(smem_raw, d.nx, d.nu);
+  const int tid = threadIdx.x, nx = d.nx, nu = d.nu, T = d.T;
+  if (d.dyn == TACD_DYN_LTI) {
+    for (int i = tid; i < nx * nx; i += kGenThreads) s.A[i] = P.dyn_A[i];
+    for (int i = tid; i < nx * nu; i += kGenThreads) s.Bm[i] = P.dyn_B[i];
+  }
+  __syncthreads();
+  for (int b = blockIdx.x; b < P.B; b += gridDim.x) {
+    R* Xb = X + (size_t)b * (T + 1) * nx;
+    const R* Ub = U + (size_t)b * T * nu;
+    for (int i = tid; i < nx; i += kGenThreads) Xb[i] = x0[(size_t)b * nx + i];
+    __syncthreads();
+    for (int t = 0; t < T; ++t) {
+      gen_dyn_step<R>(P, d, s.A, s.Bm, 1, Xb + (size_t)t * nx, Ub + (size_t)t * nu, Xb + (size_t)(t + 1) * nx);
+      __syncthreads();
+    }
+  }
+}
+
+template <typename R>
+__global__ void __launch_bounds__(kGenThreads) stage_linearize(const DevProblem<R> P, const GenDims<R> d, const R* X, const R* U, R* A, R* Bm) {
+  // one thread per (b, t)
+  const int nx = d.nx, nu = d.nu, T = d.T;
+  const size_t total = (size_t)P.B * T;
+  for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = w / T, t = w % T;
+    R* Ao = A + w * nx * nx;
+    R* Bo = Bm + w * nx * nu;
+    if (d.dyn == TACD_DYN_LTI) {
+      for (int i = 0; i < nx * nx; ++i) Ao[i] = P.dyn_A[i];
+      for (int i = 0; i < nx * nu; ++i) Bo[i] = P.dyn_B[i];
+    } else {
+      gen_dyn_jac_scalar<R>(P, d.dyn, X + (b * (T + 1) + t) * nx, U + w * nu, Ao, Bo);
+    }
+  }
+}
+
+template <typename R>
+__global__ void __launch_bounds__(kGenThreads) stage_objective(const DevProblem<R> P, const GenDims<R> d, const R* X, const R* U, const R* C,
+                                                                const R* c, const R* Cf, const R* cf, const R* xref, const R* uref, R* cost) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  GenSmem<R> s = gen_carve<R>(smem_raw, d.nx, d.nu);
+  const int nx = d.nx, nu = d.nu, n = d.n, T = d.T;
+  const size_t szX = (size_t)(T + 1) * nx, szU = (size_t)T * nu;
+  for (int b = blockIdx.x; b < P.B; b += gridDim.x) {
+    const R v = gen_objective<R>(d, s, X + b * szX, U + b * szU, C + (P.C_batched ? (size_t)b * T * n * n : 0),
+                                 c + (P.C_batched ? (size_t)b * T * n : 0), Cf + (P.Cf_batched ? (size_t)b * n * n : 0),
+                                 cf + (P.Cf_batched ? (size_t)b * n : 0), xref + (P.xref_batched ? b * szX : 0),
+                                 uref + (P.uref_batched ? b * szU : 0));
+    if (threadIdx.x == 0) cost[b] = v;
+  }
+}
+
+template <typename R>
+__global__ void __launch_bounds__(kGenThreads) stage_riccati(const DevProblem<R> P, const GenDims<R> d, const R* A, const R* Bm, const R* lx,
+                                                              const R* lu, const R* lxx, const R* lxu, const R* luu, const R* lxN,
+                                                              const R* lxxN, R* K, R* k, uint8_t* flags) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  GenSmem<R> s = gen_carve<R>(smem_raw, d.nx, d.nu);
+  const int tid = threadIdx.x, nx = d.nx, nu = d.nu, T = d.T;
+  for (int b = blockIdx.x; b < P.B; b += gridDim.x) {
+    bool nonpd = false;
+    for (int i = tid; i < nx * nx; i += kGenThreads) s.V[i] = lxxN[(size_t)b * nx * nx + i];
+    for (int i = tid; i < nx; i += kGenThreads) s.v[i] = lxN[(size_t)b * nx + i];
+    __syncthreads();
+    for (int t = T - 1; t >= 0; --t) {
+      const size_t bt = (size_t)b * T + t;
+      for (int i = tid; i < nx * nx; i += kGenThreads) { s.A[i] = A[bt * nx * nx + i]; s.Qxx[i] = lxx[bt * nx * nx + i]; }
+      for (int i = tid; i < nx * nu; i += kGenThreads) { s.Bm[i] = Bm[bt * nx * nu + i]; s.Qxu[i] = lxu[bt * nx * nu + i]; }
+      for (int i = tid; i < nu * nu; i += kGenThreads) s.Quu[i] = luu[bt * nu * nu + i];
+      for (int i = tid; i < nx; i += kGenThreads) s.qx[i] = lx[bt * nx + i];
+      for (int i = tid; i < nu; i += kGenThreads) s.qu[i] = lu[bt * nu + i];
+      __syncthreads();
+      nonpd = gen_value_step<R>(P, d, s, false, nullptr, nullptr) || nonpd;
+      for (int i = tid; i < nu * nx; i += kGenThreads) K[bt * nu * nx + i] = s.Kt[i];
+      for (int i = tid; i < nu; i += kGenThreads) k[bt * nu + i] = s.kt[i];
+      __syncthreads();
+    }
+    if (flags && tid == 0) flags[b] = nonpd ? TACD_FLAG_NONPD : 0;
+  }
+}
+
+template <typename R>
+__global__ void __launch_bounds__(kGenThreads) stage_linesearch(const DevProblem<R> P, const GenDims<R> d, const R* x0, const R* X, const R* U,
+                                                                 const R* K, const R* k, const R* C, const R* c, const R* Cf, const R* cf,
+                                                                 const R* xref, const R* uref, R* Xc, R* Uc, R* costs) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  GenSmem<R> s = gen_carve<R>(smem_raw, d.nx, d.nu);
+  const int tid = threadIdx.x, nx = d.nx, nu = d.nu, n = d.n, T = d.T, na = P.n_alpha;
+  const size_t szX = (size_t)(T + 1) * nx, szU = (size_t)T * nu;
+  if (d.dyn == TACD_DYN_LTI) {
+    for (int i = tid; i < nx * nx; i += kGenThreads) s.A[i] = P.dyn_A[i];
+    for (int i = tid; i < nx * nu; i += kGenThreads) s.Bm[i] = P.dyn_B[i];
+  }
+  __syncthreads();
+  for (int b = blockIdx.x; b < P.B; b += gridDim.x) {
+    const R* Xb = X + b * szX;
+    const R* Ub = U + b * szU;
+    const R* Kb = K + (size_t)b * T * nu * nx;
+    const R* kb = k + b * szU;
+    R* Xcb = Xc + (size_t)b * na * szX;
+    R* Ucb = Uc + (size_t)b * na * szU;
+    for (int idx = tid; idx < na * nx; idx += kGenThreads) Xcb[(idx / nx) * szX + (idx % nx)] = x0[(size_t)b * nx + idx % nx];
+    __syncthreads();
+    for (int t = 0; t < T; ++t) {
+      for (int idx = tid; idx < na * nx; idx += kGenThreads) s.xa[idx] = Xcb[(idx / nx) * szX + (size_t)t * nx + idx % nx];
+      __syncthreads();
+      for (int idx = tid; idx < na * nu; idx += kGenThreads) {
+        const int a = idx / nu, i = idx % nu;
+        R acc = 0;
+        for (int j = 0; j < nx; ++j) acc += Kb[(size_t)t * nu * nx + i * nx + j] * (s.xa[a * nx + j] - Xb[(size_t)t * nx + j]);
+        R ui = Ub[(size_t)t * nu + i] + (P.alphas[a] * kb[(size_t)t * nu + i] + acc);
+        if (P.has_umin) ui = tmax<R>(ui, P.umin[i]);
+        if (P.has_umax) ui = tmin<R>(ui, P.umax[i]);
+        s.ua[idx] = ui;
+        Ucb[a * szU + (size_t)t * nu + i] = ui;
+      }
+      __syncthreads();
+      gen_dyn_step<R>(P, d, s.A, s.Bm, na, s.xa, s.ua, s.xan);
+      __syncthreads();
+      for (int idx = tid; idx < na * nx; idx += kGenThreads) Xcb[(idx / nx) * szX + (size_t)(t + 1) * nx + idx % nx] = s.xan[idx];
+      __syncthreads();
+    }
+    for (int a = 0; a < na; ++a) {
+      const R v = gen_objective<R>(d, s, Xcb + a * szX, Ucb + a * szU, C + (P.C_batched ? (size_t)b * T * n * n : 0),
+                                   c + (P.C_batched ? (size_t)b * T * n : 0), Cf + (P.Cf_batched ? (size_t)b * n * n : 0),
+                                   cf + (P.Cf_batched ? (size_t)b * n : 0), xref + (P.xref_batched ? b * szX : 0),
+                                   uref + (P.uref_batched ? b * szU : 0));
+      if (tid == 0) costs[(size_t)b * na + a] = v;
+    }
+  }
+}
+
+template <typename R>
+__global__ void stage_pnqp(int N, int m, const R* H, const R* q, const R* lo, const R* hi, R* x, int32_t* iters, R* scratch) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  R* w = scratch + (size_t)i * (m * m + 4 * m);
+  int piv[TACD_MAX_NU];
+  const int it = gen_pnqp<R>(m, H + (size_t)i * m * m, q + (size_t)i * m, lo + (size_t)i * m, hi + (size_t)i * m, x + (size_t)i * m, w, piv);
+  if (iters) iters[i] = it;
+}
+
+// ---------------------------------------------------------------------------
+// host launchers
+template <typename K>
+static int prep_smem(K kernel, size_t bytes) {
+  const DeviceInfo di = device_info();
+  if (bytes > (size_t)di.smem_optin) { set_error("generic kernel needs %zu B shared memory (> %d)", bytes, di.smem_optin); return TACD_EUNSUPPORTED; }
+  return check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes), "smem attr");
+}
+
+template <typename R>
+static FwdPtrs<R> fwd_ptrs(const tacd_forward_io* io) {
+  FwdPtrs<R> f;
+  f.x0 = (const R*)io->x0; f.C = (const R*)io->C; f.c = (const R*)io->c; f.Cf = (const R*)io->Cf; f.cf = (const R*)io->cf;
+  f.C_ls = (const R*)io->C_ls; f.c_ls = (const R*)io->c_ls; f.Cf_ls = (const R*)io->Cf_ls; f.cf_ls = (const R*)io->cf_ls;
+  f.xref = (const R*)io->xref; f.uref = (const R*)io->uref; f.Uinit = (const R*)io->Uinit;
+  f.replay_iters = io->replay_iters; f.replay_alpha = io->replay_alpha; f.replay_flags = io->replay_flags;
+  f.X = (R*)io->X; f.U = (R*)io->U; f.A = (R*)io->A; f.Bm = (R*)io->Bm;
+  f.tight = io->tight; f.iters = io->iters; f.alpha_trace = io->alpha_trace; f.flags = io->flags;
+  f.cost = (R*)io->cost; f.cost_trace = (R*)io->cost_trace; f.counter = nullptr;
+  return f;
+}
+
+template <typename R>
+int launch_forward_generic(const tacd_problem* p, const tacd_forward_io* io, void* ws, size_t ws_bytes, cudaStream_t s) {
+  const size_t slice = gen_slice_scalars(p);
+  const int grid = gen_grid(p);
+  if (ws_bytes < (size_t)grid * slice * sizeof(R)) { set_error("forward workspace too small: %zu < %zu", ws_bytes, (size_t)grid * slice * sizeof(R)); return TACD_EWORKSPACE; }
+  const size_t smem = gen_smem_bytes<R>(p->nx, p->nu);
+  auto kernel = ilqr_forward_generic<R>;
+  if (int rc = prep_smem(kernel, smem)) return rc;
+  kernel<<<grid, kGenThreads, smem, s>>>(to_dev<R>(p), dims_of<R>(p), fwd_ptrs<R>(io), (R*)ws, slice);
+  return check_cuda(cudaPeekAtLastError(), "ilqr_forward_generic launch");
+}
+
+template <typename R>
+int launch_backward_generic(const tacd_problem* p, const tacd_backward_io* io, void* ws, size_t ws_bytes, cudaStream_t s) {
+  const size_t slice = gen_slice_scalars(p);
+  const int grid = gen_grid(p);
+  if (ws_bytes < (size_t)grid * slice * sizeof(R)) { set_error("backward workspace too small"); return TACD_EWORKSPACE; }
+  const size_t smem = gen_smem_bytes<R>(p->nx, p->nu);
+  auto kernel = ilqr_backward_generic<R>;
+  if (int rc = prep_smem(kernel, smem)) return rc;
+  const size_t T = p->T, nx = p->nx, nu = p->nu, n = nx + nu, szX = (T + 1) * nx, szU = T * nu;
+  if (io->grad_C && !p->C_batched) if (int rc = check_cuda(cudaMemsetAsync(io->grad_C, 0, T * n * n * sizeof(R), s), "memset")) return rc;
+  if (io->grad_c && !p->C_batched) if (int rc = check_cuda(cudaMemsetAsync(io->grad_c, 0, T * n * sizeof(R), s), "memset")) return rc;
+  if (io->grad_Cf && !p->Cf_batched) if (int rc = check_cuda(cudaMemsetAsync(io->grad_Cf, 0, n * n * sizeof(R), s), "memset")) return rc;
+  if (io->grad_cf && !p->Cf_batched) if (int rc = check_cuda(cudaMemsetAsync(io->grad_cf, 0, n * sizeof(R), s), "memset")) return rc;
+  if (io->grad_xref && !p->xref_batched) if (int rc = check_cuda(cudaMemsetAsync(io->grad_xref, 0, szX * sizeof(R), s), "memset")) return rc;
+  if (io->grad_uref && !p->uref_batched) if (int rc = check_cuda(cudaMemsetAsync(io->grad_uref, 0, szU * sizeof(R), s), "memset")) return rc;
+  BwdPtrs<R> f;
+  f.X = (const R*)io->X; f.U = (const R*)io->U; f.C = (const R*)io->C; f.xref = (const R*)io->xref; f.uref = (const R*)io->uref;
+  f.A = (const R*)io->A; f.Bm = (const R*)io->Bm; f.gX = (const R*)io->gX; f.gU = (const R*)io->gU; f.tight = io->tight;
+  f.grad_C = (R*)io->grad_C; f.grad_c = (R*)io->grad_c; f.grad_Cf = (R*)io->grad_Cf; f.grad_cf = (R*)io->grad_cf;
+  f.grad_x0 = (R*)io->grad_x0; f.grad_xref = (R*)io->grad_xref; f.grad_uref = (R*)io->grad_uref; f.dX = (R*)io->dX; f.dU = (R*)io->dU;
+  kernel<<<grid, kGenThreads, smem, s>>>(to_dev<R>(p), dims_of<R>(p), f, (R*)ws, slice);
+  return check_cuda(cudaPeekAtLastError(), "ilqr_backward_generic launch");
+}
+
+template int launch_forward_generic<float>(const tacd_problem*, const tacd_forward_io*, void*, size_t, cudaStream_t);
+template int launch_forward_generic<double>(const tacd_problem*, const tacd_forward_io*, void*, size_t, cudaStream_t);
+template int launch_backward_generic<float>(const tacd_problem*, const tacd_backward_io*, void*, size_t, cudaStream_t);
+template int launch_backward_generic<double>(const tacd_problem*, const tacd_backward_io*, void*, size_t, cudaStream_t);
+
+template <typename R>
+static int stage_common(const tacd_problem* p) {
+  if (!p) { set_error("null problem"); return TACD_EINVAL; }
+  if (p->nx < 1 || p->nu < 1 || p->nx > TACD_MAX_NX || p->nu > TACD_MAX_NU || p->T < 1 || p->B < 0) { set_error("bad sizes"); return TACD_EINVAL; }
+  return TACD_OK;
+}
+
+template <typename R>
+static int run_rollout(const tacd_problem* p, const void* x0, const void* U, void* X, cudaStream_t s) {
+  auto kernel = stage_rollout<R>;
+  const size_t smem = gen_smem_bytes<R>(p->nx, p->nu);
+  if (int rc = prep_smem(kernel, smem)) return rc;
+  kernel<<<gen_grid(p), kGenThreads, smem, s>>>(to_dev<R>(p), dims_of<R>(p), (const R*)x0, (const R*)U, (R*)X);
+  return check_cuda(cudaPeekAtLastError(), "stage_rollout launch");
+}
+template <typename R>
+static int run_linearize(const tacd_problem* p, const void* X, const void* U, void* A, void* Bm, cudaStream_t s) {
+  const size_t total = (size_t)p->B * p->T;
+  int grid = (int)((total + kGenThreads - 1) / kGenThreads);
+  if (grid > 148 * 16) grid = 148 * 16;
+  stage_linearize<R><<<grid, kGenThreads, 0, s>>>(to_dev<R>(p), dims_of<R>(p), (const R*)X, (const R*)U, (R*)A, (R*)Bm);
+  return check_cuda(cudaPeekAtLastError(), "stage_linearize launch");
+}
+template <typename R>
+static int run_objective(const tacd_problem* p, const void* X, const void* U, const void* C, const void* c, const void* Cf, const void* cf,
+                         const void* xref, const void* uref, void* cost, cudaStream_t s) {
+  auto kernel = stage_objective<R>;
+  const size_t smem = gen_smem_bytes<R>(p->nx, p->nu);
+  if (int rc = prep_smem(kernel, smem)) return rc;
+  kernel<<<gen_grid(p), kGenThreads, smem, s>>>(to_dev<R>(p), dims_of<R>(p), (const R*)X, (const R*)U, (const R*)C, (const R*)c, (const R*)Cf,
+                                                 (const R*)cf, (const R*)xref, (const R*)uref, (R*)cost);
+  return check_cuda(cudaPeekAtLastError(), "stage_objective launch");
+}
+template <typename R>
+static int run_riccati(const tacd_problem* p, const void* A, const void* Bm, const void* lx, const void* lu, const void* lxx, const void* lxu,
+                       const void* luu, const void* lxN, const void* lxxN, void* K, void* k, uint8_t* flags, cudaStream_t s) {
+  auto kernel = stage_riccati<R>;
+  const size_t smem = gen_smem_bytes<R>(p->nx, p->nu);
+  if (int rc = prep_smem(kernel, smem)) return rc;
+  kernel<<<gen_grid(p), kGenThreads, smem, s>>>(to_dev<R>(p), dims_of<R>(p), (const R*)A, (const R*)Bm, (const R*)lx, (const R*)lu, (const R*)lxx,
+                                                 (const R*)lxu, (const R*)luu, (const R*)lxN, (const R*)lxxN, (R*)K, (R*)k, flags);
+  return check_cuda(cudaPeekAtLastError(), "stage_riccati launch");
+}
+template <typename R>
+static int run_linesearch(const tacd_problem* p, const void* x0, const void* X, const void* U, const void* K, const void* k, const void* C,
+                          const void* c, const void* Cf, const void* cf, const void* xref, const void* uref, void* Xc, void* Uc, void* costs,
+                          cudaStream_t s) {
+  auto kernel = stage_linesearch<R>;
+  const size_t smem = gen_smem_bytes<R>(p->nx, p->nu);
+  if (int rc = prep_smem(kernel, smem)) return rc;
+  kernel<<<gen_grid(p), kGenThreads, smem, s>>>(to_dev<R>(p), dims_of<R>(p), (const R*)x0, (const R*)X, (const R*)U, (const R*)K, (const R*)k,
+                                                 (const R*)C, (const R*)c, (const R*)Cf, (const R*)cf, (const R*)xref, (const R*)uref, (R*)Xc,
+                                                 (R*)Uc, (R*)costs);
+  return check_cuda(cudaPeekAtLastError(), "stage_linesearch launch");
+}
+
+}  // namespace tacd
+
+using namespace tacd;
+
+#define TACD_DISPATCH(p, fn, ...) ((p)->dtype == TACD_F32 ? fn<float>(__VA_ARGS__) : fn<double>(__VA_ARGS__))
+
+extern "C" {
+
+int tacd_rollout(const tacd_problem* p, const void* x0, const void* U, void* X, void* stream) {
+  if (int rc = stage_common<float>(p)) return rc;
+  if (p->dyn_id == TACD_DYN_EXTERNAL) { set_error("rollout needs embedded dynamics"); return TACD_EINVAL; }
+  if (p->B == 0) return TACD_OK;
+  return TACD_DISPATCH(p, run_rollout, p, x0, U, X, (cudaStream_t)stream);
+}
+int tacd_linearize(const tacd_problem* p, const void* X, const void* U, void* A, void* Bm, void* stream) {
+  if (int rc = stage_common<float>(p)) return rc;
+  if (p->dyn_id == TACD_DYN_EXTERNAL) { set_error("linearize needs embedded dynamics"); return TACD_EINVAL; }
+  if (p->B == 0) return TACD_OK;
+  return TACD_DISPATCH(p, run_linearize, p, X, U, A, Bm, (cudaStream_t)stream);
+}
+int tacd_objective(const tacd_problem* p, const void* X, const void* U, const void* C, const void* c, const void* Cf, const void* cf,
+                   const void* xref, const void* uref, void* cost, void* stream) {
+  if (int rc = stage_common<float>(p)) return rc;
+  if (p->B == 0) return TACD_OK;
+  return TACD_DISPATCH(p, run_objective, p, X, U, C, c, Cf, cf, xref, uref, cost, (cudaStream_t)stream);
+}
+int tacd_riccati(const tacd_problem* p, const void* A, const void* Bm, const void* lx, const void* lu, const void* lxx, const void* lxu,
+                 const void* luu, const void* lxN, const void* lxxN, void* K, void* k, uint8_t* flags, void* stream) {
+  if (int rc = stage_common<float>(p)) return rc;
+  if (p->B == 0) return TACD_OK;
+  return TACD_DISPATCH(p, run_riccati, p, A, Bm, lx, lu, lxx, lxu, luu, lxN, lxxN, K, k, flags, (cudaStream_t)stream);
+}
+int tacd_linesearch(const tacd_problem* p, const void* x0, const void* X, const void* U, const void* K, const void* k, const void* C,
+                    const void* c, const void* Cf, const void* cf, const void* xref, const void* uref, void* Xc, void* Uc, void* costs,
+                    void* stream) {
+  if (int rc = stage_common<float>(p)) return rc;
+  if (p->dyn_id == TACD_DYN_EXTERNAL) { set_error("linesearch needs embedded dynamics"); return TACD_EINVAL; }
+  if (p->B == 0) return TACD_OK;
+  return TACD_DISPATCH(p, run_linesearch, p, x0, X, U, K, k, C, c, Cf, cf, xref, uref, Xc, Uc, costs, (cudaStream_t)stream);
+}
+int tacd_pnqp(int32_t dtype, int32_t N, int32_t m, const void* H, const void* q, const void* lo, const void* hi, void* x, int32_t* iters,
+              void* stream) {
+  if (m < 1 || m > TACD_MAX_NU || N < 0) { set_error("pnqp: 1 <= m <= %d", TACD_MAX_NU); return TACD_EINVAL; }
+  if (N == 0) return TACD_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t es = dtype == TACD_F32 ? 4 : 8;
+  void* scratch = nullptr;
+  if (int rc = check_cuda(cudaMallocAsync(&scratch, (size_t)N * (m * m + 4 * m) * es, s), "pnqp scratch")) return rc;
+  const int grid = (N + 127) / 128;
+  if (dtype == TACD_F32) stage_pnqp<float><<<grid, 128, 0, s>>>(N, m, (const float*)H, (const float*)q, (const float*)lo, (const float*)hi, (float*)x, iters, (float*)scratch);
+  else stage_pnqp<double><<<grid, 128, 0, s>>>(N, m, (const double*)H, (const double*)q, (const double*)lo, (const double*)hi, (double*)x, iters, (double*)scratch);
+  int rc = check_cuda(cudaPeekAtLastError(), "stage_pnqp launch");
+  cudaFreeAsync(scratch, s);
+  return rc;
+}
+
+}  // extern "C"

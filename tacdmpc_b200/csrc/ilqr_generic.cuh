@@ -1,0 +1,450 @@
+// ilqr_generic.cuh — run-time-dimension kernels: ONE CTA PER BATCH ELEMENT.
+//
+// Covers every (nx <= 64, nu <= 16, dynamics) the thread-per-element kernels have
+// no instantiation for (config 5: LTI nx in {8,16,32}, nu in {4,8}, T=50) and the
+// stand-alone stage entry points.  Per-step matrices (V, Q*, A, B, C_t, gains) live
+// in shared memory; the trajectory state that must survive between passes
+// (X, U, K, k) lives in a per-CTA slice of the caller's workspace (contiguous, so
+// CTA-wide accesses coalesce and the slice stays L2-resident).  Every matrix
+// product is a CTA-parallel loop over output entries; the nu x nu factorizations
+// and the box QP run on one thread.
+#pragma once
+#include "tacd_dev.cuh"
+
+namespace tacd {
+
+constexpr int kGenThreads = 128;
+
+template <typename R>
+struct GenDims {
+  int nx, nu, n, T, dyn;
+};
+
+// ---- run-time-dimension dynamics on one thread (non-LTI plugins are tiny) ----
+template <typename R>
+__device__ void gen_dyn_step_scalar(const DevProblem<R>& P, int dyn, const R* x, const R* u, R* xn) {
+  if (dyn == TACD_DYN_CARTPOLE) {
+    R xx[4] = {x[0], x[1], x[2], x[3]}, uu[1] = {u[0]}, o[4];
+    cartpole_step<R>(P.dynp, P.dt, xx, uu, o);
+    for (int i = 0; i < 4; ++i) xn[i] = o[i];
+  } else {
+    R xx[3] = {x[0], x[1], x[2]}, uu[2] = {u[0], u[1]}, o[3];
+    if (dyn == TACD_DYN_UNICYCLE) unicycle_step<R, false>(P.dt, xx, uu, o);
+    else unicycle_step<R, true>(P.dt, xx, uu, o);
+    for (int i = 0; i < 3; ++i) xn[i] = o[i];
+  }
+}
+template <typename R>
+__device__ void gen_dyn_jac_scalar(const DevProblem<R>& P, int dyn, const R* x, const R* u, R* A, R* Bm) {
+  if (dyn == TACD_DYN_CARTPOLE) {
+    R xx[4] = {x[0], x[1], x[2], x[3]}, uu[1] = {u[0]}, a[16], b[4];
+    if (P.jac_mode == TACD_JAC_FINITE_DIFF) Dyn<R, 4, 1, TACD_DYN_CARTPOLE>::jac_fd(P, nullptr, nullptr, xx, uu, a, b);
+    else cartpole_jac<R>(P.dynp, P.dt, xx, uu, a, b);
+    for (int i = 0; i < 16; ++i) A[i] = a[i];
+    for (int i = 0; i < 4; ++i) Bm[i] = b[i];
+  } else {
+    R xx[3] = {x[0], x[1], x[2]}, uu[2] = {u[0], u[1]}, a[9], b[6];
+    if (P.jac_mode == TACD_JAC_FINITE_DIFF) {
+      if (dyn == TACD_DYN_UNICYCLE) Dyn<R, 3, 2, TACD_DYN_UNICYCLE>::jac_fd(P, nullptr, nullptr, xx, uu, a, b);
+      else Dyn<R, 3, 2, TACD_DYN_UNICYCLE_WRAPPED>::jac_fd(P, nullptr, nullptr, xx, uu, a, b);
+    } else unicycle_jac<R>(P.dt, xx, uu, a, b);
+    for (int i = 0; i < 9; ++i) A[i] = a[i];
+    for (int i = 0; i < 6; ++i) Bm[i] = b[i];
+  }
+}
+
+// CTA-parallel x+ = f(x,u) for `na` independent (x,u) pairs laid out [a][nx], [a][nu]
+template <typename R>
+__device__ void gen_dyn_step(const DevProblem<R>& P, const GenDims<R>& d, const R* sA, const R* sB, int na, const R* x, const R* u, R* xn) {
+  const int tid = threadIdx.x;
+  if (d.dyn == TACD_DYN_LTI) {
+    for (int idx = tid; idx < na * d.nx; idx += kGenThreads) {
+      const int a = idx / d.nx, i = idx % d.nx;
+      R s = 0, s2 = 0;
+      for (int j = 0; j < d.nx; ++j) s += sA[i * d.nx + j] * x[a * d.nx + j];
+      for (int j = 0; j < d.nu; ++j) s2 += sB[i * d.nu + j] * u[a * d.nu + j];
+      xn[a * d.nx + i] = s + s2;
+    }
+  } else {
+    if (tid < na) gen_dyn_step_scalar<R>(P, d.dyn, x + tid * d.nx, u + tid * d.nu, xn + tid * d.nx);
+  }
+}
+
+// A_t, B_t at (x,u) into shared memory (LTI: already resident, nothing to do).
+// LTI + finite differences reproduces A,B up to rounding; the reference's FD mode is
+// unreachable (controller.py:468-471 raises), so LTI always uses the matrices themselves.
+template <typename R>
+__device__ void gen_dyn_jac(const DevProblem<R>& P, const GenDims<R>& d, const R* x, const R* u, R* sA, R* sB) {
+  if (d.dyn == TACD_DYN_LTI) return;
+  if (threadIdx.x == 0) gen_dyn_jac_scalar<R>(P, d.dyn, x, u, sA, sB);
+}
+
+// ---- single-thread nu x nu factorizations on shared memory -------------------
+template <typename R>
+__device__ bool gen_chol(R* M, int m) {
+  for (int j = 0; j < m; ++j) {
+    R dd = M[j * m + j];
+    for (int k = 0; k < j; ++k) dd -= M[j * m + k] * M[j * m + k];
+    if (!(dd > 0)) return false;
+    dd = sqrt_<R>(dd);
+    M[j * m + j] = dd;
+    for (int i = j + 1; i < m; ++i) {
+      R s = M[i * m + j];
+      for (int k = 0; k < j; ++k) s -= M[i * m + k] * M[j * m + k];
+      M[i * m + j] = s / dd;
+    }
+  }
+  return true;
+}
+// LU with partial pivoting in place; piv[j] = row swapped with j at step j
+template <typename R>
+__device__ void gen_lu(R* M, int m, int* piv) {
+  for (int j = 0; j < m; ++j) {
+    int p = j;
+    R best = abs_<R>(M[j * m + j]);
+    for (int i = j + 1; i < m; ++i) {
+      const R a = abs_<R>(M[i * m + j]);
+      if (a > best) { best = a; p = i; }
+    }
+    piv[j] = p;
+    if (p != j)
+      for (int k = 0; k < m; ++k) { const R t = M[j * m + k]; M[j * m + k] = M[p * m + k]; M[p * m + k] = t; }
+    const R dd = M[j * m + j];
+    for (int i = j + 1; i < m; ++i) {
+      const R f = M[i * m + j] / dd;
+      M[i * m + j] = f;
+      for (int k = j + 1; k < m; ++k) M[i * m + k] -= f * M[j * m + k];
+    }
+  }
+}
+// solve with the factors above for column r of rhs [m, nr] (one thread per column)
+template <typename R>
+__device__ void gen_lu_solve_col(const R* M, int m, const int* piv, R* rhs, int nr, int r) {
+  for (int j = 0; j < m; ++j) {
+    const int p = piv[j];
+    if (p != j) { const R t = rhs[j * nr + r]; rhs[j * nr + r] = rhs[p * nr + r]; rhs[p * nr + r] = t; }
+    for (int i = j + 1; i < m; ++i) rhs[i * nr + r] -= M[i * m + j] * rhs[j * nr + r];
+  }
+  for (int i = m - 1; i >= 0; --i) {
+    R s = rhs[i * nr + r];
+    for (int k = i + 1; k < m; ++k) s -= M[i * m + k] * rhs[k * nr + r];
+    rhs[i * nr + r] = s / M[i * m + i];
+  }
+}
+template <typename R>
+__device__ void gen_chol_solve_col(const R* L, int m, R* rhs, int nr, int r) {
+  for (int i = 0; i < m; ++i) {
+    R s = rhs[i * nr + r];
+    for (int k = 0; k < i; ++k) s -= L[i * m + k] * rhs[k * nr + r];
+    rhs[i * nr + r] = s / L[i * m + i];
+  }
+  for (int i = m - 1; i >= 0; --i) {
+    R s = rhs[i * nr + r];
+    for (int k = i + 1; k < m; ++k) s -= L[k * m + i] * rhs[k * nr + r];
+    rhs[i * nr + r] = s / L[i * m + i];
+  }
+}
+
+// pnqp (utils.py:66-124) on one thread, compacted problem of size m, scratch in `w`
+// (needs m*m + 4m scalars and m ints).
+template <typename R>
+__device__ int gen_pnqp(int m, const R* H, const R* q, const R* lo, const R* hi, R* x, R* w, int* piv) {
+  R* M = w;
+  R* g = M + m * m;
+  R* dx = g + m;
+  R* xn = dx + m;
+  R* frv = xn + m;
+  auto lu_solve1 = [&](R* rhs) {
+    gen_lu<R>(M, m, piv);
+    gen_lu_solve_col<R>(M, m, piv, rhs, 1, 0);
+  };
+  auto obj = [&](const R* z) {
+    R quad = 0, lin = 0;
+    for (int i = 0; i < m; ++i) {
+      R s = 0;
+      for (int j = 0; j < m; ++j) s += H[i * m + j] * z[j];
+      quad += z[i] * s;
+      lin += q[i] * z[i];
+    }
+    return (R)0.5 * quad + lin;
+  };
+  if (m == 1) {
+    x[0] = -(q[0] / H[0]);
+  } else {
+    for (int i = 0; i < m * m; ++i) M[i] = H[i];
+    for (int i = 0; i < m; ++i) x[i] = q[i];
+    lu_solve1(x);
+    for (int i = 0; i < m; ++i) x[i] = -x[i];
+  }
+  for (int i = 0; i < m; ++i) x[i] = tmax<R>(tmin<R>(x[i], hi[i]), lo[i]);
+  int it = 0;
+  for (it = 0; it < 20; ++it) {
+    for (int i = 0; i < m; ++i) {
+      R s = 0;
+      for (int j = 0; j < m; ++j) s += H[i * m + j] * x[j];
+      g[i] = s + q[i];
+    }
+    for (int i = 0; i < m; ++i) {
+      const bool at_lo = (x[i] <= lo[i]) && (g[i] > 0);
+      const bool at_hi = (x[i] >= hi[i]) && (g[i] < 0);
+      frv[i] = (at_lo || at_hi) ? (R)0 : (R)1;
+    }
+    for (int i = 0; i < m; ++i) {
+      for (int j = 0; j < m; ++j) M[i * m + j] = H[i * m + j] * (frv[i] * frv[j]) + ((i == j) ? (R)1e-10 : (R)0);
+      dx[i] = g[i] * frv[i];
+    }
+    if (m == 1) {
+      dx[0] = -dx[0] / M[0];
+    } else {
+      lu_solve1(dx);
+      for (int i = 0; i < m; ++i) dx[i] = -dx[i];
+    }
+    R mx = 0;
+    bool isnan_ = false;
+    for (int i = 0; i < m; ++i) {
+      const R a = abs_<R>(dx[i]);
+      if (a != a) isnan_ = true;
+      if (a > mx) mx = a;
+    }
+    if (!isnan_ && mx < (R)1e-5) break;
+    R alpha = 1;
+    const R fx = obj(x);
+    for (int ls = 0; ls < 10; ++ls) {
+      R gd = 0;
+      for (int i = 0; i < m; ++i) {
+        xn[i] = tmax<R>(tmin<R>(x[i] + alpha * dx[i], hi[i]), lo[i]);
+        gd += g[i] * (xn[i] - x[i]);
+      }
+      if (obj(xn) <= fx + (R)0.1 * gd) break;
+      alpha *= (R)0.5;
+    }
+    for (int i = 0; i < m; ++i) x[i] = xn[i];
+  }
+  return (it < 20) ? it + 1 : 20;
+}
+
+// ---- shared-memory carve-up ---------------------------------------------------
+template <typename R>
+struct GenSmem {
+  R *V, *Vn, *v, *vn, *A, *Bm, *Ct, *ct, *Qxx, *Qxu, *Quu, *qx, *qu, *AtV, *BtV, *Kt, *kt, *L, *rhs, *QK, *Qk, *tau, *x, *u;
+  R *xa, *xan, *ua, *part1, *part2, *red, *scr;
+  int* piv;
+  int* flag;
+};
+__host__ __device__ inline size_t gen_smem_scalars(int nx, int nu) {
+  const size_t n = nx + nu, na = TACD_MAX_ALPHA;
+  return 2 * nx * nx + 2 * nx + nx * nx + nx * nu + n * n + n + nx * nx + nx * nu + nu * nu + nx + nu + nx * nx + nu * nx + nu * nx + nu +
+         nu * nu + nu * (nx + 1) + nu * nx + nu + n + nx + nu +
+         2 * na * nx + na * nu + 2 * na * n + kGenThreads + (2 * nu * nu + 8 * nu + 8);
+}
+template <typename R>
+__host__ __device__ inline size_t gen_smem_bytes(int nx, int nu) {
+  return gen_smem_scalars(nx, nu) * sizeof(R) + (TACD_MAX_NU + 8) * sizeof(int);
+}
+template <typename R>
+__device__ GenSmem<R> gen_carve(unsigned char* raw, int nx, int nu) {
+  const int n = nx + nu, na = TACD_MAX_ALPHA;
+  GenSmem<R> s;
+  R* p = reinterpret_cast<R*>(raw);
+  auto take = [&](size_t k) { R* q = p; p += k; return q; };
+  s.V = take(nx * nx); s.Vn = take(nx * nx); s.v = take(nx); s.vn = take(nx);
+  s.A = take(nx * nx); s.Bm = take(nx * nu); s.Ct = take(n * n); s.ct = take(n);
+  s.Qxx = take(nx * nx); s.Qxu = take(nx * nu); s.Quu = take(nu * nu); s.qx = take(nx); s.qu = take(nu);
+  s.AtV = take(nx * nx); s.BtV = take(nu * nx); s.Kt = take(nu * nx); s.kt = take(nu);
+  s.L = take(nu * nu); s.rhs = take(nu * (nx + 1)); s.QK = take(nu * nx); s.Qk = take(nu);
+  s.tau = take(n); s.x = take(nx); s.u = take(nu);
+  s.xa = take(na * nx); s.xan = take(na * nx); s.ua = take(na * nu);
+  s.part1 = take(na * n); s.part2 = take(na * n); s.red = take(kGenThreads); s.scr = take(2 * nu * nu + 8 * nu + 8);
+  s.piv = reinterpret_cast<int*>(p);
+  s.flag = s.piv + TACD_MAX_NU;
+  return s;
+}
+
+// block-wide sum (all threads get the result)
+template <typename R>
+__device__ R gen_block_sum(R val, R* red) {
+  const int tid = threadIdx.x;
+  red[tid] = val;
+  __syncthreads();
+  for (int o = kGenThreads / 2; o > 0; o >>= 1) {
+    if (tid < o) red[tid] += red[tid + o];
+    __syncthreads();
+  }
+  const R r = red[0];
+  __syncthreads();
+  return r;
+}
+
+// objective of one trajectory held in global memory (cost.py:37-62), CTA-parallel
+template <typename R>
+__device__ R gen_objective(const GenDims<R>& d, GenSmem<R>& s, const R* X, const R* U, const R* C, const R* c, const R* Cf, const R* cf,
+                           const R* xr, const R* ur) {
+  const int tid = threadIdx.x, nx = d.nx, nu = d.nu, n = d.n, T = d.T;
+  R acc_q = 0, acc_l = 0;
+  // work item = (t, i): tau_i * (C_t[i,:] . tau) and c_t[i] tau_i
+  for (int idx = tid; idx < T * n; idx += kGenThreads) {
+    const int t = idx / n, i = idx % n;
+    const R* Ct = C + (size_t)t * n * n + (size_t)i * n;
+    R sdot = 0;
+    for (int j = 0; j < nx; ++j) sdot += Ct[j] * (X[t * nx + j] - xr[t * nx + j]);
+    for (int j = 0; j < nu; ++j) sdot += Ct[nx + j] * (U[t * nu + j] - ur[t * nu + j]);
+    const R ti = (i < nx) ? (X[t * nx + i] - xr[t * nx + i]) : (U[t * nu + (i - nx)] - ur[t * nu + (i - nx)]);
+    acc_q += ti * sdot;
+    acc_l += c[(size_t)t * n + i] * ti;
+  }
+  R accN_q = 0, accN_l = 0;
+  for (int i = tid; i < nx; i += kGenThreads) {
+    R sdot = 0;
+    for (int j = 0; j < nx; ++j) sdot += Cf[i * n + j] * (X[T * nx + j] - xr[T * nx + j]);
+    const R ti = X[T * nx + i] - xr[T * nx + i];
+    accN_q += ti * sdot;
+    accN_l += cf[i] * ti;
+  }
+  const R q = gen_block_sum<R>(acc_q, s.red), l = gen_block_sum<R>(acc_l, s.red);
+  const R qN = gen_block_sum<R>(accN_q, s.red), lN = gen_block_sum<R>(accN_l, s.red);
+  return ((R)0.5 * q + l) + ((R)0.5 * qN + lN);
+}
+
+// One Riccati/KKT value-recursion step on shared memory.  On entry s.Qxx/Qxu/Quu/qx/qu
+// hold the cost blocks, s.A/s.Bm the Jacobians, s.V/s.v the value at t+1.  `kkt`
+// selects the backward-pass variant (box QP for k, LU gain with 1e-8 reg; controller.py:736-767).
+template <typename R>
+__device__ bool gen_value_step(const DevProblem<R>& P, const GenDims<R>& d, GenSmem<R>& s, bool kkt, const uint8_t* tight_t, const R* U_t) {
+  const int tid = threadIdx.x, nx = d.nx, nu = d.nu;
+  const int nr = nx + 1;
+  bool nonpd = false;
+  for (int idx = tid; idx < nx * nx; idx += kGenThreads) {
+    const int i = idx / nx, j = idx % nx;
+    R a = 0;
+    for (int k = 0; k < nx; ++k) a += s.A[k * nx + i] * s.V[k * nx + j];
+    s.AtV[idx] = a;
+  }
+  for (int idx = tid; idx < nu * nx; idx += kGenThreads) {
+    const int i = idx / nx, j = idx % nx;
+    R a = 0;
+    for (int k = 0; k < nx; ++k) a += s.Bm[k * nu + i] * s.V[k * nx + j];
+    s.BtV[idx] = a;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < nx * nx; idx += kGenThreads) {
+    const int i = idx / nx, j = idx % nx;
+    R a = 0;
+    for (int k = 0; k < nx; ++k) a += s.AtV[i * nx + k] * s.A[k * nx + j];
+    s.Qxx[idx] += a;
+  }
+  for (int idx = tid; idx < nx * nu; idx += kGenThreads) {
+    const int i = idx / nu, j = idx % nu;
+    R a = 0;
+    for (int k = 0; k < nx; ++k) a += s.AtV[i * nx + k] * s.Bm[k * nu + j];
+    s.Qxu[idx] += a;
+  }
+  for (int idx = tid; idx < nu * nu; idx += kGenThreads) {
+    const int i = idx / nu, j = idx % nu;
+    R a = 0;
+    for (int k = 0; k < nx; ++k) a += s.BtV[i * nx + k] * s.Bm[k * nu + j];
+    s.Quu[idx] += a + ((i == j) ? P.reg : (R)0);
+  }
+  for (int i = tid; i < nx; i += kGenThreads) {
+    R a = 0;
+    for (int k = 0; k < nx; ++k) a += s.A[k * nx + i] * s.v[k];
+    s.qx[i] += a;
+  }
+  for (int i = tid; i < nu; i += kGenThreads) {
+    R a = 0;
+    for (int k = 0; k < nx; ++k) a += s.Bm[k * nu + i] * s.v[k];
+    s.qu[i] += a;
+  }
+  __syncthreads();
+  // rhs = [Q_ux | q_u], L = Q_uu + reg' I
+  const R reg2 = kkt ? (R)1e-8 * P.reg : P.reg;
+  for (int idx = tid; idx < nu * nr; idx += kGenThreads) {
+    const int i = idx / nr, j = idx % nr;
+    s.rhs[idx] = (j < nx) ? s.Qxu[j * nu + i] : s.qu[i];
+  }
+  for (int idx = tid; idx < nu * nu; idx += kGenThreads) s.L[idx] = s.Quu[idx] + ((idx / nu == idx % nu) ? reg2 : (R)0);
+  __syncthreads();
+  if (tid == 0) {
+    if (kkt) {
+      // k_t: box QP over the free coordinates (compacted, as the reference does)
+      int m = 0;
+      int* idxs = s.piv;  // reuse: free index list, overwritten by gen_lu afterwards
+      R* w = s.scr;
+      R* Hf = w + nu * nu + 4 * nu;
+      R* qf = Hf + nu * nu;
+      R* lof = qf + nu;
+      R* hif = lof + nu;
+      R* duf = hif + nu;
+      int freeidx[TACD_MAX_NU];
+      for (int i = 0; i < nu; ++i) { s.kt[i] = 0; if (!tight_t[i]) freeidx[m++] = i; }
+      if (m > 0) {
+        for (int i = 0; i < m; ++i) {
+          for (int j = 0; j < m; ++j) Hf[i * m + j] = s.Quu[freeidx[i] * nu + freeidx[j]];
+          qf[i] = s.qu[freeidx[i]];
+          if (P.has_umin) { lof[i] = P.umin[freeidx[i]] - U_t[freeidx[i]]; hif[i] = P.umax[freeidx[i]] - U_t[freeidx[i]]; }
+          else { lof[i] = -inf_<R>(); hif[i] = inf_<R>(); }
+        }
+        gen_pnqp<R>(m, Hf, qf, lof, hif, duf, w, idxs);
+        for (int i = 0; i < m; ++i) s.kt[freeidx[i]] = duf[i];
+      }
+      gen_lu<R>(s.L, nu, s.piv);
+      s.flag[0] = 0;
+    } else {
+      const bool pd = gen_chol<R>(s.L, nu);
+      s.flag[0] = pd ? 1 : 0;
+      if (!pd) {
+        for (int idx = 0; idx < nu * nu; ++idx) s.L[idx] = s.Quu[idx] + ((idx / nu == idx % nu) ? reg2 : (R)0);
+        gen_lu<R>(s.L, nu, s.piv);
+      }
+    }
+  }
+  __syncthreads();
+  const bool use_chol = s.flag[0] != 0;
+  if (!kkt && !use_chol) nonpd = true;
+  const int ncols = kkt ? nx : nr;  // the KKT pass takes k from the box QP, not from the solve
+  for (int r = tid; r < ncols; r += kGenThreads) {
+    if (use_chol) gen_chol_solve_col<R>(s.L, nu, s.rhs, nr, r);
+    else gen_lu_solve_col<R>(s.L, nu, s.piv, s.rhs, nr, r);
+  }
+  __syncthreads();
+  for (int idx = tid; idx < nu * nx; idx += kGenThreads) s.Kt[idx] = -s.rhs[(idx / nx) * nr + (idx % nx)];
+  if (!kkt) for (int i = tid; i < nu; i += kGenThreads) s.kt[i] = -s.rhs[i * nr + nx];
+  __syncthreads();
+  for (int idx = tid; idx < nu * nx; idx += kGenThreads) {
+    const int i = idx / nx, j = idx % nx;
+    R a = 0;
+    for (int m = 0; m < nu; ++m) a += s.Quu[i * nu + m] * s.Kt[m * nx + j];
+    s.QK[idx] = a;
+  }
+  for (int i = tid; i < nu; i += kGenThreads) {
+    R a = 0;
+    for (int m = 0; m < nu; ++m) a += s.Quu[i * nu + m] * s.kt[m];
+    s.Qk[i] = a;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < nx * nx; idx += kGenThreads) {
+    const int i = idx / nx, j = idx % nx;
+    R a = 0, b = 0, c = 0;
+    for (int m = 0; m < nu; ++m) {
+      a += s.Kt[m * nx + i] * s.QK[m * nx + j];
+      b += s.Kt[m * nx + i] * s.Qxu[j * nu + m];
+      c += s.Qxu[i * nu + m] * s.Kt[m * nx + j];
+    }
+    s.Vn[idx] = ((s.Qxx[idx] + a) + b) + c;
+  }
+  for (int i = tid; i < nx; i += kGenThreads) {
+    R a = 0, b = 0, c = 0;
+    for (int m = 0; m < nu; ++m) {
+      a += s.Kt[m * nx + i] * s.Qk[m];
+      b += s.Kt[m * nx + i] * s.qu[m];
+      c += s.Qxu[i * nu + m] * s.kt[m];
+    }
+    s.vn[i] = ((s.qx[i] + a) + b) + c;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < nx * nx; idx += kGenThreads) s.V[idx] = s.Vn[idx];
+  for (int i = tid; i < nx; i += kGenThreads) s.v[i] = s.vn[i];
+  __syncthreads();
+  return nonpd;
+}
+
+}  // namespace tacd

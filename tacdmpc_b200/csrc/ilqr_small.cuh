@@ -1,0 +1,657 @@
+// ilqr_small.cuh — whole-solve kernels for small systems (nx <= ~6, nu <= 2):
+// ONE THREAD PER BATCH ELEMENT, persistent over a work queue.
+//
+// Layout: the per-element trajectory state that must survive
+// between passes — nominal X[(T+1)nx], U[T nu] and the gains K[T nu nx], k[T nu]
+// — lives in shared memory as [word][thread] (bank = thread, conflict-free);
+// every per-step matrix (V, Q*, A, B, C_t) lives in registers with NX/NU known at
+// compile time.  A lane that finishes its element immediately pulls the next one
+// from a global counter, so the spread in iLQR iteration counts (2..40) does not
+// idle lanes for a whole solve, only for the short init/finalise phases.
+//
+// Forward = solve_step (controller.py:275-315): per iteration a reverse Riccati
+// pass (quadraticize + linearize + backward_lqr fused), one forward pass that
+// rolls out ALL line-search candidates at once (evaluate_alphas) and an in-place
+// re-rollout of the accepted candidate.
+#pragma once
+#include "tacd_dev.cuh"
+
+namespace tacd {
+
+template <typename R>
+struct FwdPtrs {
+  const R *x0, *C, *c, *Cf, *cf, *C_ls, *c_ls, *Cf_ls, *cf_ls, *xref, *uref, *Uinit;
+  const int32_t* replay_iters;
+  const uint8_t* replay_alpha;
+  const uint8_t* replay_flags;
+  R *X, *U, *A, *Bm;
+  uint8_t* tight;
+  int32_t* iters;
+  uint8_t* alpha_trace;
+  uint8_t* flags;
+  R* cost;
+  R* cost_trace;
+  unsigned int* counter;  // work queue head, zeroed before launch
+};
+
+template <typename R>
+struct BwdPtrs {
+  const R *X, *U, *C, *xref, *uref, *A, *Bm, *gX, *gU;
+  const uint8_t* tight;
+  R *grad_C, *grad_c, *grad_Cf, *grad_cf, *grad_x0, *grad_xref, *grad_uref, *dX, *dU;
+};
+
+constexpr int kNA = 5;  // line-search candidates rolled out together (the reference has 5 alphas)
+
+// words of shared memory per thread for the forward state
+__host__ __device__ inline int fwd_words(int T, int nx, int nu) { return (T + 1) * nx + T * nu + T * nu * nx + T * nu; }
+__host__ __device__ inline int bwd_words(int T, int nx, int nu) { return T * nu * nx + T * nu; }
+
+// tau^T C tau and c^T tau with C [N,N] row-major in registers
+template <typename R, int N>
+TACD_DEV void quad_terms(const R (&Ct)[N * N], const R (&ct)[N], const R (&tau)[N], R& quad, R& lin) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    R s = 0;
+#pragma unroll
+    for (int j = 0; j < N; ++j) s += Ct[i * N + j] * tau[j];
+    quad += tau[i] * s;
+    lin += ct[i] * tau[i];
+  }
+}
+
+template <typename R, int NX, int NU, int DYN, bool LSSEP>
+__global__ void __launch_bounds__(256, 1) ilqr_forward_small(const DevProblem<R> P, const FwdPtrs<R> io) {
+  constexpr int N = NX + NU;
+  using D = Dyn<R, NX, NU, DYN>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int NT = blockDim.x, tid = threadIdx.x;
+  const int T = P.T;
+  R* sX = reinterpret_cast<R*>(smem_raw);
+  R* sU = sX + (size_t)(T + 1) * NX * NT;
+  R* sK = sU + (size_t)T * NU * NT;
+  R* sk = sK + (size_t)T * NU * NX * NT;
+  R* sA = sk + (size_t)T * NU * NT;  // LTI matrices, shared by the CTA
+  R* sB = sA + NX * NX;
+  if (DYN == TACD_DYN_LTI) {
+    for (int i = tid; i < NX * NX; i += NT) sA[i] = P.dyn_A[i];
+    for (int i = tid; i < NX * NU; i += NT) sB[i] = P.dyn_B[i];
+    __syncthreads();
+  }
+#define SX(t, i) sX[((size_t)(t) * NX + (i)) * NT + tid]
+#define SU(t, i) sU[((size_t)(t) * NU + (i)) * NT + tid]
+#define SK(t, i) sK[((size_t)(t) * NU * NX + (i)) * NT + tid]
+#define Sk(t, i) sk[((size_t)(t) * NU + (i)) * NT + tid]
+
+  const size_t szX = (size_t)(T + 1) * NX, szU = (size_t)T * NU;
+  bool has = false, exhausted = false;
+  int b = 0, it = 0;
+  unsigned flg = 0;
+  R best = 0;
+  const R *Cp = nullptr, *cp = nullptr, *Cfp = nullptr, *cfp = nullptr, *xr = nullptr, *ur = nullptr;
+
+  while (true) {
+    // ---------------------------------------------------------------- refill
+    if (!has && !exhausted) {
+      const unsigned nb = atomicAdd(io.counter, 1u);
+      if (nb < (unsigned)P.B) {
+        b = (int)nb;
+        has = true;
+        it = 0;
+        flg = 0;
+        Cp = io.C + (P.C_batched ? (size_t)b * T * N * N : 0);
+        cp = io.c + (P.C_batched ? (size_t)b * T * N : 0);
+        Cfp = io.Cf + (P.Cf_batched ? (size_t)b * N * N : 0);
+        cfp = io.cf + (P.Cf_batched ? (size_t)b * N : 0);
+        xr = io.xref + (P.xref_batched ? (size_t)b * szX : 0);
+        ur = io.uref + (P.uref_batched ? (size_t)b * szU : 0);
+        // rollout_trajectory (controller.py:361-398, no clamping) + objective (cost.py:37-62)
+        R x[NX], u[NU], xn[NX];
+        R quad = 0, lin = 0;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) { x[i] = io.x0[(size_t)b * NX + i]; SX(0, i) = x[i]; }
+        for (int t = 0; t < T; ++t) {
+          R tau[N], Ct[N * N], ct[N];
+#pragma unroll
+          for (int i = 0; i < NU; ++i) { u[i] = io.Uinit[(size_t)b * szU + t * NU + i]; SU(t, i) = u[i]; }
+#pragma unroll
+          for (int i = 0; i < NX; ++i) tau[i] = x[i] - xr[t * NX + i];
+#pragma unroll
+          for (int i = 0; i < NU; ++i) tau[NX + i] = u[i] - ur[t * NU + i];
+#pragma unroll
+          for (int i = 0; i < N * N; ++i) Ct[i] = Cp[(size_t)t * N * N + i];
+#pragma unroll
+          for (int i = 0; i < N; ++i) ct[i] = cp[(size_t)t * N + i];
+          quad_terms<R, N>(Ct, ct, tau, quad, lin);
+          D::step(P, sA, sB, x, u, xn);
+#pragma unroll
+          for (int i = 0; i < NX; ++i) { x[i] = xn[i]; SX(t + 1, i) = x[i]; }
+        }
+        R qN = 0, lN = 0;
+        {
+          R tauN[NX];
+#pragma unroll
+          for (int i = 0; i < NX; ++i) tauN[i] = x[i] - xr[T * NX + i];
+#pragma unroll
+          for (int i = 0; i < NX; ++i) {
+            R s = 0;
+#pragma unroll
+            for (int j = 0; j < NX; ++j) s += Cfp[i * N + j] * tauN[j];
+            qN += tauN[i] * s;
+            lN += cfp[i] * tauN[i];
+          }
+        }
+        best = ((R)0.5 * quad + lin) + ((R)0.5 * qN + lN);
+        if (io.alpha_trace)
+          for (int j = 0; j < P.max_iter; ++j) io.alpha_trace[(size_t)b * P.max_iter + j] = 0xFF;
+      } else {
+        exhausted = true;
+      }
+    }
+    if (__ballot_sync(0xffffffffu, has) == 0u) break;
+    if (!has) continue;
+
+    bool stop = true;
+    const bool replay = io.replay_iters != nullptr;
+    if (it < P.max_iter && !(replay && it >= io.replay_iters[b])) {
+      // ------------------------------------------------ reverse Riccati pass
+      // quadraticize (cost.py:64-100) + linearize (controller.py:448-471) +
+      // backward_lqr (controller.py:546-578), one time step at a time
+      {
+        R V[NX * NX], v[NX];
+        {
+          R tauN[NX];
+#pragma unroll
+          for (int i = 0; i < NX; ++i) tauN[i] = SX(T, i) - xr[T * NX + i];
+#pragma unroll
+          for (int i = 0; i < NX; ++i) {
+            R s = 0;
+#pragma unroll
+            for (int j = 0; j < NX; ++j) { const R cij = Cfp[i * N + j]; V[i * NX + j] = cij; s += cij * tauN[j]; }
+            v[i] = s + cfp[i];
+          }
+        }
+        for (int t = T - 1; t >= 0; --t) {
+          R x[NX], u[NU], tau[N], Ct[N * N];
+          R Qxx[NX * NX], Qxu[NX * NU], Quu[NU * NU], qx[NX], qu[NU];
+#pragma unroll
+          for (int i = 0; i < NX; ++i) { x[i] = SX(t, i); tau[i] = x[i] - xr[t * NX + i]; }
+#pragma unroll
+          for (int i = 0; i < NU; ++i) { u[i] = SU(t, i); tau[NX + i] = u[i] - ur[t * NU + i]; }
+#pragma unroll
+          for (int i = 0; i < N * N; ++i) Ct[i] = Cp[(size_t)t * N * N + i];
+#pragma unroll
+          for (int i = 0; i < N; ++i) {
+            R s = 0;
+#pragma unroll
+            for (int j = 0; j < N; ++j) s += Ct[i * N + j] * tau[j];
+            s += cp[(size_t)t * N + i];
+            if (i < NX) qx[i] = s; else qu[i - NX] = s;
+          }
+#pragma unroll
+          for (int i = 0; i < NX; ++i) {
+#pragma unroll
+            for (int j = 0; j < NX; ++j) Qxx[i * NX + j] = Ct[i * N + j];
+#pragma unroll
+            for (int j = 0; j < NU; ++j) Qxu[i * NU + j] = Ct[i * N + NX + j];
+          }
+#pragma unroll
+          for (int i = 0; i < NU; ++i)
+#pragma unroll
+            for (int j = 0; j < NU; ++j) Quu[i * NU + j] = Ct[(NX + i) * N + NX + j];
+          R A[NX * NX], Bm[NX * NU];
+          D::jac(P, sA, sB, x, u, A, Bm);
+          q_blocks<R, NX, NU>(P.reg, A, Bm, V, v, Qxx, Qxu, Quu, qx, qu);
+          R Kt[NU * NX], kt[NU];
+          if (gains<R, NX, NU>(P.reg, Qxu, Quu, qu, Kt, kt)) flg |= TACD_FLAG_NONPD;
+#pragma unroll
+          for (int i = 0; i < NU * NX; ++i) SK(t, i) = Kt[i];
+#pragma unroll
+          for (int i = 0; i < NU; ++i) Sk(t, i) = kt[i];
+          value_update<R, NX, NU>(Qxx, Qxu, Quu, qx, qu, Kt, kt, V, v);
+        }
+      }
+      // -------------------------------------- all line-search candidates at once
+      // evaluate_alphas (controller.py:589-620).  Candidate costs use the line-search
+      // cost (element 0's when costs are per-element, quirk Q4); with LSSEP the
+      // element's own cost of every candidate is accumulated alongside, so the
+      // acceptance cost (controller.py:298) needs no extra pass.
+      R costs[TACD_MAX_ALPHA], own[TACD_MAX_ALPHA];
+      const R* Cl = LSSEP ? io.C_ls : Cp;
+      const R* cl = LSSEP ? io.c_ls : cp;
+      const R* Cfl = LSSEP ? io.Cf_ls : Cfp;
+      const R* cfl = LSSEP ? io.cf_ls : cfp;
+      for (int a0 = 0; a0 < P.n_alpha; a0 += kNA) {
+        R xa[kNA][NX], q1[kNA], l1[kNA], q2[kNA], l2[kNA], al[kNA];
+#pragma unroll
+        for (int a = 0; a < kNA; ++a) {
+          al[a] = P.alphas[(a0 + a < P.n_alpha) ? a0 + a : P.n_alpha - 1];
+          q1[a] = l1[a] = q2[a] = l2[a] = 0;
+#pragma unroll
+          for (int i = 0; i < NX; ++i) xa[a][i] = SX(0, i);
+        }
+        for (int t = 0; t < T; ++t) {
+          R Xt[NX], Ut[NU], Kt[NU * NX], kt[NU], xrt[NX], urt[NU], Ct[N * N], ct[N];
+#pragma unroll
+          for (int i = 0; i < NX; ++i) { Xt[i] = SX(t, i); xrt[i] = xr[t * NX + i]; }
+#pragma unroll
+          for (int i = 0; i < NU; ++i) { Ut[i] = SU(t, i); kt[i] = Sk(t, i); urt[i] = ur[t * NU + i]; }
+#pragma unroll
+          for (int i = 0; i < NU * NX; ++i) Kt[i] = SK(t, i);
+#pragma unroll
+          for (int i = 0; i < N * N; ++i) Ct[i] = Cl[(size_t)t * N * N + i];
+#pragma unroll
+          for (int i = 0; i < N; ++i) ct[i] = cl[(size_t)t * N + i];
+          R ua[kNA][NU];
+#pragma unroll
+          for (int a = 0; a < kNA; ++a) {
+            R tau[N];
+#pragma unroll
+            for (int i = 0; i < NU; ++i) {
+              R s = 0;
+#pragma unroll
+              for (int j = 0; j < NX; ++j) s += Kt[i * NX + j] * (xa[a][j] - Xt[j]);
+              R ui = Ut[i] + (al[a] * kt[i] + s);
+              if (P.has_umin) ui = tmax<R>(ui, P.umin[i]);
+              if (P.has_umax) ui = tmin<R>(ui, P.umax[i]);
+              ua[a][i] = ui;
+              tau[NX + i] = ui - urt[i];
+            }
+#pragma unroll
+            for (int i = 0; i < NX; ++i) tau[i] = xa[a][i] - xrt[i];
+            quad_terms<R, N>(Ct, ct, tau, q1[a], l1[a]);
+          }
+          if (LSSEP) {
+#pragma unroll
+            for (int i = 0; i < N * N; ++i) Ct[i] = Cp[(size_t)t * N * N + i];
+#pragma unroll
+            for (int i = 0; i < N; ++i) ct[i] = cp[(size_t)t * N + i];
+#pragma unroll
+            for (int a = 0; a < kNA; ++a) {
+              R tau[N];
+#pragma unroll
+              for (int i = 0; i < NX; ++i) tau[i] = xa[a][i] - xrt[i];
+#pragma unroll
+              for (int i = 0; i < NU; ++i) tau[NX + i] = ua[a][i] - urt[i];
+              quad_terms<R, N>(Ct, ct, tau, q2[a], l2[a]);
+            }
+          }
+#pragma unroll
+          for (int a = 0; a < kNA; ++a) {
+            R xn[NX];
+            D::step(P, sA, sB, xa[a], ua[a], xn);
+#pragma unroll
+            for (int i = 0; i < NX; ++i) xa[a][i] = xn[i];
+          }
+        }
+#pragma unroll
+        for (int a = 0; a < kNA; ++a) {
+          R tauN[NX];
+#pragma unroll
+          for (int i = 0; i < NX; ++i) tauN[i] = xa[a][i] - xr[T * NX + i];
+          R qN = 0, lN = 0, qN2 = 0, lN2 = 0;
+#pragma unroll
+          for (int i = 0; i < NX; ++i) {
+            R s = 0, s2 = 0;
+#pragma unroll
+            for (int j = 0; j < NX; ++j) {
+              s += Cfl[i * N + j] * tauN[j];
+              if (LSSEP) s2 += Cfp[i * N + j] * tauN[j];
+            }
+            qN += tauN[i] * s;
+            lN += cfl[i] * tauN[i];
+            if (LSSEP) { qN2 += tauN[i] * s2; lN2 += cfp[i] * tauN[i]; }
+          }
+          if (a0 + a < P.n_alpha) {
+            costs[a0 + a] = ((R)0.5 * q1[a] + l1[a]) + ((R)0.5 * qN + lN);
+            own[a0 + a] = LSSEP ? ((R)0.5 * q2[a] + l2[a]) + ((R)0.5 * qN2 + lN2) : costs[a0 + a];
+          }
+        }
+      }
+      // ------------------------------------------------------------- accept
+      // argmin (first minimum, NaN wins) + strict improvement (controller.py:292-301)
+      int ai = 0;
+      for (int a = 1; a < P.n_alpha; ++a) {
+        if (costs[ai] != costs[ai]) break;
+        if (costs[a] < costs[ai] || costs[a] != costs[a]) ai = a;
+      }
+      if (replay) ai = io.replay_alpha[(size_t)b * P.max_iter + it];
+      R newc = own[0];
+      for (int a = 1; a < P.n_alpha; ++a) newc = (a == ai) ? own[a] : newc;
+      bool improved = newc < best;
+      if (replay) improved = (it < io.replay_iters[b] - 1) || ((io.replay_flags[b] & TACD_FLAG_MAXITER) != 0);
+      if (io.alpha_trace) io.alpha_trace[(size_t)b * P.max_iter + it] = (uint8_t)ai;
+      if (io.cost_trace) {
+        R* ctr = io.cost_trace + ((size_t)b * P.max_iter + it) * (P.n_alpha + 2);
+        for (int a = 0; a < P.n_alpha; ++a) ctr[a] = costs[a];
+        ctr[P.n_alpha] = newc;
+        ctr[P.n_alpha + 1] = best;
+      }
+      it += 1;
+      if (improved) {
+        best = newc;
+        // re-rollout of the accepted candidate, in place (X_{t+1} is read before it is overwritten)
+        R alpha = P.alphas[0];
+        for (int a = 1; a < P.n_alpha; ++a) alpha = (a == ai) ? P.alphas[a] : alpha;
+        R x[NX], Xold[NX];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) { x[i] = SX(0, i); Xold[i] = x[i]; }
+        for (int t = 0; t < T; ++t) {
+          R u[NU], xn[NX];
+#pragma unroll
+          for (int i = 0; i < NU; ++i) {
+            R s = 0;
+#pragma unroll
+            for (int j = 0; j < NX; ++j) s += SK(t, i * NX + j) * (x[j] - Xold[j]);
+            R ui = SU(t, i) + (alpha * Sk(t, i) + s);
+            if (P.has_umin) ui = tmax<R>(ui, P.umin[i]);
+            if (P.has_umax) ui = tmin<R>(ui, P.umax[i]);
+            u[i] = ui;
+          }
+#pragma unroll
+          for (int i = 0; i < NU; ++i) SU(t, i) = u[i];
+          D::step(P, sA, sB, x, u, xn);
+#pragma unroll
+          for (int i = 0; i < NX; ++i) { Xold[i] = SX(t + 1, i); x[i] = xn[i]; SX(t + 1, i) = xn[i]; }
+        }
+        stop = (it >= P.max_iter);
+        if (stop) flg |= TACD_FLAG_MAXITER;
+      }
+    }
+    if (stop) {
+      // ------------------------------------------------------------ finalise
+      // outputs + final re-linearisation (controller.py:311-314) + active set (636-642)
+      for (int t = 0; t <= T; ++t)
+#pragma unroll
+        for (int i = 0; i < NX; ++i) io.X[(size_t)b * szX + t * NX + i] = SX(t, i);
+      for (int t = 0; t < T; ++t) {
+#pragma unroll
+        for (int i = 0; i < NU; ++i) {
+          const R ui = SU(t, i);
+          io.U[(size_t)b * szU + t * NU + i] = ui;
+          bool m = false;
+          if (P.has_umin) m = m || isclose_<R>(ui, P.umin[i]);
+          if (P.has_umax) m = m || isclose_<R>(ui, P.umax[i]);
+          io.tight[(size_t)b * szU + t * NU + i] = m ? 1 : 0;
+        }
+        if (io.A != nullptr || io.Bm != nullptr) {
+          R x[NX], u[NU], A[NX * NX], Bm[NX * NU];
+#pragma unroll
+          for (int i = 0; i < NX; ++i) x[i] = SX(t, i);
+#pragma unroll
+          for (int i = 0; i < NU; ++i) u[i] = SU(t, i);
+          D::jac(P, sA, sB, x, u, A, Bm);
+          if (io.A)
+#pragma unroll
+            for (int i = 0; i < NX * NX; ++i) io.A[((size_t)b * T + t) * NX * NX + i] = A[i];
+          if (io.Bm)
+#pragma unroll
+            for (int i = 0; i < NX * NU; ++i) io.Bm[((size_t)b * T + t) * NX * NU + i] = Bm[i];
+        }
+      }
+      io.iters[b] = it;
+      io.flags[b] = (uint8_t)flg;
+      if (io.cost) io.cost[b] = best;
+      has = false;
+    }
+  }
+#undef SX
+#undef SU
+#undef SK
+#undef Sk
+}
+
+// ---------------------------------------------------------------------------
+// Backward: ILQRSolve.backward + _zero_constrained_lqr (controller.py:63-115,
+// 707-788).  One thread per element; gains K_t,k_t in shared memory [word][thread];
+// A_t,B_t are recomputed from (X*,U*) with the embedded dynamics (or read, for
+// TACD_DYN_EXTERNAL).  Shared-cost gradients are reduced over the warp with
+// shuffles and accumulated with one atomicAdd per warp and value.
+template <typename R>
+TACD_DEV R warp_sum(R v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename R, int NX, int NU, int DYN>
+__global__ void __launch_bounds__(256, 1) ilqr_backward_small(const DevProblem<R> P, const BwdPtrs<R> io) {
+  constexpr int N = NX + NU;
+  using D = Dyn<R, NX, NU, (DYN == TACD_DYN_EXTERNAL ? TACD_DYN_LTI : DYN)>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int NT = blockDim.x, tid = threadIdx.x;
+  const int T = P.T;
+  R* sK = reinterpret_cast<R*>(smem_raw);
+  R* sk = sK + (size_t)T * NU * NX * NT;
+  R* sA = sk + (size_t)T * NU * NT;
+  R* sB = sA + NX * NX;
+  if (DYN == TACD_DYN_LTI) {
+    for (int i = tid; i < NX * NX; i += NT) sA[i] = P.dyn_A[i];
+    for (int i = tid; i < NX * NU; i += NT) sB[i] = P.dyn_B[i];
+    __syncthreads();
+  }
+#define SK(t, i) sK[((size_t)(t) * NU * NX + (i)) * NT + tid]
+#define Sk(t, i) sk[((size_t)(t) * NU + (i)) * NT + tid]
+  const size_t szX = (size_t)(T + 1) * NX, szU = (size_t)T * NU;
+  const int lane = tid & 31;
+  // every lane of a warp iterates the same number of times so the shuffles stay convergent
+  const int stride = gridDim.x * NT;
+  for (int b0 = blockIdx.x * NT + (tid - lane); b0 < P.B; b0 += stride) {
+    const int b = b0 + lane;
+    const bool live = b < P.B;
+    const int bb = live ? b : P.B - 1;  // dead lanes shadow the last element, outputs masked
+    const R* X = io.X + (size_t)bb * szX;
+    const R* U = io.U + (size_t)bb * szU;
+    const R* Cp = io.C + (P.C_batched ? (size_t)bb * T * N * N : 0);
+    const R* xr = io.xref + (P.xref_batched ? (size_t)bb * szX : 0);
+    const R* ur = io.uref + (P.uref_batched ? (size_t)bb * szU : 0);
+    const R* gX = io.gX + (size_t)bb * szX;
+    const R* gU = io.gU + (size_t)bb * szU;
+    const uint8_t* tg = io.tight + (size_t)bb * szU;
+
+    auto load_AB = [&](int t, R(&A)[NX * NX], R(&Bm)[NX * NU]) {
+      if constexpr (DYN == TACD_DYN_EXTERNAL) {
+#pragma unroll
+        for (int i = 0; i < NX * NX; ++i) A[i] = io.A[((size_t)bb * T + t) * NX * NX + i];
+#pragma unroll
+        for (int i = 0; i < NX * NU; ++i) Bm[i] = io.Bm[((size_t)bb * T + t) * NX * NU + i];
+      } else {
+        R x[NX], u[NU];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) x[i] = X[t * NX + i];
+#pragma unroll
+        for (int i = 0; i < NU; ++i) u[i] = U[t * NU + i];
+        D::jac(P, sA, sB, x, u, A, Bm);
+      }
+    };
+
+    // ---- reverse pass: V = H_xx[T-1], v = -grad_X[T-1] (quirks Q1, Q2)
+    R V[NX * NX], v[NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+#pragma unroll
+      for (int j = 0; j < NX; ++j) V[i * NX + j] = Cp[(size_t)(T - 1) * N * N + i * N + j];
+      v[i] = -gX[(T - 1) * NX + i];
+    }
+    for (int t = T - 1; t >= 0; --t) {
+      R Qxx[NX * NX], Qxu[NX * NU], Quu[NU * NU], qx[NX], qu[NU], A[NX * NX], Bm[NX * NU];
+      const R* Ct = Cp + (size_t)t * N * N;
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+#pragma unroll
+        for (int j = 0; j < NX; ++j) Qxx[i * NX + j] = Ct[i * N + j];
+#pragma unroll
+        for (int j = 0; j < NU; ++j) Qxu[i * NU + j] = Ct[i * N + NX + j];
+        qx[i] = -gX[t * NX + i];
+      }
+#pragma unroll
+      for (int i = 0; i < NU; ++i) {
+#pragma unroll
+        for (int j = 0; j < NU; ++j) Quu[i * NU + j] = Ct[(NX + i) * N + NX + j];
+        qu[i] = -gU[t * NU + i];
+      }
+      load_AB(t, A, Bm);
+      q_blocks<R, NX, NU>(P.reg, A, Bm, V, v, Qxx, Qxu, Quu, qx, qu);
+      // box QP on the free coordinates (controller.py:737-763); tight ones pinned to 0
+      R kt[NU];
+      {
+        bool fixed[NU];
+        bool any_free = false;
+#pragma unroll
+        for (int i = 0; i < NU; ++i) { fixed[i] = tg[t * NU + i] != 0; any_free = any_free || !fixed[i]; }
+        R H[NU * NU], q[NU], lo[NU], hi[NU];
+#pragma unroll
+        for (int i = 0; i < NU; ++i) {
+#pragma unroll
+          for (int j = 0; j < NU; ++j)
+            H[i * NU + j] = (fixed[i] || fixed[j]) ? ((i == j) ? (R)1 : (R)0) : Quu[i * NU + j];
+          q[i] = fixed[i] ? (R)0 : qu[i];
+          if (fixed[i]) { lo[i] = 0; hi[i] = 0; }
+          else if (P.has_umin) { lo[i] = P.umin[i] - U[t * NU + i]; hi[i] = P.umax[i] - U[t * NU + i]; }  // quirk Q10
+          else { lo[i] = -inf_<R>(); hi[i] = inf_<R>(); }
+        }
+        if (any_free) {
+          pnqp<R, NU>(H, q, lo, hi, kt);
+#pragma unroll
+          for (int i = 0; i < NU; ++i) kt[i] = fixed[i] ? (R)0 : kt[i];
+        } else {
+#pragma unroll
+          for (int i = 0; i < NU; ++i) kt[i] = 0;
+        }
+      }
+      // K_t = -solve(Q_uu + 1e-8 reg I, Q_ux) — not masked by the active set (quirk Q6)
+      R Kt[NU * NX];
+      {
+        R M[NU * NU];
+#pragma unroll
+        for (int i = 0; i < NU; ++i) {
+#pragma unroll
+          for (int j = 0; j < NU; ++j) M[i * NU + j] = Quu[i * NU + j] + ((i == j) ? (R)1e-8 * P.reg : (R)0);
+#pragma unroll
+          for (int j = 0; j < NX; ++j) Kt[i * NX + j] = Qxu[j * NU + i];
+        }
+        lu_solve<R, NU, NX>(M, Kt);
+#pragma unroll
+        for (int i = 0; i < NU * NX; ++i) Kt[i] = -Kt[i];
+      }
+#pragma unroll
+      for (int i = 0; i < NU * NX; ++i) SK(t, i) = Kt[i];
+#pragma unroll
+      for (int i = 0; i < NU; ++i) Sk(t, i) = kt[i];
+      value_update<R, NX, NU>(Qxx, Qxu, Quu, qx, qu, Kt, kt, V, v);
+    }
+    // ---- forward sweep from dX_0 = 0 (quirk Q3) + gradient formulas (controller.py:84-115)
+    R dx[NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) dx[i] = 0;
+    if (io.grad_x0 && live)
+#pragma unroll
+      for (int i = 0; i < NX; ++i) io.grad_x0[(size_t)b * NX + i] = 0;
+    for (int t = 0; t <= T; ++t) {
+      R tau[N], dtau[N];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) { tau[i] = X[t * NX + i] - xr[t * NX + i]; dtau[i] = dx[i]; }
+      if (t < T) {
+        R du[NU];
+#pragma unroll
+        for (int i = 0; i < NU; ++i) {
+          R s = 0;
+#pragma unroll
+          for (int j = 0; j < NX; ++j) s += SK(t, i * NX + j) * dx[j];
+          du[i] = s + Sk(t, i);
+          tau[NX + i] = U[t * NU + i] - ur[t * NU + i];
+          dtau[NX + i] = du[i];
+        }
+        // grad_C = -1/2 (dtau (x) tau + tau (x) dtau), grad_c = -dtau
+        if (io.grad_C) {
+#pragma unroll
+          for (int i = 0; i < N; ++i)
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+              R g = (R)-0.5 * (dtau[i] * tau[j] + tau[i] * dtau[j]);
+              if (P.C_batched) { if (live) io.grad_C[((size_t)b * T + t) * N * N + i * N + j] = g; }
+              else { g = warp_sum<R>(live ? g : (R)0); if (lane == 0) atomicAdd(&io.grad_C[(size_t)t * N * N + i * N + j], g); }
+            }
+        }
+        if (io.grad_c) {
+#pragma unroll
+          for (int i = 0; i < N; ++i) {
+            R g = -dtau[i];
+            if (P.C_batched) { if (live) io.grad_c[((size_t)b * T + t) * N + i] = g; }
+            else { g = warp_sum<R>(live ? g : (R)0); if (lane == 0) atomicAdd(&io.grad_c[(size_t)t * N + i], g); }
+          }
+        }
+        if (io.grad_uref) {
+#pragma unroll
+          for (int i = 0; i < NU; ++i) {
+            R g = du[i];
+            if (P.uref_batched) { if (live) io.grad_uref[(size_t)b * szU + t * NU + i] = g; }
+            else { g = warp_sum<R>(live ? g : (R)0); if (lane == 0) atomicAdd(&io.grad_uref[t * NU + i], g); }
+          }
+        }
+        if (io.dU && live)
+#pragma unroll
+          for (int i = 0; i < NU; ++i) io.dU[(size_t)b * szU + t * NU + i] = du[i];
+        if (io.grad_xref) {
+#pragma unroll
+          for (int i = 0; i < NX; ++i) {
+            R g = dx[i];
+            if (P.xref_batched) { if (live) io.grad_xref[(size_t)b * szX + t * NX + i] = g; }
+            else { g = warp_sum<R>(live ? g : (R)0); if (lane == 0) atomicAdd(&io.grad_xref[t * NX + i], g); }
+          }
+        }
+        if (io.dX && live)
+#pragma unroll
+          for (int i = 0; i < NX; ++i) io.dX[(size_t)b * szX + t * NX + i] = dx[i];
+        R A[NX * NX], Bm[NX * NU], dxn[NX];
+        load_AB(t, A, Bm);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+          R s = 0, s2 = 0;
+#pragma unroll
+          for (int j = 0; j < NX; ++j) s += A[i * NX + j] * dx[j];
+#pragma unroll
+          for (int j = 0; j < NU; ++j) s2 += Bm[i * NU + j] * du[j];
+          dxn[i] = s + s2;
+        }
+#pragma unroll
+        for (int i = 0; i < NX; ++i) dx[i] = dxn[i];
+      } else {
+        // terminal: grad_C_final[:nx,:nx], grad_c_final[:nx]; zero padding elsewhere
+        if (io.grad_Cf) {
+#pragma unroll
+          for (int i = 0; i < N; ++i)
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+              R g = (i < NX && j < NX) ? (R)-0.5 * (dtau[i < NX ? i : 0] * tau[j < NX ? j : 0] + tau[i < NX ? i : 0] * dtau[j < NX ? j : 0]) : (R)0;
+              if (P.Cf_batched) { if (live) io.grad_Cf[(size_t)b * N * N + i * N + j] = g; }
+              else if (i < NX && j < NX) { g = warp_sum<R>(live ? g : (R)0); if (lane == 0) atomicAdd(&io.grad_Cf[i * N + j], g); }
+            }
+        }
+        if (io.grad_cf) {
+#pragma unroll
+          for (int i = 0; i < N; ++i) {
+            R g = (i < NX) ? -dtau[i < NX ? i : 0] : (R)0;
+            if (P.Cf_batched) { if (live) io.grad_cf[(size_t)b * N + i] = g; }
+            else if (i < NX) { g = warp_sum<R>(live ? g : (R)0); if (lane == 0) atomicAdd(&io.grad_cf[i], g); }
+          }
+        }
+        if (io.grad_xref) {
+#pragma unroll
+          for (int i = 0; i < NX; ++i) {
+            R g = dx[i];
+            if (P.xref_batched) { if (live) io.grad_xref[(size_t)b * szX + T * NX + i] = g; }
+            else { g = warp_sum<R>(live ? g : (R)0); if (lane == 0) atomicAdd(&io.grad_xref[T * NX + i], g); }
+          }
+        }
+        if (io.dX && live)
+#pragma unroll
+          for (int i = 0; i < NX; ++i) io.dX[(size_t)b * szX + T * NX + i] = dx[i];
+      }
+    }
+  }
+#undef SK
+#undef Sk
+}
+
+}  // namespace tacd

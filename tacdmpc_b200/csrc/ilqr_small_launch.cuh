@@ -1,0 +1,111 @@
+// ilqr_small_launch.cuh — dispatch + launch of the thread-per-element kernels.
+// Included by ilqr_small_f32.cu / ilqr_small_f64.cu, which instantiate it for one scalar type each.
+#pragma once
+#include "host_common.h"
+
+namespace tacd {
+
+// Pick the block size (multiple of 32, <= 256) that maximises resident threads per SM
+// for a kernel whose dynamic shared memory is words_per_thread * NT + extra scalars.
+template <typename K>
+static int pick_block(K kernel, size_t words_per_thread, size_t extra_words, size_t elt, int* blocks_per_sm, size_t* smem_out) {
+  const DeviceInfo di = device_info();
+  int best_nt = 0, best_blocks = 0;
+  size_t best_smem = 0;
+  for (int nt = 256; nt >= 32; nt -= 32) {
+    const size_t smem = (words_per_thread * nt + extra_words) * elt;
+    if (smem > (size_t)di.smem_optin) continue;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); continue; }
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, nt, smem) != cudaSuccess) { cudaGetLastError(); continue; }
+    if (nb * nt > best_blocks * best_nt) { best_nt = nt; best_blocks = nb; best_smem = smem; }
+  }
+  *blocks_per_sm = best_blocks;
+  *smem_out = best_smem;
+  return best_nt;
+}
+
+template <typename R, int NX, int NU, int DYN, bool LSSEP>
+static int run_forward_small(const tacd_problem* p, const tacd_forward_io* io, void* ws, cudaStream_t s) {
+  auto kernel = ilqr_forward_small<R, NX, NU, DYN, LSSEP>;
+  int bps = 0;
+  size_t smem = 0;
+  const int nt = pick_block(kernel, (size_t)fwd_words(p->T, NX, NU), (size_t)(NX * NX + NX * NU), sizeof(R), &bps, &smem);
+  if (nt == 0 || bps == 0) return TACD_EUNSUPPORTED;
+  if (int rc = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr")) return rc;
+  const DeviceInfo di = device_info();
+  int grid = di.sms * bps;
+  const int need = (p->B + nt - 1) / nt;
+  if (grid > need) grid = need;
+  if (grid < 1) grid = 1;
+  FwdPtrs<R> f;
+  f.x0 = (const R*)io->x0; f.C = (const R*)io->C; f.c = (const R*)io->c; f.Cf = (const R*)io->Cf; f.cf = (const R*)io->cf;
+  f.C_ls = (const R*)io->C_ls; f.c_ls = (const R*)io->c_ls; f.Cf_ls = (const R*)io->Cf_ls; f.cf_ls = (const R*)io->cf_ls;
+  f.xref = (const R*)io->xref; f.uref = (const R*)io->uref; f.Uinit = (const R*)io->Uinit;
+  f.replay_iters = io->replay_iters; f.replay_alpha = io->replay_alpha; f.replay_flags = io->replay_flags;
+  f.X = (R*)io->X; f.U = (R*)io->U; f.A = (R*)io->A; f.Bm = (R*)io->Bm;
+  f.tight = io->tight; f.iters = io->iters; f.alpha_trace = io->alpha_trace; f.flags = io->flags;
+  f.cost = (R*)io->cost; f.cost_trace = (R*)io->cost_trace;
+  f.counter = (unsigned int*)ws;
+  if (int rc = check_cuda(cudaMemsetAsync(ws, 0, sizeof(unsigned int), s), "memset counter")) return rc;
+  kernel<<<grid, nt, smem, s>>>(to_dev<R>(p), f);
+  return check_cuda(cudaPeekAtLastError(), "ilqr_forward_small launch");
+}
+
+template <typename R, int NX, int NU, int DYN>
+static int run_backward_small(const tacd_problem* p, const tacd_backward_io* io, cudaStream_t s) {
+  auto kernel = ilqr_backward_small<R, NX, NU, DYN>;
+  int bps = 0;
+  size_t smem = 0;
+  const int nt = pick_block(kernel, (size_t)bwd_words(p->T, NX, NU), (size_t)(NX * NX + NX * NU), sizeof(R), &bps, &smem);
+  if (nt == 0 || bps == 0) return TACD_EUNSUPPORTED;
+  if (int rc = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr")) return rc;
+  const DeviceInfo di = device_info();
+  int grid = di.sms * bps;
+  const int need = (p->B + nt - 1) / nt;
+  if (grid > need) grid = need;
+  if (grid < 1) grid = 1;
+  const size_t T = p->T, n = NX + NU, szX = (T + 1) * NX, szU = T * NU;
+  // shared (un-batched) outputs are accumulated with atomics: zero them first
+  if (io->grad_C && !p->C_batched) if (int rc = check_cuda(cudaMemsetAsync(io->grad_C, 0, T * n * n * sizeof(R), s), "memset")) return rc;
+  if (io->grad_c && !p->C_batched) if (int rc = check_cuda(cudaMemsetAsync(io->grad_c, 0, T * n * sizeof(R), s), "memset")) return rc;
+  if (io->grad_Cf && !p->Cf_batched) if (int rc = check_cuda(cudaMemsetAsync(io->grad_Cf, 0, n * n * sizeof(R), s), "memset")) return rc;
+  if (io->grad_cf && !p->Cf_batched) if (int rc = check_cuda(cudaMemsetAsync(io->grad_cf, 0, n * sizeof(R), s), "memset")) return rc;
+  if (io->grad_xref && !p->xref_batched) if (int rc = check_cuda(cudaMemsetAsync(io->grad_xref, 0, szX * sizeof(R), s), "memset")) return rc;
+  if (io->grad_uref && !p->uref_batched) if (int rc = check_cuda(cudaMemsetAsync(io->grad_uref, 0, szU * sizeof(R), s), "memset")) return rc;
+  BwdPtrs<R> f;
+  f.X = (const R*)io->X; f.U = (const R*)io->U; f.C = (const R*)io->C; f.xref = (const R*)io->xref; f.uref = (const R*)io->uref;
+  f.A = (const R*)io->A; f.Bm = (const R*)io->Bm; f.gX = (const R*)io->gX; f.gU = (const R*)io->gU; f.tight = io->tight;
+  f.grad_C = (R*)io->grad_C; f.grad_c = (R*)io->grad_c; f.grad_Cf = (R*)io->grad_Cf; f.grad_cf = (R*)io->grad_cf;
+  f.grad_x0 = (R*)io->grad_x0; f.grad_xref = (R*)io->grad_xref; f.grad_uref = (R*)io->grad_uref; f.dX = (R*)io->dX; f.dU = (R*)io->dU;
+  kernel<<<grid, nt, smem, s>>>(to_dev<R>(p), f);
+  return check_cuda(cudaPeekAtLastError(), "ilqr_backward_small launch");
+}
+
+// (nx, nu, dyn) combinations with a thread-per-element instantiation: the shipped plugins
+#define TACD_SMALL_FWD(X) \
+  X(1, 1, TACD_DYN_LTI) X(2, 1, TACD_DYN_LTI) X(4, 1, TACD_DYN_CARTPOLE) X(3, 2, TACD_DYN_UNICYCLE) X(3, 2, TACD_DYN_UNICYCLE_WRAPPED)
+#define TACD_SMALL_BWD(X) \
+  TACD_SMALL_FWD(X) X(1, 1, TACD_DYN_EXTERNAL) X(2, 1, TACD_DYN_EXTERNAL) X(4, 1, TACD_DYN_EXTERNAL) X(3, 2, TACD_DYN_EXTERNAL)
+
+template <typename R>
+int launch_forward_small(const tacd_problem* p, const tacd_forward_io* io, void* ws, cudaStream_t s) {
+#define X(NX_, NU_, DYN_)                                                                      \
+  if (p->nx == NX_ && p->nu == NU_ && p->dyn_id == DYN_)                                       \
+    return p->ls_cost_shared ? run_forward_small<R, NX_, NU_, DYN_, true>(p, io, ws, s)       \
+                             : run_forward_small<R, NX_, NU_, DYN_, false>(p, io, ws, s);
+  TACD_SMALL_FWD(X)
+#undef X
+  return TACD_EUNSUPPORTED;
+}
+
+template <typename R>
+int launch_backward_small(const tacd_problem* p, const tacd_backward_io* io, cudaStream_t s) {
+#define X(NX_, NU_, DYN_) \
+  if (p->nx == NX_ && p->nu == NU_ && p->dyn_id == DYN_) return run_backward_small<R, NX_, NU_, DYN_>(p, io, s);
+  TACD_SMALL_BWD(X)
+#undef X
+  return TACD_EUNSUPPORTED;
+}
+
+}  // namespace tacd

@@ -1,0 +1,249 @@
+"""Tensor-level wrappers of the C ABI (include/tacd_ilqr.h).
+
+Each function takes CUDA tensors, allocates outputs / workspace with torch, and enqueues the
+kernels on ``torch.cuda.current_stream()``.  Nothing here synchronises the host, and nothing
+falls back to PyTorch math: a non-CUDA tensor or a missing library is an error.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import torch
+
+from . import _abi, _lib
+
+_DT = {torch.float32: _abi.F32, torch.float64: _abi.F64}
+
+
+@dataclass
+class Spec:
+    """Problem family (everything of tacd_problem that does not depend on the tensors of one call)."""
+    nx: int
+    nu: int
+    T: int
+    dt: float
+    dyn_id: int
+    dyn_params: Sequence[float] = ()
+    dyn_A: Optional[torch.Tensor] = None   # LTI, device tensors in the solve dtype
+    dyn_B: Optional[torch.Tensor] = None
+    reg_eps: float = 1e-6
+    max_iter: int = 40
+    jac_mode: int = _abi.JAC_ANALYTIC
+    fd_eps: float = 1e-4
+    alphas: Sequence[float] = _abi.DEFAULT_ALPHAS
+    u_min: Optional[Sequence[float]] = None
+    u_max: Optional[Sequence[float]] = None
+    _keep: list = field(default_factory=list, repr=False)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.TacdError("tacdmpc_b200 runs on CUDA tensors only (there is no CPU path); got a "
+                                 f"{t.device} tensor")
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _problem(spec: Spec, B: int, dtype, **layout) -> _abi.Problem:
+    if dtype not in _DT:
+        raise TypeError(f"solve dtype must be float32 or float64, got {dtype}")
+    return _abi.make_problem(
+        B=B, T=spec.T, nx=spec.nx, nu=spec.nu, dtype=_DT[dtype], dyn_id=spec.dyn_id, dt=spec.dt,
+        reg_eps=spec.reg_eps, max_iter=spec.max_iter, jac_mode=spec.jac_mode, fd_eps=spec.fd_eps,
+        dyn_params=spec.dyn_params, dyn_A=_ptr(spec.dyn_A), dyn_B=_ptr(spec.dyn_B), alphas=spec.alphas,
+        umin=spec.u_min, umax=spec.u_max, **layout)
+
+
+def _prep(t, dtype, device):
+    return t.detach().to(device=device, dtype=dtype).contiguous()
+
+
+def _layout(B, Cm, Cf, xref, uref):
+    return dict(C_batched=int(Cm.ndim == 4), Cf_batched=int(Cf.ndim == 3),
+                xref_batched=int(xref.shape[0] == B), uref_batched=int(uref.shape[0] == B))
+
+
+def ilqr_forward(spec: Spec, x0, Cm, c, Cf, cf, xref, uref, Uinit, *, ls_cost=None, replay=None,
+                 want_AB=False, want_trace=True, want_cost_trace=False):
+    """solve_step (controller.py:275-315) on the GPU.  Returns a dict of device tensors:
+    X, U, tight (uint8), iters (int32), flags (uint8), cost, [alpha_trace, A, Bm, cost_trace]."""
+    _need_cuda(x0, Cm, c, Cf, cf, xref, uref, Uinit)
+    dev, dt = x0.device, x0.dtype
+    x0, Cm, c, Cf, cf, xref, uref, Uinit = (_prep(t, dt, dev) for t in (x0, Cm, c, Cf, cf, xref, uref, Uinit))
+    B, T, nx, nu = x0.shape[0], spec.T, spec.nx, spec.nu
+    if Uinit.shape != (B, T, nu):
+        raise RuntimeError(f"U_init must be [B={B}, T={T}, nu={nu}], got {tuple(Uinit.shape)}")
+    if xref.ndim != 3 or xref.shape[1:] != (T + 1, nx) or xref.shape[0] not in (1, B):
+        raise RuntimeError(f"x_ref must be [B or 1, T+1={T + 1}, nx={nx}], got {tuple(xref.shape)}")
+    if uref.ndim != 3 or uref.shape[1:] != (T, nu) or uref.shape[0] not in (1, B):
+        raise RuntimeError(f"u_ref must be [B or 1, T={T}, nu={nu}], got {tuple(uref.shape)}")
+    p = _problem(spec, B, dt, ls_cost_shared=int(ls_cost is not None), **_layout(B, Cm, Cf, xref, uref))
+    io = _abi.ForwardIO()
+    keep = [x0, Cm, c, Cf, cf, xref, uref, Uinit]
+    out = dict(X=torch.empty(B, T + 1, nx, device=dev, dtype=dt), U=torch.empty(B, T, nu, device=dev, dtype=dt),
+               tight=torch.empty(B, T, nu, device=dev, dtype=torch.uint8),
+               iters=torch.empty(B, device=dev, dtype=torch.int32), flags=torch.empty(B, device=dev, dtype=torch.uint8),
+               cost=torch.empty(B, device=dev, dtype=dt))
+    if want_trace:
+        out["alpha_trace"] = torch.empty(B, max(p.max_iter, 1), device=dev, dtype=torch.uint8)
+    if want_AB:
+        out["A"] = torch.empty(B, T, nx, nx, device=dev, dtype=dt)
+        out["Bm"] = torch.empty(B, T, nx, nu, device=dev, dtype=dt)
+    if want_cost_trace:
+        out["cost_trace"] = torch.full((B, max(p.max_iter, 1), p.n_alpha + 2), float("nan"), device=dev, dtype=dt)
+    io.x0, io.C, io.c, io.Cf, io.cf = _ptr(x0), _ptr(Cm), _ptr(c), _ptr(Cf), _ptr(cf)
+    io.xref, io.uref, io.Uinit = _ptr(xref), _ptr(uref), _ptr(Uinit)
+    if ls_cost is not None:
+        ls = [_prep(t, dt, dev) for t in ls_cost]
+        keep += ls
+        io.C_ls, io.c_ls, io.Cf_ls, io.cf_ls = (_ptr(t) for t in ls)
+    if replay is not None:
+        r = [replay["iters"].to(device=dev, dtype=torch.int32).contiguous(),
+             replay["alpha_trace"].to(device=dev, dtype=torch.uint8).contiguous(),
+             replay["flags"].to(device=dev, dtype=torch.uint8).contiguous()]
+        keep += r
+        io.replay_iters, io.replay_alpha, io.replay_flags = (_ptr(t) for t in r)
+    for k, v in out.items():
+        setattr(io, k, _ptr(v))
+    L = _lib.lib()
+    ws_bytes = int(L.tacd_forward_workspace_bytes(C.byref(p)))
+    ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+    with torch.cuda.device(dev):
+        _lib.check(L.tacd_ilqr_forward(C.byref(p), C.byref(io), C.c_void_p(ws.data_ptr()), ws_bytes, _stream()),
+                   "tacd_ilqr_forward")
+    # inputs / workspace were allocated on this stream: the caching allocator re-uses their blocks in
+    # stream order, so they may be dropped by Python while the kernel is still queued
+    del keep, ws
+    return out
+
+
+_GRAD_NAMES = ("grad_C", "grad_c", "grad_Cf", "grad_cf", "grad_x0", "grad_xref", "grad_uref", "dX", "dU")
+
+
+def ilqr_backward(spec: Spec, X, U, Cm, xref, uref, tight, gX, gU, *, A=None, Bm=None, Cf_batched=False,
+                  want=("grad_C", "grad_c", "grad_Cf", "grad_cf", "grad_x0", "grad_xref", "grad_uref")):
+    """ILQRSolve.backward (controller.py:63-115) on the GPU.  Outputs for shared (un-batched) inputs are
+    already summed over the batch."""
+    _need_cuda(X, U, Cm, xref, uref, tight, gX, gU, A, Bm)
+    dev, dt = X.device, X.dtype
+    X, U, Cm, xref, uref, gX, gU = (_prep(t, dt, dev) for t in (X, U, Cm, xref, uref, gX, gU))
+    tight = tight.to(device=dev, dtype=torch.uint8).contiguous()
+    B, T, nx, nu = X.shape[0], spec.T, spec.nx, spec.nu
+    n = nx + nu
+    Cb, xb, ub = Cm.ndim == 4, xref.shape[0] == B, uref.shape[0] == B
+    p = _problem(spec, B, dt, C_batched=int(Cb), Cf_batched=int(Cf_batched), xref_batched=int(xb), uref_batched=int(ub))
+    io = _abi.BackwardIO()
+    keep = [X, U, Cm, xref, uref, tight, gX, gU]
+    io.X, io.U, io.C, io.xref, io.uref, io.tight, io.gX, io.gU = (_ptr(t) for t in keep)
+    if A is not None:
+        A, Bm = _prep(A, dt, dev), _prep(Bm, dt, dev)
+        keep += [A, Bm]
+        io.A, io.Bm = _ptr(A), _ptr(Bm)
+    lead = lambda b: (B,) if b else ()
+    shapes = dict(grad_C=lead(Cb) + (T, n, n), grad_c=lead(Cb) + (T, n), grad_Cf=lead(Cf_batched) + (n, n),
+                  grad_cf=lead(Cf_batched) + (n,), grad_x0=(B, nx), grad_xref=((B,) if xb else (1,)) + (T + 1, nx),
+                  grad_uref=((B,) if ub else (1,)) + (T, nu), dX=(B, T + 1, nx), dU=(B, T, nu))
+    out = {k: torch.empty(shapes[k], device=dev, dtype=dt) for k in want}
+    for k, v in out.items():
+        setattr(io, k, _ptr(v))
+    L = _lib.lib()
+    ws_bytes = int(L.tacd_backward_workspace_bytes(C.byref(p)))
+    ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+    with torch.cuda.device(dev):
+        _lib.check(L.tacd_ilqr_backward(C.byref(p), C.byref(io), C.c_void_p(ws.data_ptr()), ws_bytes, _stream()),
+                   "tacd_ilqr_backward")
+    del keep, ws
+    return out
+
+
+def _vp(*ts):
+    return [C.c_void_p(_ptr(t)) for t in ts]
+
+
+def rollout(spec: Spec, x0, U):
+    _need_cuda(x0, U)
+    dev, dt = x0.device, x0.dtype
+    x0, U = _prep(x0, dt, dev), _prep(U, dt, dev)
+    B = x0.shape[0]
+    X = torch.empty(B, spec.T + 1, spec.nx, device=dev, dtype=dt)
+    p = _problem(spec, B, dt)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().tacd_rollout(C.byref(p), *_vp(x0, U, X), _stream()), "tacd_rollout")
+    return X
+
+
+def linearize(spec: Spec, X, U):
+    _need_cuda(X, U)
+    dev, dt = X.device, X.dtype
+    X, U = _prep(X, dt, dev), _prep(U, dt, dev)
+    B, T, nx, nu = X.shape[0], spec.T, spec.nx, spec.nu
+    A = torch.empty(B, T, nx, nx, device=dev, dtype=dt)
+    Bm = torch.empty(B, T, nx, nu, device=dev, dtype=dt)
+    p = _problem(spec, B, dt)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().tacd_linearize(C.byref(p), *_vp(X, U, A, Bm), _stream()), "tacd_linearize")
+    return A, Bm
+
+
+def objective(spec: Spec, X, U, Cm, c, Cf, cf, xref, uref):
+    _need_cuda(X, U, Cm, c, Cf, cf, xref, uref)
+    dev, dt = X.device, X.dtype
+    X, U, Cm, c, Cf, cf, xref, uref = (_prep(t, dt, dev) for t in (X, U, Cm, c, Cf, cf, xref, uref))
+    B = X.shape[0]
+    cost = torch.empty(B, device=dev, dtype=dt)
+    p = _problem(spec, B, dt, **_layout(B, Cm, Cf, xref, uref))
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().tacd_objective(C.byref(p), *_vp(X, U, Cm, c, Cf, cf, xref, uref, cost), _stream()),
+                   "tacd_objective")
+    return cost
+
+
+def riccati(spec: Spec, A, Bm, lx, lu, lxx, lxu, luu, lxN, lxxN):
+    _need_cuda(A, Bm, lx, lu, lxx, lxu, luu, lxN, lxxN)
+    dev, dt = A.device, A.dtype
+    ts = [_prep(t, dt, dev) for t in (A, Bm, lx, lu, lxx, lxu, luu, lxN, lxxN)]
+    B, T, nx, nu = A.shape[0], spec.T, spec.nx, spec.nu
+    K = torch.empty(B, T, nu, nx, device=dev, dtype=dt)
+    k = torch.empty(B, T, nu, device=dev, dtype=dt)
+    flags = torch.empty(B, device=dev, dtype=torch.uint8)
+    p = _problem(spec, B, dt)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().tacd_riccati(C.byref(p), *_vp(*ts, K, k, flags), _stream()), "tacd_riccati")
+    return K, k, flags
+
+
+def linesearch(spec: Spec, x0, X, U, K, k, Cm, c, Cf, cf, xref, uref):
+    _need_cuda(x0, X, U, K, k, Cm, c, Cf, cf, xref, uref)
+    dev, dt = x0.device, x0.dtype
+    ts = [_prep(t, dt, dev) for t in (x0, X, U, K, k, Cm, c, Cf, cf, xref, uref)]
+    B, T, nx, nu = x0.shape[0], spec.T, spec.nx, spec.nu
+    p = _problem(spec, B, dt, **_layout(B, ts[5], ts[7], ts[9], ts[10]))
+    na = p.n_alpha
+    Xc = torch.empty(B, na, T + 1, nx, device=dev, dtype=dt)
+    Uc = torch.empty(B, na, T, nu, device=dev, dtype=dt)
+    costs = torch.empty(B, na, device=dev, dtype=dt)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().tacd_linesearch(C.byref(p), *_vp(*ts, Xc, Uc, costs), _stream()), "tacd_linesearch")
+    return Xc, Uc, costs
+
+
+def pnqp(H, q, lo, hi):
+    """Independent box QPs: H[N,m,m], q/lo/hi[N,m] -> x[N,m], iters[N] (utils.py:66-124)."""
+    _need_cuda(H, q, lo, hi)
+    dev, dt = H.device, H.dtype
+    H, q, lo, hi = (_prep(t, dt, dev) for t in (H, q, lo, hi))
+    N, m = q.shape
+    x = torch.empty(N, m, device=dev, dtype=dt)
+    iters = torch.empty(N, device=dev, dtype=torch.int32)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().tacd_pnqp(_DT[dt], N, m, *_vp(H, q, lo, hi, x, iters), _stream()), "tacd_pnqp")
+    return x, iters

@@ -1,0 +1,165 @@
+"""-m gpu tests of the drop-in Python surface (tacdmpc_b200.DifferentialMPC) against the golden vectors:
+the calls read like the reference's own tests/examples."""
+import numpy as np
+import pytest
+import torch
+
+import parity as P
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+
+
+def _dyn(g):
+    from tacdmpc_b200 import dynamics as D
+    dyn = str(g["meta_dyn"])
+    if dyn == "lti":
+        return D.LTI(torch.from_numpy(g["meta_lti_A"]), torch.from_numpy(g["meta_lti_B"]))
+    if dyn == "cartpole":
+        return D.CartPole(*[float(v) for v in g["meta_dyn_params"]])
+    return D.Unicycle(wrapped=(dyn == "unicycle_wrapped"))
+
+
+def _build(g, f_dyn=None, f_dyn_jac=None, grad_method=None, requires_grad=False):
+    from tacdmpc_b200.DifferentialMPC import DifferentiableMPCController, GeneralQuadCost
+    t = lambda a: torch.from_numpy(a).cuda()
+    nx, nu, T, dt = int(g["meta_nx"]), int(g["meta_nu"]), int(g["meta_T"]), float(g["meta_dt"])
+    leaves = {k: t(g[k]).requires_grad_(requires_grad) for k in ("x0", "C", "c", "Cf", "cf", "xref", "uref")}
+    cm = GeneralQuadCost(nx, nu, leaves["C"], leaves["c"], leaves["Cf"], leaves["cf"], device="cuda",
+                         x_ref=leaves["xref"], u_ref=leaves["uref"])
+    cm.x_ref, cm.u_ref = leaves["xref"], leaves["uref"]
+    native = _dyn(g)
+    mpc = DifferentiableMPCController(
+        f_dyn if f_dyn is not None else native, T * dt, dt, T, cm,
+        u_min=t(g["u_min"]) if "u_min" in g else None, u_max=t(g["u_max"]) if "u_max" in g else None,
+        reg_eps=float(g["meta_reg_eps"]), device="cuda", grad_method=grad_method or str(g["meta_grad_method"]),
+        f_dyn_jac=f_dyn_jac if f_dyn is not None else native.jac, max_iter=int(g["meta_max_iter"]))
+    return mpc, cm, leaves
+
+
+@pytest.mark.parametrize("name", ["di_f64", "cartpole_shared_f32", "cartpole_shared_f64", "cartpole_actor_f64",
+                                  "unicycle_tight_f64", "unicycle_loose_f32", "lti8_f64", "lti8_mixed_f64"])
+def test_controller_forward_and_autograd(name):
+    g = P.load(name)
+    dt = g["x0"].dtype
+    mpc, cm, lv = _build(g, requires_grad=True)
+    X, U = mpc(lv["x0"], torch.from_numpy(g["Uinit"]).cuda())
+    assert X.shape == g["X"].shape and U.shape == g["U"].shape and X.dtype == lv["x0"].dtype
+    iters = mpc.iters_last.cpu().numpy()
+    same, below, bad = P.lockstep(g, iters, mpc.alpha_trace_last.cpu().numpy(), mpc.flags_last.cpu().numpy(), P.MARGIN[dt])
+    assert not bad, bad[:5]
+    # side effects (controller.py:37-41, 313-314)
+    assert cm.C is lv["C"] and cm.x_ref is lv["xref"]
+    assert mpc.converged is True and mpc.X_last is not None and mpc.tight_mask_last.dtype == torch.bool
+    assert len(mpc.H_last) == 3 and mpc.H_last[0].shape[-2:] == (mpc.nx, mpc.nx)
+    A, Bm = mpc.F_last
+    assert A.shape == g["A"].shape and Bm.shape == g["Bm"].shape
+    idx = [b for b in range(len(iters)) if iters[b] == g["iters"][b]
+           and np.array_equal(mpc.alpha_trace_last[b, :g["alpha_trace"].shape[1]].cpu().numpy(), g["alpha_trace"][b])]
+    tu = P.elem_tol(g, "U")
+    well = [b for b in idx if tu[b] <= P.TOL[dt]]
+    assert len(well) >= 1
+    assert (P.rel_err(U.detach().cpu().numpy()[well], g["U"][well]) <= P.TOL[dt]).all()
+    assert np.array_equal(mpc.tight_mask_last.cpu().numpy()[well].astype(np.uint8), g["tight"][well])
+    # autograd: loss on U only touches elements; compare gradients restricted to trace-identical elements
+    loss = (U[well] * torch.from_numpy(g["wU"]).cuda()[well]).sum() + (X[well] * torch.from_numpy(g["wX"]).cuda()[well]).sum()
+    loss.backward()
+    assert lv["x0"].grad is not None and float(lv["x0"].grad.abs().max()) == 0.0   # quirk Q3
+    for k in ("C", "c", "Cf", "cf", "xref", "uref"):
+        assert lv[k].grad is not None and lv[k].grad.shape == lv[k].shape and torch.isfinite(lv[k].grad).all()
+    if len(well) == len(iters):   # whole batch on the reference's trace: gradients comparable to golden
+        for nm in ("C", "c", "Cf", "cf", "xref", "uref"):
+            ref = g[f"grad_weighted_{nm}"]
+            scale = max(np.abs(ref).max(), 1.0)
+            err = np.abs(lv[nm].grad.cpu().numpy().astype(np.float64) - ref).max() / scale
+            assert err <= 200 * P.TOL[dt], (nm, err)
+
+
+@pytest.mark.parametrize("name,mode", [("cartpole_shared_f64", "analytic"), ("cartpole_ad_f64", "auto_diff"),
+                                       ("unicycle_loose_f64", "analytic"), ("cartpole_shared_f64", "finite_diff")])
+def test_generic_path_with_python_callable(name, mode):
+    """A user-written Python f_dyn (not a tacdmpc_b200.dynamics object) takes the generic path and still
+    reproduces the reference."""
+    g = P.load(name)
+    dt = g["x0"].dtype
+    native = _dyn(g)
+    f = lambda x, u, dt_: native(x, u, dt_)          # opaque Python callable
+    fj = (lambda x, u, dt_: native.jac(x, u, dt_)) if mode == "analytic" else None
+    mpc, cm, lv = _build(g, f_dyn=f, f_dyn_jac=fj, grad_method=mode, requires_grad=True)
+    assert not mpc._is_native()
+    X, U = mpc(lv["x0"], torch.from_numpy(g["Uinit"]).cuda())
+    scale = np.maximum(np.abs(g["cost"]), 1.0)
+    cerr = np.abs(mpc.cost_last.cpu().numpy() - g["cost"]) / scale
+    assert cerr.max() <= (1e-4 if mode == "finite_diff" else 200 * P.TOL[dt])
+    if mode != "finite_diff":
+        iters = mpc.iters_last.cpu().numpy()
+        same, below, bad = P.lockstep(g, iters, mpc.alpha_trace_last.cpu().numpy(), mpc.flags_last.cpu().numpy(), P.MARGIN[dt])
+        assert not bad, bad[:5]
+    U.sum().backward()
+    assert torch.isfinite(lv["C"].grad).all() and lv["C"].grad.abs().max() > 0
+
+
+def test_batch_tracking_closed_loop():
+    """tests/test_batch_tracking.py:25-90 adapted to the current API (per-step set_reference + forward):
+    the two agents track distinct references and reproduce the reference's closed loop."""
+    from tacdmpc_b200.DifferentialMPC import DifferentiableMPCController, GeneralQuadCost
+    from tacdmpc_b200.dynamics import DoubleIntegrator
+    g = P.load("closed_loop_batch_tracking")
+    T, N_sim, dt = int(g["meta_T"]), int(g["meta_N_sim"]), float(g["meta_dt"])
+    t = lambda a: torch.from_numpy(a).cuda()
+    cm = GeneralQuadCost(2, 1, t(g["C"]), t(g["c"]), t(g["Cf"]), t(g["cf"]), device="cuda")
+    f = DoubleIntegrator(dt)
+    mpc = DifferentiableMPCController(f, T * dt, dt, T, cm, grad_method="analytic", f_dyn_jac=f.jac, device="cuda", N_sim=N_sim)
+    x = t(g["x0"])
+    xref_full, uref_full = t(g["xref_full"]), t(g["uref_full"])
+    Xs = [x]
+    with torch.no_grad():
+        for k in range(N_sim):
+            cm.set_reference(xref_full[:, k:k + T + 1], uref_full[:, k:k + T])
+            _, U = mpc.forward(x)
+            x = f(x, U[:, 0], dt)
+            Xs.append(x)
+    Xs = torch.stack(Xs, 1).cpu().numpy()
+    assert Xs.shape == (2, N_sim + 1, 2)
+    assert not np.allclose(Xs[0], Xs[1])
+    assert np.abs(Xs - g["Xs"]).max() <= 1e-7
+
+
+def test_gradcheck_case_reproduces_reference_result():
+    """tests/test_gradcheck.py:7-51: at reference HEAD the analytical gradient w.r.t. x0 is identically 0
+    (quirk Q3), which is what a drop-in must return; X* equals the zero-input rollout."""
+    g = P.load("gradcheck_f64")
+    mpc, cm, lv = _build(g, requires_grad=True)
+    X, U = mpc.forward(lv["x0"])
+    assert np.abs(X.detach().cpu().numpy() - g["X"]).max() <= 1e-12
+    X.sum().backward()
+    assert float(lv["x0"].grad.abs().max()) == 0.0
+    assert np.array_equal(lv["x0"].grad.cpu().numpy(), g["grad_Usum_x0"])
+
+
+def test_amp_inputs_are_solved_in_fp32():
+    g = P.load("cartpole_shared_f32")
+    mpc, cm, lv = _build(g)
+    with torch.autocast("cuda", dtype=torch.float16):
+        X, U = mpc(lv["x0"].half(), torch.from_numpy(g["Uinit"]).cuda().half())
+    assert X.dtype == torch.float32
+    scale = np.maximum(np.abs(g["cost"]), 1.0)
+    assert (np.abs(mpc.cost_last.cpu().numpy() - g["cost"]) / scale).max() < 5e-2   # fp16 x0 rounding only
+
+
+def test_empty_batch_and_batch_of_one():
+    g = P.load("cartpole_shared_f32")
+    mpc, cm, lv = _build(g)
+    cm.set_reference(lv["xref"][:1], lv["uref"][:1])
+    X, U = mpc(lv["x0"][:1])
+    assert X.shape == (1, 21, 4)
+    assert P.rel_err(U.cpu().numpy(), g["U"][:1]).max() <= max(P.TOL[np.dtype(np.float32)], P.elem_tol(g, "U")[0]) or \
+        int(mpc.iters_last[0]) != int(g["iters"][0])
+    cm.set_reference(lv["xref"][:0], lv["uref"][:0])
+    X, U = mpc(lv["x0"][:0])
+    assert X.shape == (0, 21, 4) and U.shape == (0, 20, 1)
