@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""bench.py — iLQR forward+backward solves/s (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--layout shared|per_element]
+
+Workload (BASELINE.json configs[1]): cart-pole regulation, nx=4, nu=1, T=20, fp32,
+analytic Jacobians, u in [-20, 20], B = 65536 solves PER GPU (weak scaling: the batch of independent
+solves is partitioned across ranks, no data-path collective), synthetic seeded inputs.
+One "step" = one forward solve + one implicit-differentiation backward over the batch, loss = U*[:,0].sum()
+(what PPO differentiates), every input requiring a gradient.
+
+`value`   : solves/s with inputs resident in HBM, CUDA-event timed on the launching stream, L2 flushed
+            between timed steps, max over ranks.
+`e2e`     : the same metric through the public API (DifferentiableMPCController + autograd) with HOST
+            (pinned) inputs copied to the device and the actions + shared-cost gradient read back, every step.
+`roofline`: the dominant kernel (the forward solve), algorithmic bytes (SURVEY §8d formula) / its measured
+            launch duration vs the measured HBM peak; the FP32-pipe view is given beside it because the
+            forward solve is arithmetic-bound, not HBM-bound.
+`cpu_baseline`: the CPU oracle ("port": the reference is pure Python and does not travel to the GPU box)
+            on all host threads on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+NX, NU, T, DT = 4, 1, 20, 0.05
+N = NX + NU
+B_PER_GPU = 65536
+METRIC = "iLQR fwd+bwd solves/sec"
+UNIT = "solves/s"
+
+
+# ------------------------------------------------------------------------------------------- workload
+def make_inputs(B, layout, seed, torch):
+    """Q=diag(10,1,100,1), R=0.1, C_final[:4,:4]=10Q, refs 0,
+    x0=[0,0,0.2,0]+N(0,1)*[0.5,0.5,0.2,0.2], U_init=0.  layout 'per_element' scales every element's cost
+    by U(0.5,1.5) (what ActorMPC-style per-element costs look like to the kernel)."""
+    g = torch.Generator().manual_seed(seed)
+    C = torch.zeros(T, N, N)
+    C[:, :NX, :NX] = torch.diag(torch.tensor([10.0, 1.0, 100.0, 1.0]))
+    C[:, NX:, NX:] = 0.1
+    c = torch.zeros(T, N)
+    Cf = torch.zeros(N, N)
+    Cf[:NX, :NX] = 10 * C[0, :NX, :NX]
+    cf = torch.zeros(N)
+    x0 = torch.tensor([0.0, 0.0, 0.2, 0.0]) + torch.randn(B, NX, generator=g) * torch.tensor([0.5, 0.5, 0.2, 0.2])
+    if layout == "per_element":
+        s = 0.5 + torch.rand(B, 1, 1, 1, generator=g)
+        C = (C.unsqueeze(0) * s).contiguous()
+        c = c.unsqueeze(0).expand(B, T, N).contiguous()
+        Cf = (Cf.unsqueeze(0) * s[:, 0]).contiguous()
+        cf = cf.unsqueeze(0).expand(B, N).contiguous()
+    return dict(x0=x0, C=C, c=c, Cf=Cf, cf=cf, xref=torch.zeros(B, T + 1, NX), uref=torch.zeros(B, T, NU),
+                Uinit=torch.zeros(B, T, NU))
+
+
+def algorithmic_bytes(layout):
+    """fp32 bytes per solve, inputs read once and outputs written once, A/B recomputed."""
+    xu = (T + 1) * NX + T * NU
+    cost = T * N * N + T * N + N * N + N
+    fwd = 4 * (NX + xu + T * NU + T * NU) + 4 * xu + T * NU          # x0, xref+uref, U_init | X*, U*, tight
+    bwd_r = 4 * (3 * xu) + T * NU                                    # X*,U*, refs, gX,gU | tight
+    bwd_w = 4 * (xu + NX)                                            # grad_xref, grad_uref, grad_x0
+    if layout == "per_element":
+        fwd += 4 * cost
+        bwd_r += 4 * T * N * N
+        bwd_w += 4 * cost
+    return fwd, bwd_r + bwd_w
+
+
+def flops_per_solve(mean_iters):
+    """SURVEY §8d flop model (FMA = 2) for cart-pole: F_dyn=45, F_jac=90."""
+    nx, nu, n = NX, NU, N
+    F_dyn, F_jac = 45, 90
+    F_quad = T * (2 * n * n + n) + 2 * n * n + n
+    F_ric = T * (4 * nx ** 3 + 10 * nx * nx * nu + 4 * nx * nu * nu + 2 * nx * nx + 8 * nx * nu + nu ** 3 / 3 + 4 * nu * nu + nu)
+    F_ls = 5 * (T * (2 * nx * nu + 4 * nu + nx + F_dyn) + T * (2 * n * n + 3 * n) + 2 * nx * nx + 3 * nx)
+    F_acc = T * (2 * n * n + 3 * n) + 2 * nx * nx + 3 * nx
+    F_iter = F_quad + T * F_jac + F_ric + F_ls + F_acc
+    F_final = F_quad + T * F_jac
+    F_bwd = F_ric + T * (2 * nx * nx + 6 * nx * nu) + 3 * T * n * n
+    return mean_iters * F_iter + F_final, F_bwd
+
+
+# ------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------- CPU arm
+def cpu_port_run(layout, seconds_target, threads=None):
+    """Forward+backward of the same workload on the CPU oracle (kind 'port'), all host threads, on a
+    bounded sample sized to ~seconds_target of CPU work.  Returns (solves/s, cores, sample description)."""
+    import numpy as np
+    import torch
+    from oracle import oracle as orc
+    if threads:
+        orc.set_num_threads(threads)
+    cores = orc.num_threads()
+    spec = dict(nx=NX, nu=NU, T=T, dt=DT, dyn="cartpole", dyn_params=(1.0, 0.1, 0.5, 9.8), reg_eps=1e-6, max_iter=40,
+                u_min=[-20.0], u_max=[20.0])
+
+    def run(Bs):
+        inp = {k: v.numpy() for k, v in make_inputs(Bs, layout, 0, torch).items()}
+        ls = None
+        if layout == "per_element":
+            ls = (inp["C"][0], inp["c"][0], inp["Cf"][0], inp["cf"][0])
+        t0 = time.perf_counter()
+        f = orc.forward(spec, inp["x0"], inp["C"], inp["c"], inp["Cf"], inp["cf"], inp["xref"], inp["uref"], inp["Uinit"],
+                        ls_cost=ls, want_AB=False, want_trace=False)
+        gU = np.zeros_like(f["U"]); gU[:, 0] = 1
+        orc.backward(spec, f["X"], f["U"], inp["C"], inp["xref"], inp["uref"], f["tight"], np.zeros_like(f["X"]), gU,
+                     Cf_batched=int(layout == "per_element"),
+                     want=("grad_C", "grad_c", "grad_Cf", "grad_cf", "grad_x0", "grad_xref", "grad_uref"))
+        return time.perf_counter() - t0, float(f["iters"].mean())
+
+    t_probe, _ = run(2048)
+    Bs = int(min(16 * B_PER_GPU, max(2048, 2048 * seconds_target / max(t_probe, 1e-6))))
+    t, mi = run(Bs)
+    return Bs / t, cores, f"B={Bs} of the same seeded workload, fwd+bwd, {t:.1f} s, mean iters {mi:.2f}", Bs, t
+
+
+# ------------------------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--layout", default="shared", choices=["shared", "per_element"])
+    ap.add_argument("--batch", type=int, default=B_PER_GPU, help="solves per GPU")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    W = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    config = {"workload": f"cartpole regulation iLQR nx=4 nu=1 T=20 analytic Jacobians, B={args.batch} per GPU "
+                          f"(BASELINE configs[1] / SURVEY 8d config 2{'a shared C' if args.layout == 'shared' else 'b per-element C'})",
+              "cost_layout": args.layout, "B_per_gpu": args.batch, "T": T, "nx": NX, "nu": NU, "max_iter": 40,
+              "loss": "U*[:,0].sum(), all 7 inputs require grad", "sharding": f"batch x{world}, no data-path collective",
+              "l2": "flushed (256 MiB write) between timed steps"}
+
+    # ---------------------------------------------------------------- reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        vals = []
+        for i in range(args.warmup + args.steps):
+            v, cores, sample, Bs, t = cpu_port_run(args.layout, max(2.0, args.cpu_seconds / max(args.steps, 1)))
+            if i >= args.warmup:
+                vals.append((v, t, Bs))
+        value = sum(b for _, _, b in vals) / sum(t for _, t, _ in vals)
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 * sum(t for _, t, _ in vals) / len(vals), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample + " per step"},
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0,
+                "note": "CPU oracle (C restatement of the reference, OpenMP over the batch); the reference itself is "
+                        "pure Python and cannot travel to the GPU box (DESIGN.md)"}
+        print(json.dumps(line))
+        return 0
+
+    # ---------------------------------------------------------------- B200 arm
+    import torch
+    import torch.distributed as dist
+    from tacdmpc_b200 import _lib, ops, sharding
+    from tacdmpc_b200.DifferentialMPC import DifferentiableMPCController, GeneralQuadCost
+    from tacdmpc_b200.dynamics import CartPole
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
+    _lib.lib()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    host = make_inputs(B, args.layout, 1000 + rank, torch)
+    d = {k: v.to(dev) for k, v in host.items()}
+    f = CartPole()
+    spec = ops.Spec(nx=NX, nu=NU, T=T, dt=DT, dyn_id=f.dyn_id, dyn_params=f.params, reg_eps=1e-6, max_iter=40,
+                    u_min=[-20.0], u_max=[20.0])
+    ls = None
+    if args.layout == "per_element":
+        # quirk Q4: every rank's line search uses GLOBAL element 0's cost
+        ls0 = torch.cat([d["C"][0].reshape(-1), d["c"][0].reshape(-1), d["Cf"][0].reshape(-1), d["cf"][0].reshape(-1)])
+        if world > 1:
+            dist.broadcast(ls0, src=0)
+        o = 0
+        ls = []
+        for shp in ((T, N, N), (T, N), (N, N), (N,)):
+            k = 1
+            for s_ in shp:
+                k *= s_
+            ls.append(ls0[o:o + k].view(shp).contiguous())
+            o += k
+        ls = tuple(ls)
+    gX = torch.zeros(B, T + 1, NX, device=dev)
+    gU = torch.zeros(B, T, NU, device=dev)
+    gU[:, 0] = 1.0
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    want = ("grad_C", "grad_c", "grad_Cf", "grad_cf", "grad_x0", "grad_xref", "grad_uref")
+
+    def step_device():
+        fw = ops.ilqr_forward(spec, d["x0"], d["C"], d["c"], d["Cf"], d["cf"], d["xref"], d["uref"], d["Uinit"], ls_cost=ls,
+                              want_trace=False)
+        bw = ops.ilqr_backward(spec, fw["X"], fw["U"], d["C"], d["xref"], d["uref"], fw["tight"], gX, gU,
+                               Cf_batched=args.layout == "per_element", want=want)
+        if world > 1 and args.layout == "shared":
+            sharding.allreduce_sum_([bw["grad_C"], bw["grad_c"], bw["grad_Cf"], bw["grad_cf"]])
+        return fw, bw
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(W):
+        fw, bw = step_device()
+        flush.fill_(1)
+    barrier()
+    mean_iters = float(fw["iters"].float().mean().item())
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(args.steps)]
+    with ClockSampler(local_rank) as clk:
+        barrier()
+        for i in range(args.steps):
+            flush.fill_(i & 0xFF)          # L2 flush, outside the timed events
+            ev[i][0].record()
+            fw = ops.ilqr_forward(spec, d["x0"], d["C"], d["c"], d["Cf"], d["cf"], d["xref"], d["uref"], d["Uinit"],
+                                  ls_cost=ls, want_trace=False)
+            ev[i][1].record()
+            bw = ops.ilqr_backward(spec, fw["X"], fw["U"], d["C"], d["xref"], d["uref"], fw["tight"], gX, gU,
+                                   Cf_batched=args.layout == "per_element", want=want)
+            if world > 1 and args.layout == "shared":
+                sharding.allreduce_sum_([bw["grad_C"], bw["grad_c"], bw["grad_Cf"], bw["grad_cf"]])
+            ev[i][2].record()
+        barrier()
+        t_fwd = sum(e[0].elapsed_time(e[1]) for e in ev) / 1e3
+        t_tot = sum(e[0].elapsed_time(e[2]) for e in ev) / 1e3
+        clocks = clk
+    clocks = clocks.summary()
+    t_tot_max = sharding.allreduce_max_scalar(t_tot, dev)
+    t_fwd_max = sharding.allreduce_max_scalar(t_fwd, dev)
+    value = world * B * args.steps / t_tot_max
+
+    # ---------------------------------------------------------------- e2e through the public API, host buffers
+    pin = {k: v.pin_memory() for k, v in host.items()}
+    Cd = d["C"].clone().requires_grad_(True)
+    cm = GeneralQuadCost(NX, NU, Cd, d["c"], d["Cf"], d["cf"], device=str(dev), x_ref=d["xref"], u_ref=d["uref"])
+    mpc = DifferentiableMPCController(f, T * DT, DT, T, cm, u_min=torch.tensor([-20.0]), u_max=torch.tensor([20.0]),
+                                      device=str(dev), grad_method="analytic", f_dyn_jac=f.jac)
+    if ls is not None:
+        mpc.ls_cost_override = ls
+    act_host = torch.empty(B, NU).pin_memory()
+    gC_host = torch.empty(Cd.shape if args.layout == "shared" else (T, N, N)).pin_memory()
+    h2d = sum(pin[k].numel() * 4 for k in ("x0", "xref", "uref", "Uinit"))
+    d2h = act_host.numel() * 4 + gC_host.numel() * 4
+
+    def step_e2e():
+        x0 = pin["x0"].to(dev, non_blocking=True).requires_grad_(True)
+        xr = pin["xref"].to(dev, non_blocking=True).requires_grad_(True)
+        ur = pin["uref"].to(dev, non_blocking=True).requires_grad_(True)
+        U0 = pin["Uinit"].to(dev, non_blocking=True)
+        cm.set_reference(xr, ur)
+        Cd.grad = None
+        X, U = mpc(x0, U0)
+        U[:, 0].sum().backward()
+        gC = Cd.grad if args.layout == "shared" else Cd.grad[0]   # per-element: grads stay on the device, read one back
+        if world > 1:
+            sharding.allreduce_sum_([gC])
+        act_host.copy_(U.detach()[:, 0], non_blocking=True)
+        gC_host.copy_(gC, non_blocking=True)
+
+    for _ in range(W):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    t_e2e = sharding.allreduce_max_scalar(time.perf_counter() - t0, dev)
+    e2e_value = world * B * args.steps / t_e2e
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---------------------------------------------------------------- roofline + CPU baseline
+    peaks = {}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    fwd_b, bwd_b = algorithmic_bytes(args.layout)
+    fwd_ms = 1e3 * t_fwd_max / args.steps
+    bwd_ms = 1e3 * (t_tot_max - t_fwd_max) / args.steps
+    ach = fwd_b * B / (fwd_ms * 1e-3) / 1e9
+    ach_b = bwd_b * B / (bwd_ms * 1e-3) / 1e9
+    F_fwd, F_bwd = flops_per_solve(mean_iters)
+    sm_mhz = clocks.get("sm_mhz") or 1965.0
+    fp32_peak_nominal = 148 * 128 * 2 * 1.965e9 / 1e12
+    fp32_peak_at_clock = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+    traffic = None
+    tj = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tj):
+        try:
+            traffic = json.load(open(tj)).get(f"forward_{args.layout}")
+        except Exception:
+            traffic = None
+    roofline = {"kernel": "ilqr_forward_small<float,4,1,cartpole>", "bound": "hbm", "achieved": ach, "peak": hbm_peak,
+                "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_solve": fwd_b, "launch_ms": fwd_ms, "mean_iters": mean_iters,
+                "fp32_pipe": {"flops_per_solve": F_fwd, "achieved_tflops": F_fwd * B / (fwd_ms * 1e-3) / 1e12,
+                              "peak_tflops_nominal": fp32_peak_nominal, "peak_tflops_at_measured_clock": fp32_peak_at_clock,
+                              "frac_of_nominal": F_fwd * B / (fwd_ms * 1e-3) / 1e12 / fp32_peak_nominal},
+                "backward": {"kernel": "ilqr_backward_small<float,4,1,cartpole>", "bound": "hbm", "achieved": ach_b, "peak": hbm_peak,
+                             "unit": "GB/s", "frac": ach_b / hbm_peak, "algorithmic_bytes_per_solve": bwd_b, "launch_ms": bwd_ms}}
+    cpu = None
+    if not args.no_cpu_baseline:
+        v, cores, sample, _, _ = cpu_port_run(args.layout, args.cpu_seconds)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
+            "ms_per_step": 1e3 * t_tot_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * t_e2e / args.steps},
+            "gpu_launches": 2 * args.steps, "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

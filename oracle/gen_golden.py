@@ -539,6 +539,7 @@ def main():
     run_case("lti8_f32", **case_lti(F32))
     run_case("lti8_T20_f32", **case_lti(F32, T=20, B=4, seed=3))
     run_case("lti8_f64", **case_lti(F64, T=20))
+    run_case("lti8_T50_f64", **case_lti(F64, T=50, B=2, seed=4))
     run_case("lti8_mixed_f64", **case_lti(F64, T=12, mixed=True))
     run_case("lti16_f32", **case_lti(F32, nx=16, nu=4, T=20, B=2))
     run_case("lti32_f32", **case_lti(F32, nx=32, nu=8, T=10, B=2))

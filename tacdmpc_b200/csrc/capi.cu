@@ -69,6 +69,7 @@ size_t tacd_backward_workspace_bytes(const tacd_problem* p) {
 
 int tacd_ilqr_forward(const tacd_problem* p, const tacd_forward_io* io, void* workspace, size_t workspace_bytes, void* stream) {
   if (int rc = validate(p)) return rc;
+  if (p->B == 0) return TACD_OK;  // empty batch: nothing to read or write (empty tensors have null data)
   if (!io || !io->x0 || !io->C || !io->c || !io->Cf || !io->cf || !io->xref || !io->uref || !io->Uinit || !io->X || !io->U ||
       !io->tight || !io->iters || !io->flags) { set_error("tacd_ilqr_forward: required pointer is null"); return TACD_EINVAL; }
   if (p->ls_cost_shared && (!io->C_ls || !io->c_ls || !io->Cf_ls || !io->cf_ls)) { set_error("ls_cost_shared needs C_ls/c_ls/Cf_ls/cf_ls"); return TACD_EINVAL; }
@@ -87,6 +88,7 @@ int tacd_ilqr_forward(const tacd_problem* p, const tacd_forward_io* io, void* wo
 
 int tacd_ilqr_backward(const tacd_problem* p, const tacd_backward_io* io, void* workspace, size_t workspace_bytes, void* stream) {
   if (int rc = validate(p)) return rc;
+  if (p->B == 0) return TACD_OK;
   if (!io || !io->X || !io->U || !io->C || !io->xref || !io->uref || !io->tight || !io->gX || !io->gU) { set_error("tacd_ilqr_backward: required pointer is null"); return TACD_EINVAL; }
   if (p->dyn_id == TACD_DYN_EXTERNAL && (!io->A || !io->Bm)) { set_error("EXTERNAL dynamics need A and Bm"); return TACD_EINVAL; }
   if (p->has_umin && !p->has_umax) { set_error("backward assumes u_max whenever u_min is set (reference quirk Q10)"); return TACD_EINVAL; }

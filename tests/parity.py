@@ -29,7 +29,7 @@ MARGIN = {np.dtype(np.float32): 2e-5, np.dtype(np.float64): 1e-11}
 SOLVE_CASES = [
     "di_f64", "di_f32", "cartpole_shared_f32", "cartpole_shared_f64", "cartpole_actor_f32", "cartpole_actor_f64",
     "cartpole_ad_f64", "unicycle_tight_f32", "unicycle_tight_f64", "unicycle_loose_f64", "unicycle_loose_f32",
-    "unicycle_wrapped_f64", "lti8_f32", "lti8_T20_f32", "lti8_f64", "lti8_mixed_f64", "lti16_f32", "lti32_f32",
+    "unicycle_wrapped_f64", "lti8_f32", "lti8_T20_f32", "lti8_f64", "lti8_T50_f64", "lti8_mixed_f64", "lti16_f32", "lti32_f32",
     "gradcheck_f64",
 ]
 # lti8_f32 rolls an open-loop-unstable LTI system out for T=50 steps in fp32; the reference's own fp32
@@ -39,9 +39,20 @@ STAGE_SLACK = {"lti8_f32": 30.0}
 SMALL_CASES = [c for c in SOLVE_CASES if not c.startswith("lti")] 
 
 
+# Conditioning-limited cases.  lti8_T50_*: open-loop-unstable LTI rolled out for T=50 steps; the Riccati
+# recursion amplifies rounding by ~1e9 (in fp64 two correct implementations agree to ~1e-6 on K and ~3e-9
+# on U; in fp32 nothing survives, see REPRO_LIMIT below).  The tolerance of such a case is scaled.
+CASE_SLACK = {"lti8_T50_f64": 1e3}
+
+
 def load(name):
     g = dict(np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False))
+    g["__name__"] = name
     return g
+
+
+def case_tol(g):
+    return TOL[g["x0"].dtype] * CASE_SLACK.get(str(g.get("__name__", "")), 1.0)
 
 
 def spec_of(g):
@@ -82,11 +93,26 @@ def elem_tol(g, what="U", k=8.0):
     that — measured by gen_golden.py as (1) how far the reference's answer moves when x0 moves by one ulp
     with decisions held fixed (noise_*), and (2) for fp32 cases, how far the reference's fp32 answer is from
     the same decision sequence carried out in fp64 (X64/U64)."""
-    tol = TOL[g["x0"].dtype]
+    tol = case_tol(g)
     floor = np.asarray(g["noise_" + what], np.float64)
     if what + "64" in g:
         floor = np.maximum(floor, rel_err(g[what], g[what + "64"]))
     return np.maximum(tol, k * floor)
+
+
+# Above this measured noise floor the reference cannot reproduce ITS OWN answer under a one-ulp change of
+# x0 (chaotic clamped line search: unicycle_tight_f32) or its fp32 recursion has lost all digits against
+# fp64 (open-loop-unstable LTI over T=50: lti8_f32).  Such elements are excluded from value comparisons
+# (finiteness of the objective is still required); every test prints how many elements it held.
+REPRO_LIMIT = 1e-3
+
+
+def reproducible(g):
+    """Boolean mask of batch elements whose reference answer is reproducible (noise floor <= REPRO_LIMIT)."""
+    floor = np.maximum(np.asarray(g["noise_U"], np.float64), np.asarray(g["noise_X"], np.float64))
+    if "U64" in g:
+        floor = np.maximum(floor, np.maximum(rel_err(g["U"], g["U64"]), rel_err(g["X"], g["X64"])))
+    return floor <= REPRO_LIMIT
 
 
 def lockstep(g, iters, alpha_trace, flags, margin):
@@ -101,8 +127,11 @@ def lockstep(g, iters, alpha_trace, flags, margin):
     # where the reference's own trajectory is noisier than the tolerance, its cost margins are too
     floor = np.maximum(elem_tol(g, "U", k=16.0), elem_tol(g, "X", k=16.0))
     base_margin = margin
+    rep = reproducible(g)
     for b in range(B):
-        margin = max(base_margin, floor[b] if floor[b] > TOL[g["x0"].dtype] else 0.0)
+        margin = max(base_margin * CASE_SLACK.get(str(g.get("__name__", "")), 1.0), floor[b] if floor[b] > case_tol(g) else 0.0)
+        if not rep[b]:
+            margin = float("inf")
         n_ref = int(g["iters"][b])
         capped_ref = bool(g["flags"][b] & 2)
         n_imp_ref = n_ref if capped_ref else n_ref - 1
