@@ -27,6 +27,12 @@ inline DevProblem<R> to_dev(const tacd_problem* p) {
   for (int i = 0; i < TACD_MAX_ALPHA; ++i) d.alphas[i] = (R)p->alphas[i];
   for (int i = 0; i < TACD_MAX_NU; ++i) { d.umin[i] = (R)p->umin[i]; d.umax[i] = (R)p->umax[i]; }
   for (int i = 0; i < 8; ++i) d.dynp[i] = (R)p->dyn_params[i];
+  if (p->dyn_id == TACD_DYN_CARTPOLE) {
+    // derived constants, formed in the compute type exactly as the reference forms them per call
+    const R M = (R)p->dyn_params[0] + (R)p->dyn_params[1];
+    d.dynp[4] = (R)1 / M;
+    d.dynp[5] = (R)p->dyn_params[1] * (R)p->dyn_params[2];
+  }
   d.dyn_A = (const R*)p->dyn_A; d.dyn_B = (const R*)p->dyn_B;
   return d;
 }
