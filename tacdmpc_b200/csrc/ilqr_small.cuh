@@ -84,6 +84,14 @@ __global__ void __launch_bounds__(256, 1) ilqr_forward_small(const DevProblem<R>
 #define Sk(t, i) sk[((size_t)(t) * NU + (i)) * NT + tid]
 
   const size_t szX = (size_t)(T + 1) * NX, szU = (size_t)T * NU;
+  // bounds with +-inf when absent: max(u, -inf) = u and min(u, +inf) = u (NaN still propagates), so the
+  // inner loops carry no uniform branch
+  R ulo[NU], uhi[NU];
+#pragma unroll
+  for (int i = 0; i < NU; ++i) {
+    ulo[i] = P.has_umin ? P.umin[i] : -inf_<R>();
+    uhi[i] = P.has_umax ? P.umax[i] : inf_<R>();
+  }
   bool has = false, exhausted = false;
   int b = 0, it = 0;
   unsigned flg = 0;
@@ -252,8 +260,7 @@ __global__ void __launch_bounds__(256, 1) ilqr_forward_small(const DevProblem<R>
 #pragma unroll
               for (int j = 0; j < NX; ++j) s += Kt[i * NX + j] * (xa[a][j] - Xt[j]);
               R ui = Ut[i] + (al[a] * kt[i] + s);
-              if (P.has_umin) ui = tmax<R>(ui, P.umin[i]);
-              if (P.has_umax) ui = tmin<R>(ui, P.umax[i]);
+              ui = tmin<R>(tmax<R>(ui, ulo[i]), uhi[i]);
               ua[a][i] = ui;
               tau[NX + i] = ui - urt[i];
             }
@@ -344,8 +351,7 @@ __global__ void __launch_bounds__(256, 1) ilqr_forward_small(const DevProblem<R>
 #pragma unroll
             for (int j = 0; j < NX; ++j) s += SK(t, i * NX + j) * (x[j] - Xold[j]);
             R ui = SU(t, i) + (alpha * Sk(t, i) + s);
-            if (P.has_umin) ui = tmax<R>(ui, P.umin[i]);
-            if (P.has_umax) ui = tmin<R>(ui, P.umax[i]);
+            ui = tmin<R>(tmax<R>(ui, ulo[i]), uhi[i]);
             u[i] = ui;
           }
 #pragma unroll

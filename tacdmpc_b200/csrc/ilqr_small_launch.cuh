@@ -1,6 +1,8 @@
 // ilqr_small_launch.cuh — dispatch + launch of the thread-per-element kernels.
 // Included by ilqr_small_f32.cu / ilqr_small_f64.cu, which instantiate it for one scalar type each.
 #pragma once
+#include <stdlib.h>
+
 #include "host_common.h"
 
 namespace tacd {
@@ -12,7 +14,10 @@ static int pick_block(K kernel, size_t words_per_thread, size_t extra_words, siz
   const DeviceInfo di = device_info();
   int best_nt = 0, best_blocks = 0;
   size_t best_smem = 0;
-  for (int nt = 256; nt >= 32; nt -= 32) {
+  // experiment knob (profiling only): cap the block size
+  int nt_max = 256;
+  if (const char* e = getenv("TACD_NT_MAX")) { const int v = atoi(e); if (v >= 32 && v <= 256) nt_max = v - v % 32; }
+  for (int nt = nt_max; nt >= 32; nt -= 32) {
     const size_t smem = (words_per_thread * nt + extra_words) * elt;
     if (smem > (size_t)di.smem_optin) continue;
     if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); continue; }
@@ -20,6 +25,7 @@ static int pick_block(K kernel, size_t words_per_thread, size_t extra_words, siz
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, nt, smem) != cudaSuccess) { cudaGetLastError(); continue; }
     if (nb * nt > best_blocks * best_nt) { best_nt = nt; best_blocks = nb; best_smem = smem; }
   }
+  if (const char* e = getenv("TACD_BLOCKS_MAX")) { const int v = atoi(e); if (v >= 1 && v < best_blocks) best_blocks = v; }
   *blocks_per_sm = best_blocks;
   *smem_out = best_smem;
   return best_nt;
