@@ -148,8 +148,8 @@ def cpu_port_run(layout, seconds_target, threads=None):
     import numpy as np
     import torch
     from oracle import oracle as orc
-    if threads:
-        orc.set_num_threads(threads)
+    # all host threads this process may use; torchrun exports OMP_NUM_THREADS=1, which must not apply here
+    orc.set_num_threads(threads or len(os.sched_getaffinity(0)))
     cores = orc.num_threads()
     spec = dict(nx=NX, nu=NU, T=T, dt=DT, dyn="cartpole", dyn_params=(1.0, 0.1, 0.5, 9.8), reg_eps=1e-6, max_iter=40,
                 u_min=[-20.0], u_max=[20.0])
@@ -376,7 +376,7 @@ def main():
                 "backward": {"kernel": "ilqr_backward_small<float,4,1,cartpole>", "bound": "hbm", "achieved": ach_b, "peak": hbm_peak,
                              "unit": "GB/s", "frac": ach_b / hbm_peak, "algorithmic_bytes_per_solve": bwd_b, "launch_ms": bwd_ms}}
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         v, cores, sample, _, _ = cpu_port_run(args.layout, args.cpu_seconds)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,

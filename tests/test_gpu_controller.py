@@ -167,3 +167,41 @@ def test_empty_batch_and_batch_of_one():
     cm.set_reference(lv["xref"][:0], lv["uref"][:0])
     X, U = mpc(lv["x0"][:0])
     assert X.shape == (0, 21, 4) and U.shape == (0, 20, 1)
+
+
+def test_actor_mpc_call_site_pattern():
+    """The ActorMPC call site (ACMPC/actor.py:58-120) written against the drop-in: an MLP emits per-element
+    diagonal costs, the controller is built with the actor's constructor arguments (reg_eps=1e-2, no bounds,
+    grad_method='auto_diff'), forward uses U_init = 0.01 randn, and gradients must reach the MLP
+    (examples/gradientflowtest.py:54-99)."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from tacdmpc_b200.DifferentialMPC import DifferentiableMPCController, GeneralQuadCost
+    from tacdmpc_b200.dynamics import CartPole
+    torch.manual_seed(0)
+    nx, nu, T, dt, B = 4, 1, 15, 0.05, 64
+    n = nx + nu
+    dev = "cuda"
+    net = nn.Sequential(nn.Linear(nx, 64), nn.ReLU(), nn.Linear(64, 2 * T * n)).to(dev)
+    cm = GeneralQuadCost(nx, nu, torch.zeros(T, n, n, device=dev), torch.zeros(T, n, device=dev),
+                         torch.zeros(n, n, device=dev), torch.zeros(n, device=dev), device=dev)
+    mpc = DifferentiableMPCController(f_dyn=CartPole(), total_time=T, step_size=dt, horizon=T, cost_module=cm,
+                                      f_dyn_jac=None, device=dev, reg_eps=1e-2, grad_method="auto_diff")
+    x = (torch.rand(B, nx, device=dev) * 0.45 - 0.2)
+    params = net(x)
+    q, p = params.split([T * n, T * n], dim=-1)
+    C = torch.diag_embed((F.softplus(q) + 1e-2).view(B, T, n))
+    c = p.view(B, T, n)
+    cm.C, cm.c = C, c
+    cm.C_final, cm.c_final = C[:, -1].clone(), c[:, -1].clone()
+    cm.set_reference(torch.zeros(B, T + 1, nx, device=dev), torch.zeros(B, T, nu, device=dev))
+    X, U = mpc(x[:, :nx], torch.randn(B, T, nu, device=dev) * 0.01)
+    assert X.shape == (B, T + 1, nx) and U.shape == (B, T, nu)
+    dist = torch.distributions.Normal(U[:, 0], torch.ones(nu, device=dev))
+    loss = -dist.log_prob(torch.zeros(B, nu, device=dev)).sum()
+    loss.backward()
+    grads = [p_.grad for p_ in net.parameters()]
+    assert all(g is not None and torch.isfinite(g).all() for g in grads)
+    assert sum(float(g.abs().sum()) for g in grads) > 0
+    # the solve improved on the initial guess for every element
+    assert torch.isfinite(mpc.cost_last).all() and int(mpc.iters_last.min()) >= 1
