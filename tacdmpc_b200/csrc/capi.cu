@@ -58,9 +58,12 @@ extern "C" {
 int tacd_abi_version(void) { return TACD_ABI_VERSION; }
 const char* tacd_last_error(void) { return g_err; }
 
+// forward workspace: [0, kFwdHead) queue counter + bucket counters + longest-first order of the
+// thread-per-element kernel; the generic kernel's per-CTA slices follow
+static size_t fwd_head_bytes(const tacd_problem* p) { return 16384 + (((size_t)p->B * 4 + 255) / 256) * 256; }
 size_t tacd_forward_workspace_bytes(const tacd_problem* p) {
   if (validate(p)) return 0;
-  return 256 + generic_forward_ws_bytes(p);
+  return fwd_head_bytes(p) + generic_forward_ws_bytes(p);
 }
 size_t tacd_backward_workspace_bytes(const tacd_problem* p) {
   if (validate(p)) return 0;
@@ -75,14 +78,14 @@ int tacd_ilqr_forward(const tacd_problem* p, const tacd_forward_io* io, void* wo
   if (p->ls_cost_shared && (!io->C_ls || !io->c_ls || !io->Cf_ls || !io->cf_ls)) { set_error("ls_cost_shared needs C_ls/c_ls/Cf_ls/cf_ls"); return TACD_EINVAL; }
   if (p->dyn_id == TACD_DYN_EXTERNAL) { set_error("the whole solve needs embedded dynamics (dyn_id != EXTERNAL)"); return TACD_EINVAL; }
   if (io->replay_iters && (!io->replay_alpha || !io->replay_flags)) { set_error("replay needs iters, alpha and flags"); return TACD_EINVAL; }
-  if (!workspace || workspace_bytes < 256) { set_error("workspace too small (need tacd_forward_workspace_bytes)"); return TACD_EWORKSPACE; }
-  if (p->B == 0) return TACD_OK;
+  const size_t head = fwd_head_bytes(p);
+  if (!workspace || workspace_bytes < head) { set_error("workspace too small (need tacd_forward_workspace_bytes)"); return TACD_EWORKSPACE; }
   cudaStream_t s = (cudaStream_t)stream;
   int rc = (p->dtype == TACD_F32) ? launch_forward_small<float>(p, io, workspace, s) : launch_forward_small<double>(p, io, workspace, s);
   if (rc != TACD_EUNSUPPORTED) return rc;
-  char* ws = (char*)workspace + 256;
-  rc = (p->dtype == TACD_F32) ? launch_forward_generic<float>(p, io, ws, workspace_bytes - 256, s)
-                              : launch_forward_generic<double>(p, io, ws, workspace_bytes - 256, s);
+  char* ws = (char*)workspace + head;
+  rc = (p->dtype == TACD_F32) ? launch_forward_generic<float>(p, io, ws, workspace_bytes - head, s)
+                              : launch_forward_generic<double>(p, io, ws, workspace_bytes - head, s);
   return rc;
 }
 

@@ -52,8 +52,24 @@ static int run_forward_small(const tacd_problem* p, const tacd_forward_io* io, v
   f.X = (R*)io->X; f.U = (R*)io->U; f.A = (R*)io->A; f.Bm = (R*)io->Bm;
   f.tight = io->tight; f.iters = io->iters; f.alpha_trace = io->alpha_trace; f.flags = io->flags;
   f.cost = (R*)io->cost; f.cost_trace = (R*)io->cost_trace;
+  // workspace: [0,4) queue counter | [256, 256+8K) bucket counters | [16K, 16K+4B) longest-first order
   f.counter = (unsigned int*)ws;
-  if (int rc = check_cuda(cudaMemsetAsync(ws, 0, sizeof(unsigned int), s), "memset counter")) return rc;
+  const unsigned lanes = (unsigned)grid * (unsigned)nt;
+  const unsigned first_wave = lanes < (unsigned)p->B ? lanes : (unsigned)p->B;
+  f.first_wave = first_wave;
+  f.order = nullptr;
+  queue_init<<<1, 1, 0, s>>>(f.counter, first_wave);
+  const bool lpt = (unsigned)p->B > lanes && !getenv("TACD_NO_LPT");   // more than one wave: order matters
+  if (lpt) {
+    unsigned int* hist = (unsigned int*)((char*)ws + 256);
+    int32_t* order = (int32_t*)((char*)ws + 16384);
+    if (int rc = check_cuda(cudaMemsetAsync(hist, 0, kLptBuckets * sizeof(unsigned int), s), "memset hist")) return rc;
+    const int g2 = di.sms * 2 < (p->B + 255) / 256 ? di.sms * 2 : (p->B + 255) / 256;
+    lpt_histogram<R><<<g2, 256, 0, s>>>(p->B, p->T, NX, NX + NU, p->C_batched, p->xref_batched, (const R*)io->x0, (const R*)io->xref, (const R*)io->C, hist);
+    lpt_scan<<<1, 1024, 0, s>>>(hist);
+    lpt_scatter<R><<<g2, 256, 0, s>>>(p->B, p->T, NX, NX + NU, p->C_batched, p->xref_batched, (const R*)io->x0, (const R*)io->xref, (const R*)io->C, hist, order);
+    f.order = order;
+  }
   kernel<<<grid, nt, smem, s>>>(to_dev<R>(p), f);
   return check_cuda(cudaPeekAtLastError(), "ilqr_forward_small launch");
 }
