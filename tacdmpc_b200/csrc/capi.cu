@@ -65,9 +65,19 @@ size_t tacd_forward_workspace_bytes(const tacd_problem* p) {
   if (validate(p)) return 0;
   return fwd_head_bytes(p) + generic_forward_ws_bytes(p);
 }
+// backward workspace: per-CTA partial sums of the shared-input gradients (thread-per-element kernel)
+// or the generic kernel's per-CTA slices, whichever is larger
+static size_t bwd_partials_bytes(const tacd_problem* p) {
+  const size_t nx = p->nx, nu = p->nu, n = nx + nu, T = p->T;
+  const size_t nacc = T * (n * n + n + nx + nu) + nx * nx + 2 * nx;
+  const DeviceInfo di = device_info();
+  const size_t sms = di.sms > 0 ? di.sms : 148;
+  return sms * 32 * nacc * 8;
+}
 size_t tacd_backward_workspace_bytes(const tacd_problem* p) {
   if (validate(p)) return 0;
-  return 256 + generic_backward_ws_bytes(p);
+  const size_t a = bwd_partials_bytes(p), b = generic_backward_ws_bytes(p);
+  return 256 + (a > b ? a : b);
 }
 
 int tacd_ilqr_forward(const tacd_problem* p, const tacd_forward_io* io, void* workspace, size_t workspace_bytes, void* stream) {
@@ -97,10 +107,11 @@ int tacd_ilqr_backward(const tacd_problem* p, const tacd_backward_io* io, void* 
   if (p->has_umin && !p->has_umax) { set_error("backward assumes u_max whenever u_min is set (reference quirk Q10)"); return TACD_EINVAL; }
   if (p->B == 0) return TACD_OK;
   cudaStream_t s = (cudaStream_t)stream;
-  int rc = (p->dtype == TACD_F32) ? launch_backward_small<float>(p, io, s) : launch_backward_small<double>(p, io, s);
-  if (rc != TACD_EUNSUPPORTED) return rc;
   if (!workspace || workspace_bytes < 256) { set_error("workspace too small (need tacd_backward_workspace_bytes)"); return TACD_EWORKSPACE; }
   char* ws = (char*)workspace + 256;
+  int rc = (p->dtype == TACD_F32) ? launch_backward_small<float>(p, io, ws, workspace_bytes - 256, s)
+                                  : launch_backward_small<double>(p, io, ws, workspace_bytes - 256, s);
+  if (rc != TACD_EUNSUPPORTED) return rc;
   rc = (p->dtype == TACD_F32) ? launch_backward_generic<float>(p, io, ws, workspace_bytes - 256, s)
                               : launch_backward_generic<double>(p, io, ws, workspace_bytes - 256, s);
   return rc;

@@ -487,39 +487,55 @@ __global__ void __launch_bounds__(256, 1) ilqr_forward_small(const DevProblem<R>
 }
 
 // ---------------------------------------------------------------------------
-// Backward: ILQRSolve.backward + _zero_constrained_lqr (controller.py:63-115,
-// 707-788).  One thread per element; gains K_t,k_t in shared memory [word][thread];
-// A_t,B_t are recomputed from (X*,U*) with the embedded dynamics (or read, for
-// TACD_DYN_EXTERNAL).  Shared-cost gradients are reduced over the warp with
-// shuffles and accumulated with one atomicAdd per warp and value.
-template <typename R>
-TACD_DEV R warp_sum(R v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
+// Backward: ILQRSolve.backward + _zero_constrained_lqr (controller.py:63-115, 707-788).
+// One thread per element (static assignment, uniform work); gains K_t,k_t in shared memory
+// [word][thread]; A_t,B_t are recomputed from (X*,U*) with the embedded dynamics (or read, for
+// TACD_DYN_EXTERNAL).  Per-step inputs (X,U,gX,gU,tight / refs) are prefetched one step ahead so the
+// L2 latency of the strided per-element loads overlaps the Riccati arithmetic.
+// Gradients of SHARED (un-batched) inputs are sums over the batch: each warp transposes its 32 x NV
+// per-step values through a shared-memory tile, lanes sum columns into per-warp accumulators, the CTA
+// combines its warps and writes one partial vector; reduce_shared_grads() sums the CTAs in a fixed
+// order (deterministic, no atomics).
+template <int NX, int NU>
+struct BwdLayout {
+  static constexpr int N = NX + NU;
+  static constexpr int NV = N * N + N + NX + NU;    // per step: grad_C | grad_c | grad_xref | grad_uref
+  static constexpr int NVF = NX * NX + NX + NX;     // terminal: grad_Cf[:nx,:nx] | grad_cf[:nx] | grad_xref[T]
+  static constexpr int TW = NV | 1;                 // odd tile row stride: conflict-free transposed access
+  __host__ __device__ static int nacc(int T) { return T * NV + NVF; }
+};
 
 template <typename R, int NX, int NU, int DYN>
-__global__ void __launch_bounds__(256, 1) ilqr_backward_small(const DevProblem<R> P, const BwdPtrs<R> io) {
+__global__ void __launch_bounds__(256, 1) ilqr_backward_small(const DevProblem<R> P, const BwdPtrs<R> io, R* partials, int reduce) {
   constexpr int N = NX + NU;
+  using L = BwdLayout<NX, NU>;
   using D = Dyn<R, NX, NU, (DYN == TACD_DYN_EXTERNAL ? TACD_DYN_LTI : DYN)>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int NT = blockDim.x, tid = threadIdx.x;
   const int T = P.T;
+  const int lane = tid & 31, wid = tid >> 5, nw = NT >> 5;
   R* sK = reinterpret_cast<R*>(smem_raw);
   R* sk = sK + (size_t)T * NU * NX * NT;
   R* sA = sk + (size_t)T * NU * NT;
   R* sB = sA + NX * NX;
+  R* tile = sB + NX * NU;                                    // [nw][32][TW]      (only when reduce)
+  R* acc = tile + (size_t)nw * 32 * L::TW;                   // [nw][nacc]
+  const int NACC = L::nacc(T);
   if (DYN == TACD_DYN_LTI) {
     for (int i = tid; i < NX * NX; i += NT) sA[i] = P.dyn_A[i];
     for (int i = tid; i < NX * NU; i += NT) sB[i] = P.dyn_B[i];
-    __syncthreads();
   }
+  if (reduce)
+    for (int i = tid; i < nw * NACC; i += NT) acc[i] = 0;
+  __syncthreads();
+  R* mytile = tile + (size_t)wid * 32 * L::TW;
+  R* myacc = acc + (size_t)wid * NACC;
+  const bool redC = reduce && io.grad_C && !P.C_batched, redc = reduce && io.grad_c && !P.C_batched;
+  const bool redCf = reduce && io.grad_Cf && !P.Cf_batched, redcf = reduce && io.grad_cf && !P.Cf_batched;
+  const bool redx = reduce && io.grad_xref && !P.xref_batched, redu = reduce && io.grad_uref && !P.uref_batched;
 #define SK(t, i) sK[((size_t)(t) * NU * NX + (i)) * NT + tid]
 #define Sk(t, i) sk[((size_t)(t) * NU + (i)) * NT + tid]
   const size_t szX = (size_t)(T + 1) * NX, szU = (size_t)T * NU;
-  const int lane = tid & 31;
-  // every lane of a warp iterates the same number of times so the shuffles stay convergent
   const int stride = gridDim.x * NT;
   for (int b0 = blockIdx.x * NT + (tid - lane); b0 < P.B; b0 += stride) {
     const int b = b0 + lane;
@@ -534,32 +550,44 @@ __global__ void __launch_bounds__(256, 1) ilqr_backward_small(const DevProblem<R
     const R* gU = io.gU + (size_t)bb * szU;
     const uint8_t* tg = io.tight + (size_t)bb * szU;
 
-    auto load_AB = [&](int t, R(&A)[NX * NX], R(&Bm)[NX * NU]) {
+    auto load_AB = [&](int t, const R(&x)[NX], const R(&u)[NU], R(&A)[NX * NX], R(&Bm)[NX * NU]) {
       if constexpr (DYN == TACD_DYN_EXTERNAL) {
 #pragma unroll
         for (int i = 0; i < NX * NX; ++i) A[i] = io.A[((size_t)bb * T + t) * NX * NX + i];
 #pragma unroll
         for (int i = 0; i < NX * NU; ++i) Bm[i] = io.Bm[((size_t)bb * T + t) * NX * NU + i];
       } else {
-        R x[NX], u[NU];
-#pragma unroll
-        for (int i = 0; i < NX; ++i) x[i] = X[t * NX + i];
-#pragma unroll
-        for (int i = 0; i < NU; ++i) u[i] = U[t * NU + i];
         D::jac(P, sA, sB, x, u, A, Bm);
       }
     };
 
     // ---- reverse pass: V = H_xx[T-1], v = -grad_X[T-1] (quirks Q1, Q2)
     R V[NX * NX], v[NX];
+    R nx_[NX], nu_[NU], ngx[NX], ngu[NU];   // prefetched inputs of the step about to run
+    bool ntg[NU];
 #pragma unroll
     for (int i = 0; i < NX; ++i) {
 #pragma unroll
       for (int j = 0; j < NX; ++j) V[i * NX + j] = Cp[(size_t)(T - 1) * N * N + i * N + j];
-      v[i] = -gX[(T - 1) * NX + i];
+      ngx[i] = gX[(T - 1) * NX + i];
+      nx_[i] = X[(T - 1) * NX + i];
+      v[i] = -ngx[i];
     }
+#pragma unroll
+    for (int i = 0; i < NU; ++i) { nu_[i] = U[(T - 1) * NU + i]; ngu[i] = gU[(T - 1) * NU + i]; ntg[i] = tg[(T - 1) * NU + i] != 0; }
     for (int t = T - 1; t >= 0; --t) {
-      R Qxx[NX * NX], Qxu[NX * NU], Quu[NU * NU], qx[NX], qu[NU], A[NX * NX], Bm[NX * NU];
+      R x[NX], u[NU], Qxx[NX * NX], Qxu[NX * NU], Quu[NU * NU], qx[NX], qu[NU], A[NX * NX], Bm[NX * NU];
+      bool fixed[NU];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) { x[i] = nx_[i]; qx[i] = -ngx[i]; }
+#pragma unroll
+      for (int i = 0; i < NU; ++i) { u[i] = nu_[i]; qu[i] = -ngu[i]; fixed[i] = ntg[i]; }
+      if (t > 0) {   // prefetch step t-1
+#pragma unroll
+        for (int i = 0; i < NX; ++i) { nx_[i] = X[(t - 1) * NX + i]; ngx[i] = gX[(t - 1) * NX + i]; }
+#pragma unroll
+        for (int i = 0; i < NU; ++i) { nu_[i] = U[(t - 1) * NU + i]; ngu[i] = gU[(t - 1) * NU + i]; ntg[i] = tg[(t - 1) * NU + i] != 0; }
+      }
       const R* Ct = Cp + (size_t)t * N * N;
 #pragma unroll
       for (int i = 0; i < NX; ++i) {
@@ -567,23 +595,19 @@ __global__ void __launch_bounds__(256, 1) ilqr_backward_small(const DevProblem<R
         for (int j = 0; j < NX; ++j) Qxx[i * NX + j] = Ct[i * N + j];
 #pragma unroll
         for (int j = 0; j < NU; ++j) Qxu[i * NU + j] = Ct[i * N + NX + j];
-        qx[i] = -gX[t * NX + i];
       }
 #pragma unroll
-      for (int i = 0; i < NU; ++i) {
+      for (int i = 0; i < NU; ++i)
 #pragma unroll
         for (int j = 0; j < NU; ++j) Quu[i * NU + j] = Ct[(NX + i) * N + NX + j];
-        qu[i] = -gU[t * NU + i];
-      }
-      load_AB(t, A, Bm);
+      load_AB(t, x, u, A, Bm);
       q_blocks<R, NX, NU>(P.reg, A, Bm, V, v, Qxx, Qxu, Quu, qx, qu);
       // box QP on the free coordinates (controller.py:737-763); tight ones pinned to 0
       R kt[NU];
       {
-        bool fixed[NU];
         bool any_free = false;
 #pragma unroll
-        for (int i = 0; i < NU; ++i) { fixed[i] = tg[t * NU + i] != 0; any_free = any_free || !fixed[i]; }
+        for (int i = 0; i < NU; ++i) any_free = any_free || !fixed[i];
         R H[NU * NU], q[NU], lo[NU], hi[NU];
 #pragma unroll
         for (int i = 0; i < NU; ++i) {
@@ -592,7 +616,7 @@ __global__ void __launch_bounds__(256, 1) ilqr_backward_small(const DevProblem<R
             H[i * NU + j] = (fixed[i] || fixed[j]) ? ((i == j) ? (R)1 : (R)0) : Quu[i * NU + j];
           q[i] = fixed[i] ? (R)0 : qu[i];
           if (fixed[i]) { lo[i] = 0; hi[i] = 0; }
-          else if (P.has_umin) { lo[i] = P.umin[i] - U[t * NU + i]; hi[i] = P.umax[i] - U[t * NU + i]; }  // quirk Q10
+          else if (P.has_umin) { lo[i] = P.umin[i] - u[i]; hi[i] = P.umax[i] - u[i]; }  // quirk Q10
           else { lo[i] = -inf_<R>(); hi[i] = inf_<R>(); }
         }
         if (any_free) {
@@ -632,111 +656,168 @@ __global__ void __launch_bounds__(256, 1) ilqr_backward_small(const DevProblem<R
     if (io.grad_x0 && live)
 #pragma unroll
       for (int i = 0; i < NX; ++i) io.grad_x0[(size_t)b * NX + i] = 0;
-    for (int t = 0; t <= T; ++t) {
-      R tau[N], dtau[N];
+    R nxr[NX], nur[NU];
 #pragma unroll
-      for (int i = 0; i < NX; ++i) { tau[i] = X[t * NX + i] - xr[t * NX + i]; dtau[i] = dx[i]; }
-      if (t < T) {
-        R du[NU];
+    for (int i = 0; i < NX; ++i) { nx_[i] = X[i]; nxr[i] = xr[i]; }
 #pragma unroll
-        for (int i = 0; i < NU; ++i) {
-          R s = 0;
+    for (int i = 0; i < NU; ++i) { nu_[i] = U[i]; nur[i] = ur[i]; }
+    for (int t = 0; t < T; ++t) {
+      R x[NX], u[NU], tau[N], dtau[N], du[NU];
 #pragma unroll
-          for (int j = 0; j < NX; ++j) s += SK(t, i * NX + j) * dx[j];
-          du[i] = s + Sk(t, i);
-          tau[NX + i] = U[t * NU + i] - ur[t * NU + i];
-          dtau[NX + i] = du[i];
-        }
-        // grad_C = -1/2 (dtau (x) tau + tau (x) dtau), grad_c = -dtau
-        if (io.grad_C) {
+      for (int i = 0; i < NX; ++i) { x[i] = nx_[i]; tau[i] = x[i] - nxr[i]; dtau[i] = dx[i]; }
+#pragma unroll
+      for (int i = 0; i < NU; ++i) { u[i] = nu_[i]; tau[NX + i] = u[i] - nur[i]; }
+      // prefetch step t+1 (X has T+1 rows; U/u_ref only T)
+#pragma unroll
+      for (int i = 0; i < NX; ++i) { nx_[i] = X[(t + 1) * NX + i]; nxr[i] = xr[(t + 1) * NX + i]; }
+      if (t + 1 < T) {
+#pragma unroll
+        for (int i = 0; i < NU; ++i) { nu_[i] = U[(t + 1) * NU + i]; nur[i] = ur[(t + 1) * NU + i]; }
+      }
+#pragma unroll
+      for (int i = 0; i < NU; ++i) {
+        R s = 0;
+#pragma unroll
+        for (int j = 0; j < NX; ++j) s += SK(t, i * NX + j) * dx[j];
+        du[i] = s + Sk(t, i);
+        dtau[NX + i] = du[i];
+      }
+      // grad_C = -1/2 (dtau (x) tau + tau (x) dtau), grad_c = -dtau, grad_xref[t] = dx, grad_uref[t] = du
+      if (live) {
+        if (io.grad_C && P.C_batched) {
 #pragma unroll
           for (int i = 0; i < N; ++i)
 #pragma unroll
-            for (int j = 0; j < N; ++j) {
-              R g = (R)-0.5 * (dtau[i] * tau[j] + tau[i] * dtau[j]);
-              if (P.C_batched) { if (live) io.grad_C[((size_t)b * T + t) * N * N + i * N + j] = g; }
-              else { g = warp_sum<R>(live ? g : (R)0); if (lane == 0) atomicAdd(&io.grad_C[(size_t)t * N * N + i * N + j], g); }
-            }
+            for (int j = 0; j < N; ++j)
+              io.grad_C[((size_t)b * T + t) * N * N + i * N + j] = (R)-0.5 * (dtau[i] * tau[j] + tau[i] * dtau[j]);
         }
-        if (io.grad_c) {
+        if (io.grad_c && P.C_batched)
 #pragma unroll
-          for (int i = 0; i < N; ++i) {
-            R g = -dtau[i];
-            if (P.C_batched) { if (live) io.grad_c[((size_t)b * T + t) * N + i] = g; }
-            else { g = warp_sum<R>(live ? g : (R)0); if (lane == 0) atomicAdd(&io.grad_c[(size_t)t * N + i], g); }
-          }
-        }
-        if (io.grad_uref) {
+          for (int i = 0; i < N; ++i) io.grad_c[((size_t)b * T + t) * N + i] = -dtau[i];
+        if (io.grad_uref && P.uref_batched)
 #pragma unroll
-          for (int i = 0; i < NU; ++i) {
-            R g = du[i];
-            if (P.uref_batched) { if (live) io.grad_uref[(size_t)b * szU + t * NU + i] = g; }
-            else { g = warp_sum<R>(live ? g : (R)0); if (lane == 0) atomicAdd(&io.grad_uref[t * NU + i], g); }
-          }
-        }
-        if (io.dU && live)
+          for (int i = 0; i < NU; ++i) io.grad_uref[(size_t)b * szU + t * NU + i] = du[i];
+        if (io.grad_xref && P.xref_batched)
+#pragma unroll
+          for (int i = 0; i < NX; ++i) io.grad_xref[(size_t)b * szX + t * NX + i] = dx[i];
+        if (io.dU)
 #pragma unroll
           for (int i = 0; i < NU; ++i) io.dU[(size_t)b * szU + t * NU + i] = du[i];
-        if (io.grad_xref) {
-#pragma unroll
-          for (int i = 0; i < NX; ++i) {
-            R g = dx[i];
-            if (P.xref_batched) { if (live) io.grad_xref[(size_t)b * szX + t * NX + i] = g; }
-            else { g = warp_sum<R>(live ? g : (R)0); if (lane == 0) atomicAdd(&io.grad_xref[t * NX + i], g); }
-          }
-        }
-        if (io.dX && live)
+        if (io.dX)
 #pragma unroll
           for (int i = 0; i < NX; ++i) io.dX[(size_t)b * szX + t * NX + i] = dx[i];
-        R A[NX * NX], Bm[NX * NU], dxn[NX];
-        load_AB(t, A, Bm);
+      }
+      if (redC || redc || redx || redu) {   // warp-uniform
+        R* row = mytile + lane * L::TW;
 #pragma unroll
-        for (int i = 0; i < NX; ++i) {
-          R s = 0, s2 = 0;
+        for (int i = 0; i < N; ++i)
 #pragma unroll
-          for (int j = 0; j < NX; ++j) s += A[i * NX + j] * dx[j];
+          for (int j = 0; j < N; ++j) row[i * N + j] = live ? (R)-0.5 * (dtau[i] * tau[j] + tau[i] * dtau[j]) : (R)0;
 #pragma unroll
-          for (int j = 0; j < NU; ++j) s2 += Bm[i * NU + j] * du[j];
-          dxn[i] = s + s2;
+        for (int i = 0; i < N; ++i) row[N * N + i] = live ? -dtau[i] : (R)0;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) row[N * N + N + i] = live ? dx[i] : (R)0;
+#pragma unroll
+        for (int i = 0; i < NU; ++i) row[N * N + N + NX + i] = live ? du[i] : (R)0;
+        __syncwarp();
+        for (int j = lane; j < L::NV; j += 32) {
+          R sum = 0;
+#pragma unroll 8
+          for (int r = 0; r < 32; ++r) sum += mytile[r * L::TW + j];
+          myacc[t * L::NV + j] += sum;
         }
+        __syncwarp();
+      }
+      R A[NX * NX], Bm[NX * NU], dxn[NX];
+      load_AB(t, x, u, A, Bm);
 #pragma unroll
-        for (int i = 0; i < NX; ++i) dx[i] = dxn[i];
-      } else {
-        // terminal: grad_C_final[:nx,:nx], grad_c_final[:nx]; zero padding elsewhere
-        if (io.grad_Cf) {
+      for (int i = 0; i < NX; ++i) {
+        R s = 0, s2 = 0;
+#pragma unroll
+        for (int j = 0; j < NX; ++j) s += A[i * NX + j] * dx[j];
+#pragma unroll
+        for (int j = 0; j < NU; ++j) s2 += Bm[i * NU + j] * du[j];
+        dxn[i] = s + s2;
+      }
+#pragma unroll
+      for (int i = 0; i < NX; ++i) dx[i] = dxn[i];
+    }
+    {
+      // terminal: grad_C_final[:nx,:nx], grad_c_final[:nx] (zero padding elsewhere), grad_xref[T]
+      R tauN[NX];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) tauN[i] = nx_[i] - nxr[i];
+      if (live) {
+        if (io.grad_Cf && P.Cf_batched)
 #pragma unroll
           for (int i = 0; i < N; ++i)
 #pragma unroll
-            for (int j = 0; j < N; ++j) {
-              R g = (i < NX && j < NX) ? (R)-0.5 * (dtau[i < NX ? i : 0] * tau[j < NX ? j : 0] + tau[i < NX ? i : 0] * dtau[j < NX ? j : 0]) : (R)0;
-              if (P.Cf_batched) { if (live) io.grad_Cf[(size_t)b * N * N + i * N + j] = g; }
-              else if (i < NX && j < NX) { g = warp_sum<R>(live ? g : (R)0); if (lane == 0) atomicAdd(&io.grad_Cf[i * N + j], g); }
-            }
-        }
-        if (io.grad_cf) {
+            for (int j = 0; j < N; ++j)
+              io.grad_Cf[(size_t)b * N * N + i * N + j] =
+                  (i < NX && j < NX) ? (R)-0.5 * (dx[i < NX ? i : 0] * tauN[j < NX ? j : 0] + tauN[i < NX ? i : 0] * dx[j < NX ? j : 0]) : (R)0;
+        if (io.grad_cf && P.Cf_batched)
 #pragma unroll
-          for (int i = 0; i < N; ++i) {
-            R g = (i < NX) ? -dtau[i < NX ? i : 0] : (R)0;
-            if (P.Cf_batched) { if (live) io.grad_cf[(size_t)b * N + i] = g; }
-            else if (i < NX) { g = warp_sum<R>(live ? g : (R)0); if (lane == 0) atomicAdd(&io.grad_cf[i], g); }
-          }
-        }
-        if (io.grad_xref) {
+          for (int i = 0; i < N; ++i) io.grad_cf[(size_t)b * N + i] = (i < NX) ? -dx[i < NX ? i : 0] : (R)0;
+        if (io.grad_xref && P.xref_batched)
 #pragma unroll
-          for (int i = 0; i < NX; ++i) {
-            R g = dx[i];
-            if (P.xref_batched) { if (live) io.grad_xref[(size_t)b * szX + T * NX + i] = g; }
-            else { g = warp_sum<R>(live ? g : (R)0); if (lane == 0) atomicAdd(&io.grad_xref[T * NX + i], g); }
-          }
-        }
-        if (io.dX && live)
+          for (int i = 0; i < NX; ++i) io.grad_xref[(size_t)b * szX + T * NX + i] = dx[i];
+        if (io.dX)
 #pragma unroll
           for (int i = 0; i < NX; ++i) io.dX[(size_t)b * szX + T * NX + i] = dx[i];
       }
+      if (redCf || redcf || redx) {
+        R* row = mytile + lane * L::TW;
+#pragma unroll
+        for (int i = 0; i < NX; ++i)
+#pragma unroll
+          for (int j = 0; j < NX; ++j) row[i * NX + j] = live ? (R)-0.5 * (dx[i] * tauN[j] + tauN[i] * dx[j]) : (R)0;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) { row[NX * NX + i] = live ? -dx[i] : (R)0; row[NX * NX + NX + i] = live ? dx[i] : (R)0; }
+        __syncwarp();
+        for (int j = lane; j < L::NVF; j += 32) {
+          R sum = 0;
+#pragma unroll 8
+          for (int r = 0; r < 32; ++r) sum += mytile[r * L::TW + j];
+          myacc[T * L::NV + j] += sum;
+        }
+        __syncwarp();
+      }
+    }
+  }
+  if (reduce) {
+    __syncthreads();
+    for (int i = tid; i < NACC; i += NT) {
+      R sum = 0;
+      for (int w = 0; w < nw; ++w) sum += acc[(size_t)w * NACC + i];
+      partials[(size_t)blockIdx.x * NACC + i] = sum;
     }
   }
 #undef SK
 #undef Sk
+}
+
+// Sum the per-CTA partial vectors in CTA order and scatter them to the shared gradient outputs.
+template <typename R, int NX, int NU>
+__global__ void reduce_shared_grads(const DevProblem<R> P, const BwdPtrs<R> io, const R* partials, int nparts) {
+  constexpr int N = NX + NU;
+  using L = BwdLayout<NX, NU>;
+  const int T = P.T, NACC = L::nacc(T);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < NACC; i += gridDim.x * blockDim.x) {
+    R sum = 0;
+    for (int c = 0; c < nparts; ++c) sum += partials[(size_t)c * NACC + i];
+    if (i < T * L::NV) {
+      const int t = i / L::NV, j = i % L::NV;
+      if (j < N * N) { if (io.grad_C && !P.C_batched) io.grad_C[(size_t)t * N * N + j] = sum; }
+      else if (j < N * N + N) { if (io.grad_c && !P.C_batched) io.grad_c[(size_t)t * N + (j - N * N)] = sum; }
+      else if (j < N * N + N + NX) { if (io.grad_xref && !P.xref_batched) io.grad_xref[t * NX + (j - N * N - N)] = sum; }
+      else { if (io.grad_uref && !P.uref_batched) io.grad_uref[t * NU + (j - N * N - N - NX)] = sum; }
+    } else {
+      const int j = i - T * L::NV;
+      if (j < NX * NX) { if (io.grad_Cf && !P.Cf_batched) io.grad_Cf[(j / NX) * N + (j % NX)] = sum; }
+      else if (j < NX * NX + NX) { if (io.grad_cf && !P.Cf_batched) io.grad_cf[j - NX * NX] = sum; }
+      else { if (io.grad_xref && !P.xref_batched) io.grad_xref[T * NX + (j - NX * NX - NX)] = sum; }
+    }
+  }
 }
 
 }  // namespace tacd

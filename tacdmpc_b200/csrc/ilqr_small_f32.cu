@@ -2,5 +2,5 @@
 #include "ilqr_small_launch.cuh"
 namespace tacd {
 template int launch_forward_small<float>(const tacd_problem*, const tacd_forward_io*, void*, cudaStream_t);
-template int launch_backward_small<float>(const tacd_problem*, const tacd_backward_io*, cudaStream_t);
+template int launch_backward_small<float>(const tacd_problem*, const tacd_backward_io*, void*, size_t, cudaStream_t);
 }

@@ -9,16 +9,16 @@ namespace tacd {
 
 // Pick the block size (multiple of 32, <= 256) that maximises resident threads per SM
 // for a kernel whose dynamic shared memory is words_per_thread * NT + extra scalars.
-template <typename K>
-static int pick_block(K kernel, size_t words_per_thread, size_t extra_words, size_t elt, int* blocks_per_sm, size_t* smem_out) {
+template <typename K, typename SmemFn>
+static int pick_block(K kernel, SmemFn smem_of, int* blocks_per_sm, size_t* smem_out) {
   const DeviceInfo di = device_info();
   int best_nt = 0, best_blocks = 0;
   size_t best_smem = 0;
-  // experiment knob (profiling only): cap the block size
+  // experiment knobs (profiling only): cap the block size / resident blocks
   int nt_max = 256;
   if (const char* e = getenv("TACD_NT_MAX")) { const int v = atoi(e); if (v >= 32 && v <= 256) nt_max = v - v % 32; }
   for (int nt = nt_max; nt >= 32; nt -= 32) {
-    const size_t smem = (words_per_thread * nt + extra_words) * elt;
+    const size_t smem = smem_of(nt);
     if (smem > (size_t)di.smem_optin) continue;
     if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); continue; }
     int nb = 0;
@@ -36,7 +36,8 @@ static int run_forward_small(const tacd_problem* p, const tacd_forward_io* io, v
   auto kernel = ilqr_forward_small<R, NX, NU, DYN, LSSEP>;
   int bps = 0;
   size_t smem = 0;
-  const int nt = pick_block(kernel, (size_t)fwd_words(p->T, NX, NU), (size_t)(NX * NX + NX * NU), sizeof(R), &bps, &smem);
+  const size_t wpt = (size_t)fwd_words(p->T, NX, NU);
+  const int nt = pick_block(kernel, [&](int n) { return (wpt * n + NX * NX + NX * NU) * sizeof(R); }, &bps, &smem);
   if (nt == 0 || bps == 0) return TACD_EUNSUPPORTED;
   if (int rc = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr")) return rc;
   const DeviceInfo di = device_info();
@@ -75,33 +76,54 @@ static int run_forward_small(const tacd_problem* p, const tacd_forward_io* io, v
 }
 
 template <typename R, int NX, int NU, int DYN>
-static int run_backward_small(const tacd_problem* p, const tacd_backward_io* io, cudaStream_t s) {
+static int run_backward_small(const tacd_problem* p, const tacd_backward_io* io, void* ws, size_t ws_bytes, cudaStream_t s) {
   auto kernel = ilqr_backward_small<R, NX, NU, DYN>;
+  using L = BwdLayout<NX, NU>;
+  const int nacc = L::nacc(p->T);
+  const bool reduce = (io->grad_C && !p->C_batched) || (io->grad_c && !p->C_batched) || (io->grad_Cf && !p->Cf_batched) ||
+                      (io->grad_cf && !p->Cf_batched) || (io->grad_xref && !p->xref_batched) || (io->grad_uref && !p->uref_batched);
   int bps = 0;
   size_t smem = 0;
-  const int nt = pick_block(kernel, (size_t)bwd_words(p->T, NX, NU), (size_t)(NX * NX + NX * NU), sizeof(R), &bps, &smem);
+  const size_t wpt = (size_t)bwd_words(p->T, NX, NU);
+  const int nt = pick_block(kernel, [&](int n) {
+    size_t w = wpt * n + NX * NX + NX * NU;
+    if (reduce) w += (size_t)(n / 32) * (32 * L::TW + nacc);
+    return w * sizeof(R);
+  }, &bps, &smem);
   if (nt == 0 || bps == 0) return TACD_EUNSUPPORTED;
   if (int rc = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr")) return rc;
   const DeviceInfo di = device_info();
-  int grid = di.sms * bps;
-  const int need = (p->B + nt - 1) / nt;
-  if (grid > need) grid = need;
+  // balanced waves: every resident lane gets the same number of elements (work per element is uniform)
+  const long lanes = (long)di.sms * bps * nt;
+  const long waves = (p->B + lanes - 1) / lanes;
+  long per_wave = (p->B + waves - 1) / waves;
+  int grid = (int)((per_wave + nt - 1) / nt);
+  if (grid > di.sms * bps) grid = di.sms * bps;
   if (grid < 1) grid = 1;
-  const size_t T = p->T, n = NX + NU, szX = (T + 1) * NX, szU = T * NU;
-  // shared (un-batched) outputs are accumulated with atomics: zero them first
-  if (io->grad_C && !p->C_batched) if (int rc = check_cuda(cudaMemsetAsync(io->grad_C, 0, T * n * n * sizeof(R), s), "memset")) return rc;
-  if (io->grad_c && !p->C_batched) if (int rc = check_cuda(cudaMemsetAsync(io->grad_c, 0, T * n * sizeof(R), s), "memset")) return rc;
-  if (io->grad_Cf && !p->Cf_batched) if (int rc = check_cuda(cudaMemsetAsync(io->grad_Cf, 0, n * n * sizeof(R), s), "memset")) return rc;
-  if (io->grad_cf && !p->Cf_batched) if (int rc = check_cuda(cudaMemsetAsync(io->grad_cf, 0, n * sizeof(R), s), "memset")) return rc;
-  if (io->grad_xref && !p->xref_batched) if (int rc = check_cuda(cudaMemsetAsync(io->grad_xref, 0, szX * sizeof(R), s), "memset")) return rc;
-  if (io->grad_uref && !p->uref_batched) if (int rc = check_cuda(cudaMemsetAsync(io->grad_uref, 0, szU * sizeof(R), s), "memset")) return rc;
+  const size_t T = p->T, n = NX + NU;
+  R* partials = nullptr;
+  if (reduce) {
+    const size_t need = (size_t)grid * nacc * sizeof(R);
+    if (!ws || ws_bytes < need) { set_error("backward workspace too small: %zu < %zu", ws_bytes, need); return TACD_EWORKSPACE; }
+    partials = (R*)ws;
+    // the zero padding of the terminal gradients is not touched by the reduction
+    if (io->grad_Cf && !p->Cf_batched) if (int rc = check_cuda(cudaMemsetAsync(io->grad_Cf, 0, n * n * sizeof(R), s), "memset")) return rc;
+    if (io->grad_cf && !p->Cf_batched) if (int rc = check_cuda(cudaMemsetAsync(io->grad_cf, 0, n * sizeof(R), s), "memset")) return rc;
+  }
+  (void)T;
   BwdPtrs<R> f;
   f.X = (const R*)io->X; f.U = (const R*)io->U; f.C = (const R*)io->C; f.xref = (const R*)io->xref; f.uref = (const R*)io->uref;
   f.A = (const R*)io->A; f.Bm = (const R*)io->Bm; f.gX = (const R*)io->gX; f.gU = (const R*)io->gU; f.tight = io->tight;
   f.grad_C = (R*)io->grad_C; f.grad_c = (R*)io->grad_c; f.grad_Cf = (R*)io->grad_Cf; f.grad_cf = (R*)io->grad_cf;
   f.grad_x0 = (R*)io->grad_x0; f.grad_xref = (R*)io->grad_xref; f.grad_uref = (R*)io->grad_uref; f.dX = (R*)io->dX; f.dU = (R*)io->dU;
-  kernel<<<grid, nt, smem, s>>>(to_dev<R>(p), f);
-  return check_cuda(cudaPeekAtLastError(), "ilqr_backward_small launch");
+  const DevProblem<R> dp = to_dev<R>(p);
+  kernel<<<grid, nt, smem, s>>>(dp, f, partials, reduce ? 1 : 0);
+  if (int rc = check_cuda(cudaPeekAtLastError(), "ilqr_backward_small launch")) return rc;
+  if (reduce) {
+    reduce_shared_grads<R, NX, NU><<<(nacc + 127) / 128, 128, 0, s>>>(dp, f, partials, grid);
+    return check_cuda(cudaPeekAtLastError(), "reduce_shared_grads launch");
+  }
+  return TACD_OK;
 }
 
 // (nx, nu, dyn) combinations with a thread-per-element instantiation: the shipped plugins
@@ -122,9 +144,9 @@ int launch_forward_small(const tacd_problem* p, const tacd_forward_io* io, void*
 }
 
 template <typename R>
-int launch_backward_small(const tacd_problem* p, const tacd_backward_io* io, cudaStream_t s) {
+int launch_backward_small(const tacd_problem* p, const tacd_backward_io* io, void* ws, size_t ws_bytes, cudaStream_t s) {
 #define X(NX_, NU_, DYN_) \
-  if (p->nx == NX_ && p->nu == NU_ && p->dyn_id == DYN_) return run_backward_small<R, NX_, NU_, DYN_>(p, io, s);
+  if (p->nx == NX_ && p->nu == NU_ && p->dyn_id == DYN_) return run_backward_small<R, NX_, NU_, DYN_>(p, io, ws, ws_bytes, s);
   TACD_SMALL_BWD(X)
 #undef X
   return TACD_EUNSUPPORTED;
