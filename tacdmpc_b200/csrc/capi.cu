@@ -60,7 +60,19 @@ const char* tacd_last_error(void) { return g_err; }
 
 // forward workspace: [0, kFwdHead) queue counter + bucket counters + longest-first order of the
 // thread-per-element kernel; the generic kernel's per-CTA slices follow
-static size_t fwd_head_bytes(const tacd_problem* p) { return 16384 + (((size_t)p->B * 4 + 255) / 256) * 256; }
+static size_t fwd_head_bytes(const tacd_problem* p) {
+  size_t b = 16384 + (((size_t)p->B * 4 + 255) / 256) * 256;
+  if (p->C_batched) {
+    // lane-slot copy of the per-element (C, c): one slot per resident thread, bounded by shared memory
+    const size_t es = p->dtype == TACD_F32 ? 4 : 8, n = p->nx + p->nu, T = p->T;
+    const DeviceInfo di = device_info();
+    const size_t sms = di.sms > 0 ? di.sms : 148, smem = di.smem_optin > 0 ? di.smem_optin : 232448;
+    size_t per_sm = smem / ((size_t)fwd_words(p->T, p->nx, p->nu) * es);
+    if (per_sm > 2048) per_sm = 2048;
+    b += sms * per_sm * (T * n * n + T * n) * es + 256;
+  }
+  return b;
+}
 size_t tacd_forward_workspace_bytes(const tacd_problem* p) {
   if (validate(p)) return 0;
   return fwd_head_bytes(p) + generic_forward_ws_bytes(p);
@@ -91,7 +103,7 @@ int tacd_ilqr_forward(const tacd_problem* p, const tacd_forward_io* io, void* wo
   const size_t head = fwd_head_bytes(p);
   if (!workspace || workspace_bytes < head) { set_error("workspace too small (need tacd_forward_workspace_bytes)"); return TACD_EWORKSPACE; }
   cudaStream_t s = (cudaStream_t)stream;
-  int rc = (p->dtype == TACD_F32) ? launch_forward_small<float>(p, io, workspace, s) : launch_forward_small<double>(p, io, workspace, s);
+  int rc = (p->dtype == TACD_F32) ? launch_forward_small<float>(p, io, workspace, head, s) : launch_forward_small<double>(p, io, workspace, head, s);
   if (rc != TACD_EUNSUPPORTED) return rc;
   char* ws = (char*)workspace + head;
   rc = (p->dtype == TACD_F32) ? launch_forward_generic<float>(p, io, ws, workspace_bytes - head, s)

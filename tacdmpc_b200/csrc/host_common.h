@@ -39,7 +39,7 @@ inline DevProblem<R> to_dev(const tacd_problem* p) {
 
 // small-system (thread-per-element) launchers; return TACD_EUNSUPPORTED when
 // (nx, nu, dyn) has no instantiation or the per-thread state does not fit shared memory
-template <typename R> int launch_forward_small(const tacd_problem* p, const tacd_forward_io* io, void* ws, cudaStream_t s);
+template <typename R> int launch_forward_small(const tacd_problem* p, const tacd_forward_io* io, void* ws, size_t ws_bytes, cudaStream_t s);
 template <typename R> int launch_backward_small(const tacd_problem* p, const tacd_backward_io* io, void* ws, size_t ws_bytes, cudaStream_t s);
 size_t small_backward_ws_bytes(const tacd_problem* p);
 

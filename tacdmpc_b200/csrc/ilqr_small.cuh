@@ -33,6 +33,8 @@ struct FwdPtrs {
   R* cost_trace;
   unsigned int* counter;  // work queue head; set to first_wave before launch
   const int32_t* order;   // longest-first permutation of the batch (nullable = identity)
+  R* cscratch;            // per-element costs only: lane-slot copy of (C, c), [word][lane] (nullable)
+  size_t cstride;         // number of lane slots (= grid * block)
   unsigned int first_wave;  // queue positions [0, first_wave) are dealt statically, one 32-segment per warp
 };
 
@@ -166,6 +168,7 @@ __global__ void __launch_bounds__(256, 1) ilqr_forward_small(const DevProblem<R>
   unsigned flg = 0;
   R best = 0;
   const R *Cp = nullptr, *cp = nullptr, *Cfp = nullptr, *cfp = nullptr, *xr = nullptr, *ur = nullptr;
+  size_t cs = 1;  // element stride of Cp / cp (1 = caller's tensor, cstride = lane-slot scratch)
 
   while (true) {
     // ---------------------------------------------------------------- refill
@@ -188,6 +191,25 @@ __global__ void __launch_bounds__(256, 1) ilqr_forward_small(const DevProblem<R>
         flg = 0;
         Cp = io.C + (P.C_batched ? (size_t)b * T * N * N : 0);
         cp = io.c + (P.C_batched ? (size_t)b * T * N : 0);
+        if (LSSEP && P.C_batched && io.cscratch != nullptr) {
+          // Per-element costs: a thread reading its own element's C_t walks memory with a 4*T*n*n-byte
+          // stride across the warp — 32 sectors per load instruction, and C is re-read twice per
+          // iteration.  Copy it ONCE into this lane's slot of a [word][lane] scratch; every later read
+          // is then one coalesced 128-byte wavefront (and mostly an L2 hit).
+          const size_t gl = (size_t)blockIdx.x * NT + tid;
+          R* dC = io.cscratch + gl;
+          R* dc = io.cscratch + (size_t)T * N * N * io.cstride + gl;
+          const int nC = T * N * N, nc = T * N;
+#pragma unroll 8
+          for (int w = 0; w < nC; ++w) dC[(size_t)w * io.cstride] = Cp[w];
+#pragma unroll 5
+          for (int w = 0; w < nc; ++w) dc[(size_t)w * io.cstride] = cp[w];
+          Cp = dC;
+          cp = dc;
+          cs = io.cstride;
+        } else {
+          cs = 1;
+        }
         Cfp = io.Cf + (P.Cf_batched ? (size_t)b * N * N : 0);
         cfp = io.cf + (P.Cf_batched ? (size_t)b * N : 0);
         xr = io.xref + (P.xref_batched ? (size_t)b * szX : 0);
@@ -206,9 +228,9 @@ __global__ void __launch_bounds__(256, 1) ilqr_forward_small(const DevProblem<R>
 #pragma unroll
           for (int i = 0; i < NU; ++i) tau[NX + i] = u[i] - ur[t * NU + i];
 #pragma unroll
-          for (int i = 0; i < N * N; ++i) Ct[i] = Cp[(size_t)t * N * N + i];
+          for (int i = 0; i < N * N; ++i) Ct[i] = Cp[((size_t)t * N * N + i) * cs];
 #pragma unroll
-          for (int i = 0; i < N; ++i) ct[i] = cp[(size_t)t * N + i];
+          for (int i = 0; i < N; ++i) ct[i] = cp[((size_t)t * N + i) * cs];
           quad_terms<R, N>(Ct, ct, tau, quad, lin);
           D::step(P, sA, sB, x, u, xn);
 #pragma unroll
@@ -266,13 +288,13 @@ __global__ void __launch_bounds__(256, 1) ilqr_forward_small(const DevProblem<R>
 #pragma unroll
           for (int i = 0; i < NU; ++i) { u[i] = SU(t, i); tau[NX + i] = u[i] - ur[t * NU + i]; }
 #pragma unroll
-          for (int i = 0; i < N * N; ++i) Ct[i] = Cp[(size_t)t * N * N + i];
+          for (int i = 0; i < N * N; ++i) Ct[i] = Cp[((size_t)t * N * N + i) * cs];
 #pragma unroll
           for (int i = 0; i < N; ++i) {
             R s = 0;
 #pragma unroll
             for (int j = 0; j < N; ++j) s += Ct[i * N + j] * tau[j];
-            s += cp[(size_t)t * N + i];
+            s += cp[((size_t)t * N + i) * cs];
             if (i < NX) qx[i] = s; else qu[i - NX] = s;
           }
 #pragma unroll
@@ -349,9 +371,9 @@ __global__ void __launch_bounds__(256, 1) ilqr_forward_small(const DevProblem<R>
           }
           if (LSSEP) {
 #pragma unroll
-            for (int i = 0; i < N * N; ++i) Ct[i] = Cp[(size_t)t * N * N + i];
+            for (int i = 0; i < N * N; ++i) Ct[i] = Cp[((size_t)t * N * N + i) * cs];
 #pragma unroll
-            for (int i = 0; i < N; ++i) ct[i] = cp[(size_t)t * N + i];
+            for (int i = 0; i < N; ++i) ct[i] = cp[((size_t)t * N + i) * cs];
 #pragma unroll
             for (int a = 0; a < kNA; ++a) {
               R tau[N];
@@ -588,18 +610,44 @@ __global__ void __launch_bounds__(256, 1) ilqr_backward_small(const DevProblem<R
 #pragma unroll
         for (int i = 0; i < NU; ++i) { nu_[i] = U[(t - 1) * NU + i]; ngu[i] = gU[(t - 1) * NU + i]; ntg[i] = tg[(t - 1) * NU + i] != 0; }
       }
-      const R* Ct = Cp + (size_t)t * N * N;
+      if (P.C_batched) {
+        // per-element Hessians: the warp's 32 elements are consecutive, so their C_t blocks are 32 segments
+        // of n*n words at a fixed stride — fetched cooperatively (consecutive lanes read consecutive words)
+        // into the tile, then each lane picks up its own row
+        const R* base = io.C + ((size_t)b0 * T + t) * N * N;
+        for (int k = 0; k < N * N; ++k) {
+          const int idx = k * 32 + lane, r = idx / (N * N), j = idx % (N * N);
+          const int rr = (b0 + r < P.B) ? r : (P.B - 1 - b0);
+          mytile[r * L::TW + j] = base[(size_t)rr * T * N * N + j];
+        }
+        __syncwarp();
+        const R* row = mytile + lane * L::TW;
 #pragma unroll
-      for (int i = 0; i < NX; ++i) {
+        for (int i = 0; i < NX; ++i) {
 #pragma unroll
-        for (int j = 0; j < NX; ++j) Qxx[i * NX + j] = Ct[i * N + j];
+          for (int j = 0; j < NX; ++j) Qxx[i * NX + j] = row[i * N + j];
 #pragma unroll
-        for (int j = 0; j < NU; ++j) Qxu[i * NU + j] = Ct[i * N + NX + j];
+          for (int j = 0; j < NU; ++j) Qxu[i * NU + j] = row[i * N + NX + j];
+        }
+#pragma unroll
+        for (int i = 0; i < NU; ++i)
+#pragma unroll
+          for (int j = 0; j < NU; ++j) Quu[i * NU + j] = row[(NX + i) * N + NX + j];
+        __syncwarp();
+      } else {
+        const R* Ct = Cp + (size_t)t * N * N;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+#pragma unroll
+          for (int j = 0; j < NX; ++j) Qxx[i * NX + j] = Ct[i * N + j];
+#pragma unroll
+          for (int j = 0; j < NU; ++j) Qxu[i * NU + j] = Ct[i * N + NX + j];
+        }
+#pragma unroll
+        for (int i = 0; i < NU; ++i)
+#pragma unroll
+          for (int j = 0; j < NU; ++j) Quu[i * NU + j] = Ct[(NX + i) * N + NX + j];
       }
-#pragma unroll
-      for (int i = 0; i < NU; ++i)
-#pragma unroll
-        for (int j = 0; j < NU; ++j) Quu[i * NU + j] = Ct[(NX + i) * N + NX + j];
       load_AB(t, x, u, A, Bm);
       q_blocks<R, NX, NU>(P.reg, A, Bm, V, v, Qxx, Qxu, Quu, qx, qu);
       // box QP on the free coordinates (controller.py:737-763); tight ones pinned to 0
@@ -682,32 +730,11 @@ __global__ void __launch_bounds__(256, 1) ilqr_backward_small(const DevProblem<R
         du[i] = s + Sk(t, i);
         dtau[NX + i] = du[i];
       }
-      // grad_C = -1/2 (dtau (x) tau + tau (x) dtau), grad_c = -dtau, grad_xref[t] = dx, grad_uref[t] = du
-      if (live) {
-        if (io.grad_C && P.C_batched) {
-#pragma unroll
-          for (int i = 0; i < N; ++i)
-#pragma unroll
-            for (int j = 0; j < N; ++j)
-              io.grad_C[((size_t)b * T + t) * N * N + i * N + j] = (R)-0.5 * (dtau[i] * tau[j] + tau[i] * dtau[j]);
-        }
-        if (io.grad_c && P.C_batched)
-#pragma unroll
-          for (int i = 0; i < N; ++i) io.grad_c[((size_t)b * T + t) * N + i] = -dtau[i];
-        if (io.grad_uref && P.uref_batched)
-#pragma unroll
-          for (int i = 0; i < NU; ++i) io.grad_uref[(size_t)b * szU + t * NU + i] = du[i];
-        if (io.grad_xref && P.xref_batched)
-#pragma unroll
-          for (int i = 0; i < NX; ++i) io.grad_xref[(size_t)b * szX + t * NX + i] = dx[i];
-        if (io.dU)
-#pragma unroll
-          for (int i = 0; i < NU; ++i) io.dU[(size_t)b * szU + t * NU + i] = du[i];
-        if (io.dX)
-#pragma unroll
-          for (int i = 0; i < NX; ++i) io.dX[(size_t)b * szX + t * NX + i] = dx[i];
-      }
-      if (redC || redc || redx || redu) {   // warp-uniform
+      // grad_C = -1/2 (dtau (x) tau + tau (x) dtau), grad_c = -dtau, grad_xref[t] = dx, grad_uref[t] = du.
+      // Every lane writes its NV values into its tile row; shared inputs: lanes sum columns into the
+      // warp's accumulators; per-element inputs: the warp stores the rows cooperatively (consecutive
+      // lanes write consecutive words of the [B,T,...] outputs instead of 32 scattered segments).
+      {
         R* row = mytile + lane * L::TW;
 #pragma unroll
         for (int i = 0; i < N; ++i)
@@ -720,11 +747,50 @@ __global__ void __launch_bounds__(256, 1) ilqr_backward_small(const DevProblem<R
 #pragma unroll
         for (int i = 0; i < NU; ++i) row[N * N + N + NX + i] = live ? du[i] : (R)0;
         __syncwarp();
-        for (int j = lane; j < L::NV; j += 32) {
-          R sum = 0;
+        if (redC || redc || redx || redu) {   // warp-uniform
+          for (int j = lane; j < L::NV; j += 32) {
+            R sum = 0;
 #pragma unroll 8
-          for (int r = 0; r < 32; ++r) sum += mytile[r * L::TW + j];
-          myacc[t * L::NV + j] += sum;
+            for (int r = 0; r < 32; ++r) sum += mytile[r * L::TW + j];
+            myacc[t * L::NV + j] += sum;
+          }
+        }
+        const int nlive = (P.B - b0 < 32) ? (P.B - b0) : 32;
+        if (io.grad_C && P.C_batched) {
+          R* dst = io.grad_C + ((size_t)b0 * T + t) * N * N;
+          for (int idx = lane; idx < nlive * N * N; idx += 32) {
+            const int r = idx / (N * N), j = idx % (N * N);
+            dst[(size_t)r * T * N * N + j] = mytile[r * L::TW + j];
+          }
+        }
+        if (io.grad_c && P.C_batched) {
+          R* dst = io.grad_c + ((size_t)b0 * T + t) * N;
+          for (int idx = lane; idx < nlive * N; idx += 32) {
+            const int r = idx / N, j = idx % N;
+            dst[(size_t)r * T * N + j] = mytile[r * L::TW + N * N + j];
+          }
+        }
+        if (io.grad_xref && P.xref_batched) {
+          R* dst = io.grad_xref + (size_t)b0 * szX + t * NX;
+          for (int idx = lane; idx < nlive * NX; idx += 32) {
+            const int r = idx / NX, j = idx % NX;
+            dst[(size_t)r * szX + j] = mytile[r * L::TW + N * N + N + j];
+          }
+        }
+        if (io.grad_uref && P.uref_batched) {
+          R* dst = io.grad_uref + (size_t)b0 * szU + t * NU;
+          for (int idx = lane; idx < nlive * NU; idx += 32) {
+            const int r = idx / NU, j = idx % NU;
+            dst[(size_t)r * szU + j] = mytile[r * L::TW + N * N + N + NX + j];
+          }
+        }
+        if (live) {
+          if (io.dU)
+#pragma unroll
+            for (int i = 0; i < NU; ++i) io.dU[(size_t)b * szU + t * NU + i] = du[i];
+          if (io.dX)
+#pragma unroll
+            for (int i = 0; i < NX; ++i) io.dX[(size_t)b * szX + t * NX + i] = dx[i];
         }
         __syncwarp();
       }

@@ -32,7 +32,7 @@ static int pick_block(K kernel, SmemFn smem_of, int* blocks_per_sm, size_t* smem
 }
 
 template <typename R, int NX, int NU, int DYN, bool LSSEP>
-static int run_forward_small(const tacd_problem* p, const tacd_forward_io* io, void* ws, cudaStream_t s) {
+static int run_forward_small(const tacd_problem* p, const tacd_forward_io* io, void* ws, size_t ws_bytes, cudaStream_t s) {
   auto kernel = ilqr_forward_small<R, NX, NU, DYN, LSSEP>;
   int bps = 0;
   size_t smem = 0;
@@ -59,6 +59,13 @@ static int run_forward_small(const tacd_problem* p, const tacd_forward_io* io, v
   const unsigned first_wave = lanes < (unsigned)p->B ? lanes : (unsigned)p->B;
   f.first_wave = first_wave;
   f.order = nullptr;
+  f.cscratch = nullptr;
+  f.cstride = (size_t)lanes;
+  const size_t order_bytes = 16384 + (((size_t)p->B * 4 + 255) / 256) * 256;
+  if (LSSEP && p->C_batched && !getenv("TACD_NO_CSCRATCH")) {
+    const size_t need = order_bytes + (size_t)lanes * ((size_t)p->T * (NX + NU) * (NX + NU) + (size_t)p->T * (NX + NU)) * sizeof(R);
+    if (ws_bytes >= need) f.cscratch = (R*)((char*)ws + order_bytes);
+  }
   queue_init<<<1, 1, 0, s>>>(f.counter, first_wave);
   const bool lpt = (unsigned)p->B > lanes && !getenv("TACD_NO_LPT");   // more than one wave: order matters
   if (lpt) {
@@ -86,8 +93,8 @@ static int run_backward_small(const tacd_problem* p, const tacd_backward_io* io,
   size_t smem = 0;
   const size_t wpt = (size_t)bwd_words(p->T, NX, NU);
   const int nt = pick_block(kernel, [&](int n) {
-    size_t w = wpt * n + NX * NX + NX * NU;
-    if (reduce) w += (size_t)(n / 32) * (32 * L::TW + nacc);
+    size_t w = wpt * n + NX * NX + NX * NU + (size_t)(n / 32) * 32 * L::TW;   // gains + LTI matrices + one tile per warp
+    if (reduce) w += (size_t)(n / 32) * nacc;                                   // per-warp accumulators
     return w * sizeof(R);
   }, &bps, &smem);
   if (nt == 0 || bps == 0) return TACD_EUNSUPPORTED;
@@ -133,11 +140,11 @@ static int run_backward_small(const tacd_problem* p, const tacd_backward_io* io,
   TACD_SMALL_FWD(X) X(1, 1, TACD_DYN_EXTERNAL) X(2, 1, TACD_DYN_EXTERNAL) X(4, 1, TACD_DYN_EXTERNAL) X(3, 2, TACD_DYN_EXTERNAL)
 
 template <typename R>
-int launch_forward_small(const tacd_problem* p, const tacd_forward_io* io, void* ws, cudaStream_t s) {
+int launch_forward_small(const tacd_problem* p, const tacd_forward_io* io, void* ws, size_t ws_bytes, cudaStream_t s) {
 #define X(NX_, NU_, DYN_)                                                                      \
   if (p->nx == NX_ && p->nu == NU_ && p->dyn_id == DYN_)                                       \
-    return p->ls_cost_shared ? run_forward_small<R, NX_, NU_, DYN_, true>(p, io, ws, s)       \
-                             : run_forward_small<R, NX_, NU_, DYN_, false>(p, io, ws, s);
+    return p->ls_cost_shared ? run_forward_small<R, NX_, NU_, DYN_, true>(p, io, ws, ws_bytes, s)       \
+                             : run_forward_small<R, NX_, NU_, DYN_, false>(p, io, ws, ws_bytes, s);
   TACD_SMALL_FWD(X)
 #undef X
   return TACD_EUNSUPPORTED;
