@@ -524,6 +524,8 @@ struct BwdLayout {
   static constexpr int NV = N * N + N + NX + NU;    // per step: grad_C | grad_c | grad_xref | grad_uref
   static constexpr int NVF = NX * NX + NX + NX;     // terminal: grad_Cf[:nx,:nx] | grad_cf[:nx] | grad_xref[T]
   static constexpr int TW = NV | 1;                 // odd tile row stride: conflict-free transposed access
+  static constexpr int CW = (N * N) | 1;            // row stride of the two C_t prefetch buffers
+  static constexpr int TILE = (32 * TW > 64 * CW) ? 32 * TW : 64 * CW;   // words per warp
   __host__ __device__ static int nacc(int T) { return T * NV + NVF; }
 };
 
@@ -541,7 +543,7 @@ __global__ void __launch_bounds__(256, 1) ilqr_backward_small(const DevProblem<R
   R* sA = sk + (size_t)T * NU * NT;
   R* sB = sA + NX * NX;
   R* tile = sB + NX * NU;                                    // [nw][32][TW]      (only when reduce)
-  R* acc = tile + (size_t)nw * 32 * L::TW;                   // [nw][nacc]
+  R* acc = tile + (size_t)nw * L::TILE;                      // [nw][nacc]
   const int NACC = L::nacc(T);
   if (DYN == TACD_DYN_LTI) {
     for (int i = tid; i < NX * NX; i += NT) sA[i] = P.dyn_A[i];
@@ -550,7 +552,7 @@ __global__ void __launch_bounds__(256, 1) ilqr_backward_small(const DevProblem<R
   if (reduce)
     for (int i = tid; i < nw * NACC; i += NT) acc[i] = 0;
   __syncthreads();
-  R* mytile = tile + (size_t)wid * 32 * L::TW;
+  R* mytile = tile + (size_t)wid * L::TILE;
   R* myacc = acc + (size_t)wid * NACC;
   const bool redC = reduce && io.grad_C && !P.C_batched, redc = reduce && io.grad_c && !P.C_batched;
   const bool redCf = reduce && io.grad_Cf && !P.Cf_batched, redcf = reduce && io.grad_cf && !P.Cf_batched;
@@ -597,6 +599,16 @@ __global__ void __launch_bounds__(256, 1) ilqr_backward_small(const DevProblem<R
     }
 #pragma unroll
     for (int i = 0; i < NU; ++i) { nu_[i] = U[(T - 1) * NU + i]; ngu[i] = gU[(T - 1) * NU + i]; ntg[i] = tg[(T - 1) * NU + i] != 0; }
+    auto fetch_C = [&](int t) {
+      const R* base = io.C + ((size_t)b0 * T + t) * N * N;
+      R* buf = mytile + (t & 1) * 32 * L::CW;
+      for (int k = 0; k < N * N; ++k) {
+        const int idx = k * 32 + lane, r = idx / (N * N), j = idx % (N * N);
+        const int rr = (b0 + r < P.B) ? r : (P.B - 1 - b0);
+        cp_async<R>(&buf[r * L::CW + j], &base[(size_t)rr * T * N * N + j]);
+      }
+    };
+    if (P.C_batched) { __syncwarp(); fetch_C(T - 1); }
     for (int t = T - 1; t >= 0; --t) {
       R x[NX], u[NU], Qxx[NX * NX], Qxu[NX * NU], Quu[NU * NU], qx[NX], qu[NU], A[NX * NX], Bm[NX * NU];
       bool fixed[NU];
@@ -613,15 +625,11 @@ __global__ void __launch_bounds__(256, 1) ilqr_backward_small(const DevProblem<R
       if (P.C_batched) {
         // per-element Hessians: the warp's 32 elements are consecutive, so their C_t blocks are 32 segments
         // of n*n words at a fixed stride — fetched cooperatively (consecutive lanes read consecutive words)
-        // into the tile, then each lane picks up its own row
-        const R* base = io.C + ((size_t)b0 * T + t) * N * N;
-        for (int k = 0; k < N * N; ++k) {
-          const int idx = k * 32 + lane, r = idx / (N * N), j = idx % (N * N);
-          const int rr = (b0 + r < P.B) ? r : (P.B - 1 - b0);
-          mytile[r * L::TW + j] = base[(size_t)rr * T * N * N + j];
-        }
+        // with cp.async into one of two buffers, one step ahead of use, so the DRAM latency of streaming C
+        // overlaps the Riccati arithmetic of the current step
+        cp_async_wait_all();
         __syncwarp();
-        const R* row = mytile + lane * L::TW;
+        const R* row = mytile + ((t & 1) * 32 + lane) * L::CW;
 #pragma unroll
         for (int i = 0; i < NX; ++i) {
 #pragma unroll
@@ -633,7 +641,7 @@ __global__ void __launch_bounds__(256, 1) ilqr_backward_small(const DevProblem<R
         for (int i = 0; i < NU; ++i)
 #pragma unroll
           for (int j = 0; j < NU; ++j) Quu[i * NU + j] = row[(NX + i) * N + NX + j];
-        __syncwarp();
+        if (t > 0) fetch_C(t - 1);
       } else {
         const R* Ct = Cp + (size_t)t * N * N;
 #pragma unroll

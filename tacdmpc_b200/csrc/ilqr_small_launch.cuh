@@ -93,7 +93,7 @@ static int run_backward_small(const tacd_problem* p, const tacd_backward_io* io,
   size_t smem = 0;
   const size_t wpt = (size_t)bwd_words(p->T, NX, NU);
   const int nt = pick_block(kernel, [&](int n) {
-    size_t w = wpt * n + NX * NX + NX * NU + (size_t)(n / 32) * 32 * L::TW;   // gains + LTI matrices + one tile per warp
+    size_t w = wpt * n + NX * NX + NX * NU + (size_t)(n / 32) * L::TILE;   // gains + LTI matrices + one tile per warp
     if (reduce) w += (size_t)(n / 32) * nacc;                                   // per-warp accumulators
     return w * sizeof(R);
   }, &bps, &smem);
