@@ -62,6 +62,7 @@ const char* tacd_last_error(void) { return g_err; }
 // thread-per-element kernel; the generic kernel's per-CTA slices follow
 static size_t fwd_head_bytes(const tacd_problem* p) {
   size_t b = 16384 + (((size_t)p->B * 4 + 255) / 256) * 256;
+  b += (((size_t)p->B * 8 + 255) / 256) * 256;   // initial cost of every element (group kernel)
   if (p->C_batched) {
     // lane-slot copy of the per-element (C, c): one slot per resident thread, bounded by shared memory
     const size_t es = p->dtype == TACD_F32 ? 4 : 8, n = p->nx + p->nu, T = p->T;
@@ -103,7 +104,9 @@ int tacd_ilqr_forward(const tacd_problem* p, const tacd_forward_io* io, void* wo
   const size_t head = fwd_head_bytes(p);
   if (!workspace || workspace_bytes < head) { set_error("workspace too small (need tacd_forward_workspace_bytes)"); return TACD_EWORKSPACE; }
   cudaStream_t s = (cudaStream_t)stream;
-  int rc = (p->dtype == TACD_F32) ? launch_forward_small<float>(p, io, workspace, head, s) : launch_forward_small<double>(p, io, workspace, head, s);
+  int rc = (p->dtype == TACD_F32) ? launch_forward_group<float>(p, io, workspace, head, s) : launch_forward_group<double>(p, io, workspace, head, s);
+  if (rc != TACD_EUNSUPPORTED) return rc;
+  rc = (p->dtype == TACD_F32) ? launch_forward_small<float>(p, io, workspace, head, s) : launch_forward_small<double>(p, io, workspace, head, s);
   if (rc != TACD_EUNSUPPORTED) return rc;
   char* ws = (char*)workspace + head;
   rc = (p->dtype == TACD_F32) ? launch_forward_generic<float>(p, io, ws, workspace_bytes - head, s)

@@ -1,0 +1,712 @@
+// ilqr_group.cuh — whole-solve forward kernel for small systems, FIVE LANES PER BATCH ELEMENT.
+//
+// Why a second formulation (profiles/r1_forward_v3): with one thread per element a single
+// iLQR iteration is one serial chain of ~26 k instructions (~35 us), the iteration count per element spans
+// 2..19, and the kernel cannot end before its longest chain: 0.68 ms of the 0.85 ms forward was that tail,
+// with 20 of 32 lanes active on average.  Here an element is owned by a group of G = 5 consecutive lanes
+// (6 elements per warp, 2 lanes spare), which shortens the chain 5x and gives the work queue 6x more waves:
+//
+//   reverse pass   lane j owns ROW j of the (n x n) Q-function  Q = C_t + F' V F,  F = [A_t | B_t]  (n = 5 for
+//                  both shipped non-linear plugins), and element j of q = C_t tau + c_t + F' v.  The gains
+//                  are computed redundantly by every lane from 6..12 shuffled entries (Q_xu, Q_uu, q_u), the
+//                  new value-function row i by lane i; V is all-gathered through 80 bytes of shared memory
+//                  per element with 128-bit accesses.  Jacobians are evaluated five time steps at a time
+//                  (lane j takes step t - j) in compact form (6 numbers for the cart-pole, 4 for the
+//                  unicycle) and broadcast with shuffles; the structural zeros / ones of F are skipped.
+//   line search    lane a rolls out candidate alpha_a and keeps its trajectory in its own shared-memory
+//                  buffer (6 buffers per element: nominal + 5 candidates), so accepting a candidate is a
+//                  buffer-index swap — there is no re-rollout pass.
+//   queue          groups pull elements from a global counter; the initial rollout + cost of every element
+//                  is done up front by ilqr_init_rollout (thread per element), so a refill is two coalesced
+//                  copies and all six groups of a warp stay in the same phase.
+//
+// Shared costs (C, c, C_final, c_final not batched, and the line-search cost of quirk Q4) are staged once
+// per CTA in shared memory.  Reference lines restated: controller.py:275-315 (solve_step), 546-578
+// (backward_lqr), 589-620 (evaluate_alphas), 636-642 (tight mask); cost.py:37-100.
+#pragma once
+#include "ilqr_small.cuh"
+
+namespace tacd {
+
+constexpr int kG = 5;              // lanes per element = line-search candidates rolled out together
+constexpr int kEPW = 32 / kG;      // elements per warp
+constexpr int kNBUF = kG + 1;      // trajectory buffers per element
+
+// ---- structured Jacobians ---------------------------------------------------------------------------------
+// F = [A | B] (NX x N) of the shipped plugins in compact form: jc[NJ] holds the entries that depend on (x,u);
+// col() returns column j of F for a run-time j, mulF() returns w' F skipping structural zeros.
+// col() is written as chains of single selects on lane-invariant predicates: a nested ?: over j compiles to a
+// divergent branch tree (profiles/r1_forward_group_v1: 60 of 280 instructions per step, 6..20 lanes active).
+template <typename R, int NX, int NU, int DYN>
+struct GDyn {  // LTI: dense F, shared by the CTA in shared memory (row-major NX x N)
+  static constexpr int N = NX + NU;
+  static constexpr int NJ = 1;
+  static constexpr bool kHasJac = false;
+  static TACD_DEV void jac(const DevProblem<R>&, const R (&)[NX], const R (&)[NU], R (&jc)[NJ]) { jc[0] = 0; }
+  static TACD_DEV void col(const DevProblem<R>&, const R* sF, const R (&)[NJ], int j, R (&f)[NX]) {
+#pragma unroll
+    for (int i = 0; i < NX; ++i) f[i] = sF[i * N + j];
+  }
+  static TACD_DEV void mulF(const DevProblem<R>&, const R* sF, const R (&)[NJ], const R (&w)[NX], R (&o)[N]) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      R s = 0;
+#pragma unroll
+      for (int l = 0; l < NX; ++l) s += w[l] * sF[l * N + k];
+      o[k] = s;
+    }
+  }
+};
+
+// cart-pole: A = [[1,dt,0,0],[0,1,a,b],[0,0,1,dt],[0,0,c,d]], B = [0,e,0,f]'  (tacd_dev.cuh::cartpole_jac)
+template <typename R>
+struct GDyn<R, 4, 1, TACD_DYN_CARTPOLE> {
+  static constexpr int NJ = 6;
+  static constexpr bool kHasJac = true;
+  static TACD_DEV void jac(const DevProblem<R>& P, const R (&x)[4], const R (&u)[1], R (&jc)[6]) {
+    R A[16], Bm[4];
+    cartpole_jac<R>(P.dynp, P.dt, x, u, A, Bm);
+    jc[0] = A[6]; jc[1] = A[7]; jc[2] = A[14]; jc[3] = A[15]; jc[4] = Bm[1]; jc[5] = Bm[3];
+  }
+  static TACD_DEV void col(const DevProblem<R>& P, const R*, const R (&jc)[6], int j, R (&f)[4]) {
+    const R dt = P.dt;
+    const bool p1 = j == 1, p2 = j == 2, p3 = j == 3, p4 = j == 4;
+    R f0 = (j == 0) ? (R)1 : (R)0; f0 = p1 ? dt : f0;
+    R f1 = p1 ? (R)1 : (R)0; f1 = p2 ? jc[0] : f1; f1 = p3 ? jc[1] : f1; f1 = p4 ? jc[4] : f1;
+    R f2 = p2 ? (R)1 : (R)0; f2 = p3 ? dt : f2;
+    R f3 = p2 ? jc[2] : (R)0; f3 = p3 ? jc[3] : f3; f3 = p4 ? jc[5] : f3;
+    f[0] = f0; f[1] = f1; f[2] = f2; f[3] = f3;
+  }
+  static TACD_DEV void mulF(const DevProblem<R>& P, const R*, const R (&jc)[6], const R (&w)[4], R (&o)[5]) {
+    const R dt = P.dt;
+    o[0] = w[0];
+    o[1] = w[0] * dt + w[1];
+    o[2] = (w[1] * jc[0] + w[2]) + w[3] * jc[2];
+    o[3] = (w[1] * jc[1] + w[2] * dt) + w[3] * jc[3];
+    o[4] = w[1] * jc[4] + w[3] * jc[5];
+  }
+};
+
+// unicycle: A = [[1,0,a],[0,1,b],[0,0,1]], B = [[p,0],[q,0],[0,dt]]  (tacd_dev.cuh::unicycle_jac)
+template <typename R, int DYN>
+struct GDynUnicycle {
+  static constexpr int NJ = 4;
+  static constexpr bool kHasJac = true;
+  static TACD_DEV void jac(const DevProblem<R>& P, const R (&x)[3], const R (&u)[2], R (&jc)[4]) {
+    R A[9], Bm[6];
+    unicycle_jac<R>(P.dt, x, u, A, Bm);
+    jc[0] = A[2]; jc[1] = A[5]; jc[2] = Bm[0]; jc[3] = Bm[2];
+  }
+  static TACD_DEV void col(const DevProblem<R>& P, const R*, const R (&jc)[4], int j, R (&f)[3]) {
+    const bool p2 = j == 2, p3 = j == 3;
+    R f0 = (j == 0) ? (R)1 : (R)0; f0 = p2 ? jc[0] : f0; f0 = p3 ? jc[2] : f0;
+    R f1 = (j == 1) ? (R)1 : (R)0; f1 = p2 ? jc[1] : f1; f1 = p3 ? jc[3] : f1;
+    R f2 = p2 ? (R)1 : (R)0; f2 = (j == 4) ? P.dt : f2;
+    f[0] = f0; f[1] = f1; f[2] = f2;
+  }
+  static TACD_DEV void mulF(const DevProblem<R>& P, const R*, const R (&jc)[4], const R (&w)[3], R (&o)[5]) {
+    o[0] = w[0];
+    o[1] = w[1];
+    o[2] = (w[0] * jc[0] + w[1] * jc[1]) + w[2];
+    o[3] = w[0] * jc[2] + w[1] * jc[3];
+    o[4] = w[2] * P.dt;
+  }
+};
+template <typename R> struct GDyn<R, 3, 2, TACD_DYN_UNICYCLE> : GDynUnicycle<R, TACD_DYN_UNICYCLE> {};
+template <typename R> struct GDyn<R, 3, 2, TACD_DYN_UNICYCLE_WRAPPED> : GDynUnicycle<R, TACD_DYN_UNICYCLE_WRAPPED> {};
+
+// a[i] for a run-time i < M with a in registers
+template <int M, typename R>
+TACD_DEV R pick(const R* a, int i) {
+  R r = a[0];
+#pragma unroll
+  for (int k = 1; k < M; ++k) r = (i == k) ? a[k] : r;
+  return r;
+}
+
+template <typename R> struct alignas(16) Row4 { R v[4]; };
+
+// shared-memory words of one warp's region (6 element slots)
+__host__ __device__ inline int group_traj_words(int T, int nx, int nu) { return (T + 1) * nx + T * nu; }
+// offset of the value-function exchange block (16-byte aligned) and size of the whole region
+__host__ __device__ inline int group_voff_words(int T, int nx, int nu) {
+  return (group_traj_words(T, nx, nu) * kNBUF * kEPW + T * nu * (nx + 1) * kEPW + 3) & ~3;
+}
+__host__ __device__ inline int group_warp_words(int T, int nx, int nu) {
+  return group_voff_words(T, nx, nu) + kEPW * (nx + 1) * 4;
+}
+// CTA-shared staging of the un-batched costs (+ the separate line-search cost) and the LTI matrices.
+// Running cost of step t: [C_t (n*n) | c_t (n) | pad] at stride group_cost_stride(n) (multiple of 4 words, so the
+// line search reads it with 128-bit loads); terminal cost: [C_final | c_final | pad].
+__host__ __device__ inline int group_cost_stride(int n) { return (n * n + n + 3) & ~3; }
+__host__ __device__ inline int group_cost_words(int T, int nx, int nu, int C_batched, int Cf_batched, int lssep, int lti) {
+  const int n = nx + nu, run = T * group_cost_stride(n), fin = group_cost_stride(n);
+  int w = 0;
+  if (!C_batched) w += run;
+  if (!Cf_batched) w += fin;
+  if (lssep) w += run + fin;
+  if (lti) w += (nx * n + 3) & ~3;
+  return w;
+}
+
+// [C_t | c_t] of one step from a 16-byte aligned staged block
+template <typename R, int N>
+TACD_DEV void load_cost_vec(const R* p, R (&Ct)[N * N], R (&ct)[N]) {
+  constexpr int NW = N * N + N, NV = (NW + 3) / 4;
+  R tmp[NV * 4];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const Row4<R> r = *reinterpret_cast<const Row4<R>*>(p + 4 * v);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) tmp[4 * v + c] = r.v[c];
+  }
+#pragma unroll
+  for (int i = 0; i < N * N; ++i) Ct[i] = tmp[i];
+#pragma unroll
+  for (int i = 0; i < N; ++i) ct[i] = tmp[N * N + i];
+}
+
+// Initial rollout + objective of every element (controller.py:277-279, 361-398; cost.py:37-62), one thread
+// per element: X_init -> io.X (re-used as the hand-over buffer), cost -> cost0.
+template <typename R, int NX, int NU, int DYN>
+__global__ void __launch_bounds__(128) ilqr_init_rollout(const DevProblem<R> P, const FwdPtrs<R> io, R* cost0) {
+  constexpr int N = NX + NU;
+  using D = Dyn<R, NX, NU, DYN>;
+  __shared__ R sAB[NX * NX + NX * NU];
+  R* sA = sAB;
+  R* sB = sAB + NX * NX;
+  if (DYN == TACD_DYN_LTI) {
+    for (int i = threadIdx.x; i < NX * NX; i += blockDim.x) sA[i] = P.dyn_A[i];
+    for (int i = threadIdx.x; i < NX * NU; i += blockDim.x) sB[i] = P.dyn_B[i];
+    __syncthreads();
+  }
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= P.B) return;
+  const int T = P.T;
+  const size_t szX = (size_t)(T + 1) * NX, szU = (size_t)T * NU;
+  const R* Cp = io.C + (P.C_batched ? (size_t)b * T * N * N : 0);
+  const R* cp = io.c + (P.C_batched ? (size_t)b * T * N : 0);
+  const R* Cfp = io.Cf + (P.Cf_batched ? (size_t)b * N * N : 0);
+  const R* cfp = io.cf + (P.Cf_batched ? (size_t)b * N : 0);
+  const R* xr = io.xref + (P.xref_batched ? (size_t)b * szX : 0);
+  const R* ur = io.uref + (P.uref_batched ? (size_t)b * szU : 0);
+  R* Xo = io.X + (size_t)b * szX;
+  R x[NX], u[NU], xn[NX];
+  R quad = 0, lin = 0;
+#pragma unroll
+  for (int i = 0; i < NX; ++i) { x[i] = io.x0[(size_t)b * NX + i]; Xo[i] = x[i]; }
+  for (int t = 0; t < T; ++t) {
+    R tau[N], Ct[N * N], ct[N];
+#pragma unroll
+    for (int i = 0; i < NU; ++i) u[i] = io.Uinit[(size_t)b * szU + t * NU + i];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) tau[i] = x[i] - xr[t * NX + i];
+#pragma unroll
+    for (int i = 0; i < NU; ++i) tau[NX + i] = u[i] - ur[t * NU + i];
+#pragma unroll
+    for (int i = 0; i < N * N; ++i) Ct[i] = Cp[(size_t)t * N * N + i];
+#pragma unroll
+    for (int i = 0; i < N; ++i) ct[i] = cp[(size_t)t * N + i];
+    quad_terms<R, N>(Ct, ct, tau, quad, lin);
+    D::step(P, sA, sB, x, u, xn);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) { x[i] = xn[i]; Xo[(t + 1) * NX + i] = x[i]; }
+  }
+  R qN = 0, lN = 0;
+#pragma unroll
+  for (int i = 0; i < NX; ++i) {
+    R s = 0;
+#pragma unroll
+    for (int j = 0; j < NX; ++j) s += Cfp[i * N + j] * (x[j] - xr[T * NX + j]);
+    qN += (x[i] - xr[T * NX + i]) * s;
+    lN += cfp[i] * (x[i] - xr[T * NX + i]);
+  }
+  cost0[b] = ((R)0.5 * quad + lin) + ((R)0.5 * qN + lN);
+}
+
+// CSH: the element's own running cost (C, c) is shared by the batch and staged in shared memory (layout 2a);
+// otherwise it is per-element and read from global memory.  LSSEP: candidates are scored with the separate
+// shared line-search cost (quirk Q4), always staged.
+template <typename R, int NX, int NU, int DYN, bool LSSEP, bool CSH>
+__global__ void __launch_bounds__(512, 1) ilqr_forward_group(const DevProblem<R> P, const FwdPtrs<R> io, const R* cost0) {
+  constexpr int N = NX + NU;
+  static_assert(N <= kG, "one lane per row of the Q-function");
+  static_assert(NX <= 4, "value-function rows travel as one 4-word vector");
+  using D = Dyn<R, NX, NU, DYN>;
+  using GD = GDyn<R, NX, NU, DYN>;
+  constexpr int NJ = GD::NJ;
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr int WS = kNBUF * kEPW;             // words between consecutive trajectory words of one buffer
+  constexpr int CS = (N * N + N + 3) & ~3;     // staged cost stride per step
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int T = P.T;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const bool valid = lane < kEPW * kG;         // lanes 30, 31 are spare: they run along, own nothing
+  const int e = valid ? lane / kG : 0;
+  const int j = valid ? lane - e * kG : kG;    // position in the group
+  const int base = e * kG;                     // first lane of the group (shuffle source)
+  const int jj = j < N ? j : N - 1;            // row of the Q-function this lane computes
+  const int XW = (T + 1) * NX, W = XW + T * NU;
+  const size_t szX = (size_t)XW, szU = (size_t)T * NU;
+
+  // ---- shared memory: CTA-wide cost staging, then one region per warp
+  R* sm = reinterpret_cast<R*>(smem_raw);
+  const bool ownCf_sh = !P.Cf_batched;
+  R *sC = sm, *sCf = sm, *sCl = sm, *sCfl = sm, *sF = sm;
+  {
+    int o = 0;
+    const int NT = blockDim.x;
+    auto stage_run = [&](R* dst, const R* Cg, const R* cg) {
+      for (int i = tid; i < T * CS; i += NT) {
+        const int t = i / CS, k = i - t * CS;
+        dst[i] = (k < N * N) ? Cg[t * N * N + k] : (k < N * N + N) ? cg[t * N + (k - N * N)] : (R)0;
+      }
+    };
+    auto stage_fin = [&](R* dst, const R* Cg, const R* cg) {
+      for (int k = tid; k < CS; k += NT) dst[k] = (k < N * N) ? Cg[k] : (k < N * N + N) ? cg[k - N * N] : (R)0;
+    };
+    if (CSH) { sC = sm + o; o += T * CS; stage_run(sC, io.C, io.c); }
+    if (ownCf_sh) { sCf = sm + o; o += CS; stage_fin(sCf, io.Cf, io.cf); }
+    if (LSSEP) {
+      sCl = sm + o; o += T * CS; stage_run(sCl, io.C_ls, io.c_ls);
+      sCfl = sm + o; o += CS; stage_fin(sCfl, io.Cf_ls, io.cf_ls);
+    }
+    if (DYN == TACD_DYN_LTI) {
+      sF = sm + o; o += (NX * N + 3) & ~3;
+      for (int i = tid; i < NX * N; i += NT) {
+        const int r = i / N, k = i % N;
+        sF[i] = (k < NX) ? P.dyn_A[r * NX + k] : P.dyn_B[r * NU + (k - NX)];
+      }
+    }
+    sm += o;
+  }
+  __syncthreads();
+  R* wreg = sm + (size_t)wid * group_warp_words(T, NX, NU);
+  R* ebuf = wreg + e;                                              // [word][buf][e]
+  R* eK = wreg + (size_t)W * WS + e;                               // [T*NU*NX][e]
+  R* ek = eK + (size_t)T * NU * NX * kEPW;                         // [T*NU][e]
+  R* myV = wreg + group_voff_words(T, NX, NU) + (size_t)e * (NX + 1) * 4;   // [e][NX+1][4]: rows of V, then v
+  // Dyn<> (LTI) wants A and B separately: straight from global memory (uniform, cached)
+  const R* sA = P.dyn_A;
+  const R* sB = P.dyn_B;
+
+  R ulo[NU], uhi[NU];
+#pragma unroll
+  for (int i = 0; i < NU; ++i) {
+    ulo[i] = P.has_umin ? P.umin[i] : -inf_<R>();
+    uhi[i] = P.has_umax ? P.umax[i] : inf_<R>();
+  }
+  const R alpha = P.alphas[(j < P.n_alpha) ? j : P.n_alpha - 1];
+  const bool replay = io.replay_iters != nullptr;
+
+  // group state, replicated in the lanes of the group
+  bool has = false, exhausted = !valid;
+  int b = 0, it = 0, nom = 0;
+  unsigned flg = 0;
+  R best = 0;
+  const R *Cp = io.C, *cp = io.c, *Cfp = io.Cf, *cfp = io.cf, *xr = io.xref, *ur = io.uref;
+
+  while (true) {
+    // ------------------------------------------------------------------ refill (queue pop by the group leader)
+    {
+      const bool need = !has && !exhausted;
+      unsigned nb = 0xffffffffu;
+      if (need && j == 0) nb = atomicAdd(io.counter, 1u);
+      nb = __shfl_sync(FULL, nb, base);
+      if (need) {
+        if (nb < (unsigned)P.B) {
+          b = io.order ? io.order[nb] : (int)nb;
+          has = true; it = 0; flg = 0; nom = 0;
+          Cp = io.C + (P.C_batched ? (size_t)b * T * N * N : 0);
+          cp = io.c + (P.C_batched ? (size_t)b * T * N : 0);
+          Cfp = io.Cf + (P.Cf_batched ? (size_t)b * N * N : 0);
+          cfp = io.cf + (P.Cf_batched ? (size_t)b * N : 0);
+          xr = io.xref + (P.xref_batched ? (size_t)b * szX : 0);
+          ur = io.uref + (P.uref_batched ? (size_t)b * szU : 0);
+          const R* Xi = io.X + (size_t)b * szX;
+          const R* Ui = io.Uinit + (size_t)b * szU;
+          for (int w = j; w < XW; w += kG) ebuf[(size_t)w * WS] = Xi[w];
+          for (int w = j; w < W - XW; w += kG) ebuf[(size_t)(XW + w) * WS] = Ui[w];
+          best = cost0[b];
+          if (io.alpha_trace)
+            for (int w = j; w < P.max_iter; w += kG) io.alpha_trace[(size_t)b * P.max_iter + w] = 0xFF;
+        } else {
+          exhausted = true;
+        }
+      }
+    }
+    __syncwarp();
+    if (__ballot_sync(FULL, has) == 0u) break;
+
+    bool run = has && it < P.max_iter;
+    if (run && replay) run = it < io.replay_iters[b];
+    bool improved = false;
+    if (__ballot_sync(FULL, run) != 0u) {
+      const R* nomp = ebuf + nom * kEPW;   // nominal trajectory: word w at nomp[w * WS]
+      // terminal cost of this element: staged or global (generic pointers; read twice per pass)
+      const R* Cfo = ownCf_sh ? sCf : Cfp;
+      const R* cfo = ownCf_sh ? sCf + N * N : cfp;
+      // ---------------------------------------------------------------- reverse Riccati pass
+      // quadraticize (cost.py:64-100) + linearize (controller.py:448-471) + backward_lqr (546-578)
+      {
+        R V[NX * NX], v[NX];
+        {
+          R tauN[NX];
+#pragma unroll
+          for (int i = 0; i < NX; ++i) tauN[i] = nomp[(size_t)(T * NX + i) * WS] - xr[T * NX + i];
+#pragma unroll
+          for (int i = 0; i < NX; ++i) {
+            R s = 0;
+#pragma unroll
+            for (int k = 0; k < NX; ++k) {
+              const R cik = Cfo[i * N + k];
+              V[i * NX + k] = cik;
+              s += cik * tauN[k];
+            }
+            v[i] = s + cfo[i];
+          }
+        }
+        R jcm[NJ];   // compact Jacobian of the step this lane evaluated in the current block of kG steps
+#pragma unroll
+        for (int m = 0; m < NJ; ++m) jcm[m] = 0;
+        // running pointers of step t (all decremented once per step)
+        const R* px = nomp + (size_t)(T - 1) * NX * WS;
+        const R* pu = nomp + (size_t)(XW + (T - 1) * NU) * WS;
+        R* pK = eK + (size_t)(T - 1) * NU * NX * kEPW;
+        R* pk = ek + (size_t)(T - 1) * NU * kEPW;
+        const R* pxr = xr + (T - 1) * NX;
+        const R* pur = ur + (T - 1) * NU;
+        const R* pCrow = CSH ? sC + (size_t)(T - 1) * CS + jj * N : Cp + ((size_t)(T - 1) * N + jj) * N;
+        const R* pcj = CSH ? sC + (size_t)(T - 1) * CS + N * N + jj : cp + (size_t)(T - 1) * N + jj;
+        R nxr[NX], nur[NU];   // references of the step about to run (prefetched)
+#pragma unroll
+        for (int i = 0; i < NX; ++i) nxr[i] = pxr[i];
+#pragma unroll
+        for (int i = 0; i < NU; ++i) nur[i] = pur[i];
+        int s_in_blk = 0;
+        for (int t = T - 1; t >= 0; --t) {
+          if (GD::kHasJac && s_in_blk == 0) {
+            const int back = (j <= t) ? j : t;      // lane j evaluates step t - j (clamped at 0)
+            const R* qx = px - (size_t)back * NX * WS;
+            const R* qu = pu - (size_t)back * NU * WS;
+            R xj[NX], uj[NU];
+#pragma unroll
+            for (int i = 0; i < NX; ++i) xj[i] = qx[i * WS];
+#pragma unroll
+            for (int i = 0; i < NU; ++i) uj[i] = qu[i * WS];
+            GD::jac(P, xj, uj, jcm);
+          }
+          R jc[NJ];
+          if (GD::kHasJac) {
+#pragma unroll
+            for (int m = 0; m < NJ; ++m) jc[m] = __shfl_sync(FULL, jcm[m], base + s_in_blk);
+          } else {
+#pragma unroll
+            for (int m = 0; m < NJ; ++m) jc[m] = 0;
+          }
+          s_in_blk = (s_in_blk == kG - 1) ? 0 : s_in_blk + 1;
+          R tau[N];
+#pragma unroll
+          for (int i = 0; i < NX; ++i) tau[i] = px[i * WS] - nxr[i];
+#pragma unroll
+          for (int i = 0; i < NU; ++i) tau[NX + i] = pu[i * WS] - nur[i];
+          if (t > 0) {
+            pxr -= NX; pur -= NU;
+#pragma unroll
+            for (int i = 0; i < NX; ++i) nxr[i] = pxr[i];
+#pragma unroll
+            for (int i = 0; i < NU; ++i) nur[i] = pur[i];
+          }
+          // row jj of C_t, l_j = C_t[j,:] tau + c_t[j]
+          R Qrow[N], qj;
+          {
+            R s = 0;
+#pragma unroll
+            for (int k = 0; k < N; ++k) {
+              Qrow[k] = pCrow[k];
+              s += Qrow[k] * tau[k];
+            }
+            qj = s + pcj[0];
+          }
+          // row jj of F' V F and element jj of F' v
+          {
+            R f[NX], w[NX], o[N];
+            GD::col(P, sF, jc, jj, f);
+#pragma unroll
+            for (int l = 0; l < NX; ++l) {
+              R s = 0;
+#pragma unroll
+              for (int i = 0; i < NX; ++i) s += f[i] * V[i * NX + l];
+              w[l] = s;
+            }
+            GD::mulF(P, sF, jc, w, o);
+#pragma unroll
+            for (int k = 0; k < N; ++k) Qrow[k] += (k >= NX && k == jj) ? o[k] + P.reg : o[k];
+            R s = 0;
+#pragma unroll
+            for (int i = 0; i < NX; ++i) s += f[i] * v[i];
+            qj += s;
+          }
+          // gather Q_xu, Q_uu, q_u; every lane computes the gains
+          R Qxu[NX * NU], Quu[NU * NU], qu[NU];
+#pragma unroll
+          for (int m = 0; m < NU; ++m) {
+#pragma unroll
+            for (int i = 0; i < NX; ++i) Qxu[i * NU + m] = __shfl_sync(FULL, Qrow[NX + m], base + i);
+#pragma unroll
+            for (int m2 = 0; m2 < NU; ++m2) Quu[m * NU + m2] = __shfl_sync(FULL, Qrow[NX + m2], base + NX + m);
+            qu[m] = __shfl_sync(FULL, qj, base + NX + m);
+          }
+          R Kt[NU * NX], kt[NU];
+          const bool npd = gains<R, NX, NU>(P.reg, Qxu, Quu, qu, Kt, kt);
+          if (run && npd) flg |= TACD_FLAG_NONPD;
+          if (j < NX) {
+#pragma unroll
+            for (int m = 0; m < NU; ++m) pK[(m * NX + j) * kEPW] = pick<NX, R>(&Kt[m * NX], j);
+          } else if (j < N) {
+            pk[(j - NX) * kEPW] = pick<NU, R>(kt, j - NX);
+          }
+          // row i = j of the value update (controller.py:573-574), association as value_update<>
+          {
+            R QK[NU * NX], Qk[NU], Ki[NU];
+#pragma unroll
+            for (int m = 0; m < NU; ++m) {
+#pragma unroll
+              for (int c = 0; c < NX; ++c) {
+                R s = 0;
+#pragma unroll
+                for (int m2 = 0; m2 < NU; ++m2) s += Quu[m * NU + m2] * Kt[m2 * NX + c];
+                QK[m * NX + c] = s;
+              }
+              R s = 0;
+#pragma unroll
+              for (int m2 = 0; m2 < NU; ++m2) s += Quu[m * NU + m2] * kt[m2];
+              Qk[m] = s;
+              Ki[m] = pick<NX, R>(&Kt[m * NX], jj < NX ? jj : 0);
+            }
+            Row4<R> vr;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) vr.v[c] = 0;
+#pragma unroll
+            for (int c = 0; c < NX; ++c) {
+              R a = 0, bb = 0, cc = 0;
+#pragma unroll
+              for (int m = 0; m < NU; ++m) {
+                a += Ki[m] * QK[m * NX + c];
+                bb += Ki[m] * Qxu[c * NU + m];
+                cc += Qrow[NX + m] * Kt[m * NX + c];
+              }
+              vr.v[c] = ((Qrow[c] + a) + bb) + cc;
+            }
+            R a = 0, bb = 0, cc = 0;
+#pragma unroll
+            for (int m = 0; m < NU; ++m) {
+              a += Ki[m] * Qk[m];
+              bb += Ki[m] * qu[m];
+              cc += Qrow[NX + m] * kt[m];
+            }
+            const R vi = ((qj + a) + bb) + cc;
+            if (j < NX) {
+              *reinterpret_cast<Row4<R>*>(myV + j * 4) = vr;
+              myV[NX * 4 + j] = vi;
+            }
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < NX; ++i) {
+            const Row4<R> r = *reinterpret_cast<const Row4<R>*>(myV + i * 4);
+#pragma unroll
+            for (int c = 0; c < NX; ++c) V[i * NX + c] = r.v[c];
+          }
+          {
+            const Row4<R> r = *reinterpret_cast<const Row4<R>*>(myV + NX * 4);
+#pragma unroll
+            for (int c = 0; c < NX; ++c) v[c] = r.v[c];
+          }
+          __syncwarp();
+          px -= NX * WS; pu -= NU * WS; pK -= NU * NX * kEPW; pk -= NU * kEPW;
+          pCrow -= CSH ? CS : N * N; pcj -= CSH ? CS : N;
+        }
+      }
+      // ---------------------------------------------------------------- line search: lane a = candidate a
+      // evaluate_alphas (controller.py:589-620); the candidate trajectory goes to this lane's buffer
+      R cost_ls, cost_own;
+      {
+        const int cb = j + (j >= nom ? 1 : 0);   // the five buffers that are not the nominal one
+        R* cbp = ebuf + (valid ? cb : nom) * kEPW;
+        R x[NX], q1 = 0, l1 = 0, q2 = 0, l2 = 0;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) { x[i] = nomp[i * WS]; if (valid) cbp[i * WS] = x[i]; }
+        const R* px = nomp;
+        const R* pu = nomp + (size_t)XW * WS;
+        R* cx = cbp + NX * WS;                   // candidate X_{t+1}
+        R* cu = cbp + (size_t)XW * WS;           // candidate U_t
+        const R* pK = eK;
+        const R* pk = ek;
+        const R* pxr = xr;
+        const R* pur = ur;
+        const R* pCl = sCl;                      // staged line-search cost of step t
+        const R* pCo = CSH ? sC : Cp;            // own cost of step t (staged block or global C_t)
+        const R* pco = cp;
+        R nxr[NX], nur[NU];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) nxr[i] = pxr[i];
+#pragma unroll
+        for (int i = 0; i < NU; ++i) nur[i] = pur[i];
+        for (int t = 0; t < T; ++t) {
+          R u[NU], tau[N], dx[NX], Ct[N * N], ct[N], xn[NX];
+#pragma unroll
+          for (int k = 0; k < NX; ++k) dx[k] = x[k] - px[k * WS];
+#pragma unroll
+          for (int i = 0; i < NU; ++i) {
+            R s = 0;
+#pragma unroll
+            for (int k = 0; k < NX; ++k) s += pK[(i * NX + k) * kEPW] * dx[k];
+            R ui = pu[i * WS] + (alpha * pk[i * kEPW] + s);
+            ui = tmin<R>(tmax<R>(ui, ulo[i]), uhi[i]);
+            u[i] = ui;
+            tau[NX + i] = ui - nur[i];
+          }
+#pragma unroll
+          for (int i = 0; i < NX; ++i) tau[i] = x[i] - nxr[i];
+          // prefetch the next step's references (x_ref has T+1 rows, u_ref T)
+          pxr += NX; pur += NU;
+#pragma unroll
+          for (int i = 0; i < NX; ++i) nxr[i] = pxr[i];
+          if (t + 1 < T) {
+#pragma unroll
+            for (int i = 0; i < NU; ++i) nur[i] = pur[i];
+          }
+          if (LSSEP) {
+            load_cost_vec<R, N>(pCl, Ct, ct);
+            quad_terms<R, N>(Ct, ct, tau, q1, l1);
+            pCl += CS;
+          }
+          if (CSH) {
+            load_cost_vec<R, N>(pCo, Ct, ct);
+            pCo += CS;
+          } else {
+#pragma unroll
+            for (int i = 0; i < N * N; ++i) Ct[i] = pCo[i];
+#pragma unroll
+            for (int i = 0; i < N; ++i) ct[i] = pco[i];
+            pCo += N * N; pco += N;
+          }
+          quad_terms<R, N>(Ct, ct, tau, q2, l2);
+          D::step(P, sA, sB, x, u, xn);
+          if (valid) {
+#pragma unroll
+            for (int i = 0; i < NU; ++i) cu[i * WS] = u[i];
+#pragma unroll
+            for (int i = 0; i < NX; ++i) cx[i * WS] = xn[i];
+          }
+#pragma unroll
+          for (int i = 0; i < NX; ++i) x[i] = xn[i];
+          px += NX * WS; pu += NU * WS; cx += NX * WS; cu += NU * WS; pK += NU * NX * kEPW; pk += NU * kEPW;
+        }
+        R tauN[NX];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) tauN[i] = x[i] - nxr[i];
+        R qN = 0, lN = 0, qN2 = 0, lN2 = 0;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+          R s = 0, s2 = 0;
+#pragma unroll
+          for (int k = 0; k < NX; ++k) {
+            if (LSSEP) s += sCfl[i * N + k] * tauN[k];
+            s2 += Cfo[i * N + k] * tauN[k];
+          }
+          if (LSSEP) { qN += tauN[i] * s; lN += sCfl[N * N + i] * tauN[i]; }
+          qN2 += tauN[i] * s2;
+          lN2 += cfo[i] * tauN[i];
+        }
+        cost_own = ((R)0.5 * q2 + l2) + ((R)0.5 * qN2 + lN2);
+        cost_ls = LSSEP ? ((R)0.5 * q1 + l1) + ((R)0.5 * qN + lN) : cost_own;
+      }
+      // ---------------------------------------------------------------- accept
+      // argmin (first minimum, NaN wins) + strict improvement (controller.py:292-301)
+      R costs[kG];
+#pragma unroll
+      for (int a = 0; a < kG; ++a) costs[a] = __shfl_sync(FULL, cost_ls, base + a);
+      int ai = 0;
+      {
+        R cbest = costs[0];
+        bool done = false;
+#pragma unroll
+        for (int a = 1; a < kG; ++a) {
+          if (a < P.n_alpha && !done) {
+            if (cbest != cbest) done = true;
+            else if (costs[a] < cbest || costs[a] != costs[a]) { ai = a; cbest = costs[a]; }
+          }
+        }
+      }
+      if (run && replay) ai = io.replay_alpha[(size_t)b * P.max_iter + it];
+      const R newc = __shfl_sync(FULL, cost_own, base + ai);
+      improved = newc < best;
+      if (run && replay) improved = (it < io.replay_iters[b] - 1) || ((io.replay_flags[b] & TACD_FLAG_MAXITER) != 0);
+      if (run && j == 0) {
+        if (io.alpha_trace) io.alpha_trace[(size_t)b * P.max_iter + it] = (uint8_t)ai;
+        if (io.cost_trace) {
+          R* ctr = io.cost_trace + ((size_t)b * P.max_iter + it) * (P.n_alpha + 2);
+#pragma unroll
+          for (int a = 0; a < kG; ++a)
+            if (a < P.n_alpha) ctr[a] = costs[a];
+          ctr[P.n_alpha] = newc;
+          ctr[P.n_alpha + 1] = best;
+        }
+      }
+      if (run) {
+        it += 1;
+        if (improved) {
+          best = newc;
+          nom = ai + (ai >= nom ? 1 : 0);
+        }
+      }
+      __syncwarp();   // candidate buffers written by one lane are read by the whole group from here on
+    }
+    // -------------------------------------------------------------------- finalise
+    // outputs + final re-linearisation (controller.py:311-314) + active set (636-642)
+    const bool keep_going = run && improved && it < P.max_iter;
+    if (has && !keep_going) {
+      if (run && improved) flg |= TACD_FLAG_MAXITER;
+      const R* nomp = ebuf + nom * kEPW;
+      R* Xo = io.X + (size_t)b * szX;
+      R* Uo = io.U + (size_t)b * szU;
+      for (int w = j; w < XW; w += kG) Xo[w] = nomp[(size_t)w * WS];
+      for (int w = j; w < W - XW; w += kG) {
+        const R ui = nomp[(size_t)(XW + w) * WS];
+        Uo[w] = ui;
+        const int i = w % NU;
+        bool m = false;
+        if (P.has_umin) m = m || isclose_<R>(ui, P.umin[i]);
+        if (P.has_umax) m = m || isclose_<R>(ui, P.umax[i]);
+        io.tight[(size_t)b * szU + w] = m ? 1 : 0;
+      }
+      if (io.A != nullptr || io.Bm != nullptr) {
+        for (int t = j; t < T; t += kG) {
+          R x[NX], u[NU], A[NX * NX], Bm[NX * NU];
+#pragma unroll
+          for (int i = 0; i < NX; ++i) x[i] = nomp[(size_t)(t * NX + i) * WS];
+#pragma unroll
+          for (int i = 0; i < NU; ++i) u[i] = nomp[(size_t)(XW + t * NU + i) * WS];
+          D::jac(P, sA, sB, x, u, A, Bm);
+          if (io.A)
+#pragma unroll
+            for (int i = 0; i < NX * NX; ++i) io.A[((size_t)b * T + t) * NX * NX + i] = A[i];
+          if (io.Bm)
+#pragma unroll
+            for (int i = 0; i < NX * NU; ++i) io.Bm[((size_t)b * T + t) * NX * NU + i] = Bm[i];
+        }
+      }
+      if (j == 0) {
+        io.iters[b] = it;
+        io.flags[b] = (uint8_t)flg;
+        if (io.cost) io.cost[b] = best;
+      }
+      has = false;
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace tacd

@@ -1,0 +1,5 @@
+// fp64 instantiation of the five-lanes-per-element forward kernel
+#include "ilqr_group_launch.cuh"
+namespace tacd {
+template int launch_forward_group<double>(const tacd_problem*, const tacd_forward_io*, void*, size_t, cudaStream_t);
+}

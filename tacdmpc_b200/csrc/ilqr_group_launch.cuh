@@ -1,0 +1,76 @@
+// ilqr_group_launch.cuh — dispatch + launch of the five-lanes-per-element forward kernel.
+// Included by ilqr_group_f32.cu / ilqr_group_f64.cu, which instantiate it for one scalar type each.
+#pragma once
+#include <stdlib.h>
+#include <string.h>
+
+#include "host_common.h"
+#include "ilqr_group.cuh"
+
+namespace tacd {
+
+template <typename R, int NX, int NU, int DYN, bool LSSEP, bool CSH>
+static int run_forward_group(const tacd_problem* p, const tacd_forward_io* io, void* ws, size_t ws_bytes, cudaStream_t s) {
+  auto kernel = ilqr_forward_group<R, NX, NU, DYN, LSSEP, CSH>;
+  const DeviceInfo di = device_info();
+  const size_t cost_b = (size_t)group_cost_words(p->T, NX, NU, p->C_batched, p->Cf_batched, LSSEP ? 1 : 0, DYN == TACD_DYN_LTI) * sizeof(R);
+  const size_t warp_b = (size_t)group_warp_words(p->T, NX, NU) * sizeof(R);
+  if (cost_b + warp_b > (size_t)di.smem_optin) return TACD_EUNSUPPORTED;   // horizon too long for 6 buffers per element
+  int nw = (int)(((size_t)di.smem_optin - cost_b) / warp_b);
+  if (nw > 16) nw = 16;
+  if (const char* e = getenv("TACD_GROUP_WARPS")) { const int v = atoi(e); if (v >= 1 && v < nw) nw = v; }
+  // small batches: spread the elements over all SMs before stacking warps on one
+  const int spread = (p->B + di.sms * kEPW - 1) / (di.sms * kEPW);
+  if (nw > spread) nw = spread < 1 ? 1 : spread;
+  const size_t smem = cost_b + warp_b * nw;
+  if (int rc = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr")) return rc;
+  int grid = (p->B + nw * kEPW - 1) / (nw * kEPW);
+  if (grid > di.sms) grid = di.sms;
+  if (grid < 1) grid = 1;
+  // workspace: [0,4) queue counter | ... | [16K + order, +B*sizeof(R)) initial cost of every element
+  const size_t order_bytes = 16384 + (((size_t)p->B * 4 + 255) / 256) * 256;
+  if (ws_bytes < order_bytes + (size_t)p->B * sizeof(R)) { set_error("forward workspace too small for the initial costs"); return TACD_EWORKSPACE; }
+  R* cost0 = (R*)((char*)ws + order_bytes);
+  FwdPtrs<R> f;
+  memset(&f, 0, sizeof(f));
+  f.x0 = (const R*)io->x0; f.C = (const R*)io->C; f.c = (const R*)io->c; f.Cf = (const R*)io->Cf; f.cf = (const R*)io->cf;
+  f.C_ls = (const R*)io->C_ls; f.c_ls = (const R*)io->c_ls; f.Cf_ls = (const R*)io->Cf_ls; f.cf_ls = (const R*)io->cf_ls;
+  f.xref = (const R*)io->xref; f.uref = (const R*)io->uref; f.Uinit = (const R*)io->Uinit;
+  f.replay_iters = io->replay_iters; f.replay_alpha = io->replay_alpha; f.replay_flags = io->replay_flags;
+  f.X = (R*)io->X; f.U = (R*)io->U; f.A = (R*)io->A; f.Bm = (R*)io->Bm;
+  f.tight = io->tight; f.iters = io->iters; f.alpha_trace = io->alpha_trace; f.flags = io->flags;
+  f.cost = (R*)io->cost; f.cost_trace = (R*)io->cost_trace;
+  f.counter = (unsigned int*)ws;
+  f.order = nullptr;
+  const DevProblem<R> dp = to_dev<R>(p);
+  queue_init<<<1, 1, 0, s>>>(f.counter, 0u);
+  ilqr_init_rollout<R, NX, NU, DYN><<<(p->B + 127) / 128, 128, 0, s>>>(dp, f, cost0);
+  if (int rc = check_cuda(cudaPeekAtLastError(), "ilqr_init_rollout launch")) return rc;
+  kernel<<<grid, nw * 32, smem, s>>>(dp, f, cost0);
+  return check_cuda(cudaPeekAtLastError(), "ilqr_forward_group launch");
+}
+
+// (nx, nu, dyn) combinations with an instantiation: the shipped plugins (n = nx + nu <= kG)
+#define TACD_GROUP_FWD(X) \
+  X(1, 1, TACD_DYN_LTI) X(2, 1, TACD_DYN_LTI) X(4, 1, TACD_DYN_CARTPOLE) X(3, 2, TACD_DYN_UNICYCLE) X(3, 2, TACD_DYN_UNICYCLE_WRAPPED)
+
+// Eligibility: analytic / auto-diff Jacobians of a shipped plugin (finite differences stay on the
+// thread-per-element kernel), at most kG line-search candidates.
+template <typename R>
+int launch_forward_group(const tacd_problem* p, const tacd_forward_io* io, void* ws, size_t ws_bytes, cudaStream_t s) {
+  if (p->jac_mode == TACD_JAC_FINITE_DIFF || p->n_alpha > kG) return TACD_EUNSUPPORTED;
+  if (const char* e = getenv("TACD_FWD_KERNEL")) if (!strcmp(e, "thread")) return TACD_EUNSUPPORTED;
+#define X(NX_, NU_, DYN_)                                                                      \
+  if (p->nx == NX_ && p->nu == NU_ && p->dyn_id == DYN_) {                                     \
+    if (p->ls_cost_shared)                                                                     \
+      return p->C_batched ? run_forward_group<R, NX_, NU_, DYN_, true, false>(p, io, ws, ws_bytes, s)   \
+                          : run_forward_group<R, NX_, NU_, DYN_, true, true>(p, io, ws, ws_bytes, s);   \
+    return p->C_batched ? run_forward_group<R, NX_, NU_, DYN_, false, false>(p, io, ws, ws_bytes, s)    \
+                        : run_forward_group<R, NX_, NU_, DYN_, false, true>(p, io, ws, ws_bytes, s);    \
+  }
+  TACD_GROUP_FWD(X)
+#undef X
+  return TACD_EUNSUPPORTED;
+}
+
+}  // namespace tacd

@@ -162,8 +162,12 @@ def test_empty_batch_and_batch_of_one():
     cm.set_reference(lv["xref"][:1], lv["uref"][:1])
     X, U = mpc(lv["x0"][:1])
     assert X.shape == (1, 21, 4)
-    assert P.rel_err(U.cpu().numpy(), g["U"][:1]).max() <= max(P.TOL[np.dtype(np.float32)], P.elem_tol(g, "U")[0]) or \
-        int(mpc.iters_last[0]) != int(g["iters"][0])
+    # free-running: values are only comparable when the same decisions were taken (tests/parity.py protocol)
+    same = int(mpc.iters_last[0]) == int(g["iters"][0]) and mpc.alpha_trace_last is not None and \
+        np.array_equal(mpc.alpha_trace_last[0, :g["alpha_trace"].shape[1]].cpu().numpy(), g["alpha_trace"][0])
+    assert not same or P.rel_err(U.cpu().numpy(), g["U"][:1]).max() <= max(P.TOL[np.dtype(np.float32)], P.elem_tol(g, "U")[0])
+    scale = max(abs(float(g["cost"][0])), 1.0)
+    assert abs(float(mpc.cost_last[0]) - float(g["cost"][0])) / scale <= 200 * P.TOL[np.dtype(np.float32)]
     cm.set_reference(lv["xref"][:0], lv["uref"][:0])
     X, U = mpc(lv["x0"][:0])
     assert X.shape == (0, 21, 4) and U.shape == (0, 20, 1)

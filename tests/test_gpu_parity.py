@@ -19,8 +19,26 @@ def G():
     return gpu_common
 
 
+@pytest.fixture(params=["group", "thread"])
+def fwd_kernel(request, monkeypatch):
+    """The shipped small plugins have two whole-solve forward kernels: five lanes per element (default,
+    csrc/ilqr_group.cuh) and one thread per element (csrc/ilqr_small.cuh; finite differences, > 5 alphas).
+    TACD_FWD_KERNEL=thread forces the second; both are held to the same parity bar."""
+    if request.param == "thread":
+        monkeypatch.setenv("TACD_FWD_KERNEL", "thread")
+    else:
+        monkeypatch.delenv("TACD_FWD_KERNEL", raising=False)
+    return request.param
+
+
+def _skip_dup(name, fwd_kernel):
+    if fwd_kernel == "thread" and name not in P.SMALL_CASES:
+        pytest.skip("generic CTA-per-element path: no second kernel to select")
+
+
 @pytest.mark.parametrize("name", P.SOLVE_CASES)
-def test_forward_replay_matches_reference(G, name):
+def test_forward_replay_matches_reference(G, name, fwd_kernel):
+    _skip_dup(name, fwd_kernel)
     g = P.load(name)
     spec = P.spec_of(g)
     tol = P.case_tol(g)
@@ -42,7 +60,8 @@ def test_forward_replay_matches_reference(G, name):
 
 
 @pytest.mark.parametrize("name", P.SOLVE_CASES)
-def test_forward_lockstep_decisions(G, name):
+def test_forward_lockstep_decisions(G, name, fwd_kernel):
+    _skip_dup(name, fwd_kernel)
     g = P.load(name)
     spec = P.spec_of(g)
     dt = g["x0"].dtype
@@ -67,8 +86,9 @@ def test_forward_lockstep_decisions(G, name):
 
 
 @pytest.mark.parametrize("name", P.SOLVE_CASES)
-def test_forward_matches_oracle_in_replay(G, oracle, name):
+def test_forward_matches_oracle_in_replay(G, oracle, name, fwd_kernel):
     """CUDA vs CPU oracle on the same inputs and the same decision sequence."""
+    _skip_dup(name, fwd_kernel)
     g = P.load(name)
     spec = P.spec_of(g)
     rp = dict(iters=g["iters"], alpha_trace=g["alpha_trace"], flags=g["flags"])
