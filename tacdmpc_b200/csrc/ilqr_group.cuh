@@ -30,11 +30,12 @@ namespace tacd {
 
 constexpr int kG = 5;              // lanes per element = line-search candidates rolled out together
 constexpr int kEPW = 32 / kG;      // elements per warp
-constexpr int kNBUF = kG + 1;      // trajectory buffers per element
+constexpr int kNBUF = kG + 1;      // trajectory buffers per element (nominal + one per candidate)
+constexpr int kNSLOT = kNBUF + 1;  // + the element's references (x_ref, u_ref) in the same layout
 
 // ---- structured Jacobians ---------------------------------------------------------------------------------
 // F = [A | B] (NX x N) of the shipped plugins in compact form: jc[NJ] holds the entries that depend on (x,u);
-// col() returns column j of F for a run-time j, mulF() returns w' F skipping structural zeros.
+// col() returns column j of F for a run-time j, mulF() accumulates w' F onto o skipping structural zeros.
 // col() is written as chains of single selects on lane-invariant predicates: a nested ?: over j compiles to a
 // divergent branch tree (profiles/r1_forward_group_v1: 60 of 280 instructions per step, 6..20 lanes active).
 template <typename R, int NX, int NU, int DYN>
@@ -50,7 +51,7 @@ struct GDyn {  // LTI: dense F, shared by the CTA in shared memory (row-major NX
   static TACD_DEV void mulF(const DevProblem<R>&, const R* sF, const R (&)[NJ], const R (&w)[NX], R (&o)[N]) {
 #pragma unroll
     for (int k = 0; k < N; ++k) {
-      R s = 0;
+      R s = o[k];
 #pragma unroll
       for (int l = 0; l < NX; ++l) s += w[l] * sF[l * N + k];
       o[k] = s;
@@ -79,11 +80,11 @@ struct GDyn<R, 4, 1, TACD_DYN_CARTPOLE> {
   }
   static TACD_DEV void mulF(const DevProblem<R>& P, const R*, const R (&jc)[6], const R (&w)[4], R (&o)[5]) {
     const R dt = P.dt;
-    o[0] = w[0];
-    o[1] = w[0] * dt + w[1];
-    o[2] = (w[1] * jc[0] + w[2]) + w[3] * jc[2];
-    o[3] = (w[1] * jc[1] + w[2] * dt) + w[3] * jc[3];
-    o[4] = w[1] * jc[4] + w[3] * jc[5];
+    o[0] += w[0];
+    o[1] = (o[1] + w[0] * dt) + w[1];
+    o[2] = ((o[2] + w[1] * jc[0]) + w[2]) + w[3] * jc[2];
+    o[3] = ((o[3] + w[1] * jc[1]) + w[2] * dt) + w[3] * jc[3];
+    o[4] = (o[4] + w[1] * jc[4]) + w[3] * jc[5];
   }
 };
 
@@ -105,11 +106,11 @@ struct GDynUnicycle {
     f[0] = f0; f[1] = f1; f[2] = f2;
   }
   static TACD_DEV void mulF(const DevProblem<R>& P, const R*, const R (&jc)[4], const R (&w)[3], R (&o)[5]) {
-    o[0] = w[0];
-    o[1] = w[1];
-    o[2] = (w[0] * jc[0] + w[1] * jc[1]) + w[2];
-    o[3] = w[0] * jc[2] + w[1] * jc[3];
-    o[4] = w[2] * P.dt;
+    o[0] += w[0];
+    o[1] += w[1];
+    o[2] = ((o[2] + w[0] * jc[0]) + w[1] * jc[1]) + w[2];
+    o[3] = (o[3] + w[0] * jc[2]) + w[1] * jc[3];
+    o[4] += w[2] * P.dt;
   }
 };
 template <typename R> struct GDyn<R, 3, 2, TACD_DYN_UNICYCLE> : GDynUnicycle<R, TACD_DYN_UNICYCLE> {};
@@ -130,7 +131,7 @@ template <typename R> struct alignas(16) Row4 { R v[4]; };
 __host__ __device__ inline int group_traj_words(int T, int nx, int nu) { return (T + 1) * nx + T * nu; }
 // offset of the value-function exchange block (16-byte aligned) and size of the whole region
 __host__ __device__ inline int group_voff_words(int T, int nx, int nu) {
-  return (group_traj_words(T, nx, nu) * kNBUF * kEPW + T * nu * (nx + 1) * kEPW + 3) & ~3;
+  return (group_traj_words(T, nx, nu) * kNSLOT * kEPW + T * nu * (nx + 1) * kEPW + 3) & ~3;
 }
 __host__ __device__ inline int group_warp_words(int T, int nx, int nu) {
   return group_voff_words(T, nx, nu) + kEPW * (nx + 1) * 4;
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(128) ilqr_init_rollout(const DevProblem<R> P, 
 // otherwise it is per-element and read from global memory.  LSSEP: candidates are scored with the separate
 // shared line-search cost (quirk Q4), always staged.
 template <typename R, int NX, int NU, int DYN, bool LSSEP, bool CSH>
-__global__ void __launch_bounds__(512, 1) ilqr_forward_group(const DevProblem<R> P, const FwdPtrs<R> io, const R* cost0) {
+__global__ void __launch_bounds__(384, 1) ilqr_forward_group(const DevProblem<R> P, const FwdPtrs<R> io, const R* cost0) {
   constexpr int N = NX + NU;
   static_assert(N <= kG, "one lane per row of the Q-function");
   static_assert(NX <= 4, "value-function rows travel as one 4-word vector");
@@ -236,7 +237,7 @@ __global__ void __launch_bounds__(512, 1) ilqr_forward_group(const DevProblem<R>
   using GD = GDyn<R, NX, NU, DYN>;
   constexpr int NJ = GD::NJ;
   constexpr unsigned FULL = 0xffffffffu;
-  constexpr int WS = kNBUF * kEPW;             // words between consecutive trajectory words of one buffer
+  constexpr int WS = kNSLOT * kEPW;            // words between consecutive trajectory words of one buffer
   constexpr int CS = (N * N + N + 3) & ~3;     // staged cost stride per step
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int T = P.T;
@@ -253,22 +254,29 @@ __global__ void __launch_bounds__(512, 1) ilqr_forward_group(const DevProblem<R>
   R* sm = reinterpret_cast<R*>(smem_raw);
   const bool ownCf_sh = !P.Cf_batched;
   R *sC = sm, *sCf = sm, *sCl = sm, *sCfl = sm, *sF = sm;
+  bool same_own = true, same_ls = true;
   {
     int o = 0;
     const int NT = blockDim.x;
+    // returns false if this thread saw a step whose cost differs from step 0's
     auto stage_run = [&](R* dst, const R* Cg, const R* cg) {
+      bool same = true;
       for (int i = tid; i < T * CS; i += NT) {
         const int t = i / CS, k = i - t * CS;
-        dst[i] = (k < N * N) ? Cg[t * N * N + k] : (k < N * N + N) ? cg[t * N + (k - N * N)] : (R)0;
+        const R val = (k < N * N) ? Cg[t * N * N + k] : (k < N * N + N) ? cg[t * N + (k - N * N)] : (R)0;
+        const R v0 = (k < N * N) ? Cg[k] : (k < N * N + N) ? cg[k - N * N] : (R)0;
+        same = same && (val == v0);
+        dst[i] = val;
       }
+      return same;
     };
     auto stage_fin = [&](R* dst, const R* Cg, const R* cg) {
       for (int k = tid; k < CS; k += NT) dst[k] = (k < N * N) ? Cg[k] : (k < N * N + N) ? cg[k - N * N] : (R)0;
     };
-    if (CSH) { sC = sm + o; o += T * CS; stage_run(sC, io.C, io.c); }
+    if (CSH) { sC = sm + o; o += T * CS; same_own = stage_run(sC, io.C, io.c); }
     if (ownCf_sh) { sCf = sm + o; o += CS; stage_fin(sCf, io.Cf, io.cf); }
     if (LSSEP) {
-      sCl = sm + o; o += T * CS; stage_run(sCl, io.C_ls, io.c_ls);
+      sCl = sm + o; o += T * CS; same_ls = stage_run(sCl, io.C_ls, io.c_ls);
       sCfl = sm + o; o += CS; stage_fin(sCfl, io.Cf_ls, io.cf_ls);
     }
     if (DYN == TACD_DYN_LTI) {
@@ -280,9 +288,16 @@ __global__ void __launch_bounds__(512, 1) ilqr_forward_group(const DevProblem<R>
     }
     sm += o;
   }
-  __syncthreads();
+  // Time-invariant running cost (C_t, c_t equal for all t — the usual regulation / tracking cost): the line
+  // search keeps it in registers for the whole pass instead of re-reading 30 words per step and lane.  The
+  // shared-memory / L1 data path (128 B/clk per SM, also carrying shuffles and global loads) is what bounds
+  // this kernel (profiles/r1_forward_group_v2: 115 data-path cycles per warp-step against 380 issue slots
+  // shared by four schedulers), and those reads were a third of its traffic.
+  const bool constOwn = __syncthreads_and(same_own ? 1 : 0) != 0 && CSH;
+  const bool constLs = __syncthreads_and(same_ls ? 1 : 0) != 0 && LSSEP;
   R* wreg = sm + (size_t)wid * group_warp_words(T, NX, NU);
-  R* ebuf = wreg + e;                                              // [word][buf][e]
+  R* ebuf = wreg + e;                                              // [word][slot][e], slot kNBUF = references
+  const R* refp = ebuf + kNBUF * kEPW;                             // x_ref word w at refp[w * WS], u_ref after XW words
   R* eK = wreg + (size_t)W * WS + e;                               // [T*NU*NX][e]
   R* ek = eK + (size_t)T * NU * NX * kEPW;                         // [T*NU][e]
   R* myV = wreg + group_voff_words(T, NX, NU) + (size_t)e * (NX + 1) * 4;   // [e][NX+1][4]: rows of V, then v
@@ -304,7 +319,7 @@ __global__ void __launch_bounds__(512, 1) ilqr_forward_group(const DevProblem<R>
   int b = 0, it = 0, nom = 0;
   unsigned flg = 0;
   R best = 0;
-  const R *Cp = io.C, *cp = io.c, *Cfp = io.Cf, *cfp = io.cf, *xr = io.xref, *ur = io.uref;
+  const R *Cp = io.C, *cp = io.c, *Cfp = io.Cf, *cfp = io.cf;
 
   while (true) {
     // ------------------------------------------------------------------ refill (queue pop by the group leader)
@@ -321,12 +336,17 @@ __global__ void __launch_bounds__(512, 1) ilqr_forward_group(const DevProblem<R>
           cp = io.c + (P.C_batched ? (size_t)b * T * N : 0);
           Cfp = io.Cf + (P.Cf_batched ? (size_t)b * N * N : 0);
           cfp = io.cf + (P.Cf_batched ? (size_t)b * N : 0);
-          xr = io.xref + (P.xref_batched ? (size_t)b * szX : 0);
-          ur = io.uref + (P.uref_batched ? (size_t)b * szU : 0);
+          // nominal trajectory (initial rollout) and references: global -> shared, once per element.  The
+          // references are read ten times per step and trip; from global memory (6 lines per request, a
+          // ~15 KB L1 next to 217 KB of shared memory) they were 35 of 123 data-path cycles per warp-step
+          // (profiles/r1_forward_group_v3).
+          const R* xr = io.xref + (P.xref_batched ? (size_t)b * szX : 0);
+          const R* ur = io.uref + (P.uref_batched ? (size_t)b * szU : 0);
           const R* Xi = io.X + (size_t)b * szX;
           const R* Ui = io.Uinit + (size_t)b * szU;
-          for (int w = j; w < XW; w += kG) ebuf[(size_t)w * WS] = Xi[w];
-          for (int w = j; w < W - XW; w += kG) ebuf[(size_t)(XW + w) * WS] = Ui[w];
+          R* rp = ebuf + kNBUF * kEPW;
+          for (int w = j; w < XW; w += kG) { ebuf[(size_t)w * WS] = Xi[w]; rp[(size_t)w * WS] = xr[w]; }
+          for (int w = j; w < W - XW; w += kG) { ebuf[(size_t)(XW + w) * WS] = Ui[w]; rp[(size_t)(XW + w) * WS] = ur[w]; }
           best = cost0[b];
           if (io.alpha_trace)
             for (int w = j; w < P.max_iter; w += kG) io.alpha_trace[(size_t)b * P.max_iter + w] = 0xFF;
@@ -353,7 +373,7 @@ __global__ void __launch_bounds__(512, 1) ilqr_forward_group(const DevProblem<R>
         {
           R tauN[NX];
 #pragma unroll
-          for (int i = 0; i < NX; ++i) tauN[i] = nomp[(size_t)(T * NX + i) * WS] - xr[T * NX + i];
+          for (int i = 0; i < NX; ++i) tauN[i] = nomp[(size_t)(T * NX + i) * WS] - refp[(size_t)(T * NX + i) * WS];
 #pragma unroll
           for (int i = 0; i < NX; ++i) {
             R s = 0;
@@ -374,15 +394,14 @@ __global__ void __launch_bounds__(512, 1) ilqr_forward_group(const DevProblem<R>
         const R* pu = nomp + (size_t)(XW + (T - 1) * NU) * WS;
         R* pK = eK + (size_t)(T - 1) * NU * NX * kEPW;
         R* pk = ek + (size_t)(T - 1) * NU * kEPW;
-        const R* pxr = xr + (T - 1) * NX;
-        const R* pur = ur + (T - 1) * NU;
         const R* pCrow = CSH ? sC + (size_t)(T - 1) * CS + jj * N : Cp + ((size_t)(T - 1) * N + jj) * N;
         const R* pcj = CSH ? sC + (size_t)(T - 1) * CS + N * N + jj : cp + (size_t)(T - 1) * N + jj;
-        R nxr[NX], nur[NU];   // references of the step about to run (prefetched)
+        const R* pxr = refp + (size_t)(T - 1) * NX * WS;
+        const R* pur = refp + (size_t)(XW + (T - 1) * NU) * WS;
+        R Crow[N], cj;        // row jj of C_t and c_t[jj]; loaded once when the running cost is time-invariant
 #pragma unroll
-        for (int i = 0; i < NX; ++i) nxr[i] = pxr[i];
-#pragma unroll
-        for (int i = 0; i < NU; ++i) nur[i] = pur[i];
+        for (int k = 0; k < N; ++k) Crow[k] = pCrow[k];
+        cj = pcj[0];
         int s_in_blk = 0;
         for (int t = T - 1; t >= 0; --t) {
           if (GD::kHasJac && s_in_blk == 0) {
@@ -407,30 +426,28 @@ __global__ void __launch_bounds__(512, 1) ilqr_forward_group(const DevProblem<R>
           s_in_blk = (s_in_blk == kG - 1) ? 0 : s_in_blk + 1;
           R tau[N];
 #pragma unroll
-          for (int i = 0; i < NX; ++i) tau[i] = px[i * WS] - nxr[i];
+          for (int i = 0; i < NX; ++i) tau[i] = px[i * WS] - pxr[i * WS];
 #pragma unroll
-          for (int i = 0; i < NU; ++i) tau[NX + i] = pu[i * WS] - nur[i];
-          if (t > 0) {
-            pxr -= NX; pur -= NU;
-#pragma unroll
-            for (int i = 0; i < NX; ++i) nxr[i] = pxr[i];
-#pragma unroll
-            for (int i = 0; i < NU; ++i) nur[i] = pur[i];
-          }
+          for (int i = 0; i < NU; ++i) tau[NX + i] = pu[i * WS] - pur[i * WS];
           // row jj of C_t, l_j = C_t[j,:] tau + c_t[j]
           R Qrow[N], qj;
           {
+            if (!constOwn) {
+#pragma unroll
+              for (int k = 0; k < N; ++k) Crow[k] = pCrow[k];
+              cj = pcj[0];
+            }
             R s = 0;
 #pragma unroll
             for (int k = 0; k < N; ++k) {
-              Qrow[k] = pCrow[k];
-              s += Qrow[k] * tau[k];
+              Qrow[k] = Crow[k];
+              s += Crow[k] * tau[k];
             }
-            qj = s + pcj[0];
+            qj = s + cj;   // l = C tau + c (cost.py:86-88)
           }
           // row jj of F' V F and element jj of F' v
           {
-            R f[NX], w[NX], o[N];
+            R f[NX], w[NX];
             GD::col(P, sF, jc, jj, f);
 #pragma unroll
             for (int l = 0; l < NX; ++l) {
@@ -439,13 +456,11 @@ __global__ void __launch_bounds__(512, 1) ilqr_forward_group(const DevProblem<R>
               for (int i = 0; i < NX; ++i) s += f[i] * V[i * NX + l];
               w[l] = s;
             }
-            GD::mulF(P, sF, jc, w, o);
+            GD::mulF(P, sF, jc, w, Qrow);          // Qrow = C_t[j,:] + w' F
 #pragma unroll
-            for (int k = 0; k < N; ++k) Qrow[k] += (k >= NX && k == jj) ? o[k] + P.reg : o[k];
-            R s = 0;
+            for (int k = NX; k < N; ++k) Qrow[k] = (k == jj) ? Qrow[k] + P.reg : Qrow[k];   // Q_uu + reg I (controller.py:554)
 #pragma unroll
-            for (int i = 0; i < NX; ++i) s += f[i] * v[i];
-            qj += s;
+            for (int i = 0; i < NX; ++i) qj += f[i] * v[i];
           }
           // gather Q_xu, Q_uu, q_u; every lane computes the gains
           R Qxu[NX * NU], Quu[NU * NU], qu[NU];
@@ -489,23 +504,22 @@ __global__ void __launch_bounds__(512, 1) ilqr_forward_group(const DevProblem<R>
             for (int c = 0; c < 4; ++c) vr.v[c] = 0;
 #pragma unroll
             for (int c = 0; c < NX; ++c) {
-              R a = 0, bb = 0, cc = 0;
+              R acc = Qrow[c];
 #pragma unroll
-              for (int m = 0; m < NU; ++m) {
-                a += Ki[m] * QK[m * NX + c];
-                bb += Ki[m] * Qxu[c * NU + m];
-                cc += Qrow[NX + m] * Kt[m * NX + c];
-              }
-              vr.v[c] = ((Qrow[c] + a) + bb) + cc;
-            }
-            R a = 0, bb = 0, cc = 0;
+              for (int m = 0; m < NU; ++m) acc += Ki[m] * QK[m * NX + c];
 #pragma unroll
-            for (int m = 0; m < NU; ++m) {
-              a += Ki[m] * Qk[m];
-              bb += Ki[m] * qu[m];
-              cc += Qrow[NX + m] * kt[m];
+              for (int m = 0; m < NU; ++m) acc += Ki[m] * Qxu[c * NU + m];
+#pragma unroll
+              for (int m = 0; m < NU; ++m) acc += Qrow[NX + m] * Kt[m * NX + c];
+              vr.v[c] = acc;
             }
-            const R vi = ((qj + a) + bb) + cc;
+            R vi = qj;
+#pragma unroll
+            for (int m = 0; m < NU; ++m) vi += Ki[m] * Qk[m];
+#pragma unroll
+            for (int m = 0; m < NU; ++m) vi += Ki[m] * qu[m];
+#pragma unroll
+            for (int m = 0; m < NU; ++m) vi += Qrow[NX + m] * kt[m];
             if (j < NX) {
               *reinterpret_cast<Row4<R>*>(myV + j * 4) = vr;
               myV[NX * 4 + j] = vi;
@@ -524,7 +538,7 @@ __global__ void __launch_bounds__(512, 1) ilqr_forward_group(const DevProblem<R>
             for (int c = 0; c < NX; ++c) v[c] = r.v[c];
           }
           __syncwarp();
-          px -= NX * WS; pu -= NU * WS; pK -= NU * NX * kEPW; pk -= NU * kEPW;
+          px -= NX * WS; pu -= NU * WS; pxr -= NX * WS; pur -= NU * WS; pK -= NU * NX * kEPW; pk -= NU * kEPW;
           pCrow -= CSH ? CS : N * N; pcj -= CSH ? CS : N;
         }
       }
@@ -543,18 +557,16 @@ __global__ void __launch_bounds__(512, 1) ilqr_forward_group(const DevProblem<R>
         R* cu = cbp + (size_t)XW * WS;           // candidate U_t
         const R* pK = eK;
         const R* pk = ek;
-        const R* pxr = xr;
-        const R* pur = ur;
         const R* pCl = sCl;                      // staged line-search cost of step t
         const R* pCo = CSH ? sC : Cp;            // own cost of step t (staged block or global C_t)
         const R* pco = cp;
-        R nxr[NX], nur[NU];
-#pragma unroll
-        for (int i = 0; i < NX; ++i) nxr[i] = pxr[i];
-#pragma unroll
-        for (int i = 0; i < NU; ++i) nur[i] = pur[i];
+        const R* pxr = refp;
+        const R* pur = refp + (size_t)XW * WS;
+        R Ct[N * N], ct[N], Cl[LSSEP ? N * N : 1], cl[LSSEP ? N : 1];
+        if (CSH) load_cost_vec<R, N>(pCo, Ct, ct);
+        if constexpr (LSSEP) load_cost_vec<R, N>(pCl, Cl, cl);
         for (int t = 0; t < T; ++t) {
-          R u[NU], tau[N], dx[NX], Ct[N * N], ct[N], xn[NX];
+          R u[NU], tau[N], dx[NX], xn[NX];
 #pragma unroll
           for (int k = 0; k < NX; ++k) dx[k] = x[k] - px[k * WS];
 #pragma unroll
@@ -565,25 +577,17 @@ __global__ void __launch_bounds__(512, 1) ilqr_forward_group(const DevProblem<R>
             R ui = pu[i * WS] + (alpha * pk[i * kEPW] + s);
             ui = tmin<R>(tmax<R>(ui, ulo[i]), uhi[i]);
             u[i] = ui;
-            tau[NX + i] = ui - nur[i];
+            tau[NX + i] = ui - pur[i * WS];
           }
 #pragma unroll
-          for (int i = 0; i < NX; ++i) tau[i] = x[i] - nxr[i];
-          // prefetch the next step's references (x_ref has T+1 rows, u_ref T)
-          pxr += NX; pur += NU;
-#pragma unroll
-          for (int i = 0; i < NX; ++i) nxr[i] = pxr[i];
-          if (t + 1 < T) {
-#pragma unroll
-            for (int i = 0; i < NU; ++i) nur[i] = pur[i];
-          }
-          if (LSSEP) {
-            load_cost_vec<R, N>(pCl, Ct, ct);
-            quad_terms<R, N>(Ct, ct, tau, q1, l1);
+          for (int i = 0; i < NX; ++i) tau[i] = x[i] - pxr[i * WS];
+          if constexpr (LSSEP) {
+            if (!constLs) load_cost_vec<R, N>(pCl, Cl, cl);
+            quad_terms<R, N>(Cl, cl, tau, q1, l1);
             pCl += CS;
           }
           if (CSH) {
-            load_cost_vec<R, N>(pCo, Ct, ct);
+            if (!constOwn) load_cost_vec<R, N>(pCo, Ct, ct);
             pCo += CS;
           } else {
 #pragma unroll
@@ -602,11 +606,12 @@ __global__ void __launch_bounds__(512, 1) ilqr_forward_group(const DevProblem<R>
           }
 #pragma unroll
           for (int i = 0; i < NX; ++i) x[i] = xn[i];
-          px += NX * WS; pu += NU * WS; cx += NX * WS; cu += NU * WS; pK += NU * NX * kEPW; pk += NU * kEPW;
+          px += NX * WS; pu += NU * WS; pxr += NX * WS; pur += NU * WS; cx += NX * WS; cu += NU * WS;
+          pK += NU * NX * kEPW; pk += NU * kEPW;
         }
         R tauN[NX];
 #pragma unroll
-        for (int i = 0; i < NX; ++i) tauN[i] = x[i] - nxr[i];
+        for (int i = 0; i < NX; ++i) tauN[i] = x[i] - pxr[i * WS];
         R qN = 0, lN = 0, qN2 = 0, lN2 = 0;
 #pragma unroll
         for (int i = 0; i < NX; ++i) {

@@ -17,7 +17,7 @@ static int run_forward_group(const tacd_problem* p, const tacd_forward_io* io, v
   const size_t warp_b = (size_t)group_warp_words(p->T, NX, NU) * sizeof(R);
   if (cost_b + warp_b > (size_t)di.smem_optin) return TACD_EUNSUPPORTED;   // horizon too long for 6 buffers per element
   int nw = (int)(((size_t)di.smem_optin - cost_b) / warp_b);
-  if (nw > 16) nw = 16;
+  if (nw > 12) nw = 12;   // __launch_bounds__(384, 1)
   if (const char* e = getenv("TACD_GROUP_WARPS")) { const int v = atoi(e); if (v >= 1 && v < nw) nw = v; }
   // small batches: spread the elements over all SMs before stacking warps on one
   const int spread = (p->B + di.sms * kEPW - 1) / (di.sms * kEPW);

