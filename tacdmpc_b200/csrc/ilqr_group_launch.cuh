@@ -44,7 +44,18 @@ static int run_forward_group(const tacd_problem* p, const tacd_forward_io* io, v
   f.order = nullptr;
   const DevProblem<R> dp = to_dev<R>(p);
   queue_init<<<1, 1, 0, s>>>(f.counter, 0u);
-  ilqr_init_rollout<R, NX, NU, DYN><<<(p->B + 127) / 128, 128, 0, s>>>(dp, f, cost0);
+  {
+    auto init = ilqr_init_rollout<R, NX, NU, DYN>;
+    // a horizon whose tile does not fit goes to the thread-per-element kernel
+    const size_t tile_b = init_warp_words(p->T, NX, NU, p->C_batched) * sizeof(R);
+    // one warp per CTA: the finest granularity for the last wave (2048 warps over 148 SMs at B = 65536)
+    if (tile_b > (size_t)di.smem_optin) return TACD_EUNSUPPORTED;
+    int iw = 1;
+    if (const char* e = getenv("TACD_INIT_WARPS")) { const int v = atoi(e); if (v >= 1 && v <= 4 && tile_b * v <= (size_t)di.smem_optin) iw = v; }
+    if (int rc = check_cuda(cudaFuncSetAttribute(init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(tile_b * iw)), "smem attr")) return rc;
+    const int nwarp = (p->B + 31) / 32;
+    init<<<(nwarp + iw - 1) / iw, iw * 32, tile_b * iw, s>>>(dp, f, cost0);
+  }
   if (int rc = check_cuda(cudaPeekAtLastError(), "ilqr_init_rollout launch")) return rc;
   kernel<<<grid, nw * 32, smem, s>>>(dp, f, cost0);
   return check_cuda(cudaPeekAtLastError(), "ilqr_forward_group launch");
