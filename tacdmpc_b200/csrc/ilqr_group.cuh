@@ -131,7 +131,7 @@ template <typename R> struct alignas(16) Row4 { R v[4]; };
 __host__ __device__ inline int group_traj_words(int T, int nx, int nu) { return (T + 1) * nx + T * nu; }
 // offset of the value-function exchange block (16-byte aligned) and size of the whole region
 __host__ __device__ inline int group_voff_words(int T, int nx, int nu) {
-  return (group_traj_words(T, nx, nu) * kNSLOT * kEPW + T * nu * (nx + 1) * kEPW + 3) & ~3;
+  return (group_traj_words(T, nx, nu) * kNSLOT * kEPW + 3) & ~3;
 }
 __host__ __device__ inline int group_warp_words(int T, int nx, int nu) {
   return group_voff_words(T, nx, nu) + kEPW * (nx + 1) * 4;
@@ -368,8 +368,10 @@ __global__ void __launch_bounds__(384, 1) ilqr_forward_group(const DevProblem<R>
   R* wreg = sm + (size_t)wid * group_warp_words(T, NX, NU);
   R* ebuf = wreg + e;                                              // [word][slot][e], slot kNBUF = references
   const R* refp = ebuf + kNBUF * kEPW;                             // x_ref word w at refp[w * WS], u_ref after XW words
-  R* eK = wreg + (size_t)W * WS + e;                               // [T*NU*NX][e]
-  R* ek = eK + (size_t)T * NU * NX * kEPW;                         // [T*NU][e]
+  // The gains have no storage of their own: between the reverse pass that produces them and the line search
+  // that consumes them the five non-nominal buffers are dead, and candidate a overwrites X_{t+1} / U_t of its
+  // buffer only at the end of step t.  K_t[m][:] lives in the X_{t+1} slot of the m-th dead buffer, k_t in
+  // the U_t slot of the first one; the line search reads them at the top of step t.
   R* myV = wreg + group_voff_words(T, NX, NU) + (size_t)e * (NX + 1) * 4;   // [e][NX+1][4]: rows of V, then v
   // Dyn<> (LTI) wants A and B separately: straight from global memory (uniform, cached)
   const R* sA = P.dyn_A;
@@ -433,6 +435,9 @@ __global__ void __launch_bounds__(384, 1) ilqr_forward_group(const DevProblem<R>
     bool improved = false;
     if (__ballot_sync(FULL, run) != 0u) {
       const R* nomp = ebuf + nom * kEPW;   // nominal trajectory: word w at nomp[w * WS]
+      int dK[NU];                          // offset of the m-th non-nominal buffer relative to the nominal one
+#pragma unroll
+      for (int m = 0; m < NU; ++m) dK[m] = (m + (m >= nom ? 1 : 0) - nom) * kEPW;
       // terminal cost of this element: staged or global (generic pointers; read twice per pass)
       const R* Cfo = ownCf_sh ? sCf : Cfp;
       const R* cfo = ownCf_sh ? sCf + N * N : cfp;
@@ -462,8 +467,8 @@ __global__ void __launch_bounds__(384, 1) ilqr_forward_group(const DevProblem<R>
         // running pointers of step t (all decremented once per step)
         const R* px = nomp + (size_t)(T - 1) * NX * WS;
         const R* pu = nomp + (size_t)(XW + (T - 1) * NU) * WS;
-        R* pK = eK + (size_t)(T - 1) * NU * NX * kEPW;
-        R* pk = ek + (size_t)(T - 1) * NU * kEPW;
+        R* gx = const_cast<R*>(px) + NX * WS;   // X_{t+1} slot (nominal buffer); + dK[m] = m-th dead buffer
+        R* gu = const_cast<R*>(pu);             // U_t slot
         const R* pCrow = CSH ? sC + (size_t)(T - 1) * CS + jj * N : Cp + ((size_t)(T - 1) * N + jj) * N;
         const R* pcj = CSH ? sC + (size_t)(T - 1) * CS + N * N + jj : cp + (size_t)(T - 1) * N + jj;
         const R* pxr = refp + (size_t)(T - 1) * NX * WS;
@@ -547,9 +552,9 @@ __global__ void __launch_bounds__(384, 1) ilqr_forward_group(const DevProblem<R>
           if (run && npd) flg |= TACD_FLAG_NONPD;
           if (j < NX) {
 #pragma unroll
-            for (int m = 0; m < NU; ++m) pK[(m * NX + j) * kEPW] = pick<NX, R>(&Kt[m * NX], j);
+            for (int m = 0; m < NU; ++m) gx[dK[m] + j * WS] = pick<NX, R>(&Kt[m * NX], j);
           } else if (j < N) {
-            pk[(j - NX) * kEPW] = pick<NU, R>(kt, j - NX);
+            gu[dK[0] + (j - NX) * WS] = pick<NU, R>(kt, j - NX);
           }
           // row i = j of the value update (controller.py:573-574), association as value_update<>
           {
@@ -608,7 +613,7 @@ __global__ void __launch_bounds__(384, 1) ilqr_forward_group(const DevProblem<R>
             for (int c = 0; c < NX; ++c) v[c] = r.v[c];
           }
           __syncwarp();
-          px -= NX * WS; pu -= NU * WS; pxr -= NX * WS; pur -= NU * WS; pK -= NU * NX * kEPW; pk -= NU * kEPW;
+          px -= NX * WS; pu -= NU * WS; pxr -= NX * WS; pur -= NU * WS; gx -= NX * WS; gu -= NU * WS;
           pCrow -= CSH ? CS : N * N; pcj -= CSH ? CS : N;
         }
       }
@@ -625,8 +630,6 @@ __global__ void __launch_bounds__(384, 1) ilqr_forward_group(const DevProblem<R>
         const R* pu = nomp + (size_t)XW * WS;
         R* cx = cbp + NX * WS;                   // candidate X_{t+1}
         R* cu = cbp + (size_t)XW * WS;           // candidate U_t
-        const R* pK = eK;
-        const R* pk = ek;
         const R* pCl = sCl;                      // staged line-search cost of step t
         const R* pCo = CSH ? sC : Cp;            // own cost of step t (staged block or global C_t)
         const R* pco = cp;
@@ -643,8 +646,8 @@ __global__ void __launch_bounds__(384, 1) ilqr_forward_group(const DevProblem<R>
           for (int i = 0; i < NU; ++i) {
             R s = 0;
 #pragma unroll
-            for (int k = 0; k < NX; ++k) s += pK[(i * NX + k) * kEPW] * dx[k];
-            R ui = pu[i * WS] + (alpha * pk[i * kEPW] + s);
+            for (int k = 0; k < NX; ++k) s += px[NX * WS + dK[i] + k * WS] * dx[k];
+            R ui = pu[i * WS] + (alpha * pu[dK[0] + i * WS] + s);
             ui = tmin<R>(tmax<R>(ui, ulo[i]), uhi[i]);
             u[i] = ui;
             tau[NX + i] = ui - pur[i * WS];
@@ -668,6 +671,7 @@ __global__ void __launch_bounds__(384, 1) ilqr_forward_group(const DevProblem<R>
           }
           quad_terms<R, N>(Ct, ct, tau, q2, l2);
           D::step(P, sA, sB, x, u, xn);
+          __syncwarp();   // every lane of the group has read K_t, k_t from the slots overwritten below
           if (valid) {
 #pragma unroll
             for (int i = 0; i < NU; ++i) cu[i * WS] = u[i];
@@ -677,7 +681,6 @@ __global__ void __launch_bounds__(384, 1) ilqr_forward_group(const DevProblem<R>
 #pragma unroll
           for (int i = 0; i < NX; ++i) x[i] = xn[i];
           px += NX * WS; pu += NU * WS; pxr += NX * WS; pur += NU * WS; cx += NX * WS; cu += NU * WS;
-          pK += NU * NX * kEPW; pk += NU * kEPW;
         }
         R tauN[NX];
 #pragma unroll

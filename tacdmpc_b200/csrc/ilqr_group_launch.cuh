@@ -44,6 +44,18 @@ static int run_forward_group(const tacd_problem* p, const tacd_forward_io* io, v
   f.order = nullptr;
   const DevProblem<R> dp = to_dev<R>(p);
   queue_init<<<1, 1, 0, s>>>(f.counter, 0u);
+  // longest-first queue order (ilqr_small.cuh): with more than one wave of elements the long chains must
+  // not be popped last (profiles/r1_forward_group_v4: schedulers idle 13 % of the kernel in the tail)
+  if ((long)p->B > (long)grid * nw * kEPW && !getenv("TACD_NO_LPT")) {
+    unsigned int* hist = (unsigned int*)((char*)ws + 256);
+    int32_t* order = (int32_t*)((char*)ws + 16384);
+    if (int rc = check_cuda(cudaMemsetAsync(hist, 0, kLptBuckets * sizeof(unsigned int), s), "memset hist")) return rc;
+    const int g2 = di.sms * 2 < (p->B + 255) / 256 ? di.sms * 2 : (p->B + 255) / 256;
+    lpt_histogram<R><<<g2, 256, 0, s>>>(p->B, p->T, NX, NX + NU, p->C_batched, p->xref_batched, (const R*)io->x0, (const R*)io->xref, (const R*)io->C, hist);
+    lpt_scan<<<1, 1024, 0, s>>>(hist);
+    lpt_scatter<R><<<g2, 256, 0, s>>>(p->B, p->T, NX, NX + NU, p->C_batched, p->xref_batched, (const R*)io->x0, (const R*)io->xref, (const R*)io->C, hist, order);
+    f.order = order;
+  }
   {
     auto init = ilqr_init_rollout<R, NX, NU, DYN>;
     // a horizon whose tile does not fit goes to the thread-per-element kernel
