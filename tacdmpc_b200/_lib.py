@@ -20,6 +20,7 @@ _VP = C.c_void_p
 _SIGS = {
     "tacd_abi_version": (C.c_int, []),
     "tacd_last_error": (C.c_char_p, []),
+    "tacd_kernel_launches": (C.c_ulonglong, []),
     "tacd_forward_workspace_bytes": (C.c_size_t, [C.POINTER(_abi.Problem)]),
     "tacd_backward_workspace_bytes": (C.c_size_t, [C.POINTER(_abi.Problem)]),
     "tacd_ilqr_forward": (C.c_int, [C.POINTER(_abi.Problem), C.POINTER(_abi.ForwardIO), _VP, C.c_size_t, _VP]),

@@ -3,6 +3,8 @@
 // CTA-per-element kernels, error reporting.  Nothing here synchronises the host.
 #include <string.h>
 
+#include <atomic>
+
 #include "host_common.h"
 
 namespace tacd {
@@ -15,6 +17,10 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+// number of kernels of this library enqueued by the process (diagnostic; read by bench.py for gpu_launches)
+static std::atomic<unsigned long long> g_launches{0};
+void note_launches(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
 int check_cuda(cudaError_t e, const char* what) {
   if (e == cudaSuccess) return TACD_OK;
@@ -57,6 +63,7 @@ extern "C" {
 
 int tacd_abi_version(void) { return TACD_ABI_VERSION; }
 const char* tacd_last_error(void) { return g_err; }
+unsigned long long tacd_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }
 
 // forward workspace: [0, kFwdHead) queue counter + bucket counters + longest-first order of the
 // thread-per-element kernel; the generic kernel's per-CTA slices follow

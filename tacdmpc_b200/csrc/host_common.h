@@ -11,6 +11,7 @@ namespace tacd {
 
 void set_error(const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);
+void note_launches(int n);
 
 struct DeviceInfo { int sms; int smem_optin; };
 DeviceInfo device_info();

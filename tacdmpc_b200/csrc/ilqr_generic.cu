@@ -548,6 +548,7 @@ int launch_forward_generic(const tacd_problem* p, const tacd_forward_io* io, voi
   auto kernel = ilqr_forward_generic<R>;
   if (int rc = prep_smem(kernel, smem)) return rc;
   kernel<<<grid, kGenThreads, smem, s>>>(to_dev<R>(p), dims_of<R>(p), fwd_ptrs<R>(io), (R*)ws, slice);
+  note_launches(1);
   return check_cuda(cudaPeekAtLastError(), "ilqr_forward_generic launch");
 }
 
@@ -572,6 +573,7 @@ int launch_backward_generic(const tacd_problem* p, const tacd_backward_io* io, v
   f.grad_C = (R*)io->grad_C; f.grad_c = (R*)io->grad_c; f.grad_Cf = (R*)io->grad_Cf; f.grad_cf = (R*)io->grad_cf;
   f.grad_x0 = (R*)io->grad_x0; f.grad_xref = (R*)io->grad_xref; f.grad_uref = (R*)io->grad_uref; f.dX = (R*)io->dX; f.dU = (R*)io->dU;
   kernel<<<grid, kGenThreads, smem, s>>>(to_dev<R>(p), dims_of<R>(p), f, (R*)ws, slice);
+  note_launches(1);
   return check_cuda(cudaPeekAtLastError(), "ilqr_backward_generic launch");
 }
 
@@ -593,6 +595,7 @@ static int run_rollout(const tacd_problem* p, const void* x0, const void* U, voi
   const size_t smem = gen_smem_bytes<R>(p->nx, p->nu);
   if (int rc = prep_smem(kernel, smem)) return rc;
   kernel<<<gen_grid(p), kGenThreads, smem, s>>>(to_dev<R>(p), dims_of<R>(p), (const R*)x0, (const R*)U, (R*)X);
+  note_launches(1);
   return check_cuda(cudaPeekAtLastError(), "stage_rollout launch");
 }
 template <typename R>
@@ -601,6 +604,7 @@ static int run_linearize(const tacd_problem* p, const void* X, const void* U, vo
   int grid = (int)((total + kGenThreads - 1) / kGenThreads);
   if (grid > 148 * 16) grid = 148 * 16;
   stage_linearize<R><<<grid, kGenThreads, 0, s>>>(to_dev<R>(p), dims_of<R>(p), (const R*)X, (const R*)U, (R*)A, (R*)Bm);
+  note_launches(1);
   return check_cuda(cudaPeekAtLastError(), "stage_linearize launch");
 }
 template <typename R>
@@ -611,6 +615,7 @@ static int run_objective(const tacd_problem* p, const void* X, const void* U, co
   if (int rc = prep_smem(kernel, smem)) return rc;
   kernel<<<gen_grid(p), kGenThreads, smem, s>>>(to_dev<R>(p), dims_of<R>(p), (const R*)X, (const R*)U, (const R*)C, (const R*)c, (const R*)Cf,
                                                  (const R*)cf, (const R*)xref, (const R*)uref, (R*)cost);
+  note_launches(1);
   return check_cuda(cudaPeekAtLastError(), "stage_objective launch");
 }
 template <typename R>
@@ -621,6 +626,7 @@ static int run_riccati(const tacd_problem* p, const void* A, const void* Bm, con
   if (int rc = prep_smem(kernel, smem)) return rc;
   kernel<<<gen_grid(p), kGenThreads, smem, s>>>(to_dev<R>(p), dims_of<R>(p), (const R*)A, (const R*)Bm, (const R*)lx, (const R*)lu, (const R*)lxx,
                                                  (const R*)lxu, (const R*)luu, (const R*)lxN, (const R*)lxxN, (R*)K, (R*)k, flags);
+  note_launches(1);
   return check_cuda(cudaPeekAtLastError(), "stage_riccati launch");
 }
 template <typename R>
@@ -633,6 +639,7 @@ static int run_linesearch(const tacd_problem* p, const void* x0, const void* X, 
   kernel<<<gen_grid(p), kGenThreads, smem, s>>>(to_dev<R>(p), dims_of<R>(p), (const R*)x0, (const R*)X, (const R*)U, (const R*)K, (const R*)k,
                                                  (const R*)C, (const R*)c, (const R*)Cf, (const R*)cf, (const R*)xref, (const R*)uref, (R*)Xc,
                                                  (R*)Uc, (R*)costs);
+  note_launches(1);
   return check_cuda(cudaPeekAtLastError(), "stage_linesearch launch");
 }
 
@@ -687,6 +694,7 @@ int tacd_pnqp(int32_t dtype, int32_t N, int32_t m, const void* H, const void* q,
   const int grid = (N + 127) / 128;
   if (dtype == TACD_F32) stage_pnqp<float><<<grid, 128, 0, s>>>(N, m, (const float*)H, (const float*)q, (const float*)lo, (const float*)hi, (float*)x, iters, (float*)scratch);
   else stage_pnqp<double><<<grid, 128, 0, s>>>(N, m, (const double*)H, (const double*)q, (const double*)lo, (const double*)hi, (double*)x, iters, (double*)scratch);
+  note_launches(1);
   int rc = check_cuda(cudaPeekAtLastError(), "stage_pnqp launch");
   cudaFreeAsync(scratch, s);
   return rc;

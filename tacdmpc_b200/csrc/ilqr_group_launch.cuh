@@ -44,6 +44,7 @@ static int run_forward_group(const tacd_problem* p, const tacd_forward_io* io, v
   f.order = nullptr;
   const DevProblem<R> dp = to_dev<R>(p);
   queue_init<<<1, 1, 0, s>>>(f.counter, 0u);
+  note_launches(1);
   // longest-first queue order (ilqr_small.cuh): with more than one wave of elements the long chains must
   // not be popped last (profiles/r1_forward_group_v4: schedulers idle 13 % of the kernel in the tail)
   if ((long)p->B > (long)grid * nw * kEPW && !getenv("TACD_NO_LPT")) {
@@ -52,8 +53,11 @@ static int run_forward_group(const tacd_problem* p, const tacd_forward_io* io, v
     if (int rc = check_cuda(cudaMemsetAsync(hist, 0, kLptBuckets * sizeof(unsigned int), s), "memset hist")) return rc;
     const int g2 = di.sms * 2 < (p->B + 255) / 256 ? di.sms * 2 : (p->B + 255) / 256;
     lpt_histogram<R><<<g2, 256, 0, s>>>(p->B, p->T, NX, NX + NU, p->C_batched, p->xref_batched, (const R*)io->x0, (const R*)io->xref, (const R*)io->C, hist);
+    note_launches(1);
     lpt_scan<<<1, 1024, 0, s>>>(hist);
+    note_launches(1);
     lpt_scatter<R><<<g2, 256, 0, s>>>(p->B, p->T, NX, NX + NU, p->C_batched, p->xref_batched, (const R*)io->x0, (const R*)io->xref, (const R*)io->C, hist, order);
+    note_launches(1);
     f.order = order;
   }
   {
@@ -67,9 +71,11 @@ static int run_forward_group(const tacd_problem* p, const tacd_forward_io* io, v
     if (int rc = check_cuda(cudaFuncSetAttribute(init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(tile_b * iw)), "smem attr")) return rc;
     const int nwarp = (p->B + 31) / 32;
     init<<<(nwarp + iw - 1) / iw, iw * 32, tile_b * iw, s>>>(dp, f, cost0);
+    note_launches(1);
   }
   if (int rc = check_cuda(cudaPeekAtLastError(), "ilqr_init_rollout launch")) return rc;
   kernel<<<grid, nw * 32, smem, s>>>(dp, f, cost0);
+  note_launches(1);
   return check_cuda(cudaPeekAtLastError(), "ilqr_forward_group launch");
 }
 

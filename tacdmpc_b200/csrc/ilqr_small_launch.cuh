@@ -67,6 +67,7 @@ static int run_forward_small(const tacd_problem* p, const tacd_forward_io* io, v
     if (ws_bytes >= need) f.cscratch = (R*)((char*)ws + order_bytes);
   }
   queue_init<<<1, 1, 0, s>>>(f.counter, first_wave);
+  note_launches(1);
   const bool lpt = (unsigned)p->B > lanes && !getenv("TACD_NO_LPT");   // more than one wave: order matters
   if (lpt) {
     unsigned int* hist = (unsigned int*)((char*)ws + 256);
@@ -74,11 +75,15 @@ static int run_forward_small(const tacd_problem* p, const tacd_forward_io* io, v
     if (int rc = check_cuda(cudaMemsetAsync(hist, 0, kLptBuckets * sizeof(unsigned int), s), "memset hist")) return rc;
     const int g2 = di.sms * 2 < (p->B + 255) / 256 ? di.sms * 2 : (p->B + 255) / 256;
     lpt_histogram<R><<<g2, 256, 0, s>>>(p->B, p->T, NX, NX + NU, p->C_batched, p->xref_batched, (const R*)io->x0, (const R*)io->xref, (const R*)io->C, hist);
+    note_launches(1);
     lpt_scan<<<1, 1024, 0, s>>>(hist);
+    note_launches(1);
     lpt_scatter<R><<<g2, 256, 0, s>>>(p->B, p->T, NX, NX + NU, p->C_batched, p->xref_batched, (const R*)io->x0, (const R*)io->xref, (const R*)io->C, hist, order);
+    note_launches(1);
     f.order = order;
   }
   kernel<<<grid, nt, smem, s>>>(to_dev<R>(p), f);
+  note_launches(1);
   return check_cuda(cudaPeekAtLastError(), "ilqr_forward_small launch");
 }
 
@@ -125,9 +130,11 @@ static int run_backward_small(const tacd_problem* p, const tacd_backward_io* io,
   f.grad_x0 = (R*)io->grad_x0; f.grad_xref = (R*)io->grad_xref; f.grad_uref = (R*)io->grad_uref; f.dX = (R*)io->dX; f.dU = (R*)io->dU;
   const DevProblem<R> dp = to_dev<R>(p);
   kernel<<<grid, nt, smem, s>>>(dp, f, partials, reduce ? 1 : 0);
+  note_launches(1);
   if (int rc = check_cuda(cudaPeekAtLastError(), "ilqr_backward_small launch")) return rc;
   if (reduce) {
     reduce_shared_grads<R, NX, NU><<<(nacc + 127) / 128, 128, 0, s>>>(dp, f, partials, grid);
+    note_launches(1);
     return check_cuda(cudaPeekAtLastError(), "reduce_shared_grads launch");
   }
   return TACD_OK;
