@@ -56,12 +56,15 @@ def make_inputs(B, layout, seed, torch):
     Cf[:NX, :NX] = 10 * C[0, :NX, :NX]
     cf = torch.zeros(N)
     x0 = torch.tensor([0.0, 0.0, 0.2, 0.0]) + torch.randn(B, NX, generator=g) * torch.tensor([0.5, 0.5, 0.2, 0.2])
-    if layout == "per_element":
+    if layout in ("per_element", "diag"):
         s = 0.5 + torch.rand(B, 1, 1, 1, generator=g)
         C = (C.unsqueeze(0) * s).contiguous()
         c = c.unsqueeze(0).expand(B, T, N).contiguous()
         Cf = (Cf.unsqueeze(0) * s[:, 0]).contiguous()
         cf = cf.unsqueeze(0).expand(B, N).contiguous()
+        if layout == "diag":   # the same per-element costs as compact diagonals (ActorMPC layout)
+            C = torch.diagonal(C, dim1=-2, dim2=-1).contiguous()
+            Cf = torch.diagonal(Cf, dim1=-2, dim2=-1).contiguous()
     return dict(x0=x0, C=C, c=c, Cf=Cf, cf=cf, xref=torch.zeros(B, T + 1, NX), uref=torch.zeros(B, T, NU),
                 Uinit=torch.zeros(B, T, NU))
 
@@ -77,6 +80,10 @@ def algorithmic_bytes(layout):
         fwd += 4 * cost
         bwd_r += 4 * T * N * N
         bwd_w += 4 * cost
+    if layout == "diag":
+        fwd += 4 * (2 * T * N + 2 * N)
+        bwd_r += 4 * T * N
+        bwd_w += 4 * (2 * T * N + 2 * N)
     return fwd, bwd_r + bwd_w
 
 
@@ -157,16 +164,17 @@ def cpu_port_run(layout, seconds_target, threads=None):
                 u_min=[-20.0], u_max=[20.0])
 
     def run(Bs):
-        inp = {k: v.numpy() for k, v in make_inputs(Bs, layout, 0, torch).items()}
+        # the oracle restates the reference, which only knows dense costs: 'diag' is timed as 'per_element'
+        inp = {k: v.numpy() for k, v in make_inputs(Bs, "per_element" if layout == "diag" else layout, 0, torch).items()}
         ls = None
-        if layout == "per_element":
+        if layout != "shared":
             ls = (inp["C"][0], inp["c"][0], inp["Cf"][0], inp["cf"][0])
         t0 = time.perf_counter()
         f = orc.forward(spec, inp["x0"], inp["C"], inp["c"], inp["Cf"], inp["cf"], inp["xref"], inp["uref"], inp["Uinit"],
                         ls_cost=ls, want_AB=False, want_trace=False)
         gU = np.zeros_like(f["U"]); gU[:, 0] = 1
         orc.backward(spec, f["X"], f["U"], inp["C"], inp["xref"], inp["uref"], f["tight"], np.zeros_like(f["X"]), gU,
-                     Cf_batched=int(layout == "per_element"),
+                     Cf_batched=int(layout != "shared"),
                      want=("grad_C", "grad_c", "grad_Cf", "grad_cf", "grad_x0", "grad_xref", "grad_uref"))
         return time.perf_counter() - t0, float(f["iters"].mean())
 
@@ -183,7 +191,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--layout", default="shared", choices=["shared", "per_element"])
+    ap.add_argument("--layout", default="shared", choices=["shared", "per_element", "diag"])
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="solves per GPU")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -193,7 +201,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     W = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     config = {"workload": f"cartpole regulation iLQR nx=4 nu=1 T=20 analytic Jacobians, B={args.batch} per GPU "
-                          f"(BASELINE configs[1] / SURVEY 8d config 2{'a shared C' if args.layout == 'shared' else 'b per-element C'})",
+                          f"(BASELINE configs[1] / SURVEY 8d config 2{dict(shared='a shared C', per_element='b per-element C', diag='b per-element diagonal C in compact form (8f N1)')[args.layout]})",
               "cost_layout": args.layout, "B_per_gpu": args.batch, "T": T, "nx": NX, "nu": NU, "max_iter": 40,
               "loss": "U*[:,0].sum(), all 7 inputs require grad", "sharding": f"batch x{world}, no data-path collective",
               "l2": "flushed (256 MiB write) between timed steps"}
@@ -240,14 +248,15 @@ def main():
     spec = ops.Spec(nx=NX, nu=NU, T=T, dt=DT, dyn_id=f.dyn_id, dyn_params=f.params, reg_eps=1e-6, max_iter=40,
                     u_min=[-20.0], u_max=[20.0])
     ls = None
-    if args.layout == "per_element":
+    diag = args.layout == "diag"
+    if args.layout != "shared":
         # quirk Q4: every rank's line search uses GLOBAL element 0's cost
         ls0 = torch.cat([d["C"][0].reshape(-1), d["c"][0].reshape(-1), d["Cf"][0].reshape(-1), d["cf"][0].reshape(-1)])
         if world > 1:
             dist.broadcast(ls0, src=0)
         o = 0
         ls = []
-        for shp in ((T, N, N), (T, N), (N, N), (N,)):
+        for shp in (((T, N), (T, N), (N,), (N,)) if diag else ((T, N, N), (T, N), (N, N), (N,))):
             k = 1
             for s_ in shp:
                 k *= s_
@@ -262,9 +271,9 @@ def main():
 
     def step_device():
         fw = ops.ilqr_forward(spec, d["x0"], d["C"], d["c"], d["Cf"], d["cf"], d["xref"], d["uref"], d["Uinit"], ls_cost=ls,
-                              want_trace=False)
+                              want_trace=False, C_diag=diag)
         bw = ops.ilqr_backward(spec, fw["X"], fw["U"], d["C"], d["xref"], d["uref"], fw["tight"], gX, gU,
-                               Cf_batched=args.layout == "per_element", want=want)
+                               Cf_batched=args.layout != "shared", want=want, C_diag=diag)
         if world > 1 and args.layout == "shared":
             sharding.allreduce_sum_([bw["grad_C"], bw["grad_c"], bw["grad_Cf"], bw["grad_cf"]])
         return fw, bw
@@ -288,15 +297,16 @@ def main():
             flush.fill_(i & 0xFF)          # L2 flush, outside the timed events
             ev[i][0].record()
             fw = ops.ilqr_forward(spec, d["x0"], d["C"], d["c"], d["Cf"], d["cf"], d["xref"], d["uref"], d["Uinit"],
-                                  ls_cost=ls, want_trace=False)
+                                  ls_cost=ls, want_trace=False, C_diag=diag)
             ev[i][1].record()
             bw = ops.ilqr_backward(spec, fw["X"], fw["U"], d["C"], d["xref"], d["uref"], fw["tight"], gX, gU,
-                                   Cf_batched=args.layout == "per_element", want=want)
+                                   Cf_batched=args.layout != "shared", want=want, C_diag=diag)
             if world > 1 and args.layout == "shared":
                 sharding.allreduce_sum_([bw["grad_C"], bw["grad_c"], bw["grad_Cf"], bw["grad_cf"]])
             ev[i][2].record()
         barrier()
         gpu_launches = int(_lib.lib().tacd_kernel_launches()) - launches0
+        mean_iters = float(fw["iters"].float().mean().item())
         t_fwd = sum(e[0].elapsed_time(e[1]) for e in ev) / 1e3
         t_tot = sum(e[0].elapsed_time(e[2]) for e in ev) / 1e3
         clocks = clk
@@ -308,13 +318,17 @@ def main():
     # ---------------------------------------------------------------- e2e through the public API, host buffers
     pin = {k: v.pin_memory() for k, v in host.items()}
     Cd = d["C"].clone().requires_grad_(True)
-    cm = GeneralQuadCost(NX, NU, Cd, d["c"], d["Cf"], d["cf"], device=str(dev), x_ref=d["xref"], u_ref=d["uref"])
+    if diag:
+        from tacdmpc_b200.DifferentialMPC import DiagQuadCost
+        cm = DiagQuadCost(NX, NU, Cd, d["c"], d["Cf"], d["cf"], device=str(dev), x_ref=d["xref"], u_ref=d["uref"])
+    else:
+        cm = GeneralQuadCost(NX, NU, Cd, d["c"], d["Cf"], d["cf"], device=str(dev), x_ref=d["xref"], u_ref=d["uref"])
     mpc = DifferentiableMPCController(f, T * DT, DT, T, cm, u_min=torch.tensor([-20.0]), u_max=torch.tensor([20.0]),
                                       device=str(dev), grad_method="analytic", f_dyn_jac=f.jac)
     if ls is not None:
         mpc.ls_cost_override = ls
     act_host = torch.empty(B, NU).pin_memory()
-    gC_host = torch.empty(Cd.shape if args.layout == "shared" else (T, N, N)).pin_memory()
+    gC_host = torch.empty(Cd.shape if args.layout == "shared" else Cd.shape[1:]).pin_memory()
     h2d = sum(pin[k].numel() * 4 for k in ("x0", "Uinit"))
     d2h = act_host.numel() * 4 + gC_host.numel() * 4
 

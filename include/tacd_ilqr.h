@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define TACD_ABI_VERSION 1
+#define TACD_ABI_VERSION 2
 
 #define TACD_MAX_ALPHA 8
 #define TACD_MAX_NU 16
@@ -94,6 +94,13 @@ typedef struct tacd_problem {
   double alphas[TACD_MAX_ALPHA];
   int32_t has_umin, has_umax;
   double umin[TACD_MAX_NU], umax[TACD_MAX_NU];
+  /* Diagonal per-element cost in compact form (what ACMPC/actor.py:58-81 builds with diag_embed):
+   * 1 = C[B,T,n] and C_final[B,n] hold the DIAGONALS (c, c_final unchanged); grad_C / grad_Cf come back
+   * in the same compact shape; the shared line-search cost (C_ls[T,n], Cf_ls[n]) is compact too.
+   * Requires C_batched = Cf_batched = 1.  Supported by tacd_ilqr_forward (five-lanes-per-element kernel)
+   * and tacd_ilqr_backward (thread-per-element kernel); otherwise TACD_EUNSUPPORTED — expand to dense. */
+  int32_t C_diag;
+  int32_t reserved_;
 } tacd_problem;
 
 /* ---- whole solve ------------------------------------------------------- */

@@ -1,0 +1,85 @@
+"""ActorMPC (ACMPC/actor.py:13-120) with the cost kept as diagonals end to end.
+
+The reference maps an observation through an MLP to ``q_diag, p`` of shape ``[B, T, n]``, expands
+``C = diag_embed(q_diag)`` to ``[B, T, n, n]`` and differentiates back through the dense tensor
+(actor.py:58-81).  Here the same numbers reach the kernels as ``q_diag, p`` (``DiagQuadCost`` /
+``tacd_problem.C_diag``) and come back as ``grad_q_diag, grad_p``; constructor, ``forward`` and
+``evaluate_actions`` keep the reference's signatures and return values.  ``fused=False`` runs the
+reference's dense formulation through the same kernels (used by the parity tests).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch import Tensor
+from torch.distributions import Normal
+
+from ..DifferentialMPC import DiagQuadCost, DifferentiableMPCController, GeneralQuadCost
+
+
+class ActorMPC(nn.Module):
+    def __init__(self, nx: int, nu: int, horizon: int, dt: float, f_dyn, f_dyn_jac=None, device: str = "cuda",
+                 grad_method: str = "auto_diff", observation_dim: Optional[int] = None, fused: bool = True):
+        super().__init__()
+        self.nx, self.nu, self.horizon, self.dt = nx, nu, horizon, dt
+        self.device = torch.device(device)
+        self.dtype = torch.float32
+        self.fused = fused
+        n = nx + nu
+        input_dim = observation_dim if observation_dim is not None else nx
+        self.cost_map_net = nn.Sequential(
+            nn.Linear(input_dim, 512), nn.ReLU(),
+            nn.Linear(512, 512), nn.ReLU(),
+            nn.Linear(512, horizon * n * 2),
+        ).to(self.device, dtype=self.dtype)
+        z = lambda *s: torch.zeros(*s, device=self.device, dtype=self.dtype)
+        if fused:
+            cost_module = DiagQuadCost(nx, nu, z(1, horizon, n), z(1, horizon, n), z(1, n), z(1, n), device=device)
+        else:
+            cost_module = GeneralQuadCost(nx=nx, nu=nu, C=z(horizon, n, n), c=z(horizon, n), C_final=z(n, n),
+                                          c_final=z(n), device=device)
+        self.mpc = DifferentiableMPCController(
+            f_dyn=f_dyn, total_time=horizon, step_size=dt, horizon=horizon, cost_module=cost_module,
+            f_dyn_jac=f_dyn_jac, device=device, reg_eps=1e-2, grad_method=grad_method)
+        self.log_std = nn.Parameter(torch.full((nu,), 0.0, device=self.device, dtype=self.dtype))
+
+    def _update_cost_module(self, x: Tensor):
+        """softplus(raw) + 1e-2 on the diagonal, raw linear term, C_final = C[:, -1] (actor.py:58-81)."""
+        B, n = x.shape[0], self.nx + self.nu
+        params = self.cost_map_net(x)
+        q_raw, p_raw = params.split([self.horizon * n, self.horizon * n], dim=-1)
+        q_diag = (F.softplus(q_raw) + 1e-2).view(B, self.horizon, n)
+        p = p_raw.view(B, self.horizon, n)
+        cm = self.mpc.cost_module
+        if self.fused:
+            cm.set_diag(q_diag, p, q_diag[:, -1].clone(), p[:, -1].clone())
+        else:
+            C = torch.diag_embed(q_diag)
+            cm.C, cm.c = C, p
+            cm.C_final, cm.c_final = C[:, -1].clone(), p[:, -1].clone()
+        cm.set_reference(torch.zeros(B, self.horizon + 1, self.nx, device=self.device, dtype=self.dtype),
+                         torch.zeros(B, self.horizon, self.nu, device=self.device, dtype=self.dtype))
+
+    def forward(self, x: Tensor, deterministic: bool = False) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+        if x.ndim == 1:
+            x = x.unsqueeze(0)
+        self._update_cost_module(x)
+        U_init = torch.randn(x.shape[0], self.horizon, self.nu, device=self.device, dtype=self.dtype) * 0.01
+        predicted_states, predicted_actions = self.mpc(x[:, :self.nx], U_init)
+        u_mpc_mean = predicted_actions[:, 0]
+        dist = Normal(u_mpc_mean, self.log_std.exp())
+        action = u_mpc_mean if deterministic else dist.rsample()
+        log_prob = dist.log_prob(action).sum(dim=-1)
+        return action, log_prob, predicted_states, predicted_actions
+
+    def evaluate_actions(self, x: Tensor, actions: Tensor) -> Tuple[Tensor, Tensor]:
+        if x.ndim == 1:
+            x = x.unsqueeze(0)
+        self._update_cost_module(x)
+        U_init = torch.zeros(x.shape[0], self.horizon, self.nu, device=self.device, dtype=self.dtype)
+        _, predicted_actions = self.mpc(x[:, :self.nx], U_init)
+        dist = Normal(predicted_actions[:, 0], self.log_std.exp())
+        return dist.log_prob(actions).sum(dim=-1), dist.entropy().sum(dim=-1)

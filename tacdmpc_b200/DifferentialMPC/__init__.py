@@ -3,13 +3,15 @@ same constructor arguments, same side effects — the solve itself runs in hand-
 
     import tacdmpc_b200.DifferentialMPC as DifferentialMPC
 """
-from .cost import GeneralQuadCost
-from .controller import DifferentiableMPCController, GradMethod, ILQRSolve
+from .cost import DiagQuadCost, GeneralQuadCost
+from .controller import DifferentiableMPCController, GradMethod, ILQRSolve, ILQRSolveDiag
 from .utils import pnqp, batched_jacobian, jacobian_finite_diff_batched
 
 __all__ = [
     "GeneralQuadCost",
+    "DiagQuadCost",
     "ILQRSolve",
+    "ILQRSolveDiag",
     "DifferentiableMPCController",
     "GradMethod",
     "pnqp",

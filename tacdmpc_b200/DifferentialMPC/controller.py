@@ -27,7 +27,7 @@ from torch import Tensor
 
 from .. import _abi, ops
 from ..dynamics import NativeDynamics
-from .cost import GeneralQuadCost
+from .cost import DiagQuadCost, GeneralQuadCost
 from .utils import batched_jacobian, jacobian_finite_diff_batched
 
 
@@ -90,6 +90,52 @@ class ILQRSolve(torch.autograd.Function):
         for nm, shape, dt in zip(names, ctx.shapes, ctx.in_dtypes):
             g = out.get(nm)
             if g is not None:
+                g = g.reshape(shape).to(dt)
+            grads.append(g)
+        return (*grads, None, None)
+
+
+class ILQRSolveDiag(torch.autograd.Function):
+    """ILQRSolve for a ``DiagQuadCost``: forward(x0, q, p, q_final, p_final, x_ref, u_ref, controller, U_init).
+    Same solve and same implicit differentiation (controller.py:25-115); the cost enters and its gradient
+    leaves as diagonals, never expanded to ``[B,T,n,n]``."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x0, q, p, q_final, p_final, x_ref, u_ref, controller, U_init):
+        cm = controller.cost_module
+        cm.set_diag(q, p, q_final, p_final)
+        cm.set_reference(x_ref, u_ref)
+        X, U = controller.solve_step(x0, U_init)
+        if (not controller.converged) and controller.detach_unconverged:
+            X, U = X.detach(), U.detach()
+        ctx.spec = controller._last_spec
+        ctx.diag = controller._last_diag
+        ctx.shapes = tuple(t.shape for t in (x0, q, p, q_final, p_final, x_ref, u_ref))
+        ctx.in_dtypes = tuple(t.dtype for t in (x0, q, p, q_final, p_final, x_ref, u_ref))
+        saved = [X, U, controller._last_C, controller._last_xref, controller._last_uref, controller._last_tight_u8]
+        if controller._last_AB is not None:
+            saved += list(controller._last_AB)
+        ctx.save_for_backward(*saved)
+        return X, U
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, grad_X, grad_U):
+        saved = ctx.saved_tensors
+        X, U, Cm, xref, uref, tight = saved[:6]
+        A, Bm = (saved[6], saved[7]) if len(saved) > 6 else (None, None)
+        need = ctx.needs_input_grad
+        names = ("grad_x0", "grad_C", "grad_c", "grad_Cf", "grad_cf", "grad_xref", "grad_uref")
+        want = tuple(nm for nm, nd in zip(names, need[:7]) if nd)
+        out = ops.ilqr_backward(ctx.spec, X, U, Cm, xref, uref, tight, grad_X.to(X.dtype), grad_U.to(U.dtype),
+                                A=A, Bm=Bm, Cf_batched=True, want=want, C_diag=ctx.diag) if want else {}
+        grads = []
+        for nm, shape, dt in zip(names, ctx.shapes, ctx.in_dtypes):
+            g = out.get(nm)
+            if g is not None:
+                if not ctx.diag and nm in ("grad_C", "grad_Cf"):   # dense fallback path: keep the diagonal
+                    g = torch.diagonal(g, dim1=-2, dim2=-1)
                 g = g.reshape(shape).to(dt)
             grads.append(g)
         return (*grads, None, None)
@@ -160,6 +206,8 @@ class DifferentiableMPCController(torch.nn.Module):
         self.compat = compat
         # multi-GPU: the sharding helper installs the GLOBAL element 0's cost here (quirk Q4)
         self.ls_cost_override = None
+        self.force_dense_cost = False   # DiagQuadCost: expand to dense [B,T,n,n] before the kernels (A/B tests)
+        self._last_diag = False
         self.U_prev = None
         self.reset()
         self.converged = True
@@ -189,7 +237,14 @@ class DifferentiableMPCController(torch.nn.Module):
 
     # ------------------------------------------------------------------ problem description
     def _is_native(self) -> bool:
-        return isinstance(self.f_dyn, NativeDynamics) and type(self.cost_module) is GeneralQuadCost
+        return isinstance(self.f_dyn, NativeDynamics) and type(self.cost_module) in (GeneralQuadCost, DiagQuadCost)
+
+    def _diag_eligible(self) -> bool:
+        """Compact diagonal costs go to the kernels as they are when the fused five-lanes-per-element forward
+        kernel takes the problem (shipped non-LTI plugin or small LTI, analytic / auto-diff Jacobians)."""
+        return (isinstance(self.cost_module, DiagQuadCost) and isinstance(self.f_dyn, NativeDynamics)
+                and self.nx + self.nu <= 5 and self.nx <= 4 and self.grad_method != GradMethod.FINITE_DIFF
+                and not self.force_dense_cost)
 
     def _spec(self, dtype, device) -> ops.Spec:
         f = self.f_dyn
@@ -213,6 +268,17 @@ class DifferentiableMPCController(torch.nn.Module):
 
     def _costs(self, B, dtype, device):
         cm = self.cost_module
+        if self._diag_eligible() and cm.q.shape[0] == B:
+            q, p, qf, pf = (t.detach().to(device=device, dtype=dtype).contiguous() for t in (cm.q, cm.p, cm.q_final, cm.p_final))
+            xref = cm.x_ref.detach().to(device=device, dtype=dtype).contiguous()
+            uref = cm.u_ref.detach().to(device=device, dtype=dtype).contiguous()
+            ls = None
+            if self.compat == "reference":   # quirk Q4, compact as well
+                ls = tuple(t.detach().to(device=device, dtype=dtype).contiguous() for t in self.ls_cost_override) \
+                    if self.ls_cost_override is not None else (q[0], p[0], qf[0], pf[0])
+            self._last_diag = True
+            return q, p, qf, pf, xref, uref, ls
+        self._last_diag = False
         C, c, Cf, cf = (t.detach().to(device=device, dtype=dtype).contiguous() for t in (cm.C, cm.c, cm.C_final, cm.c_final))
         if C.ndim == 4 and C.shape[0] == 1 and B > 1:
             C, c = C[0], c[0]
@@ -237,6 +303,8 @@ class DifferentiableMPCController(torch.nn.Module):
         if U_init is None:
             U_init = torch.zeros(B, self.horizon, self.nu, device=x0.device, dtype=x0.dtype)
         cm = self.cost_module
+        if isinstance(cm, DiagQuadCost):
+            return ILQRSolveDiag.apply(x0, cm.q, cm.p, cm.q_final, cm.p_final, cm.x_ref, cm.u_ref, self, U_init)
         return ILQRSolve.apply(x0, cm.C, cm.c, cm.C_final, cm.c_final, cm.x_ref, cm.u_ref, self, U_init)
 
     def solve_step(self, x0: Tensor, U_init: Tensor) -> Tuple[Tensor, Tensor]:
@@ -252,7 +320,8 @@ class DifferentiableMPCController(torch.nn.Module):
         x0d = x0.detach().to(dtype)
         U0 = U_init.detach().to(device=device, dtype=dtype)
         if self._is_native():
-            out = ops.ilqr_forward(spec, x0d, C, c, Cf, cf, xref, uref, U0, ls_cost=ls, want_trace=True)
+            out = ops.ilqr_forward(spec, x0d, C, c, Cf, cf, xref, uref, U0, ls_cost=ls, want_trace=True,
+                                   C_diag=self._last_diag)
             AB = None
         else:
             out, AB = self._solve_generic(spec, x0d, C, c, Cf, cf, xref, uref, U0, ls)
@@ -263,8 +332,11 @@ class DifferentiableMPCController(torch.nn.Module):
         self.iters_last, self.flags_last, self.cost_last = out["iters"], out["flags"], out["cost"]
         self.alpha_trace_last = out.get("alpha_trace")
         nx = self.nx
-        Cb = C if C.ndim == 4 else C.unsqueeze(0).expand(B, *C.shape)
-        self.H_last = (Cb[..., :nx, :nx], Cb[..., nx:, nx:], Cb[..., :nx, nx:])
+        if self._last_diag:
+            self.H_last = None   # dense Hessian blocks are not materialised on the compact path (cost_module.C is)
+        else:
+            Cb = C if C.ndim == 4 else C.unsqueeze(0).expand(B, *C.shape)
+            self.H_last = (Cb[..., :nx, :nx], Cb[..., nx:, nx:], Cb[..., :nx, nx:])
         self._F_last = AB
         self._last_spec, self._last_C, self._last_xref, self._last_uref = spec, C, xref, uref
         self._last_tight_u8, self._last_AB = out["tight"], AB

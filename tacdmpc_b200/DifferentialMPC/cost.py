@@ -92,3 +92,41 @@ class GeneralQuadCost(torch.nn.Module):
         lN = (Cf @ tauN.unsqueeze(-1)).squeeze(-1) + cf
         out = (l[..., :nx], l[..., nx:], C[..., :nx, :nx], C[..., :nx, nx:], C[..., nx:, nx:], lN[..., :nx], Cf[..., :nx, :nx])
         return tuple(t.squeeze(0) for t in out) if squeeze else out
+
+
+class DiagQuadCost(GeneralQuadCost):
+    """Per-element DIAGONAL quadratic cost kept in compact form — the cost ``ACMPC/actor.py:58-81`` builds with
+    ``torch.diag_embed``.
+
+    ``q [B,T,n]`` and ``q_final [B,n]`` are the diagonals of ``C`` / ``C_final``; ``p``, ``p_final`` are ``c`` /
+    ``c_final``.  The controller hands them to the kernels as they are (``tacd_problem.C_diag``): 2n instead of
+    n*n + n words per step go through the solve, and the backward writes ``grad_q``, ``grad_p`` instead of a dense
+    ``grad_C``.  ``C``, ``c``, ``C_final``, ``c_final`` remain readable (materialised on access) so code written
+    against ``GeneralQuadCost`` keeps working; results are identical to passing the dense tensors.
+    """
+
+    def __init__(self, nx: int, nu: int, q: Tensor, p: Tensor, q_final: Tensor, p_final: Tensor, **kwargs):
+        torch.nn.Module.__init__(self)
+        self.device = torch.device(kwargs.get("device", q.device))
+        self.nx, self.nu = nx, nu
+        self.set_diag(q, p, q_final, p_final)
+        horizon = q.shape[-2]
+        x_ref, u_ref = kwargs.get("x_ref"), kwargs.get("u_ref")
+        self.register_buffer("x_ref", x_ref if x_ref is not None else torch.zeros(1, horizon + 1, nx, device=self.device))
+        self.register_buffer("u_ref", u_ref if u_ref is not None else torch.zeros(1, horizon, nu, device=self.device))
+        self.set_reference(self.x_ref, self.u_ref)
+
+    def set_diag(self, q: Tensor, p: Tensor, q_final: Optional[Tensor] = None, p_final: Optional[Tensor] = None):
+        """Install per-element diagonals; the terminal cost defaults to the last running step (actor.py:76-77)."""
+        n = self.nx + self.nu
+        if q.ndim != 3 or q.shape[-1] != n or p.shape != q.shape:
+            raise RuntimeError(f"q, p must be [B, T, n={n}]; got {tuple(q.shape)}, {tuple(p.shape)}")
+        self.q, self.p = q.to(self.device), p.to(self.device)
+        self.q_final = (q_final if q_final is not None else q[:, -1].clone()).to(self.device)
+        self.p_final = (p_final if p_final is not None else p[:, -1].clone()).to(self.device)
+
+    # dense views for code written against GeneralQuadCost (reads only; assign q/p to change the cost)
+    C = property(lambda self: torch.diag_embed(self.q))
+    c = property(lambda self: self.p)
+    C_final = property(lambda self: torch.diag_embed(self.q_final))
+    c_final = property(lambda self: self.p_final)

@@ -52,6 +52,7 @@ static int validate(const tacd_problem* p) {
   if (p->dyn_id == TACD_DYN_CARTPOLE && !(p->nx == 4 && p->nu == 1)) { set_error("cartpole is nx=4, nu=1"); return TACD_EINVAL; }
   if ((p->dyn_id == TACD_DYN_UNICYCLE || p->dyn_id == TACD_DYN_UNICYCLE_WRAPPED) && !(p->nx == 3 && p->nu == 2)) { set_error("unicycle is nx=3, nu=2"); return TACD_EINVAL; }
   if (p->dyn_id < 0 || p->dyn_id > TACD_DYN_EXTERNAL) { set_error("unknown dyn_id %d", p->dyn_id); return TACD_EINVAL; }
+  if (p->C_diag && !(p->C_batched && p->Cf_batched)) { set_error("C_diag needs per-element costs (C_batched = Cf_batched = 1)"); return TACD_EINVAL; }
   return TACD_OK;
 }
 
@@ -113,6 +114,7 @@ int tacd_ilqr_forward(const tacd_problem* p, const tacd_forward_io* io, void* wo
   cudaStream_t s = (cudaStream_t)stream;
   int rc = (p->dtype == TACD_F32) ? launch_forward_group<float>(p, io, workspace, head, s) : launch_forward_group<double>(p, io, workspace, head, s);
   if (rc != TACD_EUNSUPPORTED) return rc;
+  if (p->C_diag) { set_error("C_diag: this problem is not eligible for the five-lanes-per-element kernel; pass dense costs"); return TACD_EUNSUPPORTED; }
   rc = (p->dtype == TACD_F32) ? launch_forward_small<float>(p, io, workspace, head, s) : launch_forward_small<double>(p, io, workspace, head, s);
   if (rc != TACD_EUNSUPPORTED) return rc;
   char* ws = (char*)workspace + head;
@@ -134,6 +136,7 @@ int tacd_ilqr_backward(const tacd_problem* p, const tacd_backward_io* io, void* 
   int rc = (p->dtype == TACD_F32) ? launch_backward_small<float>(p, io, ws, workspace_bytes - 256, s)
                                   : launch_backward_small<double>(p, io, ws, workspace_bytes - 256, s);
   if (rc != TACD_EUNSUPPORTED) return rc;
+  if (p->C_diag) { set_error("C_diag: no thread-per-element backward kernel for this (nx, nu, dyn); pass dense costs"); return TACD_EUNSUPPORTED; }
   rc = (p->dtype == TACD_F32) ? launch_backward_generic<float>(p, io, ws, workspace_bytes - 256, s)
                               : launch_backward_generic<double>(p, io, ws, workspace_bytes - 256, s);
   return rc;

@@ -150,6 +150,23 @@ __host__ __device__ inline int group_cost_words(int T, int nx, int nu, int C_bat
   return w;
 }
 
+// Diagonal cost: quad += sum_i tau_i (q_i tau_i), lin += sum_i c_i tau_i, bit-identical to quad_terms<> on the
+// expanded matrix for finite tau (the skipped terms are exact zeros).  `chk` restores the one visible
+// difference: the dense form multiplies every tau_k by a zero of C, so a non-finite tau_k makes the
+// cost NaN (and NaN wins the argmin, controller.py:297); chk = sum_k 0 * tau_k is NaN exactly then.
+template <typename R, int N>
+TACD_DEV void quad_terms_diag(const R (&q)[N], const R (&ct)[N], const R (&tau)[N], R& quad, R& lin) {
+  R chk = 0;
+#pragma unroll
+  for (int i = 0; i < N; ++i) chk += tau[i] * (R)0;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const R s = q[i] * tau[i] + chk;
+    quad += tau[i] * s;
+    lin += ct[i] * tau[i];
+  }
+}
+
 // [C_t | c_t] of one step from a 16-byte aligned staged block
 template <typename R, int N>
 TACD_DEV void load_cost_vec(const R* p, R (&Ct)[N * N], R (&ct)[N]) {
@@ -208,10 +225,11 @@ __global__ void __launch_bounds__(128) ilqr_init_rollout(const DevProblem<R> P, 
     if (P.C_batched && c < nchunk) {
       const int t0 = c * kInitChunk, nst = (T - t0 < kInitChunk) ? T - t0 : kInitChunk;
       R* buf = ctile + (size_t)(c & 1) * 32 * RSC;
+      const int cw = P.C_diag ? N : N * N;   // words of C per step (compact diagonal or dense)
       for (int r = 0; r < nlive; ++r) {
-        const R* Cg = io.C + ((size_t)(b0 + r) * T + t0) * N * N;
+        const R* Cg = io.C + ((size_t)(b0 + r) * T + t0) * cw;
         const R* cg = io.c + ((size_t)(b0 + r) * T + t0) * N;
-        for (int w = lane; w < nst * N * N; w += 32) cp_async<R>(&buf[(size_t)r * RSC + w], &Cg[w]);
+        for (int w = lane; w < nst * cw; w += 32) cp_async<R>(&buf[(size_t)r * RSC + w], &Cg[w]);
         for (int w = lane; w < nst * N; w += 32) cp_async<R>(&buf[(size_t)r * RSC + kInitChunk * N * N + w], &cg[w]);
       }
     }
@@ -230,7 +248,7 @@ __global__ void __launch_bounds__(128) ilqr_init_rollout(const DevProblem<R> P, 
   const int b = b0 + (lane < nlive ? lane : nlive - 1);   // dead lanes shadow the last element, outputs masked
   const R* Cp = io.C;    // shared cost: uniform loads
   const R* cp = io.c;
-  const R* Cfp = io.Cf + (P.Cf_batched ? (size_t)b * N * N : 0);
+  const R* Cfp = io.Cf + (P.Cf_batched ? (size_t)b * (P.C_diag ? N : N * N) : 0);
   const R* cfp = io.cf + (P.Cf_batched ? (size_t)b * N : 0);
   R* row = tile + (size_t)(lane < nlive ? lane : nlive - 1) * RSI;
   const R* ur = row + XW;
@@ -252,7 +270,12 @@ __global__ void __launch_bounds__(128) ilqr_init_rollout(const DevProblem<R> P, 
       for (int i = 0; i < NX; ++i) { tau[i] = x[i] - row[t * NX + i]; row[t * NX + i] = x[i]; }
 #pragma unroll
       for (int i = 0; i < NU; ++i) tau[NX + i] = u[i] - ur[t * NU + i];
-      if (P.C_batched) {
+      if (P.C_diag) {   // expanded to dense: same arithmetic as the dense layout (diag_embed, actor.py:74)
+#pragma unroll
+        for (int i = 0; i < N * N; ++i) Ct[i] = (i / N == i % N) ? cbuf[(t - t0) * N + i / N] : (R)0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) ct[i] = cbuf[kInitChunk * N * N + (t - t0) * N + i];
+      } else if (P.C_batched) {
 #pragma unroll
         for (int i = 0; i < N * N; ++i) Ct[i] = cbuf[(t - t0) * N * N + i];
 #pragma unroll
@@ -280,7 +303,7 @@ __global__ void __launch_bounds__(128) ilqr_init_rollout(const DevProblem<R> P, 
     for (int i = 0; i < NX; ++i) {
       R s = 0;
 #pragma unroll
-      for (int j = 0; j < NX; ++j) s += Cfp[i * N + j] * tauN[j];
+      for (int j = 0; j < NX; ++j) s += (P.C_diag ? ((i == j) ? Cfp[i] : (R)0) : Cfp[i * N + j]) * tauN[j];
       qN += tauN[i] * s;
       lN += cfp[i] * tauN[i];
     }
@@ -298,13 +321,17 @@ __global__ void __launch_bounds__(128) ilqr_init_rollout(const DevProblem<R> P, 
 // CSH: the element's own running cost (C, c) is shared by the batch and staged in shared memory (layout 2a);
 // otherwise it is per-element and read from global memory.  LSSEP: candidates are scored with the separate
 // shared line-search cost (quirk Q4), always staged.
-template <typename R, int NX, int NU, int DYN, bool LSSEP, bool CSH>
+// DIAG (only with per-element costs, CSH = false): tacd_problem.C_diag — C, C_final (and the line-search cost)
+// are compact diagonals, the ActorMPC layout (ACMPC/actor.py:58-81); 2n instead of n*n + n words per step.
+template <typename R, int NX, int NU, int DYN, bool LSSEP, bool CSH, bool DIAG>
 __global__ void __launch_bounds__(384, 1) ilqr_forward_group(const DevProblem<R> P, const FwdPtrs<R> io, const R* cost0) {
   constexpr int N = NX + NU;
   static_assert(N <= kG, "one lane per row of the Q-function");
   static_assert(NX <= 4, "value-function rows travel as one 4-word vector");
+  static_assert(!(DIAG && CSH), "compact diagonal costs are per-element");
   using D = Dyn<R, NX, NU, DYN>;
   using GD = GDyn<R, NX, NU, DYN>;
+  constexpr int CW = DIAG ? N : N * N;         // words of C per step / of C_final in global memory
   constexpr int NJ = GD::NJ;
   constexpr unsigned FULL = 0xffffffffu;
   constexpr int WS = kNSLOT * kEPW;            // words between consecutive trajectory words of one buffer
@@ -333,15 +360,20 @@ __global__ void __launch_bounds__(384, 1) ilqr_forward_group(const DevProblem<R>
       bool same = true;
       for (int i = tid; i < T * CS; i += NT) {
         const int t = i / CS, k = i - t * CS;
-        const R val = (k < N * N) ? Cg[t * N * N + k] : (k < N * N + N) ? cg[t * N + (k - N * N)] : (R)0;
-        const R v0 = (k < N * N) ? Cg[k] : (k < N * N + N) ? cg[k - N * N] : (R)0;
+        // (a compact diagonal source is expanded to the dense staged layout)
+        const int kc = DIAG ? ((k < N * N && k / N == k % N) ? k / N : -1) : k;
+        const R val = (k < N * N) ? (kc >= 0 ? Cg[t * CW + kc] : (R)0) : (k < N * N + N) ? cg[t * N + (k - N * N)] : (R)0;
+        const R v0 = (k < N * N) ? (kc >= 0 ? Cg[kc] : (R)0) : (k < N * N + N) ? cg[k - N * N] : (R)0;
         same = same && (val == v0);
         dst[i] = val;
       }
       return same;
     };
     auto stage_fin = [&](R* dst, const R* Cg, const R* cg) {
-      for (int k = tid; k < CS; k += NT) dst[k] = (k < N * N) ? Cg[k] : (k < N * N + N) ? cg[k - N * N] : (R)0;
+      for (int k = tid; k < CS; k += NT) {
+        const int kc = DIAG ? ((k < N * N && k / N == k % N) ? k / N : -1) : k;
+        dst[k] = (k < N * N) ? (kc >= 0 ? Cg[kc] : (R)0) : (k < N * N + N) ? cg[k - N * N] : (R)0;
+      }
     };
     if (CSH) { sC = sm + o; o += T * CS; same_own = stage_run(sC, io.C, io.c); }
     if (ownCf_sh) { sCf = sm + o; o += CS; stage_fin(sCf, io.Cf, io.cf); }
@@ -404,9 +436,9 @@ __global__ void __launch_bounds__(384, 1) ilqr_forward_group(const DevProblem<R>
         if (nb < (unsigned)P.B) {
           b = io.order ? io.order[nb] : (int)nb;
           has = true; it = 0; flg = 0; nom = 0;
-          Cp = io.C + (P.C_batched ? (size_t)b * T * N * N : 0);
+          Cp = io.C + (P.C_batched ? (size_t)b * T * CW : 0);
           cp = io.c + (P.C_batched ? (size_t)b * T * N : 0);
-          Cfp = io.Cf + (P.Cf_batched ? (size_t)b * N * N : 0);
+          Cfp = io.Cf + (P.Cf_batched ? (size_t)b * CW : 0);
           cfp = io.cf + (P.Cf_batched ? (size_t)b * N : 0);
           // nominal trajectory (initial rollout) and references: global -> shared, once per element.  The
           // references are read ten times per step and trip; from global memory (6 lines per request, a
@@ -454,7 +486,7 @@ __global__ void __launch_bounds__(384, 1) ilqr_forward_group(const DevProblem<R>
             R s = 0;
 #pragma unroll
             for (int k = 0; k < NX; ++k) {
-              const R cik = Cfo[i * N + k];
+              const R cik = DIAG ? ((i == k) ? Cfo[i] : (R)0) : Cfo[i * N + k];
               V[i * NX + k] = cik;
               s += cik * tauN[k];
             }
@@ -469,13 +501,19 @@ __global__ void __launch_bounds__(384, 1) ilqr_forward_group(const DevProblem<R>
         const R* pu = nomp + (size_t)(XW + (T - 1) * NU) * WS;
         R* gx = const_cast<R*>(px) + NX * WS;   // X_{t+1} slot (nominal buffer); + dK[m] = m-th dead buffer
         R* gu = const_cast<R*>(pu);             // U_t slot
-        const R* pCrow = CSH ? sC + (size_t)(T - 1) * CS + jj * N : Cp + ((size_t)(T - 1) * N + jj) * N;
+        const R* pCrow = CSH ? sC + (size_t)(T - 1) * CS + jj * N : DIAG ? Cp + (size_t)(T - 1) * N + jj : Cp + ((size_t)(T - 1) * N + jj) * N;
         const R* pcj = CSH ? sC + (size_t)(T - 1) * CS + N * N + jj : cp + (size_t)(T - 1) * N + jj;
         const R* pxr = refp + (size_t)(T - 1) * NX * WS;
         const R* pur = refp + (size_t)(XW + (T - 1) * NU) * WS;
         R Crow[N], cj;        // row jj of C_t and c_t[jj]; loaded once when the running cost is time-invariant
+        if (DIAG) {
+          const R qd = pCrow[0];
 #pragma unroll
-        for (int k = 0; k < N; ++k) Crow[k] = pCrow[k];
+          for (int k = 0; k < N; ++k) Crow[k] = (k == jj) ? qd : (R)0;
+        } else {
+#pragma unroll
+          for (int k = 0; k < N; ++k) Crow[k] = pCrow[k];
+        }
         cj = pcj[0];
         int s_in_blk = 0;
         for (int t = T - 1; t >= 0; --t) {
@@ -507,7 +545,12 @@ __global__ void __launch_bounds__(384, 1) ilqr_forward_group(const DevProblem<R>
           // row jj of C_t, l_j = C_t[j,:] tau + c_t[j]
           R Qrow[N], qj;
           {
-            if (!constOwn) {
+            if (DIAG) {
+              const R qd = pCrow[0];
+#pragma unroll
+              for (int k = 0; k < N; ++k) Crow[k] = (k == jj) ? qd : (R)0;
+              cj = pcj[0];
+            } else if (!constOwn) {
 #pragma unroll
               for (int k = 0; k < N; ++k) Crow[k] = pCrow[k];
               cj = pcj[0];
@@ -614,7 +657,7 @@ __global__ void __launch_bounds__(384, 1) ilqr_forward_group(const DevProblem<R>
           }
           __syncwarp();
           px -= NX * WS; pu -= NU * WS; pxr -= NX * WS; pur -= NU * WS; gx -= NX * WS; gu -= NU * WS;
-          pCrow -= CSH ? CS : N * N; pcj -= CSH ? CS : N;
+          pCrow -= CSH ? CS : CW; pcj -= CSH ? CS : N;
         }
       }
       // ---------------------------------------------------------------- line search: lane a = candidate a
@@ -662,6 +705,10 @@ __global__ void __launch_bounds__(384, 1) ilqr_forward_group(const DevProblem<R>
           if (CSH) {
             if (!constOwn) load_cost_vec<R, N>(pCo, Ct, ct);
             pCo += CS;
+          } else if (DIAG) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) { Ct[i] = pCo[i]; ct[i] = pco[i]; }
+            pCo += N; pco += N;
           } else {
 #pragma unroll
             for (int i = 0; i < N * N; ++i) Ct[i] = pCo[i];
@@ -669,7 +716,14 @@ __global__ void __launch_bounds__(384, 1) ilqr_forward_group(const DevProblem<R>
             for (int i = 0; i < N; ++i) ct[i] = pco[i];
             pCo += N * N; pco += N;
           }
-          quad_terms<R, N>(Ct, ct, tau, q2, l2);
+          if (DIAG) {
+            R qd[N];
+#pragma unroll
+            for (int i = 0; i < N; ++i) qd[i] = Ct[i];
+            quad_terms_diag<R, N>(qd, ct, tau, q2, l2);
+          } else {
+            quad_terms<R, N>(Ct, ct, tau, q2, l2);
+          }
           D::step(P, sA, sB, x, u, xn);
           __syncwarp();   // every lane of the group has read K_t, k_t from the slots overwritten below
           if (valid) {
@@ -692,7 +746,7 @@ __global__ void __launch_bounds__(384, 1) ilqr_forward_group(const DevProblem<R>
 #pragma unroll
           for (int k = 0; k < NX; ++k) {
             if (LSSEP) s += sCfl[i * N + k] * tauN[k];
-            s2 += Cfo[i * N + k] * tauN[k];
+            s2 += (DIAG ? ((i == k) ? Cfo[i] : (R)0) : Cfo[i * N + k]) * tauN[k];
           }
           if (LSSEP) { qN += tauN[i] * s; lN += sCfl[N * N + i] * tauN[i]; }
           qN2 += tauN[i] * s2;

@@ -9,9 +9,9 @@
 
 namespace tacd {
 
-template <typename R, int NX, int NU, int DYN, bool LSSEP, bool CSH>
+template <typename R, int NX, int NU, int DYN, bool LSSEP, bool CSH, bool DIAG>
 static int run_forward_group(const tacd_problem* p, const tacd_forward_io* io, void* ws, size_t ws_bytes, cudaStream_t s) {
-  auto kernel = ilqr_forward_group<R, NX, NU, DYN, LSSEP, CSH>;
+  auto kernel = ilqr_forward_group<R, NX, NU, DYN, LSSEP, CSH, DIAG>;
   const DeviceInfo di = device_info();
   const size_t cost_b = (size_t)group_cost_words(p->T, NX, NU, p->C_batched, p->Cf_batched, LSSEP ? 1 : 0, DYN == TACD_DYN_LTI) * sizeof(R);
   const size_t warp_b = (size_t)group_warp_words(p->T, NX, NU) * sizeof(R);
@@ -52,11 +52,12 @@ static int run_forward_group(const tacd_problem* p, const tacd_forward_io* io, v
     int32_t* order = (int32_t*)((char*)ws + 16384);
     if (int rc = check_cuda(cudaMemsetAsync(hist, 0, kLptBuckets * sizeof(unsigned int), s), "memset hist")) return rc;
     const int g2 = di.sms * 2 < (p->B + 255) / 256 ? di.sms * 2 : (p->B + 255) / 256;
-    lpt_histogram<R><<<g2, 256, 0, s>>>(p->B, p->T, NX, NX + NU, p->C_batched, p->xref_batched, (const R*)io->x0, (const R*)io->xref, (const R*)io->C, hist);
+    const int nkey = p->C_diag ? -(NX + NU) : NX + NU;
+    lpt_histogram<R><<<g2, 256, 0, s>>>(p->B, p->T, NX, nkey, p->C_batched, p->xref_batched, (const R*)io->x0, (const R*)io->xref, (const R*)io->C, hist);
     note_launches(1);
     lpt_scan<<<1, 1024, 0, s>>>(hist);
     note_launches(1);
-    lpt_scatter<R><<<g2, 256, 0, s>>>(p->B, p->T, NX, NX + NU, p->C_batched, p->xref_batched, (const R*)io->x0, (const R*)io->xref, (const R*)io->C, hist, order);
+    lpt_scatter<R><<<g2, 256, 0, s>>>(p->B, p->T, NX, nkey, p->C_batched, p->xref_batched, (const R*)io->x0, (const R*)io->xref, (const R*)io->C, hist, order);
     note_launches(1);
     f.order = order;
   }
@@ -91,11 +92,14 @@ int launch_forward_group(const tacd_problem* p, const tacd_forward_io* io, void*
   if (const char* e = getenv("TACD_FWD_KERNEL")) if (!strcmp(e, "thread")) return TACD_EUNSUPPORTED;
 #define X(NX_, NU_, DYN_)                                                                      \
   if (p->nx == NX_ && p->nu == NU_ && p->dyn_id == DYN_) {                                     \
+    if (p->C_diag)                                                                             \
+      return p->ls_cost_shared ? run_forward_group<R, NX_, NU_, DYN_, true, false, true>(p, io, ws, ws_bytes, s)   \
+                               : run_forward_group<R, NX_, NU_, DYN_, false, false, true>(p, io, ws, ws_bytes, s); \
     if (p->ls_cost_shared)                                                                     \
-      return p->C_batched ? run_forward_group<R, NX_, NU_, DYN_, true, false>(p, io, ws, ws_bytes, s)   \
-                          : run_forward_group<R, NX_, NU_, DYN_, true, true>(p, io, ws, ws_bytes, s);   \
-    return p->C_batched ? run_forward_group<R, NX_, NU_, DYN_, false, false>(p, io, ws, ws_bytes, s)    \
-                        : run_forward_group<R, NX_, NU_, DYN_, false, true>(p, io, ws, ws_bytes, s);    \
+      return p->C_batched ? run_forward_group<R, NX_, NU_, DYN_, true, false, false>(p, io, ws, ws_bytes, s)   \
+                          : run_forward_group<R, NX_, NU_, DYN_, true, true, false>(p, io, ws, ws_bytes, s);   \
+    return p->C_batched ? run_forward_group<R, NX_, NU_, DYN_, false, false, false>(p, io, ws, ws_bytes, s)    \
+                        : run_forward_group<R, NX_, NU_, DYN_, false, true, false>(p, io, ws, ws_bytes, s);    \
   }
   TACD_GROUP_FWD(X)
 #undef X

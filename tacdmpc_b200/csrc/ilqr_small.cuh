@@ -45,16 +45,20 @@ struct FwdPtrs {
 // iteration count correlates (Spearman 0.65) with the initial stage cost tau_0' C_0 tau_0, so the queue is
 // sorted by that key, descending, with a 2048-bucket counting sort on the float's exponent + 3 mantissa
 // bits: histogram -> exclusive scan -> scatter.  Any permutation is a correct queue order; the key only
-// affects load balance.
+// affects load balance.  A negative n = -(nx+nu) marks a compact diagonal cost (tacd_problem.C_diag).
 constexpr int kLptBuckets = 2048;
 
 template <typename R>
 __device__ __forceinline__ int lpt_bucket(const R* x0, const R* xr0, const R* C0, int nx, int n) {
   float q = 0.f;
-  for (int i = 0; i < nx; ++i) {
-    float s = 0.f;
-    for (int j = 0; j < nx; ++j) s += (float)C0[i * n + j] * (float)(x0[j] - xr0[j]);
-    q += (float)(x0[i] - xr0[i]) * s;
+  if (n < 0) {   // compact diagonal cost (tacd_problem.C_diag): C0 holds the diagonal
+    for (int i = 0; i < nx; ++i) q += (float)C0[i] * (float)(x0[i] - xr0[i]) * (float)(x0[i] - xr0[i]);
+  } else {
+    for (int i = 0; i < nx; ++i) {
+      float s = 0.f;
+      for (int j = 0; j < nx; ++j) s += (float)C0[i * n + j] * (float)(x0[j] - xr0[j]);
+      q += (float)(x0[i] - xr0[i]) * s;
+    }
   }
   if (!(q > 0.f)) return kLptBuckets - 1;               // zero / negative / NaN keys go last
   const unsigned u = __float_as_uint(q) >> 20;           // 8 exponent + 3 mantissa bits (sign is 0)
@@ -70,7 +74,7 @@ __global__ void lpt_histogram(int B, int T, int nx, int n, int C_batched, int xr
   __syncthreads();
   for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
     const int k = lpt_bucket<R>(x0 + (size_t)b * nx, xref + (xref_batched ? (size_t)b * (T + 1) * nx : 0),
-                                C + (C_batched ? (size_t)b * T * n * n : 0), nx, n);
+                                C + (C_batched ? (size_t)b * T * (n < 0 ? -n : n * n) : 0), nx, n);
     atomicAdd(&sh[k], 1u);
   }
   __syncthreads();
@@ -100,7 +104,7 @@ __global__ void lpt_scatter(int B, int T, int nx, int n, int C_batched, int xref
                             const R* C, unsigned int* offs, int32_t* order) {
   for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
     const int k = lpt_bucket<R>(x0 + (size_t)b * nx, xref + (xref_batched ? (size_t)b * (T + 1) * nx : 0),
-                                C + (C_batched ? (size_t)b * T * n * n : 0), nx, n);
+                                C + (C_batched ? (size_t)b * T * (n < 0 ? -n : n * n) : 0), nx, n);
     order[atomicAdd(&offs[k], 1u)] = b;
   }
 }
@@ -567,7 +571,8 @@ __global__ void __launch_bounds__(256, 1) ilqr_backward_small(const DevProblem<R
     const int bb = live ? b : P.B - 1;  // dead lanes shadow the last element, outputs masked
     const R* X = io.X + (size_t)bb * szX;
     const R* U = io.U + (size_t)bb * szU;
-    const R* Cp = io.C + (P.C_batched ? (size_t)bb * T * N * N : 0);
+    // tacd_problem.C_diag: C[B,T,n] holds the diagonals (ActorMPC layout), gradients come back compact too
+    const R* Cp = io.C + (P.C_batched ? (size_t)bb * T * (P.C_diag ? N : N * N) : 0);
     const R* xr = io.xref + (P.xref_batched ? (size_t)bb * szX : 0);
     const R* ur = io.uref + (P.uref_batched ? (size_t)bb * szU : 0);
     const R* gX = io.gX + (size_t)bb * szX;
@@ -592,7 +597,8 @@ __global__ void __launch_bounds__(256, 1) ilqr_backward_small(const DevProblem<R
 #pragma unroll
     for (int i = 0; i < NX; ++i) {
 #pragma unroll
-      for (int j = 0; j < NX; ++j) V[i * NX + j] = Cp[(size_t)(T - 1) * N * N + i * N + j];
+      for (int j = 0; j < NX; ++j)
+        V[i * NX + j] = P.C_diag ? ((i == j) ? Cp[(size_t)(T - 1) * N + i] : (R)0) : Cp[(size_t)(T - 1) * N * N + i * N + j];
       ngx[i] = gX[(T - 1) * NX + i];
       nx_[i] = X[(T - 1) * NX + i];
       v[i] = -ngx[i];
@@ -608,7 +614,10 @@ __global__ void __launch_bounds__(256, 1) ilqr_backward_small(const DevProblem<R
         cp_async<R>(&buf[r * L::CW + j], &base[(size_t)rr * T * N * N + j]);
       }
     };
-    if (P.C_batched) { __syncwarp(); fetch_C(T - 1); }
+    if (P.C_batched && !P.C_diag) { __syncwarp(); fetch_C(T - 1); }
+    R nqd[N];   // C_diag: diagonal of the step about to run (prefetched like the other per-step inputs)
+#pragma unroll
+    for (int i = 0; i < N; ++i) nqd[i] = P.C_diag ? Cp[(size_t)(T - 1) * N + i] : (R)0;
     for (int t = T - 1; t >= 0; --t) {
       R x[NX], u[NU], Qxx[NX * NX], Qxu[NX * NU], Quu[NU * NU], qx[NX], qu[NU], A[NX * NX], Bm[NX * NU];
       bool fixed[NU];
@@ -622,7 +631,23 @@ __global__ void __launch_bounds__(256, 1) ilqr_backward_small(const DevProblem<R
 #pragma unroll
         for (int i = 0; i < NU; ++i) { nu_[i] = U[(t - 1) * NU + i]; ngu[i] = gU[(t - 1) * NU + i]; ntg[i] = tg[(t - 1) * NU + i] != 0; }
       }
-      if (P.C_batched) {
+      if (P.C_diag) {
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+#pragma unroll
+          for (int j = 0; j < NX; ++j) Qxx[i * NX + j] = (i == j) ? nqd[i] : (R)0;
+#pragma unroll
+          for (int j = 0; j < NU; ++j) Qxu[i * NU + j] = 0;
+        }
+#pragma unroll
+        for (int i = 0; i < NU; ++i)
+#pragma unroll
+          for (int j = 0; j < NU; ++j) Quu[i * NU + j] = (i == j) ? nqd[NX + i] : (R)0;
+        if (t > 0) {
+#pragma unroll
+          for (int i = 0; i < N; ++i) nqd[i] = Cp[(size_t)(t - 1) * N + i];
+        }
+      } else if (P.C_batched) {
         // per-element Hessians: the warp's 32 elements are consecutive, so their C_t blocks are 32 segments
         // of n*n words at a fixed stride — fetched cooperatively (consecutive lanes read consecutive words)
         // with cp.async into one of two buffers, one step ahead of use, so the DRAM latency of streaming C
@@ -764,7 +789,13 @@ __global__ void __launch_bounds__(256, 1) ilqr_backward_small(const DevProblem<R
           }
         }
         const int nlive = (P.B - b0 < 32) ? (P.B - b0) : 32;
-        if (io.grad_C && P.C_batched) {
+        if (io.grad_C && P.C_diag) {   // compact: the diagonal of -1/2 (dtau (x) tau + tau (x) dtau)
+          R* dst = io.grad_C + ((size_t)b0 * T + t) * N;
+          for (int idx = lane; idx < nlive * N; idx += 32) {
+            const int r = idx / N, j = idx % N;
+            dst[(size_t)r * T * N + j] = mytile[r * L::TW + j * N + j];
+          }
+        } else if (io.grad_C && P.C_batched) {
           R* dst = io.grad_C + ((size_t)b0 * T + t) * N * N;
           for (int idx = lane; idx < nlive * N * N; idx += 32) {
             const int r = idx / (N * N), j = idx % (N * N);
@@ -822,7 +853,11 @@ __global__ void __launch_bounds__(256, 1) ilqr_backward_small(const DevProblem<R
 #pragma unroll
       for (int i = 0; i < NX; ++i) tauN[i] = nx_[i] - nxr[i];
       if (live) {
-        if (io.grad_Cf && P.Cf_batched)
+        if (io.grad_Cf && P.C_diag) {
+#pragma unroll
+          for (int i = 0; i < N; ++i)
+            io.grad_Cf[(size_t)b * N + i] = (i < NX) ? (R)-0.5 * (dx[i < NX ? i : 0] * tauN[i < NX ? i : 0] + tauN[i < NX ? i : 0] * dx[i < NX ? i : 0]) : (R)0;
+        } else if (io.grad_Cf && P.Cf_batched)
 #pragma unroll
           for (int i = 0; i < N; ++i)
 #pragma unroll

@@ -67,15 +67,17 @@ def _prep(t, dtype, device):
     return t.detach().to(device=device, dtype=dtype).contiguous()
 
 
-def _layout(B, Cm, Cf, xref, uref):
-    return dict(C_batched=int(Cm.ndim == 4), Cf_batched=int(Cf.ndim == 3),
-                xref_batched=int(xref.shape[0] == B), uref_batched=int(uref.shape[0] == B))
+def _layout(B, Cm, Cf, xref, uref, C_diag=False):
+    # compact diagonal costs (tacd_problem.C_diag) are always per-element: C[B,T,n], C_final[B,n]
+    return dict(C_batched=int(Cm.ndim == (3 if C_diag else 4)), Cf_batched=int(Cf.ndim == (2 if C_diag else 3)),
+                xref_batched=int(xref.shape[0] == B), uref_batched=int(uref.shape[0] == B), C_diag=int(C_diag))
 
 
 def ilqr_forward(spec: Spec, x0, Cm, c, Cf, cf, xref, uref, Uinit, *, ls_cost=None, replay=None,
-                 want_AB=False, want_trace=True, want_cost_trace=False):
+                 want_AB=False, want_trace=True, want_cost_trace=False, C_diag=False):
     """solve_step (controller.py:275-315) on the GPU.  Returns a dict of device tensors:
-    X, U, tight (uint8), iters (int32), flags (uint8), cost, [alpha_trace, A, Bm, cost_trace]."""
+    X, U, tight (uint8), iters (int32), flags (uint8), cost, [alpha_trace, A, Bm, cost_trace].
+    ``C_diag``: ``Cm [B,T,n]`` / ``Cf [B,n]`` (and ``ls_cost``) hold diagonals (the ActorMPC layout)."""
     _need_cuda(x0, Cm, c, Cf, cf, xref, uref, Uinit)
     dev, dt = x0.device, x0.dtype
     x0, Cm, c, Cf, cf, xref, uref, Uinit = (_prep(t, dt, dev) for t in (x0, Cm, c, Cf, cf, xref, uref, Uinit))
@@ -86,7 +88,9 @@ def ilqr_forward(spec: Spec, x0, Cm, c, Cf, cf, xref, uref, Uinit, *, ls_cost=No
         raise RuntimeError(f"x_ref must be [B or 1, T+1={T + 1}, nx={nx}], got {tuple(xref.shape)}")
     if uref.ndim != 3 or uref.shape[1:] != (T, nu) or uref.shape[0] not in (1, B):
         raise RuntimeError(f"u_ref must be [B or 1, T={T}, nu={nu}], got {tuple(uref.shape)}")
-    p = _problem(spec, B, dt, ls_cost_shared=int(ls_cost is not None), **_layout(B, Cm, Cf, xref, uref))
+    if C_diag and (Cm.shape != (B, T, nx + nu) or Cf.shape != (B, nx + nu)):
+        raise RuntimeError(f"C_diag costs must be C[B,T,n], C_final[B,n]; got {tuple(Cm.shape)}, {tuple(Cf.shape)}")
+    p = _problem(spec, B, dt, ls_cost_shared=int(ls_cost is not None), **_layout(B, Cm, Cf, xref, uref, C_diag))
     io = _abi.ForwardIO()
     keep = [x0, Cm, c, Cf, cf, xref, uref, Uinit]
     out = dict(X=torch.empty(B, T + 1, nx, device=dev, dtype=dt), U=torch.empty(B, T, nu, device=dev, dtype=dt),
@@ -130,17 +134,21 @@ _GRAD_NAMES = ("grad_C", "grad_c", "grad_Cf", "grad_cf", "grad_x0", "grad_xref",
 
 
 def ilqr_backward(spec: Spec, X, U, Cm, xref, uref, tight, gX, gU, *, A=None, Bm=None, Cf_batched=False,
-                  want=("grad_C", "grad_c", "grad_Cf", "grad_cf", "grad_x0", "grad_xref", "grad_uref")):
+                  want=("grad_C", "grad_c", "grad_Cf", "grad_cf", "grad_x0", "grad_xref", "grad_uref"), C_diag=False):
     """ILQRSolve.backward (controller.py:63-115) on the GPU.  Outputs for shared (un-batched) inputs are
-    already summed over the batch."""
+    already summed over the batch.  ``C_diag``: ``Cm [B,T,n]`` holds diagonals; ``grad_C [B,T,n]`` and
+    ``grad_Cf [B,n]`` come back as diagonals too."""
     _need_cuda(X, U, Cm, xref, uref, tight, gX, gU, A, Bm)
     dev, dt = X.device, X.dtype
     X, U, Cm, xref, uref, gX, gU = (_prep(t, dt, dev) for t in (X, U, Cm, xref, uref, gX, gU))
     tight = tight.to(device=dev, dtype=torch.uint8).contiguous()
     B, T, nx, nu = X.shape[0], spec.T, spec.nx, spec.nu
     n = nx + nu
-    Cb, xb, ub = Cm.ndim == 4, xref.shape[0] == B, uref.shape[0] == B
-    p = _problem(spec, B, dt, C_batched=int(Cb), Cf_batched=int(Cf_batched), xref_batched=int(xb), uref_batched=int(ub))
+    Cb, xb, ub = Cm.ndim == (3 if C_diag else 4), xref.shape[0] == B, uref.shape[0] == B
+    if C_diag:
+        Cf_batched = True
+    p = _problem(spec, B, dt, C_batched=int(Cb), Cf_batched=int(Cf_batched), xref_batched=int(xb), uref_batched=int(ub),
+                 C_diag=int(C_diag))
     io = _abi.BackwardIO()
     keep = [X, U, Cm, xref, uref, tight, gX, gU]
     io.X, io.U, io.C, io.xref, io.uref, io.tight, io.gX, io.gU = (_ptr(t) for t in keep)
@@ -149,7 +157,8 @@ def ilqr_backward(spec: Spec, X, U, Cm, xref, uref, tight, gX, gU, *, A=None, Bm
         keep += [A, Bm]
         io.A, io.Bm = _ptr(A), _ptr(Bm)
     lead = lambda b: (B,) if b else ()
-    shapes = dict(grad_C=lead(Cb) + (T, n, n), grad_c=lead(Cb) + (T, n), grad_Cf=lead(Cf_batched) + (n, n),
+    shapes = dict(grad_C=lead(Cb) + ((T, n) if C_diag else (T, n, n)), grad_c=lead(Cb) + (T, n),
+                  grad_Cf=lead(Cf_batched) + ((n,) if C_diag else (n, n)),
                   grad_cf=lead(Cf_batched) + (n,), grad_x0=(B, nx), grad_xref=((B,) if xb else (1,)) + (T + 1, nx),
                   grad_uref=((B,) if ub else (1,)) + (T, nu), dX=(B, T + 1, nx), dU=(B, T, nu))
     out = {k: torch.empty(shapes[k], device=dev, dtype=dt) for k in want}
