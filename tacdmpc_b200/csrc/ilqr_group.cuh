@@ -702,27 +702,29 @@ __global__ void __launch_bounds__(384, 1) ilqr_forward_group(const DevProblem<R>
             quad_terms<R, N>(Cl, cl, tau, q1, l1);
             pCl += CS;
           }
-          if (CSH) {
-            if (!constOwn) load_cost_vec<R, N>(pCo, Ct, ct);
-            pCo += CS;
-          } else if (DIAG) {
+          if constexpr (!LSSEP) {   // (with a separate line-search cost the own cost is evaluated for the winner only)
+            if (CSH) {
+              if (!constOwn) load_cost_vec<R, N>(pCo, Ct, ct);
+              pCo += CS;
+            } else if (DIAG) {
 #pragma unroll
-            for (int i = 0; i < N; ++i) { Ct[i] = pCo[i]; ct[i] = pco[i]; }
-            pCo += N; pco += N;
-          } else {
+              for (int i = 0; i < N; ++i) { Ct[i] = pCo[i]; ct[i] = pco[i]; }
+              pCo += N; pco += N;
+            } else {
 #pragma unroll
-            for (int i = 0; i < N * N; ++i) Ct[i] = pCo[i];
+              for (int i = 0; i < N * N; ++i) Ct[i] = pCo[i];
 #pragma unroll
-            for (int i = 0; i < N; ++i) ct[i] = pco[i];
-            pCo += N * N; pco += N;
-          }
-          if (DIAG) {
-            R qd[N];
+              for (int i = 0; i < N; ++i) ct[i] = pco[i];
+              pCo += N * N; pco += N;
+            }
+            if (DIAG) {
+              R qd[N];
 #pragma unroll
-            for (int i = 0; i < N; ++i) qd[i] = Ct[i];
-            quad_terms_diag<R, N>(qd, ct, tau, q2, l2);
-          } else {
-            quad_terms<R, N>(Ct, ct, tau, q2, l2);
+              for (int i = 0; i < N; ++i) qd[i] = Ct[i];
+              quad_terms_diag<R, N>(qd, ct, tau, q2, l2);
+            } else {
+              quad_terms<R, N>(Ct, ct, tau, q2, l2);
+            }
           }
           D::step(P, sA, sB, x, u, xn);
           __syncwarp();   // every lane of the group has read K_t, k_t from the slots overwritten below
@@ -746,11 +748,10 @@ __global__ void __launch_bounds__(384, 1) ilqr_forward_group(const DevProblem<R>
 #pragma unroll
           for (int k = 0; k < NX; ++k) {
             if (LSSEP) s += sCfl[i * N + k] * tauN[k];
-            s2 += (DIAG ? ((i == k) ? Cfo[i] : (R)0) : Cfo[i * N + k]) * tauN[k];
+            else s2 += (DIAG ? ((i == k) ? Cfo[i] : (R)0) : Cfo[i * N + k]) * tauN[k];
           }
           if (LSSEP) { qN += tauN[i] * s; lN += sCfl[N * N + i] * tauN[i]; }
-          qN2 += tauN[i] * s2;
-          lN2 += cfo[i] * tauN[i];
+          else { qN2 += tauN[i] * s2; lN2 += cfo[i] * tauN[i]; }
         }
         cost_own = ((R)0.5 * q2 + l2) + ((R)0.5 * qN2 + lN2);
         cost_ls = LSSEP ? ((R)0.5 * q1 + l1) + ((R)0.5 * qN + lN) : cost_own;
@@ -773,7 +774,62 @@ __global__ void __launch_bounds__(384, 1) ilqr_forward_group(const DevProblem<R>
         }
       }
       if (run && replay) ai = io.replay_alpha[(size_t)b * P.max_iter + it];
-      const R newc = __shfl_sync(FULL, cost_own, base + ai);
+      if constexpr (LSSEP) {
+        // Acceptance cost (controller.py:298): the element's OWN cost of the chosen candidate only.  Its
+        // trajectory sits in shared memory, so the five lanes split the evaluation by rows of C_t — lane i
+        // accumulates sum_t tau_i (C_t[i,:] tau) and sum_t c_t[i] tau_i — instead of every candidate lane
+        // reading the whole per-element C_t at every step of the line search (30 global words per step and
+        // lane; 6 here, 2 for a compact diagonal).  The partial sums are combined in lane order.
+        __syncwarp();                       // candidate buffers are complete
+        const R* wp = ebuf + (ai + (ai >= nom ? 1 : 0)) * kEPW;
+        const R* prow = DIAG ? Cp + jj : Cp + jj * N;
+        const R* pc = cp + jj;
+        const R* wx = wp;
+        const R* wu = wp + (size_t)XW * WS;
+        const R* rx = refp;
+        const R* ru = refp + (size_t)XW * WS;
+        R quad = 0, lin = 0;
+        for (int t = 0; t < T; ++t) {
+          R tau[N];
+#pragma unroll
+          for (int i = 0; i < NX; ++i) tau[i] = wx[i * WS] - rx[i * WS];
+#pragma unroll
+          for (int i = 0; i < NU; ++i) tau[NX + i] = wu[i * WS] - ru[i * WS];
+          const R tj = pick<N, R>(tau, jj);
+          R s = 0;
+          if (DIAG) {
+            // q_j tau_j plus the exact zeros the dense row would add (NaN if some tau_k is not finite)
+#pragma unroll
+            for (int k = 0; k < N; ++k) s += tau[k] * (R)0;
+            s += prow[0] * tj;
+          } else {
+#pragma unroll
+            for (int k = 0; k < N; ++k) s += prow[k] * tau[k];
+          }
+          quad += tj * s;
+          lin += pc[0] * tj;
+          wx += NX * WS; wu += NU * WS; rx += NX * WS; ru += NU * WS; prow += CW; pc += N;
+        }
+        R qsum = 0, lsum = 0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          qsum += __shfl_sync(FULL, quad, base + i);
+          lsum += __shfl_sync(FULL, lin, base + i);
+        }
+        R tauN[NX], qN2 = 0, lN2 = 0;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) tauN[i] = wx[i * WS] - rx[i * WS];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+          R s2 = 0;
+#pragma unroll
+          for (int k = 0; k < NX; ++k) s2 += (DIAG ? ((i == k) ? Cfo[i] : (R)0) : Cfo[i * N + k]) * tauN[k];
+          qN2 += tauN[i] * s2;
+          lN2 += cfo[i] * tauN[i];
+        }
+        cost_own = ((R)0.5 * qsum + lsum) + ((R)0.5 * qN2 + lN2);
+      }
+      const R newc = LSSEP ? cost_own : __shfl_sync(FULL, cost_own, base + ai);
       improved = newc < best;
       if (run && replay) improved = (it < io.replay_iters[b] - 1) || ((io.replay_flags[b] & TACD_FLAG_MAXITER) != 0);
       if (run && j == 0) {
