@@ -189,18 +189,21 @@ TACD_DEV void load_cost_vec(const R* p, R (&Ct)[N * N], R (&ct)[N]) {
 // A warp's 32 elements are contiguous in every [B, ...] tensor, so x_ref / u_ref / U_init come in with
 // cp.async as coalesced row copies into a shared-memory tile with an odd row stride (thread e then walks row
 // e conflict-free), X_t is written over the slot of x_ref[t] once that has been read and leaves as
-// coalesced rows; per-element costs stream through two more tiles, kInitChunk time steps at a time, one
-// chunk ahead of use.  All copies of a chunk are in flight together: read with plain strided loads this
-// kernel is one DRAM latency per time step (47 us shared-cost, ~110 us per-element at B = 65536).
-constexpr int kInitChunk = 4;
+// coalesced rows; per-element costs come in the same way, `chunk` time steps at a time: the whole horizon
+// in one piece when the tile fits (one DRAM latency for everything), else double-buffered one chunk ahead.
 __host__ __device__ inline int init_in_words(int T, int nx, int nu) { return ((T + 1) * nx + 2 * T * nu) | 1; }
-__host__ __device__ inline int init_cost_words(int nx, int nu) { return (kInitChunk * ((nx + nu) * (nx + nu) + nx + nu)) | 1; }
-__host__ __device__ inline size_t init_warp_words(int T, int nx, int nu, int C_batched) {
-  return (size_t)32 * init_in_words(T, nx, nu) + (C_batched ? (size_t)64 * init_cost_words(nx, nu) : 0);
+// row stride of a cost tile: chunk steps of [C_t (cw words: n*n dense, n compact diagonal)] then chunk steps of c_t
+__host__ __device__ inline int init_cost_words(int chunk, int nx, int nu, int C_diag) {
+  const int n = nx + nu;
+  return (chunk * ((C_diag ? n : n * n) + n)) | 1;
+}
+__host__ __device__ inline size_t init_warp_words(int T, int nx, int nu, int C_batched, int C_diag, int chunk) {
+  return (size_t)32 * init_in_words(T, nx, nu) +
+         (C_batched ? (size_t)(chunk >= T ? 32 : 64) * init_cost_words(chunk, nx, nu, C_diag) : 0);
 }
 
 template <typename R, int NX, int NU, int DYN>
-__global__ void __launch_bounds__(128) ilqr_init_rollout(const DevProblem<R> P, const FwdPtrs<R> io, R* cost0) {
+__global__ void __launch_bounds__(128) ilqr_init_rollout(const DevProblem<R> P, const FwdPtrs<R> io, R* cost0, int chunk) {
   constexpr int N = NX + NU;
   using D = Dyn<R, NX, NU, DYN>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -213,24 +216,25 @@ __global__ void __launch_bounds__(128) ilqr_init_rollout(const DevProblem<R> P, 
     __syncthreads();
   }
   const int T = P.T, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int XW = (T + 1) * NX, UW = T * NU, RSI = init_in_words(T, NX, NU), RSC = init_cost_words(NX, NU);
+  const int XW = (T + 1) * NX, UW = T * NU, RSI = init_in_words(T, NX, NU), RSC = init_cost_words(chunk, NX, NU, P.C_diag);
+  const int cw = P.C_diag ? N : N * N;   // words of C per step (compact diagonal or dense)
   // row of one element: [x_ref -> X (XW) | u_ref (UW) | U_init (UW)]
-  R* tile = reinterpret_cast<R*>(smem_raw) + (size_t)wid * init_warp_words(T, NX, NU, P.C_batched);
-  R* ctile = tile + (size_t)32 * RSI;   // [2][32][RSC]: [C_t0.. (chunk*N*N) | c_t0.. (chunk*N)]
+  R* tile = reinterpret_cast<R*>(smem_raw) + (size_t)wid * init_warp_words(T, NX, NU, P.C_batched, P.C_diag, chunk);
+  R* ctile = tile + (size_t)32 * RSI;   // [1 or 2][32][RSC]: [C_t0.. (chunk*cw) | c_t0.. (chunk*N)]
+  const int nbuf = chunk >= T ? 1 : 2;
   const int b0 = (blockIdx.x * (blockDim.x >> 5) + wid) * 32;
   if (b0 >= P.B) return;
   const int nlive = P.B - b0 < 32 ? P.B - b0 : 32;
-  const int nchunk = (T + kInitChunk - 1) / kInitChunk;
+  const int nchunk = (T + chunk - 1) / chunk;
   auto fetch_cost = [&](int c) {
     if (P.C_batched && c < nchunk) {
-      const int t0 = c * kInitChunk, nst = (T - t0 < kInitChunk) ? T - t0 : kInitChunk;
-      R* buf = ctile + (size_t)(c & 1) * 32 * RSC;
-      const int cw = P.C_diag ? N : N * N;   // words of C per step (compact diagonal or dense)
+      const int t0 = c * chunk, nst = (T - t0 < chunk) ? T - t0 : chunk;
+      R* buf = ctile + (size_t)(c & (nbuf - 1)) * 32 * RSC;
       for (int r = 0; r < nlive; ++r) {
         const R* Cg = io.C + ((size_t)(b0 + r) * T + t0) * cw;
         const R* cg = io.c + ((size_t)(b0 + r) * T + t0) * N;
         for (int w = lane; w < nst * cw; w += 32) cp_async<R>(&buf[(size_t)r * RSC + w], &Cg[w]);
-        for (int w = lane; w < nst * N; w += 32) cp_async<R>(&buf[(size_t)r * RSC + kInitChunk * N * N + w], &cg[w]);
+        for (int w = lane; w < nst * N; w += 32) cp_async<R>(&buf[(size_t)r * RSC + chunk * cw + w], &cg[w]);
       }
     }
     cp_async_commit();
@@ -260,8 +264,8 @@ __global__ void __launch_bounds__(128) ilqr_init_rollout(const DevProblem<R> P, 
   for (int c = 0; c < nchunk; ++c) {
     cp_async_wait_group<1>();
     __syncwarp();
-    const int t0 = c * kInitChunk, t1 = (t0 + kInitChunk < T) ? t0 + kInitChunk : T;
-    const R* cbuf = ctile + ((size_t)(c & 1) * 32 + (lane < nlive ? lane : nlive - 1)) * RSC;
+    const int t0 = c * chunk, t1 = (t0 + chunk < T) ? t0 + chunk : T;
+    const R* cbuf = ctile + ((size_t)(c & (nbuf - 1)) * 32 + (lane < nlive ? lane : nlive - 1)) * RSC;
     for (int t = t0; t < t1; ++t) {
       R tau[N], Ct[N * N], ct[N];
 #pragma unroll
@@ -274,12 +278,12 @@ __global__ void __launch_bounds__(128) ilqr_init_rollout(const DevProblem<R> P, 
 #pragma unroll
         for (int i = 0; i < N * N; ++i) Ct[i] = (i / N == i % N) ? cbuf[(t - t0) * N + i / N] : (R)0;
 #pragma unroll
-        for (int i = 0; i < N; ++i) ct[i] = cbuf[kInitChunk * N * N + (t - t0) * N + i];
+        for (int i = 0; i < N; ++i) ct[i] = cbuf[chunk * cw + (t - t0) * N + i];
       } else if (P.C_batched) {
 #pragma unroll
         for (int i = 0; i < N * N; ++i) Ct[i] = cbuf[(t - t0) * N * N + i];
 #pragma unroll
-        for (int i = 0; i < N; ++i) ct[i] = cbuf[kInitChunk * N * N + (t - t0) * N + i];
+        for (int i = 0; i < N; ++i) ct[i] = cbuf[chunk * cw + (t - t0) * N + i];
       } else {
 #pragma unroll
         for (int i = 0; i < N * N; ++i) Ct[i] = Cp[(size_t)t * N * N + i];

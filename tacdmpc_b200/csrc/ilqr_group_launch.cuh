@@ -64,14 +64,18 @@ static int run_forward_group(const tacd_problem* p, const tacd_forward_io* io, v
   {
     auto init = ilqr_init_rollout<R, NX, NU, DYN>;
     // a horizon whose tile does not fit goes to the thread-per-element kernel
-    const size_t tile_b = init_warp_words(p->T, NX, NU, p->C_batched) * sizeof(R);
+    // per-element costs: the whole horizon in one tile when one warp's tile stays under ~1/2 of shared memory
+    // (two resident warps per SM keep enough bytes in flight), else four steps at a time, double-buffered
+    int chunk = p->T;
+    if (p->C_batched && init_warp_words(p->T, NX, NU, 1, p->C_diag, chunk) * sizeof(R) > (size_t)di.smem_optin / 2) chunk = p->T < 4 ? p->T : 4;
+    const size_t tile_b = init_warp_words(p->T, NX, NU, p->C_batched, p->C_diag, chunk) * sizeof(R);
     // one warp per CTA: the finest granularity for the last wave (2048 warps over 148 SMs at B = 65536)
     if (tile_b > (size_t)di.smem_optin) return TACD_EUNSUPPORTED;
     int iw = 1;
     if (const char* e = getenv("TACD_INIT_WARPS")) { const int v = atoi(e); if (v >= 1 && v <= 4 && tile_b * v <= (size_t)di.smem_optin) iw = v; }
     if (int rc = check_cuda(cudaFuncSetAttribute(init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(tile_b * iw)), "smem attr")) return rc;
     const int nwarp = (p->B + 31) / 32;
-    init<<<(nwarp + iw - 1) / iw, iw * 32, tile_b * iw, s>>>(dp, f, cost0);
+    init<<<(nwarp + iw - 1) / iw, iw * 32, tile_b * iw, s>>>(dp, f, cost0, chunk);
     note_launches(1);
   }
   if (int rc = check_cuda(cudaPeekAtLastError(), "ilqr_init_rollout launch")) return rc;
