@@ -533,7 +533,7 @@ struct BwdLayout {
   __host__ __device__ static int nacc(int T) { return T * NV + NVF; }
 };
 
-template <typename R, int NX, int NU, int DYN>
+template <typename R, int NX, int NU, int DYN, bool DIAG>
 __global__ void __launch_bounds__(256, 1) ilqr_backward_small(const DevProblem<R> P, const BwdPtrs<R> io, R* partials, int reduce) {
   constexpr int N = NX + NU;
   using L = BwdLayout<NX, NU>;
@@ -572,7 +572,7 @@ __global__ void __launch_bounds__(256, 1) ilqr_backward_small(const DevProblem<R
     const R* X = io.X + (size_t)bb * szX;
     const R* U = io.U + (size_t)bb * szU;
     // tacd_problem.C_diag: C[B,T,n] holds the diagonals (ActorMPC layout), gradients come back compact too
-    const R* Cp = io.C + (P.C_batched ? (size_t)bb * T * (P.C_diag ? N : N * N) : 0);
+    const R* Cp = io.C + (P.C_batched ? (size_t)bb * T * (DIAG ? N : N * N) : 0);
     const R* xr = io.xref + (P.xref_batched ? (size_t)bb * szX : 0);
     const R* ur = io.uref + (P.uref_batched ? (size_t)bb * szU : 0);
     const R* gX = io.gX + (size_t)bb * szX;
@@ -598,7 +598,7 @@ __global__ void __launch_bounds__(256, 1) ilqr_backward_small(const DevProblem<R
     for (int i = 0; i < NX; ++i) {
 #pragma unroll
       for (int j = 0; j < NX; ++j)
-        V[i * NX + j] = P.C_diag ? ((i == j) ? Cp[(size_t)(T - 1) * N + i] : (R)0) : Cp[(size_t)(T - 1) * N * N + i * N + j];
+        V[i * NX + j] = DIAG ? ((i == j) ? Cp[(size_t)(T - 1) * N + i] : (R)0) : Cp[(size_t)(T - 1) * N * N + i * N + j];
       ngx[i] = gX[(T - 1) * NX + i];
       nx_[i] = X[(T - 1) * NX + i];
       v[i] = -ngx[i];
@@ -614,10 +614,10 @@ __global__ void __launch_bounds__(256, 1) ilqr_backward_small(const DevProblem<R
         cp_async<R>(&buf[r * L::CW + j], &base[(size_t)rr * T * N * N + j]);
       }
     };
-    if (P.C_batched && !P.C_diag) { __syncwarp(); fetch_C(T - 1); }
+    if (P.C_batched && !DIAG) { __syncwarp(); fetch_C(T - 1); }
     R nqd[N];   // C_diag: diagonal of the step about to run (prefetched like the other per-step inputs)
 #pragma unroll
-    for (int i = 0; i < N; ++i) nqd[i] = P.C_diag ? Cp[(size_t)(T - 1) * N + i] : (R)0;
+    for (int i = 0; i < N; ++i) nqd[i] = DIAG ? Cp[(size_t)(T - 1) * N + i] : (R)0;
     for (int t = T - 1; t >= 0; --t) {
       R x[NX], u[NU], Qxx[NX * NX], Qxu[NX * NU], Quu[NU * NU], qx[NX], qu[NU], A[NX * NX], Bm[NX * NU];
       bool fixed[NU];
@@ -631,7 +631,7 @@ __global__ void __launch_bounds__(256, 1) ilqr_backward_small(const DevProblem<R
 #pragma unroll
         for (int i = 0; i < NU; ++i) { nu_[i] = U[(t - 1) * NU + i]; ngu[i] = gU[(t - 1) * NU + i]; ntg[i] = tg[(t - 1) * NU + i] != 0; }
       }
-      if (P.C_diag) {
+      if (DIAG) {
 #pragma unroll
         for (int i = 0; i < NX; ++i) {
 #pragma unroll
@@ -789,7 +789,7 @@ __global__ void __launch_bounds__(256, 1) ilqr_backward_small(const DevProblem<R
           }
         }
         const int nlive = (P.B - b0 < 32) ? (P.B - b0) : 32;
-        if (io.grad_C && P.C_diag) {   // compact: the diagonal of -1/2 (dtau (x) tau + tau (x) dtau)
+        if (io.grad_C && DIAG) {   // compact: the diagonal of -1/2 (dtau (x) tau + tau (x) dtau)
           R* dst = io.grad_C + ((size_t)b0 * T + t) * N;
           for (int idx = lane; idx < nlive * N; idx += 32) {
             const int r = idx / N, j = idx % N;
@@ -853,7 +853,7 @@ __global__ void __launch_bounds__(256, 1) ilqr_backward_small(const DevProblem<R
 #pragma unroll
       for (int i = 0; i < NX; ++i) tauN[i] = nx_[i] - nxr[i];
       if (live) {
-        if (io.grad_Cf && P.C_diag) {
+        if (io.grad_Cf && DIAG) {
 #pragma unroll
           for (int i = 0; i < N; ++i)
             io.grad_Cf[(size_t)b * N + i] = (i < NX) ? (R)-0.5 * (dx[i < NX ? i : 0] * tauN[i < NX ? i : 0] + tauN[i < NX ? i : 0] * dx[i < NX ? i : 0]) : (R)0;

@@ -87,9 +87,9 @@ static int run_forward_small(const tacd_problem* p, const tacd_forward_io* io, v
   return check_cuda(cudaPeekAtLastError(), "ilqr_forward_small launch");
 }
 
-template <typename R, int NX, int NU, int DYN>
+template <typename R, int NX, int NU, int DYN, bool DIAG>
 static int run_backward_small(const tacd_problem* p, const tacd_backward_io* io, void* ws, size_t ws_bytes, cudaStream_t s) {
-  auto kernel = ilqr_backward_small<R, NX, NU, DYN>;
+  auto kernel = ilqr_backward_small<R, NX, NU, DYN, DIAG>;
   using L = BwdLayout<NX, NU>;
   const int nacc = L::nacc(p->T);
   const bool reduce = (io->grad_C && !p->C_batched) || (io->grad_c && !p->C_batched) || (io->grad_Cf && !p->Cf_batched) ||
@@ -160,7 +160,9 @@ int launch_forward_small(const tacd_problem* p, const tacd_forward_io* io, void*
 template <typename R>
 int launch_backward_small(const tacd_problem* p, const tacd_backward_io* io, void* ws, size_t ws_bytes, cudaStream_t s) {
 #define X(NX_, NU_, DYN_) \
-  if (p->nx == NX_ && p->nu == NU_ && p->dyn_id == DYN_) return run_backward_small<R, NX_, NU_, DYN_>(p, io, ws, ws_bytes, s);
+  if (p->nx == NX_ && p->nu == NU_ && p->dyn_id == DYN_)                                      \
+    return p->C_diag ? run_backward_small<R, NX_, NU_, DYN_, true>(p, io, ws, ws_bytes, s)    \
+                     : run_backward_small<R, NX_, NU_, DYN_, false>(p, io, ws, ws_bytes, s);
   TACD_SMALL_BWD(X)
 #undef X
   return TACD_EUNSUPPORTED;
