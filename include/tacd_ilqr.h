@@ -199,6 +199,17 @@ int tacd_linesearch(const tacd_problem* p, const void* x0, const void* X, const 
                     const void* C, const void* c, const void* Cf, const void* cf,
                     const void* xref, const void* uref,
                     void* Xc, void* Uc, void* costs, void* stream);
+/* One receding-horizon step of the closed loop the reference's demos and (stale) tests run in Python
+ * (examples/03_demo_unicycle_tracking.py:131-141, tests/test_batch_tracking.py:76-84), after the solve of
+ * simulation step k:  u_k = U_opt[:,0];  x <- f(x, u_k);  Xs[:,k+1] = x;  Us[:,k] = u_k;
+ * U_warm = roll(U_opt, -1) with the last input zeroed;  and, if k+1 < n_sim, the reference windows of the next
+ * solve  xref_win = xref_full[:, k+1 : k+T+2],  uref_win = uref_full[:, k+1 : k+T+1]  (contiguous copies).
+ * x[B,nx] in/out; Xs[B,n_sim+1,nx]; Us[B,n_sim,nu]; xref_full[B or 1, ref_len, nx]; uref_full[B or 1,
+ * ref_len-1, nu] (batched as tacd_problem.xref_batched / uref_batched say); U_warm, xref_win, uref_win nullable. */
+int tacd_closed_loop_advance(const tacd_problem* p, int32_t k, int32_t n_sim, void* x, const void* U_opt,
+                             void* Xs, void* Us, void* U_warm,
+                             const void* xref_full, const void* uref_full, int32_t ref_len,
+                             void* xref_win, void* uref_win, void* stream);
 /* batched projected-Newton box QP: H[N,m,m] q[N,m] lo[N,m] hi[N,m] -> x[N,m], iters[N] (nullable) */
 int tacd_pnqp(int32_t dtype, int32_t N, int32_t m, const void* H, const void* q,
               const void* lo, const void* hi, void* x, int32_t* iters, void* stream);

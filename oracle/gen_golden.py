@@ -455,6 +455,48 @@ def closed_loop_batch_tracking():
     print("closed_loop_batch_tracking       Xs", d["Xs"].shape)
 
 
+def closed_loop_unicycle_warm():
+    """examples/03_demo_unicycle_tracking.py:119-141: two unicycle agents track lemniscates in closed loop, the
+    solve warm-started with the previous plan shifted by one step (torch.roll, last input zeroed)."""
+    torch.set_default_dtype(torch.float64)
+    nx, nu, T, N_sim, dt, B = 3, 2, 10, 25, 0.1, 2
+    C, c, Cf, cf = quad_cost(torch.diag(torch.tensor([20.0, 20.0, 5.0])), torch.diag(torch.tensor([0.1, 0.1])), T)
+    C, c, Cf, cf = (t.double() for t in (C, c, Cf, cf))
+    cm = GeneralQuadCost(nx, nu, C, c, Cf, cf, device="cpu")
+    mpc = DifferentiableMPCController(EX3.f_dyn_unicycle, T * dt, dt, T, cm,
+                                      u_min=torch.tensor([-10.0, -2 * np.pi]), u_max=torch.tensor([10.0, 2 * np.pi]),
+                                      grad_method="analytic", f_dyn_jac=EX3.f_dyn_jac_unicycle, reg_eps=1e-6, device="cpu",
+                                      N_sim=N_sim)
+    ref_len = N_sim + T + 1
+    ts = torch.arange(ref_len, dtype=torch.float64) * dt
+    refs = []
+    for amp, ph in ((4.0, 0.0), (3.0, 1.0)):
+        th = 0.4 * ts + ph
+        xr, yr = amp * torch.cos(th), amp * torch.sin(th) * torch.cos(th)
+        hd = torch.atan2(torch.gradient(yr)[0], torch.gradient(xr)[0])
+        refs.append(torch.stack([xr, yr, hd], dim=1))
+    xref_full = torch.stack(refs, dim=0)
+    uref_full = torch.zeros(B, ref_len - 1, nu)
+    x0 = xref_full[:, 0].clone() + torch.tensor([[1.0, -1.0, 0.3], [-1.0, 1.0, -0.3]])
+    Xs, Us, its = [x0], [], []
+    x, warm = x0, torch.zeros(B, T, nu)
+    with torch.no_grad():
+        for k in range(N_sim):
+            cm.set_reference(xref_full[:, k:k + T + 1], uref_full[:, k:k + T])
+            _, U = mpc.forward(x, U_init=warm)
+            u = U[:, 0]
+            x = EX3.f_dyn_unicycle(x, u, dt)
+            Xs.append(x)
+            Us.append(u)
+            warm = torch.roll(U, shifts=-1, dims=1)
+            warm[:, -1] = 0.0
+    d = dict(x0=_np(x0), xref_full=_np(xref_full), uref_full=_np(uref_full), C=_np(C), c=_np(c), Cf=_np(Cf), cf=_np(cf),
+             Xs=_np(torch.stack(Xs, 1)), Us=_np(torch.stack(Us, 1)), meta_T=T, meta_N_sim=N_sim, meta_dt=dt)
+    np.savez_compressed(os.path.join(OUT, "closed_loop_unicycle_warm.npz"), **d)
+    print("closed_loop_unicycle_warm        Xs", d["Xs"].shape, "max |x - ref| at the end",
+          float((d["Xs"][:, -1, :2] - d["xref_full"][:, N_sim, :2]).__abs__().max()))
+
+
 def pnqp_kats():
     d = {}
     for dtype, tag in ((torch.float64, "f64"), (torch.float32, "f32")):
@@ -545,6 +587,7 @@ def main():
     run_case("lti32_f32", **case_lti(F32, nx=32, nu=8, T=10, B=2))
     run_case("gradcheck_f64", **case_gradcheck())
     closed_loop_batch_tracking()
+    closed_loop_unicycle_warm()
     pnqp_kats()
 
 

@@ -298,7 +298,16 @@ class DifferentiableMPCController(torch.nn.Module):
         return C, c, Cf, cf, xref, uref, ls
 
     # ------------------------------------------------------------------ public API
-    def forward(self, x0: Tensor, U_init: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+    def forward(self, x0: Tensor, U_init: Optional[Tensor] = None, *, x_ref_full: Optional[Tensor] = None,
+                u_ref_full: Optional[Tensor] = None, warm_start: bool = True) -> Tuple[Tensor, Tensor]:
+        """``mpc(x0, U_init)``: one solve, ``(X*[B,T+1,nx], U*[B,T,nu])`` (controller.py:266-273).
+
+        ``mpc(x0, x_ref_full=..., u_ref_full=...)``: the receding-horizon closed loop of the reference's demos and
+        of tests/test_batch_tracking.py:76-84 / tests/test_forward.py:92-95 — ``N_sim`` steps, each solving from the
+        current state against the reference window ``[k, k+T]`` and applying the first input; returns
+        ``(Xs[B,N_sim+1,nx], Us[B,N_sim,nu])``.  See ``simulate``."""
+        if x_ref_full is not None or u_ref_full is not None:
+            return self.simulate(x0, x_ref_full, u_ref_full, U_init=U_init, warm_start=warm_start)
         B = x0.shape[0] if x0.ndim > 1 else 1
         if U_init is None:
             U_init = torch.zeros(B, self.horizon, self.nu, device=x0.device, dtype=x0.dtype)
@@ -306,6 +315,80 @@ class DifferentiableMPCController(torch.nn.Module):
         if isinstance(cm, DiagQuadCost):
             return ILQRSolveDiag.apply(x0, cm.q, cm.p, cm.q_final, cm.p_final, cm.x_ref, cm.u_ref, self, U_init)
         return ILQRSolve.apply(x0, cm.C, cm.c, cm.C_final, cm.c_final, cm.x_ref, cm.u_ref, self, U_init)
+
+    def simulate(self, x0: Tensor, x_ref_full: Tensor, u_ref_full: Optional[Tensor] = None, *, U_init: Optional[Tensor] = None,
+                 warm_start: bool = True, N_sim: Optional[int] = None) -> Tuple[Tensor, Tensor]:
+        """Closed-loop receding-horizon simulation.
+
+        Per step k < N_sim: references = ``x_ref_full[:, k:k+T+1]``, ``u_ref_full[:, k:k+T]``; solve from the current
+        state; ``u_k = U*[:,0]``; ``x <- f(x, u_k, dt)``; the next solve starts from the previous plan shifted by
+        one step with the last input zeroed (``warm_start=True``, examples/03_demo_unicycle_tracking.py:139-140) or
+        from zeros (``False``, tests/test_batch_tracking.py).  ``x_ref_full`` is ``[B or 1, >= N_sim+T+1, nx]``.
+
+        With a shipped dynamics plugin and no gradient required the whole loop stays on the device: per step the
+        solve kernels plus ONE ``tacd_closed_loop_advance`` launch, no host synchronisation, no per-step tensor
+        allocation on the reference path.  When a gradient is required (or ``f_dyn`` is a Python callable) the same
+        loop runs through autograd, one ``ILQRSolve`` node per step."""
+        if x0.ndim != 2:
+            raise RuntimeError("x0 must be [B, nx] (quirk Q12)")
+        N = int(N_sim if N_sim is not None else self.N_sim)
+        T, nx, nu, B = self.horizon, self.nx, self.nu, x0.shape[0]
+        cm = self.cost_module
+        if x_ref_full is None:
+            raise RuntimeError("simulate needs x_ref_full [B or 1, N_sim + T + 1, nx]")
+        if x_ref_full.ndim == 2:
+            x_ref_full = x_ref_full.unsqueeze(0)
+        if u_ref_full is None:
+            u_ref_full = torch.zeros(x_ref_full.shape[0], x_ref_full.shape[1] - 1, nu, device=x_ref_full.device, dtype=x_ref_full.dtype)
+        if u_ref_full.ndim == 2:
+            u_ref_full = u_ref_full.unsqueeze(0)
+        if x_ref_full.shape[1] < N + T + 1 or u_ref_full.shape[1] < N + T:
+            raise RuntimeError(f"reference trajectories must cover N_sim + T + 1 = {N + T + 1} states and {N + T} inputs")
+        params = [x0, x_ref_full, u_ref_full] + ([cm.q, cm.p, cm.q_final, cm.p_final] if isinstance(cm, DiagQuadCost)
+                                                 else [cm.C, cm.c, cm.C_final, cm.c_final])
+        needs_grad = torch.is_grad_enabled() and any(isinstance(t, Tensor) and t.requires_grad for t in params)
+        if not needs_grad and self._is_native() and x0.is_cuda:
+            return self._simulate_device(x0, x_ref_full, u_ref_full, U_init, warm_start, N)
+        # autograd / generic path: the loop of the reference's demos, step by step
+        x = x0
+        warm = U_init if U_init is not None else torch.zeros(B, T, nu, device=x0.device, dtype=x0.dtype)
+        Xs, Us = [x0], []
+        for k in range(N):
+            cm.set_reference(x_ref_full[:, k:k + T + 1], u_ref_full[:, k:k + T])
+            _, U = self.forward(x, warm)
+            u = U[:, 0]
+            x = self.f_dyn(x, u, self.dt)
+            Xs.append(x)
+            Us.append(u)
+            if warm_start:
+                warm = torch.cat((U[:, 1:].detach(), torch.zeros(B, 1, nu, device=U.device, dtype=U.dtype)), dim=1)
+            else:
+                warm = torch.zeros(B, T, nu, device=x0.device, dtype=x0.dtype)
+        return torch.stack(Xs, dim=1), torch.stack(Us, dim=1)
+
+    def _simulate_device(self, x0, x_ref_full, u_ref_full, U_init, warm_start, N):
+        dtype, device = _solve_dtype(x0), x0.device
+        T, nx, nu, B = self.horizon, self.nx, self.nu, x0.shape[0]
+        spec = self._spec(dtype, device)
+        prep = lambda t: t.detach().to(device=device, dtype=dtype).contiguous()
+        xf, uf = prep(x_ref_full), prep(u_ref_full)
+        xw, uw = xf[:, :T + 1].contiguous(), uf[:, :T].contiguous()
+        self.cost_module.set_reference(xw, uw)
+        C, c, Cf, cf, _, _, ls = self._costs(B, dtype, device)
+        x = prep(x0).clone()
+        warm = prep(U_init).clone() if U_init is not None else torch.zeros(B, T, nu, device=device, dtype=dtype)
+        Xs = torch.empty(B, N + 1, nx, device=device, dtype=dtype)
+        Us = torch.empty(B, N, nu, device=device, dtype=dtype)
+        out = None
+        for k in range(N):
+            out = ops.ilqr_forward(spec, x, C, c, Cf, cf, xw, uw, warm, ls_cost=ls, want_trace=False, C_diag=self._last_diag)
+            ops.closed_loop_advance(spec, k, N, x, out["U"], Xs, Us, warm if warm_start else None, xf, uf, xw, uw)
+        if out is not None:
+            self.X_last, self.U_last = out["X"].to(x0.dtype), out["U"].to(x0.dtype)
+            self.tight_mask_last = out["tight"].bool()
+            self.iters_last, self.flags_last, self.cost_last = out["iters"], out["flags"], out["cost"]
+        self.converged = True
+        return Xs.to(x0.dtype), Us.to(x0.dtype)
 
     def solve_step(self, x0: Tensor, U_init: Tensor) -> Tuple[Tensor, Tensor]:
         """One full iLQR solve from (x0, U_init) (controller.py:275-315)."""

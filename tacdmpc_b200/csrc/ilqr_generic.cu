@@ -519,6 +519,53 @@ __global__ void stage_pnqp(int N, int m, const R* H, const R* q, const R* lo, co
 
 // ---------------------------------------------------------------------------
 // host launchers
+// closed-loop advance (tacd_closed_loop_advance): one thread per element, run-time dimensions
+template <typename R>
+__global__ void __launch_bounds__(128) closed_loop_advance(const DevProblem<R> P, const GenDims<R> d, int k, int n_sim, R* x, const R* U_opt,
+                                                           R* Xs, R* Us, R* U_warm, const R* xref_full, const R* uref_full, int ref_len,
+                                                           R* xref_win, R* uref_win) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= P.B) return;
+  const int nx = d.nx, nu = d.nu, T = d.T;
+  R xc[TACD_MAX_NX], xn[TACD_MAX_NX], u[TACD_MAX_NU];
+  for (int i = 0; i < nx; ++i) xc[i] = x[(size_t)b * nx + i];
+  for (int i = 0; i < nu; ++i) u[i] = U_opt[(size_t)b * T * nu + i];
+  if (d.dyn == TACD_DYN_LTI) {
+    for (int i = 0; i < nx; ++i) {
+      R s = 0, s2 = 0;
+      for (int j = 0; j < nx; ++j) s += P.dyn_A[i * nx + j] * xc[j];
+      for (int j = 0; j < nu; ++j) s2 += P.dyn_B[i * nu + j] * u[j];
+      xn[i] = s + s2;
+    }
+  } else {
+    gen_dyn_step_scalar<R>(P, d.dyn, xc, u, xn);
+  }
+  if (k == 0)
+    for (int i = 0; i < nx; ++i) Xs[(size_t)b * (n_sim + 1) * nx + i] = xc[i];
+  for (int i = 0; i < nx; ++i) {
+    x[(size_t)b * nx + i] = xn[i];
+    Xs[((size_t)b * (n_sim + 1) + k + 1) * nx + i] = xn[i];
+  }
+  for (int i = 0; i < nu; ++i) Us[((size_t)b * n_sim + k) * nu + i] = u[i];
+  if (U_warm) {
+    for (int t = 0; t + 1 < T; ++t)
+      for (int i = 0; i < nu; ++i) U_warm[((size_t)b * T + t) * nu + i] = U_opt[((size_t)b * T + t + 1) * nu + i];
+    for (int i = 0; i < nu; ++i) U_warm[((size_t)b * T + T - 1) * nu + i] = 0;
+  }
+  if (k + 1 < n_sim) {
+    if (xref_win && (P.xref_batched || b == 0)) {
+      const R* src = xref_full + ((size_t)(P.xref_batched ? b : 0) * ref_len + k + 1) * nx;
+      R* dst = xref_win + (size_t)(P.xref_batched ? b : 0) * (T + 1) * nx;
+      for (int i = 0; i < (T + 1) * nx; ++i) dst[i] = src[i];
+    }
+    if (uref_win && (P.uref_batched || b == 0)) {
+      const R* src = uref_full + ((size_t)(P.uref_batched ? b : 0) * (ref_len - 1) + k + 1) * nu;
+      R* dst = uref_win + (size_t)(P.uref_batched ? b : 0) * T * nu;
+      for (int i = 0; i < T * nu; ++i) dst[i] = src[i];
+    }
+  }
+}
+
 template <typename K>
 static int prep_smem(K kernel, size_t bytes) {
   const DeviceInfo di = device_info();
@@ -650,6 +697,30 @@ using namespace tacd;
 #define TACD_DISPATCH(p, fn, ...) ((p)->dtype == TACD_F32 ? fn<float>(__VA_ARGS__) : fn<double>(__VA_ARGS__))
 
 extern "C" {
+
+int tacd_closed_loop_advance(const tacd_problem* p, int32_t k, int32_t n_sim, void* x, const void* U_opt, void* Xs, void* Us,
+                             void* U_warm, const void* xref_full, const void* uref_full, int32_t ref_len, void* xref_win,
+                             void* uref_win, void* stream) {
+  if (!p || p->nx < 1 || p->nu < 1 || p->nx > TACD_MAX_NX || p->nu > TACD_MAX_NU || p->T < 1 || p->B < 0) { set_error("bad sizes"); return TACD_EINVAL; }
+  if (p->dyn_id == TACD_DYN_EXTERNAL) { set_error("closed-loop advance needs embedded dynamics"); return TACD_EINVAL; }
+  if (k < 0 || k >= n_sim || !x || !U_opt || !Xs || !Us) { set_error("tacd_closed_loop_advance: bad step index or null pointer"); return TACD_EINVAL; }
+  if ((xref_win && !xref_full) || (uref_win && !uref_full) || ((xref_win || uref_win) && ref_len < n_sim + p->T + 1)) {
+    set_error("reference trajectories must cover n_sim + T + 1 steps"); return TACD_EINVAL;
+  }
+  if (p->B == 0) return TACD_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int grid = (p->B + 127) / 128;
+  if (p->dtype == TACD_F32)
+    closed_loop_advance<float><<<grid, 128, 0, s>>>(to_dev<float>(p), dims_of<float>(p), k, n_sim, (float*)x, (const float*)U_opt, (float*)Xs,
+                                                    (float*)Us, (float*)U_warm, (const float*)xref_full, (const float*)uref_full, ref_len,
+                                                    (float*)xref_win, (float*)uref_win);
+  else
+    closed_loop_advance<double><<<grid, 128, 0, s>>>(to_dev<double>(p), dims_of<double>(p), k, n_sim, (double*)x, (const double*)U_opt,
+                                                     (double*)Xs, (double*)Us, (double*)U_warm, (const double*)xref_full,
+                                                     (const double*)uref_full, ref_len, (double*)xref_win, (double*)uref_win);
+  note_launches(1);
+  return check_cuda(cudaPeekAtLastError(), "closed_loop_advance launch");
+}
 
 int tacd_rollout(const tacd_problem* p, const void* x0, const void* U, void* X, void* stream) {
   if (int rc = stage_common<float>(p)) return rc;

@@ -256,3 +256,22 @@ def pnqp(H, q, lo, hi):
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().tacd_pnqp(_DT[dt], N, m, *_vp(H, q, lo, hi, x, iters), _stream()), "tacd_pnqp")
     return x, iters
+
+
+def closed_loop_advance(spec: Spec, k: int, n_sim: int, x, U_opt, Xs, Us, U_warm=None, xref_full=None, uref_full=None,
+                        xref_win=None, uref_win=None):
+    """One receding-horizon step after the solve of simulation step ``k`` (``tacd_closed_loop_advance``): applies
+    ``U_opt[:,0]`` to ``x`` in place, records ``Xs[:,k+1]``, ``Us[:,k]``, writes the shifted warm start and the
+    reference windows of the next solve.  All tensors are caller-owned, contiguous, on the device."""
+    _need_cuda(x, U_opt, Xs, Us, U_warm, xref_full, uref_full, xref_win, uref_win)
+    dt = x.dtype
+    B = x.shape[0]
+    for t in (x, U_opt, Xs, Us, U_warm, xref_full, uref_full, xref_win, uref_win):
+        if t is not None and (t.dtype != dt or not t.is_contiguous()):
+            raise RuntimeError("closed_loop_advance: tensors must be contiguous and of one dtype")
+    p = _problem(spec, B, dt, xref_batched=int(xref_full is not None and xref_full.shape[0] == B),
+                 uref_batched=int(uref_full is not None and uref_full.shape[0] == B))
+    ref_len = int(xref_full.shape[1]) if xref_full is not None else 0
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().tacd_closed_loop_advance(C.byref(p), int(k), int(n_sim), *_vp(x, U_opt, Xs, Us, U_warm, xref_full, uref_full),
+                                                       ref_len, *_vp(xref_win, uref_win), _stream()), "tacd_closed_loop_advance")
