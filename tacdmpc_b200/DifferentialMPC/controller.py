@@ -66,6 +66,8 @@ class ILQRSolve(torch.autograd.Function):
         ctx.controller = controller
         ctx.spec = controller._last_spec
         ctx.Cf_batched = C_final.ndim == 3
+        ctx.exact = controller.compat == "exact"
+        ctx.Cf = controller._last_Cf if ctx.exact else None
         ctx.shapes = tuple(t.shape for t in (x0, C, c, C_final, c_final, x_ref, u_ref))
         ctx.in_dtypes = tuple(t.dtype for t in (x0, C, c, C_final, c_final, x_ref, u_ref))
         saved = [X, U, controller._last_C, controller._last_xref, controller._last_uref, controller._last_tight_u8]
@@ -85,7 +87,7 @@ class ILQRSolve(torch.autograd.Function):
         want = tuple(nm for nm, nd in zip(names, need[:7]) if nd)
         out = ops.ilqr_backward(ctx.spec, X, U, Cm, xref, uref, tight,
                                 grad_X.to(X.dtype), grad_U.to(U.dtype), A=A, Bm=Bm,
-                                Cf_batched=ctx.Cf_batched, want=want) if want else {}
+                                Cf_batched=ctx.Cf_batched, want=want, exact=ctx.exact, Cf=ctx.Cf) if want else {}
         grads = []
         for nm, shape, dt in zip(names, ctx.shapes, ctx.in_dtypes):
             g = out.get(nm)
@@ -111,6 +113,8 @@ class ILQRSolveDiag(torch.autograd.Function):
             X, U = X.detach(), U.detach()
         ctx.spec = controller._last_spec
         ctx.diag = controller._last_diag
+        ctx.exact = controller.compat == "exact"
+        ctx.Cf = controller._last_Cf if ctx.exact else None
         ctx.shapes = tuple(t.shape for t in (x0, q, p, q_final, p_final, x_ref, u_ref))
         ctx.in_dtypes = tuple(t.dtype for t in (x0, q, p, q_final, p_final, x_ref, u_ref))
         saved = [X, U, controller._last_C, controller._last_xref, controller._last_uref, controller._last_tight_u8]
@@ -129,7 +133,7 @@ class ILQRSolveDiag(torch.autograd.Function):
         names = ("grad_x0", "grad_C", "grad_c", "grad_Cf", "grad_cf", "grad_xref", "grad_uref")
         want = tuple(nm for nm, nd in zip(names, need[:7]) if nd)
         out = ops.ilqr_backward(ctx.spec, X, U, Cm, xref, uref, tight, grad_X.to(X.dtype), grad_U.to(U.dtype),
-                                A=A, Bm=Bm, Cf_batched=True, want=want, C_diag=ctx.diag) if want else {}
+                                A=A, Bm=Bm, Cf_batched=True, want=want, C_diag=ctx.diag, exact=ctx.exact, Cf=ctx.Cf) if want else {}
         grads = []
         for nm, shape, dt in zip(names, ctx.shapes, ctx.in_dtypes):
             g = out.get(nm)
@@ -221,6 +225,7 @@ class DifferentiableMPCController(torch.nn.Module):
         self.iters_last = self.flags_last = self.cost_last = self.alpha_trace_last = None
         self._F_last = None
         self._last_spec = self._last_C = self._last_xref = self._last_uref = self._last_tight_u8 = self._last_AB = None
+        self._last_Cf = None
         self.converged = None
 
     @property
@@ -422,6 +427,7 @@ class DifferentiableMPCController(torch.nn.Module):
             self.H_last = (Cb[..., :nx, :nx], Cb[..., nx:, nx:], Cb[..., :nx, nx:])
         self._F_last = AB
         self._last_spec, self._last_C, self._last_xref, self._last_uref = spec, C, xref, uref
+        self._last_Cf = Cf
         self._last_tight_u8, self._last_AB = out["tight"], AB
         return X, U
 

@@ -39,7 +39,7 @@ class Problem(C.Structure):
         ("alphas", C.c_double * MAX_ALPHA),
         ("has_umin", C.c_int32), ("has_umax", C.c_int32),
         ("umin", C.c_double * MAX_NU), ("umax", C.c_double * MAX_NU),
-        ("C_diag", C.c_int32), ("reserved_", C.c_int32),
+        ("C_diag", C.c_int32), ("compat_exact", C.c_int32),
     ]
 
 
@@ -59,7 +59,7 @@ class BackwardIO(C.Structure):
 def make_problem(*, B, T, nx, nu, dtype, dyn_id, dt, reg_eps=1e-6, max_iter=40,
                  C_batched=0, Cf_batched=0, xref_batched=1, uref_batched=1, ls_cost_shared=0,
                  jac_mode=JAC_ANALYTIC, fd_eps=1e-4, dyn_params=(), dyn_A=None, dyn_B=None,
-                 alphas=DEFAULT_ALPHAS, umin=None, umax=None, C_diag=0) -> Problem:
+                 alphas=DEFAULT_ALPHAS, umin=None, umax=None, C_diag=0, compat_exact=0) -> Problem:
     """Fill a ``tacd_problem``.  ``dyn_A``/``dyn_B`` are raw addresses (int) or None."""
     if nx > MAX_NX or nu > MAX_NU:
         raise ValueError(f"nx<={MAX_NX}, nu<={MAX_NU} supported, got nx={nx}, nu={nu}")
@@ -71,6 +71,7 @@ def make_problem(*, B, T, nx, nu, dtype, dyn_id, dt, reg_eps=1e-6, max_iter=40,
     p.xref_batched, p.uref_batched = int(xref_batched), int(uref_batched)
     p.ls_cost_shared = int(ls_cost_shared)
     p.C_diag = int(C_diag)
+    p.compat_exact = int(compat_exact)
     p.dyn_id, p.jac_mode = int(dyn_id), int(jac_mode)
     for i, v in enumerate(dyn_params):
         p.dyn_params[i] = float(v)

@@ -129,6 +129,7 @@ int tacd_ilqr_backward(const tacd_problem* p, const tacd_backward_io* io, void* 
   if (!io || !io->X || !io->U || !io->C || !io->xref || !io->uref || !io->tight || !io->gX || !io->gU) { set_error("tacd_ilqr_backward: required pointer is null"); return TACD_EINVAL; }
   if (p->dyn_id == TACD_DYN_EXTERNAL && (!io->A || !io->Bm)) { set_error("EXTERNAL dynamics need A and Bm"); return TACD_EINVAL; }
   if (p->has_umin && !p->has_umax) { set_error("backward assumes u_max whenever u_min is set (reference quirk Q10)"); return TACD_EINVAL; }
+  if (p->compat_exact && !io->Cf) { set_error("compat_exact needs tacd_backward_io.Cf (the terminal Hessian)"); return TACD_EINVAL; }
   if (p->B == 0) return TACD_OK;
   cudaStream_t s = (cudaStream_t)stream;
   if (!workspace || workspace_bytes < 256) { set_error("workspace too small (need tacd_backward_workspace_bytes)"); return TACD_EWORKSPACE; }
@@ -137,6 +138,7 @@ int tacd_ilqr_backward(const tacd_problem* p, const tacd_backward_io* io, void* 
                                   : launch_backward_small<double>(p, io, ws, workspace_bytes - 256, s);
   if (rc != TACD_EUNSUPPORTED) return rc;
   if (p->C_diag) { set_error("C_diag: no thread-per-element backward kernel for this (nx, nu, dyn); pass dense costs"); return TACD_EUNSUPPORTED; }
+  if (p->compat_exact) { set_error("compat_exact: no thread-per-element backward kernel for this (nx, nu, dyn)"); return TACD_EUNSUPPORTED; }
   rc = (p->dtype == TACD_F32) ? launch_backward_generic<float>(p, io, ws, workspace_bytes - 256, s)
                               : launch_backward_generic<double>(p, io, ws, workspace_bytes - 256, s);
   return rc;

@@ -24,6 +24,7 @@ inline DevProblem<R> to_dev(const tacd_problem* p) {
   d.xref_batched = p->xref_batched; d.uref_batched = p->uref_batched;
   d.ls_cost_shared = p->ls_cost_shared;
   d.C_diag = p->C_diag;
+  d.exact = p->compat_exact;
   d.jac_mode = p->jac_mode; d.has_umin = p->has_umin; d.has_umax = p->has_umax;
   d.dt = (R)p->dt; d.reg = (R)p->reg_eps; d.fd_eps = (R)p->fd_eps;
   for (int i = 0; i < TACD_MAX_ALPHA; ++i) d.alphas[i] = (R)p->alphas[i];

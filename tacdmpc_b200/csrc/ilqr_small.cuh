@@ -111,7 +111,7 @@ __global__ void lpt_scatter(int B, int T, int nx, int n, int C_batched, int xref
 
 template <typename R>
 struct BwdPtrs {
-  const R *X, *U, *C, *xref, *uref, *A, *Bm, *gX, *gU;
+  const R *X, *U, *C, *Cf, *xref, *uref, *A, *Bm, *gX, *gU;
   const uint8_t* tight;
   R *grad_C, *grad_c, *grad_Cf, *grad_cf, *grad_x0, *grad_xref, *grad_uref, *dX, *dU;
 };
@@ -603,6 +603,15 @@ __global__ void __launch_bounds__(256, 1) ilqr_backward_small(const DevProblem<R
       nx_[i] = X[(T - 1) * NX + i];
       v[i] = -ngx[i];
     }
+    if (P.exact) {   // compat="exact": terminal value = C_final[:nx,:nx], -grad_X[T] (fixes quirks Q1, Q2)
+      const R* Cfe = io.Cf + (P.Cf_batched ? (size_t)bb * (DIAG ? N : N * N) : 0);
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+#pragma unroll
+        for (int j = 0; j < NX; ++j) V[i * NX + j] = DIAG ? ((i == j) ? Cfe[i] : (R)0) : Cfe[i * N + j];
+        v[i] = -gX[T * NX + i];
+      }
+    }
 #pragma unroll
     for (int i = 0; i < NU; ++i) { nu_[i] = U[(T - 1) * NU + i]; ngu[i] = gU[(T - 1) * NU + i]; ntg[i] = tg[(T - 1) * NU + i] != 0; }
     auto fetch_C = [&](int t) {
@@ -682,7 +691,8 @@ __global__ void __launch_bounds__(256, 1) ilqr_backward_small(const DevProblem<R
           for (int j = 0; j < NU; ++j) Quu[i * NU + j] = Ct[(NX + i) * N + NX + j];
       }
       load_AB(t, x, u, A, Bm);
-      q_blocks<R, NX, NU>(P.reg, A, Bm, V, v, Qxx, Qxu, Quu, qx, qu);
+      // (the reference adds reg I to Q_uu here too, controller.py:731; the exact KKT system has none)
+      q_blocks<R, NX, NU>(P.exact ? (R)0 : P.reg, A, Bm, V, v, Qxx, Qxu, Quu, qx, qu);
       // box QP on the free coordinates (controller.py:737-763); tight ones pinned to 0
       R kt[NU];
       {
@@ -700,7 +710,17 @@ __global__ void __launch_bounds__(256, 1) ilqr_backward_small(const DevProblem<R
           else if (P.has_umin) { lo[i] = P.umin[i] - u[i]; hi[i] = P.umax[i] - u[i]; }  // quirk Q10
           else { lo[i] = -inf_<R>(); hi[i] = inf_<R>(); }
         }
-        if (any_free) {
+        if (any_free && P.exact) {
+          // exact: the active inputs are frozen, the free ones solve the unconstrained Newton system
+          R M[NU * NU];
+#pragma unroll
+          for (int i = 0; i < NU * NU; ++i) M[i] = H[i] + (((i / NU) == (i % NU) && !fixed[i / NU]) ? (R)1e-8 * P.reg : (R)0);
+#pragma unroll
+          for (int i = 0; i < NU; ++i) kt[i] = q[i];
+          lu_solve<R, NU, 1>(M, kt);
+#pragma unroll
+          for (int i = 0; i < NU; ++i) kt[i] = fixed[i] ? (R)0 : -kt[i];
+        } else if (any_free) {
           pnqp<R, NU>(H, q, lo, hi, kt);
 #pragma unroll
           for (int i = 0; i < NU; ++i) kt[i] = fixed[i] ? (R)0 : kt[i];
@@ -720,6 +740,16 @@ __global__ void __launch_bounds__(256, 1) ilqr_backward_small(const DevProblem<R
 #pragma unroll
           for (int j = 0; j < NX; ++j) Kt[i * NX + j] = Qxu[j * NU + i];
         }
+        if (P.exact) {   // exact: rows of frozen inputs are zero, the free block is solved alone (fixes quirk Q6)
+#pragma unroll
+          for (int i = 0; i < NU; ++i) {
+#pragma unroll
+            for (int j = 0; j < NU; ++j)
+              if (fixed[i] || fixed[j]) M[i * NU + j] = (i == j) ? (R)1 : (R)0;
+#pragma unroll
+            for (int j = 0; j < NX; ++j) Kt[i * NX + j] = fixed[i] ? (R)0 : Kt[i * NX + j];
+          }
+        }
         lu_solve<R, NU, NX>(M, Kt);
 #pragma unroll
         for (int i = 0; i < NU * NX; ++i) Kt[i] = -Kt[i];
@@ -736,7 +766,7 @@ __global__ void __launch_bounds__(256, 1) ilqr_backward_small(const DevProblem<R
     for (int i = 0; i < NX; ++i) dx[i] = 0;
     if (io.grad_x0 && live)
 #pragma unroll
-      for (int i = 0; i < NX; ++i) io.grad_x0[(size_t)b * NX + i] = 0;
+      for (int i = 0; i < NX; ++i) io.grad_x0[(size_t)b * NX + i] = P.exact ? -v[i] : (R)0;   // exact: -lambda_0 (fixes quirk Q3)
     R nxr[NX], nur[NU];
 #pragma unroll
     for (int i = 0; i < NX; ++i) { nx_[i] = X[i]; nxr[i] = xr[i]; }
@@ -779,6 +809,19 @@ __global__ void __launch_bounds__(256, 1) ilqr_backward_small(const DevProblem<R
         for (int i = 0; i < NX; ++i) row[N * N + N + i] = live ? dx[i] : (R)0;
 #pragma unroll
         for (int i = 0; i < NU; ++i) row[N * N + N + NX + i] = live ? du[i] : (R)0;
+        if (P.exact) {   // exact: d loss / d ref_t = C_t dtau_t (tau = z - ref enters the stationarity as -C ref)
+          const R* Ce = Cp + (size_t)t * (DIAG ? N : N * N);
+#pragma unroll
+          for (int i = 0; i < N; ++i) {
+            R s = 0;
+            if (DIAG) s = Ce[i] * dtau[i];
+            else {
+#pragma unroll
+              for (int j = 0; j < N; ++j) s += Ce[i * N + j] * dtau[j];
+            }
+            row[N * N + N + i] = live ? s : (R)0;
+          }
+        }
         __syncwarp();
         if (redC || redc || redx || redu) {   // warp-uniform
           for (int j = lane; j < L::NV; j += 32) {
@@ -849,9 +892,22 @@ __global__ void __launch_bounds__(256, 1) ilqr_backward_small(const DevProblem<R
     }
     {
       // terminal: grad_C_final[:nx,:nx], grad_c_final[:nx] (zero padding elsewhere), grad_xref[T]
-      R tauN[NX];
+      R tauN[NX], gxT[NX];   // gxT = grad_xref[T]: dx_T (reference) or C_final[:nx,:nx] dx_T (exact)
 #pragma unroll
-      for (int i = 0; i < NX; ++i) tauN[i] = nx_[i] - nxr[i];
+      for (int i = 0; i < NX; ++i) { tauN[i] = nx_[i] - nxr[i]; gxT[i] = dx[i]; }
+      if (P.exact) {
+        const R* Cfe = io.Cf + (P.Cf_batched ? (size_t)bb * (DIAG ? N : N * N) : 0);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+          R s = 0;
+          if (DIAG) s = Cfe[i] * dx[i];
+          else {
+#pragma unroll
+            for (int j = 0; j < NX; ++j) s += Cfe[i * N + j] * dx[j];
+          }
+          gxT[i] = s;
+        }
+      }
       if (live) {
         if (io.grad_Cf && DIAG) {
 #pragma unroll
@@ -869,7 +925,7 @@ __global__ void __launch_bounds__(256, 1) ilqr_backward_small(const DevProblem<R
           for (int i = 0; i < N; ++i) io.grad_cf[(size_t)b * N + i] = (i < NX) ? -dx[i < NX ? i : 0] : (R)0;
         if (io.grad_xref && P.xref_batched)
 #pragma unroll
-          for (int i = 0; i < NX; ++i) io.grad_xref[(size_t)b * szX + T * NX + i] = dx[i];
+          for (int i = 0; i < NX; ++i) io.grad_xref[(size_t)b * szX + T * NX + i] = gxT[i];
         if (io.dX)
 #pragma unroll
           for (int i = 0; i < NX; ++i) io.dX[(size_t)b * szX + T * NX + i] = dx[i];
@@ -881,7 +937,7 @@ __global__ void __launch_bounds__(256, 1) ilqr_backward_small(const DevProblem<R
 #pragma unroll
           for (int j = 0; j < NX; ++j) row[i * NX + j] = live ? (R)-0.5 * (dx[i] * tauN[j] + tauN[i] * dx[j]) : (R)0;
 #pragma unroll
-        for (int i = 0; i < NX; ++i) { row[NX * NX + i] = live ? -dx[i] : (R)0; row[NX * NX + NX + i] = live ? dx[i] : (R)0; }
+        for (int i = 0; i < NX; ++i) { row[NX * NX + i] = live ? -dx[i] : (R)0; row[NX * NX + NX + i] = live ? gxT[i] : (R)0; }
         __syncwarp();
         for (int j = lane; j < L::NVF; j += 32) {
           R sum = 0;

@@ -124,7 +124,7 @@ static int run_backward_small(const tacd_problem* p, const tacd_backward_io* io,
   }
   (void)T;
   BwdPtrs<R> f;
-  f.X = (const R*)io->X; f.U = (const R*)io->U; f.C = (const R*)io->C; f.xref = (const R*)io->xref; f.uref = (const R*)io->uref;
+  f.X = (const R*)io->X; f.U = (const R*)io->U; f.C = (const R*)io->C; f.Cf = (const R*)io->Cf; f.xref = (const R*)io->xref; f.uref = (const R*)io->uref;
   f.A = (const R*)io->A; f.Bm = (const R*)io->Bm; f.gX = (const R*)io->gX; f.gU = (const R*)io->gU; f.tight = io->tight;
   f.grad_C = (R*)io->grad_C; f.grad_c = (R*)io->grad_c; f.grad_Cf = (R*)io->grad_Cf; f.grad_cf = (R*)io->grad_cf;
   f.grad_x0 = (R*)io->grad_x0; f.grad_xref = (R*)io->grad_xref; f.grad_uref = (R*)io->grad_uref; f.dX = (R*)io->dX; f.dU = (R*)io->dU;

@@ -134,10 +134,12 @@ _GRAD_NAMES = ("grad_C", "grad_c", "grad_Cf", "grad_cf", "grad_x0", "grad_xref",
 
 
 def ilqr_backward(spec: Spec, X, U, Cm, xref, uref, tight, gX, gU, *, A=None, Bm=None, Cf_batched=False,
-                  want=("grad_C", "grad_c", "grad_Cf", "grad_cf", "grad_x0", "grad_xref", "grad_uref"), C_diag=False):
+                  want=("grad_C", "grad_c", "grad_Cf", "grad_cf", "grad_x0", "grad_xref", "grad_uref"), C_diag=False,
+                  exact=False, Cf=None):
     """ILQRSolve.backward (controller.py:63-115) on the GPU.  Outputs for shared (un-batched) inputs are
     already summed over the batch.  ``C_diag``: ``Cm [B,T,n]`` holds diagonals; ``grad_C [B,T,n]`` and
-    ``grad_Cf [B,n]`` come back as diagonals too."""
+    ``grad_Cf [B,n]`` come back as diagonals too.  ``exact`` (needs ``Cf``): exact implicit differentiation instead
+    of the reference's (``tacd_problem.compat_exact``)."""
     _need_cuda(X, U, Cm, xref, uref, tight, gX, gU, A, Bm)
     dev, dt = X.device, X.dtype
     X, U, Cm, xref, uref, gX, gU = (_prep(t, dt, dev) for t in (X, U, Cm, xref, uref, gX, gU))
@@ -147,11 +149,18 @@ def ilqr_backward(spec: Spec, X, U, Cm, xref, uref, tight, gX, gU, *, A=None, Bm
     Cb, xb, ub = Cm.ndim == (3 if C_diag else 4), xref.shape[0] == B, uref.shape[0] == B
     if C_diag:
         Cf_batched = True
+    if exact:
+        if Cf is None:
+            raise RuntimeError("exact backward needs the terminal cost Cf")
+        Cf = _prep(Cf, dt, dev)
+        Cf_batched = Cf.ndim == (2 if C_diag else 3)
     p = _problem(spec, B, dt, C_batched=int(Cb), Cf_batched=int(Cf_batched), xref_batched=int(xb), uref_batched=int(ub),
-                 C_diag=int(C_diag))
+                 C_diag=int(C_diag), compat_exact=int(exact))
     io = _abi.BackwardIO()
-    keep = [X, U, Cm, xref, uref, tight, gX, gU]
-    io.X, io.U, io.C, io.xref, io.uref, io.tight, io.gX, io.gU = (_ptr(t) for t in keep)
+    if exact:
+        io.Cf = _ptr(Cf)
+    keep = [X, U, Cm, xref, uref, tight, gX, gU, Cf]
+    io.X, io.U, io.C, io.xref, io.uref, io.tight, io.gX, io.gU = (_ptr(t) for t in keep[:8])
     if A is not None:
         A, Bm = _prep(A, dt, dev), _prep(Bm, dt, dev)
         keep += [A, Bm]
