@@ -1,6 +1,8 @@
 // ilqr_generic.cu — CTA-per-element whole-solve kernels for run-time dimensions,
 // plus the stand-alone stage entry points of the C ABI (rollout, linearize,
 // objective, riccati, linesearch, pnqp).  See ilqr_generic.cuh for the layout.
+#include <stdlib.h>
+
 #include "host_common.h"
 #include "ilqr_generic.cuh"
 
@@ -41,7 +43,9 @@ __global__ void __launch_bounds__(kGenThreads) ilqr_forward_generic(const DevPro
   GenSmem<R> s = gen_carve<R>(smem_raw, d.nx, d.nu);
   const int tid = threadIdx.x, nx = d.nx, nu = d.nu, n = d.n, T = d.T;
   const size_t szX = (size_t)(T + 1) * nx, szU = (size_t)T * nu;
-  R* gXs = ws + (size_t)blockIdx.x * slice;
+  // X, U, K, k of the element in flight: in shared memory right behind the per-step matrices when they fit
+  // (ws == nullptr), else in this CTA's slice of the caller's workspace
+  R* gXs = ws ? ws + (size_t)blockIdx.x * slice : reinterpret_cast<R*>(smem_raw + gen_smem_bytes_aligned<R>(nx, nu));
   R* gUs = gXs + szX;
   R* gK = gUs + szU;
   R* gk = gK + (size_t)T * nu * nx;
@@ -252,7 +256,7 @@ __global__ void __launch_bounds__(kGenThreads) ilqr_backward_generic(const DevPr
   GenSmem<R> s = gen_carve<R>(smem_raw, d.nx, d.nu);
   const int tid = threadIdx.x, nx = d.nx, nu = d.nu, n = d.n, T = d.T;
   const size_t szX = (size_t)(T + 1) * nx, szU = (size_t)T * nu;
-  R* gK = ws + (size_t)blockIdx.x * slice;
+  R* gK = ws ? ws + (size_t)blockIdx.x * slice : reinterpret_cast<R*>(smem_raw + gen_smem_bytes_aligned<R>(nx, nu));
   R* gk = gK + (size_t)T * nu * nx;
   if (d.dyn == TACD_DYN_LTI) {
     for (int i = tid; i < nx * nx; i += kGenThreads) s.A[i] = P.dyn_A[i];
@@ -591,10 +595,15 @@ int launch_forward_generic(const tacd_problem* p, const tacd_forward_io* io, voi
   const size_t slice = gen_slice_scalars(p);
   const int grid = gen_grid(p);
   if (ws_bytes < (size_t)grid * slice * sizeof(R)) { set_error("forward workspace too small: %zu < %zu", ws_bytes, (size_t)grid * slice * sizeof(R)); return TACD_EWORKSPACE; }
-  const size_t smem = gen_smem_bytes<R>(p->nx, p->nu);
+  size_t smem = gen_smem_bytes<R>(p->nx, p->nu);
   auto kernel = ilqr_forward_generic<R>;
+  // the element's X, U, K, k in shared memory when four CTAs per SM still fit (global-memory round trips inside
+  // the per-step loops were the bulk of this kernel's time), else in the workspace slice
+  const size_t smem_slice = gen_smem_bytes_aligned<R>(p->nx, p->nu) + slice * sizeof(R);
+  const bool in_smem = smem_slice <= (size_t)device_info().smem_optin / 4 && !getenv("TACD_GENERIC_WS");
+  if (in_smem) smem = smem_slice;
   if (int rc = prep_smem(kernel, smem)) return rc;
-  kernel<<<grid, kGenThreads, smem, s>>>(to_dev<R>(p), dims_of<R>(p), fwd_ptrs<R>(io), (R*)ws, slice);
+  kernel<<<grid, kGenThreads, smem, s>>>(to_dev<R>(p), dims_of<R>(p), fwd_ptrs<R>(io), in_smem ? nullptr : (R*)ws, slice);
   note_launches(1);
   return check_cuda(cudaPeekAtLastError(), "ilqr_forward_generic launch");
 }
@@ -604,8 +613,11 @@ int launch_backward_generic(const tacd_problem* p, const tacd_backward_io* io, v
   const size_t slice = gen_slice_scalars(p);
   const int grid = gen_grid(p);
   if (ws_bytes < (size_t)grid * slice * sizeof(R)) { set_error("backward workspace too small"); return TACD_EWORKSPACE; }
-  const size_t smem = gen_smem_bytes<R>(p->nx, p->nu);
+  size_t smem = gen_smem_bytes<R>(p->nx, p->nu);
   auto kernel = ilqr_backward_generic<R>;
+  const size_t smem_slice = gen_smem_bytes_aligned<R>(p->nx, p->nu) + slice * sizeof(R);
+  const bool in_smem = smem_slice <= (size_t)device_info().smem_optin / 4 && !getenv("TACD_GENERIC_WS");
+  if (in_smem) smem = smem_slice;
   if (int rc = prep_smem(kernel, smem)) return rc;
   const size_t T = p->T, nx = p->nx, nu = p->nu, n = nx + nu, szX = (T + 1) * nx, szU = T * nu;
   if (io->grad_C && !p->C_batched) if (int rc = check_cuda(cudaMemsetAsync(io->grad_C, 0, T * n * n * sizeof(R), s), "memset")) return rc;
@@ -619,7 +631,7 @@ int launch_backward_generic(const tacd_problem* p, const tacd_backward_io* io, v
   f.A = (const R*)io->A; f.Bm = (const R*)io->Bm; f.gX = (const R*)io->gX; f.gU = (const R*)io->gU; f.tight = io->tight;
   f.grad_C = (R*)io->grad_C; f.grad_c = (R*)io->grad_c; f.grad_Cf = (R*)io->grad_Cf; f.grad_cf = (R*)io->grad_cf;
   f.grad_x0 = (R*)io->grad_x0; f.grad_xref = (R*)io->grad_xref; f.grad_uref = (R*)io->grad_uref; f.dX = (R*)io->dX; f.dU = (R*)io->dU;
-  kernel<<<grid, kGenThreads, smem, s>>>(to_dev<R>(p), dims_of<R>(p), f, (R*)ws, slice);
+  kernel<<<grid, kGenThreads, smem, s>>>(to_dev<R>(p), dims_of<R>(p), f, in_smem ? nullptr : (R*)ws, slice);
   note_launches(1);
   return check_cuda(cudaPeekAtLastError(), "ilqr_backward_generic launch");
 }

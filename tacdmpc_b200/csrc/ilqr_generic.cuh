@@ -242,6 +242,8 @@ __host__ __device__ inline size_t gen_smem_bytes(int nx, int nu) {
   return gen_smem_scalars(nx, nu) * sizeof(R) + (TACD_MAX_NU + 8) * sizeof(int);
 }
 template <typename R>
+__host__ __device__ inline size_t gen_smem_bytes_aligned(int nx, int nu) { return (gen_smem_bytes<R>(nx, nu) + 15) & ~(size_t)15; }
+template <typename R>
 __device__ GenSmem<R> gen_carve(unsigned char* raw, int nx, int nu) {
   const int n = nx + nu, na = TACD_MAX_ALPHA;
   GenSmem<R> s;
@@ -363,8 +365,16 @@ __device__ bool gen_value_step(const DevProblem<R>& P, const GenDims<R>& d, GenS
   }
   for (int idx = tid; idx < nu * nu; idx += kGenThreads) s.L[idx] = s.Quu[idx] + ((idx / nu == idx % nu) ? reg2 : (R)0);
   __syncthreads();
+  // Without input bounds nothing can be tight and the box QP of the KKT pass (utils.py:66-124 with +-inf bounds) is
+  // its own first Newton step, x = -H^-1 q, accepted at the first convergence check: k_t is then one more
+  // right-hand side of the gain solve below (Q_uu vs Q_uu + 1e-8 reg I: 1e-14 apart) instead of ~3 single-thread
+  // LU factorisations per step, which were 55 % of this kernel's instructions (profiles/r1_backward_generic).
+  const bool box = P.has_umin || P.has_umax;
   if (tid == 0) {
-    if (kkt) {
+    if (kkt && !box) {
+      gen_lu<R>(s.L, nu, s.piv);
+      s.flag[0] = 0;
+    } else if (kkt) {
       // k_t: box QP over the free coordinates (compacted, as the reference does)
       int m = 0;
       int* idxs = s.piv;  // reuse: free index list, overwritten by gen_lu afterwards
@@ -400,14 +410,14 @@ __device__ bool gen_value_step(const DevProblem<R>& P, const GenDims<R>& d, GenS
   __syncthreads();
   const bool use_chol = s.flag[0] != 0;
   if (!kkt && !use_chol) nonpd = true;
-  const int ncols = kkt ? nx : nr;  // the KKT pass takes k from the box QP, not from the solve
+  const int ncols = (kkt && box) ? nx : nr;  // with bounds the KKT pass takes k from the box QP, not from the solve
   for (int r = tid; r < ncols; r += kGenThreads) {
     if (use_chol) gen_chol_solve_col<R>(s.L, nu, s.rhs, nr, r);
     else gen_lu_solve_col<R>(s.L, nu, s.piv, s.rhs, nr, r);
   }
   __syncthreads();
   for (int idx = tid; idx < nu * nx; idx += kGenThreads) s.Kt[idx] = -s.rhs[(idx / nx) * nr + (idx % nx)];
-  if (!kkt) for (int i = tid; i < nu; i += kGenThreads) s.kt[i] = -s.rhs[i * nr + nx];
+  if (!kkt || !box) for (int i = tid; i < nu; i += kGenThreads) s.kt[i] = -s.rhs[i * nr + nx];
   __syncthreads();
   for (int idx = tid; idx < nu * nx; idx += kGenThreads) {
     const int i = idx / nx, j = idx % nx;
