@@ -43,11 +43,13 @@ static int run_forward_group(const tacd_problem* p, const tacd_forward_io* io, v
   f.counter = (unsigned int*)ws;
   f.order = nullptr;
   const DevProblem<R> dp = to_dev<R>(p);
-  queue_init<<<1, 1, 0, s>>>(f.counter, 0u);
-  note_launches(1);
   // longest-first queue order (ilqr_small.cuh): with more than one wave of elements the long chains must
   // not be popped last (profiles/r1_forward_group_v4: schedulers idle 13 % of the kernel in the tail)
-  if ((long)p->B > (long)grid * nw * kEPW && !getenv("TACD_NO_LPT")) {
+  const bool lpt = (long)p->B > (long)grid * nw * kEPW && !getenv("TACD_NO_LPT");
+  if (!lpt) {
+    queue_init<<<1, 1, 0, s>>>(f.counter, 0u);
+    note_launches(1);
+  } else {
     unsigned int* hist = (unsigned int*)((char*)ws + 256);
     int32_t* order = (int32_t*)((char*)ws + 16384);
     if (int rc = check_cuda(cudaMemsetAsync(hist, 0, kLptBuckets * sizeof(unsigned int), s), "memset hist")) return rc;
@@ -55,7 +57,7 @@ static int run_forward_group(const tacd_problem* p, const tacd_forward_io* io, v
     const int nkey = p->C_diag ? -(NX + NU) : NX + NU;
     lpt_histogram<R><<<g2, 256, 0, s>>>(p->B, p->T, NX, nkey, p->C_batched, p->xref_batched, (const R*)io->x0, (const R*)io->xref, (const R*)io->C, hist);
     note_launches(1);
-    lpt_scan<<<1, 1024, 0, s>>>(hist);
+    lpt_scan<<<1, 1024, 0, s>>>(hist, f.counter, 0u);
     note_launches(1);
     lpt_scatter<R><<<g2, 256, 0, s>>>(p->B, p->T, NX, nkey, p->C_batched, p->xref_batched, (const R*)io->x0, (const R*)io->xref, (const R*)io->C, hist, order);
     note_launches(1);

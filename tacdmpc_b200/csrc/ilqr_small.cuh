@@ -83,9 +83,10 @@ __global__ void lpt_histogram(int B, int T, int nx, int n, int C_batched, int xr
 }
 static __global__ void queue_init(unsigned int* counter, unsigned int v) { *counter = v; }
 // exclusive scan of the 2048 counters by one CTA of 1024 threads (2 per thread)
-static __global__ void lpt_scan(unsigned int* hist) {
+static __global__ void lpt_scan(unsigned int* hist, unsigned int* counter = nullptr, unsigned int counter0 = 0) {
   __shared__ unsigned int part[1024];
   const int t = threadIdx.x;
+  if (counter && t == 0) *counter = counter0;   // (the work-queue head is reset here: one launch fewer)
   const unsigned a = hist[2 * t], b = hist[2 * t + 1];
   part[t] = a + b;
   __syncthreads();
@@ -105,7 +106,15 @@ __global__ void lpt_scatter(int B, int T, int nx, int n, int C_batched, int xref
   for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
     const int k = lpt_bucket<R>(x0 + (size_t)b * nx, xref + (xref_batched ? (size_t)b * (T + 1) * nx : 0),
                                 C + (C_batched ? (size_t)b * T * (n < 0 ? -n : n * n) : 0), nx, n);
-    order[atomicAdd(&offs[k], 1u)] = b;
+    // warp-aggregated: the keys of a batch cluster in a few dozen buckets, so per-lane atomics on `offs`
+    // serialise (17.5 us at B = 65536); one atomic per distinct bucket per warp instead
+    const unsigned act = __activemask();
+    const unsigned peers = __match_any_sync(act, k);
+    const int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
+    unsigned base = 0;
+    if (lane == leader) base = atomicAdd(&offs[k], (unsigned)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    order[base + __popc(peers & ((1u << lane) - 1u))] = b;
   }
 }
 
@@ -533,8 +542,8 @@ struct BwdLayout {
   __host__ __device__ static int nacc(int T) { return T * NV + NVF; }
 };
 
-template <typename R, int NX, int NU, int DYN, bool DIAG>
-__global__ void __launch_bounds__(256, 1) ilqr_backward_small(const DevProblem<R> P, const BwdPtrs<R> io, R* partials, int reduce) {
+template <typename R, int NX, int NU, int DYN, bool DIAG, bool EXACT>
+__global__ void __launch_bounds__(256, 1) ilqr_backward_small(const DevProblem<R> P, const BwdPtrs<R> io, R* partials, int reduce, int vnt) {
   constexpr int N = NX + NU;
   using L = BwdLayout<NX, NU>;
   using D = Dyn<R, NX, NU, (DYN == TACD_DYN_EXTERNAL ? TACD_DYN_LTI : DYN)>;
@@ -564,8 +573,10 @@ __global__ void __launch_bounds__(256, 1) ilqr_backward_small(const DevProblem<R
 #define SK(t, i) sK[((size_t)(t) * NU * NX + (i)) * NT + tid]
 #define Sk(t, i) sk[((size_t)(t) * NU + (i)) * NT + tid]
   const size_t szX = (size_t)(T + 1) * NX, szU = (size_t)T * NU;
-  const int stride = gridDim.x * NT;
-  for (int b0 = blockIdx.x * NT + (tid - lane); b0 < P.B; b0 += stride) {
+  // vnt (multiple of 32, <= NT) threads of every CTA take one element per wave, so that all CTAs — and with
+  // them all SMs — carry the same load in every wave; the remaining warps of the CTA stay out of the loop
+  const int stride = gridDim.x * vnt;
+  for (int b0 = blockIdx.x * vnt + (tid - lane); b0 < P.B && tid - lane < vnt; b0 += stride) {
     const int b = b0 + lane;
     const bool live = b < P.B;
     const int bb = live ? b : P.B - 1;  // dead lanes shadow the last element, outputs masked
@@ -603,7 +614,7 @@ __global__ void __launch_bounds__(256, 1) ilqr_backward_small(const DevProblem<R
       nx_[i] = X[(T - 1) * NX + i];
       v[i] = -ngx[i];
     }
-    if (P.exact) {   // compat="exact": terminal value = C_final[:nx,:nx], -grad_X[T] (fixes quirks Q1, Q2)
+    if (EXACT) {   // compat="exact": terminal value = C_final[:nx,:nx], -grad_X[T] (fixes quirks Q1, Q2)
       const R* Cfe = io.Cf + (P.Cf_batched ? (size_t)bb * (DIAG ? N : N * N) : 0);
 #pragma unroll
       for (int i = 0; i < NX; ++i) {
@@ -692,7 +703,7 @@ __global__ void __launch_bounds__(256, 1) ilqr_backward_small(const DevProblem<R
       }
       load_AB(t, x, u, A, Bm);
       // (the reference adds reg I to Q_uu here too, controller.py:731; the exact KKT system has none)
-      q_blocks<R, NX, NU>(P.exact ? (R)0 : P.reg, A, Bm, V, v, Qxx, Qxu, Quu, qx, qu);
+      q_blocks<R, NX, NU>(EXACT ? (R)0 : P.reg, A, Bm, V, v, Qxx, Qxu, Quu, qx, qu);
       // box QP on the free coordinates (controller.py:737-763); tight ones pinned to 0
       R kt[NU];
       {
@@ -710,7 +721,7 @@ __global__ void __launch_bounds__(256, 1) ilqr_backward_small(const DevProblem<R
           else if (P.has_umin) { lo[i] = P.umin[i] - u[i]; hi[i] = P.umax[i] - u[i]; }  // quirk Q10
           else { lo[i] = -inf_<R>(); hi[i] = inf_<R>(); }
         }
-        if (any_free && P.exact) {
+        if (any_free && EXACT) {
           // exact: the active inputs are frozen, the free ones solve the unconstrained Newton system
           R M[NU * NU];
 #pragma unroll
@@ -740,7 +751,7 @@ __global__ void __launch_bounds__(256, 1) ilqr_backward_small(const DevProblem<R
 #pragma unroll
           for (int j = 0; j < NX; ++j) Kt[i * NX + j] = Qxu[j * NU + i];
         }
-        if (P.exact) {   // exact: rows of frozen inputs are zero, the free block is solved alone (fixes quirk Q6)
+        if (EXACT) {   // exact: rows of frozen inputs are zero, the free block is solved alone (fixes quirk Q6)
 #pragma unroll
           for (int i = 0; i < NU; ++i) {
 #pragma unroll
@@ -766,7 +777,7 @@ __global__ void __launch_bounds__(256, 1) ilqr_backward_small(const DevProblem<R
     for (int i = 0; i < NX; ++i) dx[i] = 0;
     if (io.grad_x0 && live)
 #pragma unroll
-      for (int i = 0; i < NX; ++i) io.grad_x0[(size_t)b * NX + i] = P.exact ? -v[i] : (R)0;   // exact: -lambda_0 (fixes quirk Q3)
+      for (int i = 0; i < NX; ++i) io.grad_x0[(size_t)b * NX + i] = EXACT ? -v[i] : (R)0;   // exact: -lambda_0 (fixes quirk Q3)
     R nxr[NX], nur[NU];
 #pragma unroll
     for (int i = 0; i < NX; ++i) { nx_[i] = X[i]; nxr[i] = xr[i]; }
@@ -809,7 +820,7 @@ __global__ void __launch_bounds__(256, 1) ilqr_backward_small(const DevProblem<R
         for (int i = 0; i < NX; ++i) row[N * N + N + i] = live ? dx[i] : (R)0;
 #pragma unroll
         for (int i = 0; i < NU; ++i) row[N * N + N + NX + i] = live ? du[i] : (R)0;
-        if (P.exact) {   // exact: d loss / d ref_t = C_t dtau_t (tau = z - ref enters the stationarity as -C ref)
+        if (EXACT) {   // exact: d loss / d ref_t = C_t dtau_t (tau = z - ref enters the stationarity as -C ref)
           const R* Ce = Cp + (size_t)t * (DIAG ? N : N * N);
 #pragma unroll
           for (int i = 0; i < N; ++i) {
@@ -895,7 +906,7 @@ __global__ void __launch_bounds__(256, 1) ilqr_backward_small(const DevProblem<R
       R tauN[NX], gxT[NX];   // gxT = grad_xref[T]: dx_T (reference) or C_final[:nx,:nx] dx_T (exact)
 #pragma unroll
       for (int i = 0; i < NX; ++i) { tauN[i] = nx_[i] - nxr[i]; gxT[i] = dx[i]; }
-      if (P.exact) {
+      if (EXACT) {
         const R* Cfe = io.Cf + (P.Cf_batched ? (size_t)bb * (DIAG ? N : N * N) : 0);
 #pragma unroll
         for (int i = 0; i < NX; ++i) {

@@ -10,7 +10,7 @@ namespace tacd {
 // Pick the block size (multiple of 32, <= 256) that maximises resident threads per SM
 // for a kernel whose dynamic shared memory is words_per_thread * NT + extra scalars.
 template <typename K, typename SmemFn>
-static int pick_block(K kernel, SmemFn smem_of, int* blocks_per_sm, size_t* smem_out) {
+static int pick_block(K kernel, SmemFn smem_of, int* blocks_per_sm, size_t* smem_out, int max_blocks = 0) {
   const DeviceInfo di = device_info();
   int best_nt = 0, best_blocks = 0;
   size_t best_smem = 0;
@@ -23,6 +23,7 @@ static int pick_block(K kernel, SmemFn smem_of, int* blocks_per_sm, size_t* smem
     if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); continue; }
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, nt, smem) != cudaSuccess) { cudaGetLastError(); continue; }
+    if (max_blocks > 0 && nb > max_blocks) nb = max_blocks;
     if (nb * nt > best_blocks * best_nt) { best_nt = nt; best_blocks = nb; best_smem = smem; }
   }
   if (const char* e = getenv("TACD_BLOCKS_MAX")) { const int v = atoi(e); if (v >= 1 && v < best_blocks) best_blocks = v; }
@@ -87,9 +88,9 @@ static int run_forward_small(const tacd_problem* p, const tacd_forward_io* io, v
   return check_cuda(cudaPeekAtLastError(), "ilqr_forward_small launch");
 }
 
-template <typename R, int NX, int NU, int DYN, bool DIAG>
+template <typename R, int NX, int NU, int DYN, bool DIAG, bool EXACT>
 static int run_backward_small(const tacd_problem* p, const tacd_backward_io* io, void* ws, size_t ws_bytes, cudaStream_t s) {
-  auto kernel = ilqr_backward_small<R, NX, NU, DYN, DIAG>;
+  auto kernel = ilqr_backward_small<R, NX, NU, DYN, DIAG, EXACT>;
   using L = BwdLayout<NX, NU>;
   const int nacc = L::nacc(p->T);
   const bool reduce = (io->grad_C && !p->C_batched) || (io->grad_c && !p->C_batched) || (io->grad_Cf && !p->Cf_batched) ||
@@ -101,17 +102,20 @@ static int run_backward_small(const tacd_problem* p, const tacd_backward_io* io,
     size_t w = wpt * n + NX * NX + NX * NU + (size_t)(n / 32) * L::TILE;   // gains + LTI matrices + one tile per warp
     if (reduce) w += (size_t)(n / 32) * nacc;                                   // per-warp accumulators
     return w * sizeof(R);
-  }, &bps, &smem);
+  }, &bps, &smem, 1);   // one CTA per SM: two smaller ones measured 15 % slower (compact-diagonal variant, 149 registers)
   if (nt == 0 || bps == 0) return TACD_EUNSUPPORTED;
   if (int rc = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr")) return rc;
   const DeviceInfo di = device_info();
-  // balanced waves: every resident lane gets the same number of elements (work per element is uniform)
-  const long lanes = (long)di.sms * bps * nt;
-  const long waves = (p->B + lanes - 1) / lanes;
-  long per_wave = (p->B + waves - 1) / waves;
-  int grid = (int)((per_wave + nt - 1) / nt);
-  if (grid > di.sms * bps) grid = di.sms * bps;
+  // balanced waves: work per element is uniform, so every resident CTA gets the same number of elements per
+  // wave (vnt of its nt threads busy) instead of packing full CTAs onto a subset of the SMs
+  int grid = di.sms * bps;
+  const int need_ctas = (p->B + 31) / 32;
+  if (grid > need_ctas) grid = need_ctas;
   if (grid < 1) grid = 1;
+  const long waves = ((long)p->B + (long)grid * nt - 1) / ((long)grid * nt);
+  const long per_cta = ((long)p->B + waves * grid - 1) / (waves * grid);
+  int vnt = (int)((per_cta + 31) / 32) * 32;
+  if (vnt > nt) vnt = nt;
   const size_t T = p->T, n = NX + NU;
   R* partials = nullptr;
   if (reduce) {
@@ -129,7 +133,7 @@ static int run_backward_small(const tacd_problem* p, const tacd_backward_io* io,
   f.grad_C = (R*)io->grad_C; f.grad_c = (R*)io->grad_c; f.grad_Cf = (R*)io->grad_Cf; f.grad_cf = (R*)io->grad_cf;
   f.grad_x0 = (R*)io->grad_x0; f.grad_xref = (R*)io->grad_xref; f.grad_uref = (R*)io->grad_uref; f.dX = (R*)io->dX; f.dU = (R*)io->dU;
   const DevProblem<R> dp = to_dev<R>(p);
-  kernel<<<grid, nt, smem, s>>>(dp, f, partials, reduce ? 1 : 0);
+  kernel<<<grid, nt, smem, s>>>(dp, f, partials, reduce ? 1 : 0, vnt);
   note_launches(1);
   if (int rc = check_cuda(cudaPeekAtLastError(), "ilqr_backward_small launch")) return rc;
   if (reduce) {
@@ -160,9 +164,13 @@ int launch_forward_small(const tacd_problem* p, const tacd_forward_io* io, void*
 template <typename R>
 int launch_backward_small(const tacd_problem* p, const tacd_backward_io* io, void* ws, size_t ws_bytes, cudaStream_t s) {
 #define X(NX_, NU_, DYN_) \
-  if (p->nx == NX_ && p->nu == NU_ && p->dyn_id == DYN_)                                      \
-    return p->C_diag ? run_backward_small<R, NX_, NU_, DYN_, true>(p, io, ws, ws_bytes, s)    \
-                     : run_backward_small<R, NX_, NU_, DYN_, false>(p, io, ws, ws_bytes, s);
+  if (p->nx == NX_ && p->nu == NU_ && p->dyn_id == DYN_) {                                    \
+    if (p->compat_exact)                                                                      \
+      return p->C_diag ? run_backward_small<R, NX_, NU_, DYN_, true, true>(p, io, ws, ws_bytes, s)    \
+                       : run_backward_small<R, NX_, NU_, DYN_, false, true>(p, io, ws, ws_bytes, s);  \
+    return p->C_diag ? run_backward_small<R, NX_, NU_, DYN_, true, false>(p, io, ws, ws_bytes, s)     \
+                     : run_backward_small<R, NX_, NU_, DYN_, false, false>(p, io, ws, ws_bytes, s);   \
+  }
   TACD_SMALL_BWD(X)
 #undef X
   return TACD_EUNSUPPORTED;
