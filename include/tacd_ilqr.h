@@ -214,6 +214,20 @@ int tacd_closed_loop_advance(const tacd_problem* p, int32_t k, int32_t n_sim, vo
                              void* Xs, void* Us, void* U_warm,
                              const void* xref_full, const void* uref_full, int32_t ref_len,
                              void* xref_win, void* uref_win, void* stream);
+/* Augmented-Lagrangian update for state box constraints x_min <= x_t <= x_max (t = 0..T) — the constraint
+ * of DifferentialMPC/AugmentedLagrangianManager.py:33-62 (g = [x - x_max; x_min - x], utils.py:31-35).  That file
+ * is un-importable at reference HEAD and its manager class is missing, so the multiplier / penalty schedule is
+ * DEFINED here: Powell-Hestenes-Rockafellar, per (element, step, state, side):
+ *     lam <- max(0, lam + rho * g(x)),  active = lam > 0      (update_lambda != 0)
+ *     active = lam + rho_next * g(x) > 0                      (update_lambda == 0: lam unchanged)
+ * and the quadratic model of the penalty of the active constraints around x_ref, which the next inner iLQR
+ * solve adds to its cost:  dq[b,t,i] (added to C_t[i,i], or to C_final[i,i] for t = T) = rho_next * (#active
+ * sides),  dp[b,t,i] (added to c_t[i] / c_final[i]) = act_hi (lam_hi + rho_next (x_ref - x_max)) -
+ * act_lo (lam_lo + rho_next (x_min - x_ref)).   viol[b] = max_t,i max(0, g).   X, lam_*, dq, dp: [B,T+1,nx];
+ * x_ref [B or 1, T+1, nx]; x_min, x_max [nx] (+-inf = unbounded side). */
+int tacd_al_update(int32_t dtype, int32_t B, int32_t T, int32_t nx, const void* X, const void* xref, int32_t xref_batched,
+                   const void* x_min, const void* x_max, void* lam_lo, void* lam_hi, double rho, double rho_next,
+                   int32_t update_lambda, void* dq, void* dp, void* viol, void* stream);
 /* batched projected-Newton box QP: H[N,m,m] q[N,m] lo[N,m] hi[N,m] -> x[N,m], iters[N] (nullable) */
 int tacd_pnqp(int32_t dtype, int32_t N, int32_t m, const void* H, const void* q,
               const void* lo, const void* hi, void* x, int32_t* iters, void* stream);

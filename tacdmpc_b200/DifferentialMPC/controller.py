@@ -28,6 +28,7 @@ from torch import Tensor
 from .. import _abi, ops
 from ..dynamics import NativeDynamics
 from .cost import DiagQuadCost, GeneralQuadCost
+from .AugmentedLagrangianManager import ConstrainedQuadCost
 from .utils import batched_jacobian, jacobian_finite_diff_batched
 
 
@@ -242,7 +243,7 @@ class DifferentiableMPCController(torch.nn.Module):
 
     # ------------------------------------------------------------------ problem description
     def _is_native(self) -> bool:
-        return isinstance(self.f_dyn, NativeDynamics) and type(self.cost_module) in (GeneralQuadCost, DiagQuadCost)
+        return isinstance(self.f_dyn, NativeDynamics) and type(self.cost_module) in (GeneralQuadCost, DiagQuadCost, ConstrainedQuadCost)
 
     def _diag_eligible(self) -> bool:
         """Compact diagonal costs go to the kernels as they are when the fused five-lanes-per-element forward
@@ -313,6 +314,8 @@ class DifferentiableMPCController(torch.nn.Module):
         ``(Xs[B,N_sim+1,nx], Us[B,N_sim,nu])``.  See ``simulate``."""
         if x_ref_full is not None or u_ref_full is not None:
             return self.simulate(x0, x_ref_full, u_ref_full, U_init=U_init, warm_start=warm_start)
+        if isinstance(self.cost_module, ConstrainedQuadCost):
+            return self.solve_constrained(x0, U_init)
         B = x0.shape[0] if x0.ndim > 1 else 1
         if U_init is None:
             U_init = torch.zeros(B, self.horizon, self.nu, device=x0.device, dtype=x0.dtype)
@@ -394,6 +397,56 @@ class DifferentiableMPCController(torch.nn.Module):
             self.iters_last, self.flags_last, self.cost_last = out["iters"], out["flags"], out["cost"]
         self.converged = True
         return Xs.to(x0.dtype), Us.to(x0.dtype)
+
+    def solve_constrained(self, x0: Tensor, U_init: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+        """State-box-constrained solve by an augmented Lagrangian (``ConstrainedQuadCost``; schedule defined in
+        ``AugmentedLagrangianManager.py``): ``n_outer`` warm-started iLQR solves on per-element costs that carry the
+        quadratic model of the active penalties, one ``tacd_al_update`` launch between them.  Forward only (no
+        gradient flows through the multipliers); the multipliers and the violation stay on ``cost_module.al_manager``."""
+        cm = self.cost_module
+        al = cm.al_manager
+        if x0.ndim != 2:
+            raise RuntimeError("x0 must be [B, nx] (quirk Q12)")
+        if not (self._is_native() and x0.is_cuda):
+            raise RuntimeError("state constraints need a shipped dynamics plugin on a CUDA device")
+        dtype, device = _solve_dtype(x0), x0.device
+        B, T, nx, nu, n = x0.shape[0], self.horizon, self.nx, self.nu, self.nx + self.nu
+        spec = self._spec(dtype, device)
+        prep = lambda t: t.detach().to(device=device, dtype=dtype).contiguous()
+        C, c, Cf, cf = prep(cm.C), prep(cm.c), prep(cm.C_final), prep(cm.c_final)
+        xref, uref = prep(cm.x_ref), prep(cm.u_ref)
+        # per-element copies the penalty model is added to (the penalty is diagonal in the state block)
+        Cb = (C if C.ndim == 4 else C.unsqueeze(0).expand(B, T, n, n)).clone()
+        cb = (c if c.ndim == 3 else c.unsqueeze(0).expand(B, T, n)).clone()
+        Cfb = (Cf if Cf.ndim == 3 else Cf.unsqueeze(0).expand(B, n, n)).clone()
+        cfb = (cf if cf.ndim == 2 else cf.unsqueeze(0).expand(B, n)).clone()
+        C0d = torch.diagonal(Cb, dim1=-2, dim2=-1)[..., :nx].clone()      # [B,T,nx] base diagonals
+        c0 = cb[..., :nx].clone()
+        Cf0d = torch.diagonal(Cfb, dim1=-2, dim2=-1)[..., :nx].clone()
+        cf0 = cfb[..., :nx].clone()
+        al.reset(B, T, nx, device, dtype)
+        x0d = prep(x0)
+        warm = prep(U_init) if U_init is not None else torch.zeros(B, T, nu, device=device, dtype=dtype)
+        out = None
+        for outer in range(max(1, int(al.n_outer))):
+            # the reference's Q4 quirk has no meaning here: every element is scored with its own cost
+            out = ops.ilqr_forward(spec, x0d, Cb, cb, Cfb, cfb, xref, uref, warm, ls_cost=None, want_trace=False)
+            rho_next = min(al.rho * al.rho_growth, al.rho_max) if outer > 0 else al.rho
+            dq, dp, viol = ops.al_update(out["X"], xref, cm.x_min, cm.x_max, al.lam_lo, al.lam_hi, al.rho, rho_next, update_lambda=True)
+            al.rho, al.violation, al.outer_iters = rho_next, viol, outer + 1
+            torch.diagonal(Cb, dim1=-2, dim2=-1)[..., :nx].copy_(C0d + dq[:, :T])
+            cb[..., :nx].copy_(c0 + dp[:, :T])
+            torch.diagonal(Cfb, dim1=-2, dim2=-1)[..., :nx].copy_(Cf0d + dq[:, T])
+            cfb[..., :nx].copy_(cf0 + dp[:, T])
+            warm = out["U"]
+            if al.tol > 0 and outer > 0 and float(viol.max()) <= al.tol:
+                break
+        X, U = out["X"].to(x0.dtype), out["U"].to(x0.dtype)
+        self.converged = True
+        self.X_last, self.U_last = X, U
+        self.tight_mask_last = out["tight"].bool()
+        self.iters_last, self.flags_last, self.cost_last = out["iters"], out["flags"], out["cost"]
+        return X, U
 
     def solve_step(self, x0: Tensor, U_init: Tensor) -> Tuple[Tensor, Tensor]:
         """One full iLQR solve from (x0, U_init) (controller.py:275-315)."""

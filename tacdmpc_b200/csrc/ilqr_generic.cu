@@ -570,6 +570,41 @@ __global__ void __launch_bounds__(128) closed_loop_advance(const DevProblem<R> P
   }
 }
 
+// tacd_al_update: one warp per element, lanes over (t, i)
+template <typename R>
+__global__ void __launch_bounds__(128) al_update(int B, int T, int nx, const R* X, const R* xref, int xref_batched, const R* xmin, const R* xmax,
+                                                 R* lam_lo, R* lam_hi, R rho, R rho_next, int update_lambda, R* dq, R* dp, R* viol) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const int W = (T + 1) * nx;
+  const R* Xb = X + (size_t)b * W;
+  const R* xr = xref + (xref_batched ? (size_t)b * W : 0);
+  R vmax = 0;
+  for (int w = lane; w < W; w += 32) {
+    const int i = w % nx;
+    const R x = Xb[w], r = xr[w];
+    const R ghi = x - xmax[i], glo = xmin[i] - x;          // -inf on an unbounded side
+    R lhi = lam_hi[(size_t)b * W + w], llo = lam_lo[(size_t)b * W + w];
+    if (update_lambda) {
+      lhi = fmax(lhi + rho * ghi, (R)0);                    // (-inf -> 0)
+      llo = fmax(llo + rho * glo, (R)0);
+      lam_hi[(size_t)b * W + w] = lhi;
+      lam_lo[(size_t)b * W + w] = llo;
+    }
+    // a constraint stays in the model while its multiplier is positive: predicting the active set with
+    // lam + rho_next g drops constraints that sit rho-tightly on their bound (g = (mu - lam)/rho < 0 when the
+    // multiplier is decreasing) as soon as rho grows, and the outer loop oscillates
+    const bool ahi = update_lambda ? lhi > 0 : lhi + rho_next * ghi > 0;
+    const bool alo = update_lambda ? llo > 0 : llo + rho_next * glo > 0;
+    dq[(size_t)b * W + w] = rho_next * (R)((ahi ? 1 : 0) + (alo ? 1 : 0));
+    dp[(size_t)b * W + w] = (ahi ? lhi + rho_next * (r - xmax[i]) : (R)0) - (alo ? llo + rho_next * (xmin[i] - r) : (R)0);
+    vmax = fmax(vmax, fmax(ghi, glo));
+  }
+  for (int o = 16; o > 0; o >>= 1) vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+  if (lane == 0 && viol) viol[b] = vmax;
+}
+
 template <typename K>
 static int prep_smem(K kernel, size_t bytes) {
   const DeviceInfo di = device_info();
@@ -732,6 +767,25 @@ int tacd_closed_loop_advance(const tacd_problem* p, int32_t k, int32_t n_sim, vo
                                                      (const double*)uref_full, ref_len, (double*)xref_win, (double*)uref_win);
   note_launches(1);
   return check_cuda(cudaPeekAtLastError(), "closed_loop_advance launch");
+}
+
+int tacd_al_update(int32_t dtype, int32_t B, int32_t T, int32_t nx, const void* X, const void* xref, int32_t xref_batched, const void* x_min,
+                   const void* x_max, void* lam_lo, void* lam_hi, double rho, double rho_next, int32_t update_lambda, void* dq, void* dp,
+                   void* viol, void* stream) {
+  if (B < 0 || T < 1 || nx < 1 || nx > TACD_MAX_NX || (dtype != TACD_F32 && dtype != TACD_F64)) { set_error("tacd_al_update: bad sizes / dtype"); return TACD_EINVAL; }
+  if (!X || !xref || !x_min || !x_max || !lam_lo || !lam_hi || !dq || !dp) { set_error("tacd_al_update: required pointer is null"); return TACD_EINVAL; }
+  if (!(rho > 0) || !(rho_next > 0)) { set_error("tacd_al_update: rho must be positive"); return TACD_EINVAL; }
+  if (B == 0) return TACD_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int grid = (B + 3) / 4;
+  if (dtype == TACD_F32)
+    al_update<float><<<grid, 128, 0, s>>>(B, T, nx, (const float*)X, (const float*)xref, xref_batched, (const float*)x_min, (const float*)x_max,
+                                          (float*)lam_lo, (float*)lam_hi, (float)rho, (float)rho_next, update_lambda, (float*)dq, (float*)dp, (float*)viol);
+  else
+    al_update<double><<<grid, 128, 0, s>>>(B, T, nx, (const double*)X, (const double*)xref, xref_batched, (const double*)x_min, (const double*)x_max,
+                                           (double*)lam_lo, (double*)lam_hi, rho, rho_next, update_lambda, (double*)dq, (double*)dp, (double*)viol);
+  note_launches(1);
+  return check_cuda(cudaPeekAtLastError(), "al_update launch");
 }
 
 int tacd_rollout(const tacd_problem* p, const void* x0, const void* U, void* X, void* stream) {

@@ -284,3 +284,23 @@ def closed_loop_advance(spec: Spec, k: int, n_sim: int, x, U_opt, Xs, Us, U_warm
     with torch.cuda.device(x.device):
         _lib.check(_lib.lib().tacd_closed_loop_advance(C.byref(p), int(k), int(n_sim), *_vp(x, U_opt, Xs, Us, U_warm, xref_full, uref_full),
                                                        ref_len, *_vp(xref_win, uref_win), _stream()), "tacd_closed_loop_advance")
+
+
+def al_update(X, xref, x_min, x_max, lam_lo, lam_hi, rho: float, rho_next: float, update_lambda: bool = True):
+    """Augmented-Lagrangian multiplier update + quadratic penalty model for state box constraints
+    (``tacd_al_update``).  ``lam_lo``/``lam_hi`` [B,T+1,nx] are updated in place; returns ``(dq, dp, viol)``:
+    additions to the diagonal / linear state cost of every step (t = T: terminal cost) and the largest violation
+    per element."""
+    _need_cuda(X, xref, x_min, x_max, lam_lo, lam_hi)
+    dt, dev = X.dtype, X.device
+    B, T1, nx = X.shape
+    X, xref = _prep(X, dt, dev), _prep(xref, dt, dev)
+    x_min, x_max = _prep(x_min, dt, dev).expand(nx).contiguous(), _prep(x_max, dt, dev).expand(nx).contiguous()
+    if lam_lo.dtype != dt or lam_hi.dtype != dt or not lam_lo.is_contiguous() or not lam_hi.is_contiguous():
+        raise RuntimeError("multipliers must be contiguous tensors of the solve dtype")
+    dq, dp = torch.empty_like(X), torch.empty_like(X)
+    viol = torch.empty(B, device=dev, dtype=dt)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().tacd_al_update(_DT[dt], B, T1 - 1, nx, *_vp(X, xref), int(xref.shape[0] == B), *_vp(x_min, x_max, lam_lo, lam_hi),
+                                             float(rho), float(rho_next), int(update_lambda), *_vp(dq, dp, viol), _stream()), "tacd_al_update")
+    return dq, dp, viol
