@@ -134,8 +134,11 @@ int tacd_ilqr_backward(const tacd_problem* p, const tacd_backward_io* io, void* 
   cudaStream_t s = (cudaStream_t)stream;
   if (!workspace || workspace_bytes < 256) { set_error("workspace too small (need tacd_backward_workspace_bytes)"); return TACD_EWORKSPACE; }
   char* ws = (char*)workspace + 256;
-  int rc = (p->dtype == TACD_F32) ? launch_backward_small<float>(p, io, ws, workspace_bytes - 256, s)
-                                  : launch_backward_small<double>(p, io, ws, workspace_bytes - 256, s);
+  int rc = (p->dtype == TACD_F32) ? launch_backward_group<float>(p, io, ws, workspace_bytes - 256, s)
+                                  : launch_backward_group<double>(p, io, ws, workspace_bytes - 256, s);
+  if (rc != TACD_EUNSUPPORTED) return rc;
+  rc = (p->dtype == TACD_F32) ? launch_backward_small<float>(p, io, ws, workspace_bytes - 256, s)
+                              : launch_backward_small<double>(p, io, ws, workspace_bytes - 256, s);
   if (rc != TACD_EUNSUPPORTED) return rc;
   if (p->C_diag) { set_error("C_diag: no thread-per-element backward kernel for this (nx, nu, dyn); pass dense costs"); return TACD_EUNSUPPORTED; }
   if (p->compat_exact) { set_error("compat_exact: no thread-per-element backward kernel for this (nx, nu, dyn)"); return TACD_EUNSUPPORTED; }

@@ -47,6 +47,7 @@ template <typename R> int launch_backward_small(const tacd_problem* p, const tac
 size_t small_backward_ws_bytes(const tacd_problem* p);
 // five-lanes-per-element forward kernel (ilqr_group.cuh); TACD_EUNSUPPORTED when not eligible
 template <typename R> int launch_forward_group(const tacd_problem* p, const tacd_forward_io* io, void* ws, size_t ws_bytes, cudaStream_t s);
+template <typename R> int launch_backward_group(const tacd_problem* p, const tacd_backward_io* io, void* ws, size_t ws_bytes, cudaStream_t s);
 
 // generic (CTA-per-element, run-time dimensions) launchers
 template <typename R> int launch_forward_generic(const tacd_problem* p, const tacd_forward_io* io, void* ws, size_t ws_bytes, cudaStream_t s);

@@ -57,6 +57,16 @@ struct GDyn {  // LTI: dense F, shared by the CTA in shared memory (row-major NX
       o[k] = s;
     }
   }
+  // o = F d  (d = [dx; du]): one step of the linearised dynamics
+  static TACD_DEV void mulFv(const DevProblem<R>&, const R* sF, const R (&)[NJ], const R (&d)[N], R (&o)[NX]) {
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      R s = 0;
+#pragma unroll
+      for (int k = 0; k < N; ++k) s += sF[i * N + k] * d[k];
+      o[i] = s;
+    }
+  }
 };
 
 // cart-pole: A = [[1,dt,0,0],[0,1,a,b],[0,0,1,dt],[0,0,c,d]], B = [0,e,0,f]'  (tacd_dev.cuh::cartpole_jac)
@@ -86,6 +96,13 @@ struct GDyn<R, 4, 1, TACD_DYN_CARTPOLE> {
     o[3] = ((o[3] + w[1] * jc[1]) + w[2] * dt) + w[3] * jc[3];
     o[4] = (o[4] + w[1] * jc[4]) + w[3] * jc[5];
   }
+  static TACD_DEV void mulFv(const DevProblem<R>& P, const R*, const R (&jc)[6], const R (&d)[5], R (&o)[4]) {
+    const R dt = P.dt;
+    o[0] = d[0] + dt * d[1];
+    o[1] = ((d[1] + jc[0] * d[2]) + jc[1] * d[3]) + jc[4] * d[4];
+    o[2] = d[2] + dt * d[3];
+    o[3] = (jc[2] * d[2] + jc[3] * d[3]) + jc[5] * d[4];
+  }
 };
 
 // unicycle: A = [[1,0,a],[0,1,b],[0,0,1]], B = [[p,0],[q,0],[0,dt]]  (tacd_dev.cuh::unicycle_jac)
@@ -111,6 +128,11 @@ struct GDynUnicycle {
     o[2] = ((o[2] + w[0] * jc[0]) + w[1] * jc[1]) + w[2];
     o[3] = (o[3] + w[0] * jc[2]) + w[1] * jc[3];
     o[4] += w[2] * P.dt;
+  }
+  static TACD_DEV void mulFv(const DevProblem<R>& P, const R*, const R (&jc)[4], const R (&d)[5], R (&o)[3]) {
+    o[0] = (d[0] + jc[0] * d[2]) + jc[2] * d[3];
+    o[1] = (d[1] + jc[1] * d[2]) + jc[3] * d[3];
+    o[2] = d[2] + P.dt * d[4];
   }
 };
 template <typename R> struct GDyn<R, 3, 2, TACD_DYN_UNICYCLE> : GDynUnicycle<R, TACD_DYN_UNICYCLE> {};

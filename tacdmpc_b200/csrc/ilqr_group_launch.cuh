@@ -6,6 +6,7 @@
 
 #include "host_common.h"
 #include "ilqr_group.cuh"
+#include "ilqr_group_bwd.cuh"
 
 namespace tacd {
 
@@ -106,6 +107,75 @@ int launch_forward_group(const tacd_problem* p, const tacd_forward_io* io, void*
                           : run_forward_group<R, NX_, NU_, DYN_, true, true, false>(p, io, ws, ws_bytes, s);   \
     return p->C_batched ? run_forward_group<R, NX_, NU_, DYN_, false, false, false>(p, io, ws, ws_bytes, s)    \
                         : run_forward_group<R, NX_, NU_, DYN_, false, true, false>(p, io, ws, ws_bytes, s);    \
+  }
+  TACD_GROUP_FWD(X)
+#undef X
+  return TACD_EUNSUPPORTED;
+}
+
+template <typename R, int NX, int NU, int DYN, bool CSH, bool DIAG>
+static int run_backward_group(const tacd_problem* p, const tacd_backward_io* io, void* ws, size_t ws_bytes, cudaStream_t s) {
+  auto kernel = ilqr_backward_group<R, NX, NU, DYN, CSH, DIAG>;
+  using L = BwdLayout<NX, NU>;
+  const DeviceInfo di = device_info();
+  const int nacc = L::nacc(p->T);
+  const bool reduce = (io->grad_C && !p->C_batched) || (io->grad_c && !p->C_batched) || (io->grad_Cf && !p->Cf_batched) ||
+                      (io->grad_cf && !p->Cf_batched) || (io->grad_xref && !p->xref_batched) || (io->grad_uref && !p->uref_batched);
+  const size_t n = NX + NU;
+  const size_t stage_b = ((CSH ? (size_t)p->T * ((n * n + n + 3) & ~(size_t)3) : 0) + (DYN == TACD_DYN_LTI ? ((NX * n + 3) & ~(size_t)3) : 0)) * sizeof(R);
+  const size_t warp_b = ((size_t)gbwd_warp_words(p->T, NX, NU) + (reduce ? (size_t)nacc : 0)) * sizeof(R);
+  if (stage_b + warp_b > (size_t)di.smem_optin) return TACD_EUNSUPPORTED;
+  int nw = (int)(((size_t)di.smem_optin - stage_b) / warp_b);
+  if (nw > 16) nw = 16;
+  if (const char* e = getenv("TACD_GROUP_WARPS")) { const int v = atoi(e); if (v >= 1 && v < nw) nw = v; }
+  const int spread = (p->B + di.sms * kEPW - 1) / (di.sms * kEPW);
+  if (nw > spread) nw = spread < 1 ? 1 : spread;
+  const size_t smem = stage_b + warp_b * nw;
+  if (int rc = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr")) return rc;
+  int grid = (p->B + nw * kEPW - 1) / (nw * kEPW);
+  if (grid > di.sms) grid = di.sms;
+  if (grid < 1) grid = 1;
+  R* partials = nullptr;
+  if (reduce) {
+    const size_t need = (size_t)grid * nacc * sizeof(R);
+    if (!ws || ws_bytes < need) { set_error("backward workspace too small: %zu < %zu", ws_bytes, need); return TACD_EWORKSPACE; }
+    partials = (R*)ws;
+    if (io->grad_Cf && !p->Cf_batched) if (int rc = check_cuda(cudaMemsetAsync(io->grad_Cf, 0, n * n * sizeof(R), s), "memset")) return rc;
+    if (io->grad_cf && !p->Cf_batched) if (int rc = check_cuda(cudaMemsetAsync(io->grad_cf, 0, n * sizeof(R), s), "memset")) return rc;
+  }
+  BwdPtrs<R> f;
+  f.X = (const R*)io->X; f.U = (const R*)io->U; f.C = (const R*)io->C; f.Cf = (const R*)io->Cf; f.xref = (const R*)io->xref; f.uref = (const R*)io->uref;
+  f.A = (const R*)io->A; f.Bm = (const R*)io->Bm; f.gX = (const R*)io->gX; f.gU = (const R*)io->gU; f.tight = io->tight;
+  f.grad_C = (R*)io->grad_C; f.grad_c = (R*)io->grad_c; f.grad_Cf = (R*)io->grad_Cf; f.grad_cf = (R*)io->grad_cf;
+  f.grad_x0 = (R*)io->grad_x0; f.grad_xref = (R*)io->grad_xref; f.grad_uref = (R*)io->grad_uref; f.dX = (R*)io->dX; f.dU = (R*)io->dU;
+  const DevProblem<R> dp = to_dev<R>(p);
+  kernel<<<grid, nw * 32, smem, s>>>(dp, f, partials, reduce ? 1 : 0);
+  note_launches(1);
+  if (int rc = check_cuda(cudaPeekAtLastError(), "ilqr_backward_group launch")) return rc;
+  if (reduce) {
+    reduce_shared_grads<R, NX, NU><<<(nacc + 127) / 128, 128, 0, s>>>(dp, f, partials, grid);
+    note_launches(1);
+    return check_cuda(cudaPeekAtLastError(), "reduce_shared_grads launch");
+  }
+  return TACD_OK;
+}
+
+// Eligibility: embedded dynamics of a shipped plugin, reference-mode gradients (compat="exact" and external
+// Jacobians stay on the thread-per-element kernel).  OPT-IN (TACD_BWD_KERNEL=group): unlike the forward solve
+// the backward does uniform work per element, so it has no tail to remove, and the redundant gains / box QP on
+// five lanes plus the cross-group reduction cost more than coalescing saves — measured at B = 65536, cart-pole:
+// 0.217 ms vs 0.146 ms (shared cost), 0.181 vs 0.135 (compact diagonal), 0.220 vs 0.210 (per-element dense);
+// equal at B <= 4096.  Kept for the parity tests and as the starting point for a leaner row split.
+template <typename R>
+int launch_backward_group(const tacd_problem* p, const tacd_backward_io* io, void* ws, size_t ws_bytes, cudaStream_t s) {
+  if (p->compat_exact || p->dyn_id == TACD_DYN_EXTERNAL) return TACD_EUNSUPPORTED;
+  const char* sel = getenv("TACD_BWD_KERNEL");
+  if (!sel || strcmp(sel, "group")) return TACD_EUNSUPPORTED;
+#define X(NX_, NU_, DYN_)                                                                      \
+  if (p->nx == NX_ && p->nu == NU_ && p->dyn_id == DYN_) {                                     \
+    if (p->C_diag) return run_backward_group<R, NX_, NU_, DYN_, false, true>(p, io, ws, ws_bytes, s);   \
+    return p->C_batched ? run_backward_group<R, NX_, NU_, DYN_, false, false>(p, io, ws, ws_bytes, s)   \
+                        : run_backward_group<R, NX_, NU_, DYN_, true, false>(p, io, ws, ws_bytes, s);   \
   }
   TACD_GROUP_FWD(X)
 #undef X

@@ -138,9 +138,23 @@ def test_first_iteration_stages(G, name):
     assert P.rel_err(cost.cpu().numpy()[:, None], g["cost"][:, None]).max() <= 10 * tol
 
 
+@pytest.fixture(params=["group", "thread"])
+def bwd_kernel(request, monkeypatch):
+    """Two backward kernels for the shipped small plugins: one thread per element (default,
+    csrc/ilqr_small.cuh) and five lanes per element (csrc/ilqr_group_bwd.cuh, opt-in with
+    TACD_BWD_KERNEL=group: measured slower at large batches).  Both are held to the same bar."""
+    if request.param == "group":
+        monkeypatch.setenv("TACD_BWD_KERNEL", "group")
+    else:
+        monkeypatch.delenv("TACD_BWD_KERNEL", raising=False)
+    return request.param
+
+
 @pytest.mark.parametrize("name", P.SOLVE_CASES)
 @pytest.mark.parametrize("loss", ["Usum", "U0sum", "weighted"])
-def test_backward_matches_reference(G, oracle, name, loss):
+def test_backward_matches_reference(G, oracle, name, loss, bwd_kernel):
+    if bwd_kernel == "group" and name not in P.SMALL_CASES:
+        pytest.skip("generic CTA-per-element path: no second kernel to select")
     from tacdmpc_b200 import ops
     g = P.load(name)
     spec = P.spec_of(g)
