@@ -186,6 +186,7 @@ class DifferentiableMPCController(torch.nn.Module):
         self.nx, self.nu = cost_module.nx, cost_module.nu
         self.u_min = u_min.to(self.device) if u_min is not None else None
         self.u_max = u_max.to(self.device) if u_max is not None else None
+        self._bounds_cache = {}
         self.reg_eps = reg_eps
         self.N_sim = N_sim if N_sim is not None else horizon
         if isinstance(grad_method, str):
@@ -262,9 +263,20 @@ class DifferentiableMPCController(torch.nn.Module):
             dynA, dynB = f.device_matrices(device, dtype)
 
         def bounds(b):
+            # The kernels take the box as launch constants (tacd_problem.umin/umax).  The tensors live on the
+            # device (controller.py:187-188 keeps them there), so reading them is a device->host copy + sync:
+            # done once per tensor version, not per solve (a per-call sync would stall the stream and break
+            # CUDA-graph capture).
             if b is None:
                 return None
-            return [float(v) for v in b.detach().to("cpu", torch.float64).flatten().expand(self.nu).tolist()]
+            key = (id(b), b._version)
+            hit = self._bounds_cache.get(key)
+            if hit is None:
+                hit = [float(v) for v in b.detach().to("cpu", torch.float64).flatten().expand(self.nu).tolist()]
+                if len(self._bounds_cache) > 8:
+                    self._bounds_cache.clear()
+                self._bounds_cache[key] = hit
+            return hit
 
         return ops.Spec(nx=self.nx, nu=self.nu, T=self.horizon, dt=float(self.dt),
                         dyn_id=f.dyn_id if native else _abi.DYN_EXTERNAL, dyn_params=tuple(getattr(f, "params", ())),

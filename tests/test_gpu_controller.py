@@ -209,3 +209,43 @@ def test_actor_mpc_call_site_pattern():
     assert sum(float(g.abs().sum()) for g in grads) > 0
     # the solve improved on the initial guess for every element
     assert torch.isfinite(mpc.cost_last).all() and int(mpc.iters_last.min()) >= 1
+
+
+def test_step_is_cuda_graph_capturable():
+    """A whole public-API step (solve + autograd backward) never synchronises the host and allocates only through
+    torch's allocator, so it can be captured in a CUDA graph and replayed on new inputs (bench.py's e2e path)."""
+    g = P.load("cartpole_shared_f32")
+    mpc, cm, lv = _build(g, requires_grad=True)
+    x_static = lv["x0"].detach().clone().requires_grad_(True)
+    U0 = torch.from_numpy(g["Uinit"]).cuda()
+
+    def step():
+        lv["C"].grad = x_static.grad = None
+        X, U = mpc(x_static, U0)
+        U[:, 0].sum().backward()
+        return X, U
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            X_e, U_e = step()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    gC_e = lv["C"].grad.clone()
+    graph = torch.cuda.CUDAGraph()
+    lv["C"].grad = x_static.grad = None
+    with torch.cuda.graph(graph):
+        X_g, U_g = step()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(U_g, U_e) and torch.equal(X_g, X_e) and torch.equal(lv["C"].grad, gC_e)
+    # new inputs through the same graph: equal to an eager solve of those inputs
+    with torch.no_grad():
+        x_static.copy_(lv["x0"].detach().flip(0))
+    graph.replay()
+    torch.cuda.synchronize()
+    U_replayed = U_g.clone()
+    with torch.no_grad():
+        X2, U2 = mpc(lv["x0"].detach().flip(0).contiguous(), U0)
+    assert torch.equal(U_replayed, U2)
