@@ -103,17 +103,55 @@ def flops_per_solve(mean_iters):
 
 # ------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md recipe).  The timed region is a
+    few tens of milliseconds, shorter than nvidia-smi's polling period, so NVML is polled directly from a thread
+    (~1 kHz); `nvidia-smi -lms` is the fallback when NVML cannot be loaded."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+    def __init__(self, index, uuid=None):
+        self.rows, self.proc, self.index, self.uuid = [], None, index, uuid
+        self.samples, self.max_mhz, self.reasons, self._stop, self.th, self.nvml = [], None, set(), False, None, None
+
+    def _nvml_loop(self):
+        n, h = self.nvml, self.handle
+        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
+        while not self._stop:
+            try:
+                self.samples.append(float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)))
+                r = int(n.nvmlDeviceGetCurrentClocksEventReasons(h)) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else int(n.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                for name, b in bits.items():
+                    if r & b:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.001)
 
     def __enter__(self):
         try:
+            import pynvml as n
+            n.nvmlInit()
+            h = None
+            if self.uuid:
+                for u in (self.uuid, "GPU-" + self.uuid):
+                    try:
+                        h = n.nvmlDeviceGetHandleByUUID(u.encode() if isinstance(u, str) else u)
+                        break
+                    except Exception:
+                        h = None
+            if h is None:
+                h = n.nvmlDeviceGetHandleByIndex(self.index)
+            self.nvml, self.handle = n, h
+            self.max_mhz = float(n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM))
+            self.th = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.th.start()
+            return self
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -126,8 +164,12 @@ class ClockSampler:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def __exit__(self, *a):
+        self._stop = True
+        if self.nvml is not None:
+            if self.th is not None:
+                self.th.join(timeout=1)
+            return
         if self.proc is not None:
-            time.sleep(0.15)
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
@@ -135,6 +177,12 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
+        if self.nvml is not None:
+            sm = sorted(self.samples)
+            if not sm:
+                return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0, "source": "nvml"}
+            return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(sm),
+                    "source": "nvml"}
         sm, mx, reasons = [], [], set()
         for r in self.rows:
             try:
@@ -145,9 +193,9 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": "nvidia-smi"}
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------- CPU arm
@@ -291,7 +339,11 @@ def main():
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
           for _ in range(args.steps)]
     launches0 = int(_lib.lib().tacd_kernel_launches())
-    with ClockSampler(local_rank) as clk:
+    try:
+        dev_uuid = str(torch.cuda.get_device_properties(dev).uuid)
+    except Exception:
+        dev_uuid = None
+    with ClockSampler(local_rank, dev_uuid) as clk:
         barrier()
         for i in range(args.steps):
             flush.fill_(i & 0xFF)          # L2 flush, outside the timed events
@@ -450,17 +502,19 @@ def main():
     sm_mhz = clocks.get("sm_mhz") or 1965.0
     fp32_peak_nominal = 148 * 128 * 2 * 1.965e9 / 1e12
     fp32_peak_at_clock = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
-    traffic = None
+    traffic = limiter = None
     tj = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tj):
         try:
-            traffic = json.load(open(tj)).get(f"forward_{args.layout}")
+            facts = json.load(open(tj))
+            traffic = facts.get(f"forward_{args.layout}")
+            limiter = facts.get(f"forward_{args.layout}_limiter")
         except Exception:
             traffic = None
     fwd_kernel = "ilqr_forward_small<float,4,1,cartpole>" if os.environ.get("TACD_FWD_KERNEL") == "thread" else \
         "ilqr_init_rollout + ilqr_forward_group<float,4,1,cartpole> (five lanes per element)"
     roofline = {"kernel": fwd_kernel, "bound": "hbm", "achieved": ach, "peak": hbm_peak,
-                "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic, "peak_source": peak_src, "limiter": limiter,
                 "algorithmic_bytes_per_solve": fwd_b, "launch_ms": fwd_ms, "mean_iters": mean_iters,
                 "fp32_pipe": {"flops_per_solve": F_fwd, "achieved_tflops": F_fwd * B / (fwd_ms * 1e-3) / 1e12,
                               "peak_tflops_nominal": fp32_peak_nominal, "peak_tflops_at_measured_clock": fp32_peak_at_clock,
