@@ -41,6 +41,21 @@ DeviceInfo device_info() {
   return di;
 }
 
+SideStream side_stream() {
+  static thread_local int cached_dev = -1;
+  static thread_local SideStream ss = {nullptr, nullptr, nullptr, false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev != cached_dev) {
+    ss.ok = cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming) == cudaSuccess;
+    if (!ss.ok) cudaGetLastError();
+    cached_dev = dev;
+  }
+  return ss;
+}
+
 static int validate(const tacd_problem* p) {
   if (!p) { set_error("null problem"); return TACD_EINVAL; }
   if (p->B < 0 || p->T < 1 || p->nx < 1 || p->nu < 1) { set_error("bad sizes B=%d T=%d nx=%d nu=%d", p->B, p->T, p->nx, p->nu); return TACD_EINVAL; }

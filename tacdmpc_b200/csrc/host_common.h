@@ -16,6 +16,12 @@ void note_launches(int n);
 struct DeviceInfo { int sms; int smem_optin; };
 DeviceInfo device_info();
 
+// A non-blocking helper stream + fork/join events per (host thread, device), created on first use and kept for
+// the life of the process: lets two independent pre-passes of one call overlap (fork from the caller's stream,
+// join back before the dependent kernel; the pattern is legal inside CUDA-graph capture).
+struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; bool ok; };
+SideStream side_stream();
+
 template <typename R>
 inline DevProblem<R> to_dev(const tacd_problem* p) {
   DevProblem<R> d;

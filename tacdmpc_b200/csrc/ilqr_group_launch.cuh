@@ -47,20 +47,30 @@ static int run_forward_group(const tacd_problem* p, const tacd_forward_io* io, v
   // longest-first queue order (ilqr_small.cuh): with more than one wave of elements the long chains must
   // not be popped last (profiles/r1_forward_group_v4: schedulers idle 13 % of the kernel in the tail)
   const bool lpt = (long)p->B > (long)grid * nw * kEPW && !getenv("TACD_NO_LPT");
+  // the queue order (3 small launches) and the initial rollout are independent: they run side by side, the
+  // order on a helper stream that forks from / joins back into the caller's stream before the solve kernel
+  SideStream ss = side_stream();
+  const bool fork = lpt && ss.ok && !getenv("TACD_NO_FORK");
+  cudaStream_t s2 = s;
+  if (fork) {
+    if (int rc = check_cuda(cudaEventRecord(ss.fork, s), "fork record")) return rc;
+    if (int rc = check_cuda(cudaStreamWaitEvent(ss.stream, ss.fork, 0), "fork wait")) return rc;
+    s2 = ss.stream;
+  }
   if (!lpt) {
     queue_init<<<1, 1, 0, s>>>(f.counter, 0u);
     note_launches(1);
   } else {
     unsigned int* hist = (unsigned int*)((char*)ws + 256);
     int32_t* order = (int32_t*)((char*)ws + 16384);
-    if (int rc = check_cuda(cudaMemsetAsync(hist, 0, kLptBuckets * sizeof(unsigned int), s), "memset hist")) return rc;
+    if (int rc = check_cuda(cudaMemsetAsync(hist, 0, kLptBuckets * sizeof(unsigned int), s2), "memset hist")) return rc;
     const int g2 = di.sms * 2 < (p->B + 255) / 256 ? di.sms * 2 : (p->B + 255) / 256;
     const int nkey = p->C_diag ? -(NX + NU) : NX + NU;
-    lpt_histogram<R><<<g2, 256, 0, s>>>(p->B, p->T, NX, nkey, p->C_batched, p->xref_batched, (const R*)io->x0, (const R*)io->xref, (const R*)io->C, hist);
+    lpt_histogram<R><<<g2, 256, 0, s2>>>(p->B, p->T, NX, nkey, p->C_batched, p->xref_batched, (const R*)io->x0, (const R*)io->xref, (const R*)io->C, hist);
     note_launches(1);
-    lpt_scan<<<1, 1024, 0, s>>>(hist, f.counter, 0u);
+    lpt_scan<<<1, 1024, 0, s2>>>(hist, f.counter, 0u);
     note_launches(1);
-    lpt_scatter<R><<<g2, 256, 0, s>>>(p->B, p->T, NX, nkey, p->C_batched, p->xref_batched, (const R*)io->x0, (const R*)io->xref, (const R*)io->C, hist, order);
+    lpt_scatter<R><<<g2, 256, 0, s2>>>(p->B, p->T, NX, nkey, p->C_batched, p->xref_batched, (const R*)io->x0, (const R*)io->xref, (const R*)io->C, hist, order);
     note_launches(1);
     f.order = order;
   }
@@ -82,6 +92,10 @@ static int run_forward_group(const tacd_problem* p, const tacd_forward_io* io, v
     note_launches(1);
   }
   if (int rc = check_cuda(cudaPeekAtLastError(), "ilqr_init_rollout launch")) return rc;
+  if (fork) {
+    if (int rc = check_cuda(cudaEventRecord(ss.join, ss.stream), "join record")) return rc;
+    if (int rc = check_cuda(cudaStreamWaitEvent(s, ss.join, 0), "join wait")) return rc;
+  }
   kernel<<<grid, nw * 32, smem, s>>>(dp, f, cost0);
   note_launches(1);
   return check_cuda(cudaPeekAtLastError(), "ilqr_forward_group launch");
