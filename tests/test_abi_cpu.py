@@ -40,15 +40,16 @@ def test_struct_layout_matches_header():
 #include <stdio.h>
 #include <stddef.h>
 #include "tacd_ilqr.h"
-int main(){printf("%zu %zu %zu %zu %zu %zu\n", sizeof(tacd_problem), sizeof(tacd_forward_io), sizeof(tacd_backward_io),
- offsetof(tacd_problem, dyn_params), offsetof(tacd_problem, alphas), offsetof(tacd_problem, umax));return 0;}'''
+int main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(tacd_problem), sizeof(tacd_forward_io), sizeof(tacd_backward_io),
+ offsetof(tacd_problem, dyn_params), offsetof(tacd_problem, alphas), offsetof(tacd_problem, umax), offsetof(tacd_problem, C_diag),
+ offsetof(tacd_problem, compat_exact));return 0;}'''
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "t.c"), "w").write(prog)
         subprocess.run(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "t.c"), "-o", os.path.join(d, "t")], check=True)
         out = subprocess.run([os.path.join(d, "t")], capture_output=True, text=True, check=True).stdout.split()
     got = [int(v) for v in out]
     exp = [C.sizeof(_abi.Problem), C.sizeof(_abi.ForwardIO), C.sizeof(_abi.BackwardIO), _abi.Problem.dyn_params.offset,
-           _abi.Problem.alphas.offset, _abi.Problem.umax.offset]
+           _abi.Problem.alphas.offset, _abi.Problem.umax.offset, _abi.Problem.C_diag.offset, _abi.Problem.compat_exact.offset]
     assert got == exp
 
 
