@@ -13,49 +13,60 @@ static inline size_t gen_slice_scalars(const tacd_problem* p) {
   const size_t nx = p->nx, nu = p->nu, T = p->T;
   return (T + 1) * nx + T * nu + T * nu * nx + T * nu;
 }
-static int gen_grid(const tacd_problem* p) {
+// Threads per element (GenDims::tpe): one warp for systems up to nx = 16, the whole CTA above.
+static int gen_tpe(const tacd_problem* p) {
+  static const char* e = getenv("TACD_GENERIC_TPE");
+  if (e) return atoi(e) == 32 ? 32 : kGenThreads;
+  return p->nx <= 16 ? 32 : kGenThreads;
+}
+// element slots in flight: four CTAs per SM, kGenThreads / tpe elements per CTA
+static int gen_slots(const tacd_problem* p, int tpe) {
   const DeviceInfo di = device_info();
-  int g = di.sms * 4;
+  int g = di.sms * 4 * (kGenThreads / tpe);
   if (g > p->B) g = p->B;
   return g < 1 ? 1 : g;
 }
+static int gen_grid(const tacd_problem* p) { return gen_slots(p, kGenThreads); }
 size_t generic_forward_ws_bytes(const tacd_problem* p) {
   const size_t es = (p->dtype == TACD_F32) ? 4 : 8;
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-  size_t g = (size_t)sms * 4;
+  const size_t g = (size_t)sms * 4 * (kGenThreads / gen_tpe(p));
   return g * gen_slice_scalars(p) * es + 256;
 }
 size_t generic_backward_ws_bytes(const tacd_problem* p) { return generic_forward_ws_bytes(p); }
 
-template <typename R>
-static GenDims<R> dims_of(const tacd_problem* p) {
-  GenDims<R> d;
-  d.nx = p->nx; d.nu = p->nu; d.n = p->nx + p->nu; d.T = p->T; d.dyn = p->dyn_id;
+template <typename R, int NXT = 0, int NUT = 0, int TPE = kGenThreads>
+static GenDims<R, NXT, NUT, TPE> dims_of(const tacd_problem* p) {
+  GenDims<R, NXT, NUT, TPE> d;
+  d.nx_ = p->nx; d.nu_ = p->nu; d.T = p->T; d.dyn = p->dyn_id;
   return d;
 }
 
 // ---------------------------------------------------------------------------
 // forward solve (solve_step, controller.py:275-315)
-template <typename R>
-__global__ void __launch_bounds__(kGenThreads) ilqr_forward_generic(const DevProblem<R> P, const GenDims<R> d, const FwdPtrs<R> io, R* ws, size_t slice) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  GenSmem<R> s = gen_carve<R>(smem_raw, d.nx, d.nu);
-  const int tid = threadIdx.x, nx = d.nx, nu = d.nu, n = d.n, T = d.T;
+template <typename R, int NXT, int NUT, int TPE>
+__global__ void __launch_bounds__(kGenThreads, sizeof(R) == 4 ? 4 : 2) ilqr_forward_generic(const DevProblem<R> P, const GenDims<R, NXT, NUT, TPE> d, const FwdPtrs<R> io, R* ws, size_t slice) {
+  using DT = GenDims<R, NXT, NUT, TPE>;
+  extern __shared__ __align__(16) unsigned char smem_cta[];
+  // each element slot of the CTA owns [matrices | (X U K k when ws == nullptr)]
+  unsigned char* smem_raw = smem_cta + (size_t)DT::sub() * gen_elem_bytes<R>(d.nx(), d.nu(), ws ? 0 : slice);
+  GenSmem<R> s = gen_carve<R>(smem_raw, d.nx(), d.nu());
+  const int tid = DT::tid(), nx = d.nx(), nu = d.nu(), n = d.n(), T = d.T;
   const size_t szX = (size_t)(T + 1) * nx, szU = (size_t)T * nu;
   // X, U, K, k of the element in flight: in shared memory right behind the per-step matrices when they fit
   // (ws == nullptr), else in this CTA's slice of the caller's workspace
-  R* gXs = ws ? ws + (size_t)blockIdx.x * slice : reinterpret_cast<R*>(smem_raw + gen_smem_bytes_aligned<R>(nx, nu));
+  R* gXs = ws ? ws + (size_t)DT::slot() * slice : reinterpret_cast<R*>(smem_raw + gen_smem_bytes_aligned<R>(nx, nu));
   R* gUs = gXs + szX;
   R* gK = gUs + szU;
   R* gk = gK + (size_t)T * nu * nx;
   if (d.dyn == TACD_DYN_LTI) {
-    for (int i = tid; i < nx * nx; i += kGenThreads) s.A[i] = P.dyn_A[i];
-    for (int i = tid; i < nx * nu; i += kGenThreads) s.Bm[i] = P.dyn_B[i];
+    for (int i = tid; i < nx * nx; i += DT::tpe) s.A[i] = P.dyn_A[i];
+    for (int i = tid; i < nx * nu; i += DT::tpe) s.Bm[i] = P.dyn_B[i];
   }
-  __syncthreads();
+  DT::sync();
   const bool lssep = P.ls_cost_shared != 0;
-  for (int b = blockIdx.x; b < P.B; b += gridDim.x) {
+  for (int b = DT::slot(); b < P.B; b += DT::nslots()) {
     const R* Cp = io.C + (P.C_batched ? (size_t)b * T * n * n : 0);
     const R* cp = io.c + (P.C_batched ? (size_t)b * T * n : 0);
     const R* Cfp = io.Cf + (P.Cf_batched ? (size_t)b * n * n : 0);
@@ -67,13 +78,13 @@ __global__ void __launch_bounds__(kGenThreads) ilqr_forward_generic(const DevPro
     const R* xr = io.xref + (P.xref_batched ? (size_t)b * szX : 0);
     const R* ur = io.uref + (P.uref_batched ? (size_t)b * szU : 0);
     // ---- init: U = U_init, X = rollout (no clamping), best = objective
-    for (int i = tid; i < (int)szU; i += kGenThreads) gUs[i] = io.Uinit[(size_t)b * szU + i];
-    for (int i = tid; i < nx; i += kGenThreads) gXs[i] = io.x0[(size_t)b * nx + i];
-    if (io.alpha_trace) for (int j = tid; j < P.max_iter; j += kGenThreads) io.alpha_trace[(size_t)b * P.max_iter + j] = 0xFF;
-    __syncthreads();
+    for (int i = tid; i < (int)szU; i += DT::tpe) gUs[i] = io.Uinit[(size_t)b * szU + i];
+    for (int i = tid; i < nx; i += DT::tpe) gXs[i] = io.x0[(size_t)b * nx + i];
+    if (io.alpha_trace) for (int j = tid; j < P.max_iter; j += DT::tpe) io.alpha_trace[(size_t)b * P.max_iter + j] = 0xFF;
+    DT::sync();
     for (int t = 0; t < T; ++t) {
       gen_dyn_step<R>(P, d, s.A, s.Bm, 1, gXs + (size_t)t * nx, gUs + (size_t)t * nu, gXs + (size_t)(t + 1) * nx);
-      __syncthreads();
+      DT::sync();
     }
     R best = gen_objective<R>(d, s, gXs, gUs, Cp, cp, Cfp, cfp, xr, ur);
     unsigned flg = 0;
@@ -81,43 +92,43 @@ __global__ void __launch_bounds__(kGenThreads) ilqr_forward_generic(const DevPro
     const bool replay = io.replay_iters != nullptr;
     while (it < P.max_iter && !(replay && it >= io.replay_iters[b])) {
       // ---- reverse Riccati pass
-      for (int i = tid; i < nx; i += kGenThreads) s.tau[i] = gXs[(size_t)T * nx + i] - xr[T * nx + i];
-      __syncthreads();
-      for (int idx = tid; idx < nx * nx; idx += kGenThreads) s.V[idx] = Cfp[(idx / nx) * n + (idx % nx)];
-      for (int i = tid; i < nx; i += kGenThreads) {
+      for (int i = tid; i < nx; i += DT::tpe) s.tau[i] = gXs[(size_t)T * nx + i] - xr[T * nx + i];
+      DT::sync();
+      for (int idx = tid; idx < nx * nx; idx += DT::tpe) s.V[idx] = Cfp[(idx / nx) * n + (idx % nx)];
+      for (int i = tid; i < nx; i += DT::tpe) {
         R a = 0;
         for (int j = 0; j < nx; ++j) a += Cfp[i * n + j] * s.tau[j];
         s.v[i] = a + cfp[i];
       }
-      __syncthreads();
+      DT::sync();
       for (int t = T - 1; t >= 0; --t) {
-        for (int i = tid; i < nx; i += kGenThreads) { s.x[i] = gXs[(size_t)t * nx + i]; s.tau[i] = s.x[i] - xr[t * nx + i]; }
-        for (int i = tid; i < nu; i += kGenThreads) { s.u[i] = gUs[(size_t)t * nu + i]; s.tau[nx + i] = s.u[i] - ur[t * nu + i]; }
-        for (int idx = tid; idx < n * n; idx += kGenThreads) s.Ct[idx] = Cp[(size_t)t * n * n + idx];
-        __syncthreads();
-        for (int i = tid; i < n; i += kGenThreads) {
+        for (int i = tid; i < nx; i += DT::tpe) { s.x[i] = gXs[(size_t)t * nx + i]; s.tau[i] = s.x[i] - xr[t * nx + i]; }
+        for (int i = tid; i < nu; i += DT::tpe) { s.u[i] = gUs[(size_t)t * nu + i]; s.tau[nx + i] = s.u[i] - ur[t * nu + i]; }
+        for (int idx = tid; idx < n * n; idx += DT::tpe) s.Ct[idx] = Cp[(size_t)t * n * n + idx];
+        DT::sync();
+        for (int i = tid; i < n; i += DT::tpe) {
           R a = 0;
           for (int j = 0; j < n; ++j) a += s.Ct[i * n + j] * s.tau[j];
           a += cp[(size_t)t * n + i];
           if (i < nx) s.qx[i] = a; else s.qu[i - nx] = a;
         }
-        for (int idx = tid; idx < nx * nx; idx += kGenThreads) s.Qxx[idx] = s.Ct[(idx / nx) * n + (idx % nx)];
-        for (int idx = tid; idx < nx * nu; idx += kGenThreads) s.Qxu[idx] = s.Ct[(idx / nu) * n + nx + (idx % nu)];
-        for (int idx = tid; idx < nu * nu; idx += kGenThreads) s.Quu[idx] = s.Ct[(nx + idx / nu) * n + nx + (idx % nu)];
+        for (int idx = tid; idx < nx * nx; idx += DT::tpe) s.Qxx[idx] = s.Ct[(idx / nx) * n + (idx % nx)];
+        for (int idx = tid; idx < nx * nu; idx += DT::tpe) s.Qxu[idx] = s.Ct[(idx / nu) * n + nx + (idx % nu)];
+        for (int idx = tid; idx < nu * nu; idx += DT::tpe) s.Quu[idx] = s.Ct[(nx + idx / nu) * n + nx + (idx % nu)];
         gen_dyn_jac<R>(P, d, s.x, s.u, s.A, s.Bm);
-        __syncthreads();
+        DT::sync();
         if (gen_value_step<R>(P, d, s, false, nullptr, nullptr)) flg |= TACD_FLAG_NONPD;
-        for (int idx = tid; idx < nu * nx; idx += kGenThreads) gK[(size_t)t * nu * nx + idx] = s.Kt[idx];
-        for (int i = tid; i < nu; i += kGenThreads) gk[(size_t)t * nu + i] = s.kt[i];
-        __syncthreads();
+        for (int idx = tid; idx < nu * nx; idx += DT::tpe) gK[(size_t)t * nu * nx + idx] = s.Kt[idx];
+        for (int i = tid; i < nu; i += DT::tpe) gk[(size_t)t * nu + i] = s.kt[i];
+        DT::sync();
       }
       // ---- all line-search candidates (evaluate_alphas, controller.py:589-620)
       const int na = P.n_alpha;
-      for (int idx = tid; idx < na * nx; idx += kGenThreads) s.xa[idx] = gXs[idx % nx];
-      for (int idx = tid; idx < na * n; idx += kGenThreads) { s.part1[idx] = 0; s.part2[idx] = 0; }
-      __syncthreads();
+      for (int idx = tid; idx < na * nx; idx += DT::tpe) s.xa[idx] = gXs[idx % nx];
+      for (int idx = tid; idx < na * n; idx += DT::tpe) { s.part1[idx] = 0; s.part2[idx] = 0; }
+      DT::sync();
       for (int t = 0; t < T; ++t) {
-        for (int idx = tid; idx < na * nu; idx += kGenThreads) {
+        for (int idx = tid; idx < na * nu; idx += DT::tpe) {
           const int a = idx / nu, i = idx % nu;
           R acc = 0;
           for (int j = 0; j < nx; ++j) acc += gK[(size_t)t * nu * nx + i * nx + j] * (s.xa[a * nx + j] - gXs[(size_t)t * nx + j]);
@@ -126,8 +137,8 @@ __global__ void __launch_bounds__(kGenThreads) ilqr_forward_generic(const DevPro
           if (P.has_umax) ui = tmin<R>(ui, P.umax[i]);
           s.ua[idx] = ui;
         }
-        __syncthreads();
-        for (int idx = tid; idx < na * n; idx += kGenThreads) {
+        DT::sync();
+        for (int idx = tid; idx < na * n; idx += DT::tpe) {
           const int a = idx / n, i = idx % n;
           const R* Ct = Cl + (size_t)t * n * n + (size_t)i * n;
           R sd = 0;
@@ -144,9 +155,9 @@ __global__ void __launch_bounds__(kGenThreads) ilqr_forward_generic(const DevPro
           }
         }
         gen_dyn_step<R>(P, d, s.A, s.Bm, na, s.xa, s.ua, s.xan);
-        __syncthreads();
-        for (int idx = tid; idx < na * nx; idx += kGenThreads) s.xa[idx] = s.xan[idx];
-        __syncthreads();
+        DT::sync();
+        for (int idx = tid; idx < na * nx; idx += DT::tpe) s.xa[idx] = s.xan[idx];
+        DT::sync();
       }
       // terminal terms + per-candidate totals (thread a sums its candidate)
       if (tid < na) {
@@ -168,7 +179,7 @@ __global__ void __launch_bounds__(kGenThreads) ilqr_forward_generic(const DevPro
         s.red[a] = tot + ((R)0.5 * qN + lN);
         s.red[TACD_MAX_ALPHA + a] = lssep ? tot2 + ((R)0.5 * qN2 + lN2) : s.red[a];
       }
-      __syncthreads();
+      DT::sync();
       int ai = 0;
       for (int a = 1; a < na; ++a) {
         if (s.red[ai] != s.red[ai]) break;
@@ -187,16 +198,16 @@ __global__ void __launch_bounds__(kGenThreads) ilqr_forward_generic(const DevPro
           ctr[na + 1] = best;
         }
       }
-      __syncthreads();
+      DT::sync();
       it += 1;
       if (!improved) break;
       best = newc;
       // ---- re-rollout of the accepted candidate in place
       const R alpha = P.alphas[ai];
-      for (int i = tid; i < nx; i += kGenThreads) { s.xa[i] = gXs[i]; s.xan[nx + i] = gXs[i]; }  // xan[nx..] = old X_t
-      __syncthreads();
+      for (int i = tid; i < nx; i += DT::tpe) { s.xa[i] = gXs[i]; s.xan[nx + i] = gXs[i]; }  // xan[nx..] = old X_t
+      DT::sync();
       for (int t = 0; t < T; ++t) {
-        for (int i = tid; i < nu; i += kGenThreads) {
+        for (int i = tid; i < nu; i += DT::tpe) {
           R acc = 0;
           for (int j = 0; j < nx; ++j) acc += gK[(size_t)t * nu * nx + i * nx + j] * (s.xa[j] - s.xan[nx + j]);
           R ui = gUs[(size_t)t * nu + i] + (alpha * gk[(size_t)t * nu + i] + acc);
@@ -204,22 +215,22 @@ __global__ void __launch_bounds__(kGenThreads) ilqr_forward_generic(const DevPro
           if (P.has_umax) ui = tmin<R>(ui, P.umax[i]);
           s.ua[i] = ui;
         }
-        __syncthreads();
-        for (int i = tid; i < nu; i += kGenThreads) gUs[(size_t)t * nu + i] = s.ua[i];
+        DT::sync();
+        for (int i = tid; i < nu; i += DT::tpe) gUs[(size_t)t * nu + i] = s.ua[i];
         gen_dyn_step<R>(P, d, s.A, s.Bm, 1, s.xa, s.ua, s.xan);
-        __syncthreads();
-        for (int i = tid; i < nx; i += kGenThreads) {
+        DT::sync();
+        for (int i = tid; i < nx; i += DT::tpe) {
           s.xan[nx + i] = gXs[(size_t)(t + 1) * nx + i];
           s.xa[i] = s.xan[i];
           gXs[(size_t)(t + 1) * nx + i] = s.xan[i];
         }
-        __syncthreads();
+        DT::sync();
       }
       if (it >= P.max_iter) flg |= TACD_FLAG_MAXITER;
     }
     // ---- finalise
-    for (int i = tid; i < (int)szX; i += kGenThreads) io.X[(size_t)b * szX + i] = gXs[i];
-    for (int i = tid; i < (int)szU; i += kGenThreads) {
+    for (int i = tid; i < (int)szX; i += DT::tpe) io.X[(size_t)b * szX + i] = gXs[i];
+    for (int i = tid; i < (int)szU; i += DT::tpe) {
       const R ui = gUs[i];
       io.U[(size_t)b * szU + i] = ui;
       bool m = false;
@@ -229,14 +240,14 @@ __global__ void __launch_bounds__(kGenThreads) ilqr_forward_generic(const DevPro
     }
     if (io.A != nullptr || io.Bm != nullptr) {
       for (int t = 0; t < T; ++t) {
-        __syncthreads();
-        for (int i = tid; i < nx; i += kGenThreads) s.x[i] = gXs[(size_t)t * nx + i];
-        for (int i = tid; i < nu; i += kGenThreads) s.u[i] = gUs[(size_t)t * nu + i];
-        __syncthreads();
+        DT::sync();
+        for (int i = tid; i < nx; i += DT::tpe) s.x[i] = gXs[(size_t)t * nx + i];
+        for (int i = tid; i < nu; i += DT::tpe) s.u[i] = gUs[(size_t)t * nu + i];
+        DT::sync();
         gen_dyn_jac<R>(P, d, s.x, s.u, s.A, s.Bm);
-        __syncthreads();
-        if (io.A) for (int i = tid; i < nx * nx; i += kGenThreads) io.A[((size_t)b * T + t) * nx * nx + i] = s.A[i];
-        if (io.Bm) for (int i = tid; i < nx * nu; i += kGenThreads) io.Bm[((size_t)b * T + t) * nx * nu + i] = s.Bm[i];
+        DT::sync();
+        if (io.A) for (int i = tid; i < nx * nx; i += DT::tpe) io.A[((size_t)b * T + t) * nx * nx + i] = s.A[i];
+        if (io.Bm) for (int i = tid; i < nx * nu; i += DT::tpe) io.Bm[((size_t)b * T + t) * nx * nu + i] = s.Bm[i];
       }
     }
     if (tid == 0) {
@@ -244,26 +255,29 @@ __global__ void __launch_bounds__(kGenThreads) ilqr_forward_generic(const DevPro
       io.flags[b] = (uint8_t)flg;
       if (io.cost) io.cost[b] = best;
     }
-    __syncthreads();
+    DT::sync();
   }
 }
 
 // ---------------------------------------------------------------------------
 // backward (ILQRSolve.backward + _zero_constrained_lqr, controller.py:63-115, 707-788)
-template <typename R>
-__global__ void __launch_bounds__(kGenThreads) ilqr_backward_generic(const DevProblem<R> P, const GenDims<R> d, const BwdPtrs<R> io, R* ws, size_t slice) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  GenSmem<R> s = gen_carve<R>(smem_raw, d.nx, d.nu);
-  const int tid = threadIdx.x, nx = d.nx, nu = d.nu, n = d.n, T = d.T;
+template <typename R, int NXT, int NUT, int TPE>
+__global__ void __launch_bounds__(kGenThreads, sizeof(R) == 4 ? 4 : 2) ilqr_backward_generic(const DevProblem<R> P, const GenDims<R, NXT, NUT, TPE> d, const BwdPtrs<R> io, R* ws, size_t slice) {
+  using DT = GenDims<R, NXT, NUT, TPE>;
+  extern __shared__ __align__(16) unsigned char smem_cta[];
+  // each element slot of the CTA owns [matrices | (X U K k when ws == nullptr)]
+  unsigned char* smem_raw = smem_cta + (size_t)DT::sub() * gen_elem_bytes<R>(d.nx(), d.nu(), ws ? 0 : slice);
+  GenSmem<R> s = gen_carve<R>(smem_raw, d.nx(), d.nu());
+  const int tid = DT::tid(), nx = d.nx(), nu = d.nu(), n = d.n(), T = d.T;
   const size_t szX = (size_t)(T + 1) * nx, szU = (size_t)T * nu;
-  R* gK = ws ? ws + (size_t)blockIdx.x * slice : reinterpret_cast<R*>(smem_raw + gen_smem_bytes_aligned<R>(nx, nu));
+  R* gK = ws ? ws + (size_t)DT::slot() * slice : reinterpret_cast<R*>(smem_raw + gen_smem_bytes_aligned<R>(nx, nu));
   R* gk = gK + (size_t)T * nu * nx;
   if (d.dyn == TACD_DYN_LTI) {
-    for (int i = tid; i < nx * nx; i += kGenThreads) s.A[i] = P.dyn_A[i];
-    for (int i = tid; i < nx * nu; i += kGenThreads) s.Bm[i] = P.dyn_B[i];
+    for (int i = tid; i < nx * nx; i += DT::tpe) s.A[i] = P.dyn_A[i];
+    for (int i = tid; i < nx * nu; i += DT::tpe) s.Bm[i] = P.dyn_B[i];
   }
-  __syncthreads();
-  for (int b = blockIdx.x; b < P.B; b += gridDim.x) {
+  DT::sync();
+  for (int b = DT::slot(); b < P.B; b += DT::nslots()) {
     const R* X = io.X + (size_t)b * szX;
     const R* U = io.U + (size_t)b * szU;
     const R* Cp = io.C + (P.C_batched ? (size_t)b * T * n * n : 0);
@@ -274,101 +288,101 @@ __global__ void __launch_bounds__(kGenThreads) ilqr_backward_generic(const DevPr
     const uint8_t* tg = io.tight + (size_t)b * szU;
     auto load_AB = [&](int t) {
       if (d.dyn == TACD_DYN_EXTERNAL) {
-        for (int i = tid; i < nx * nx; i += kGenThreads) s.A[i] = io.A[((size_t)b * T + t) * nx * nx + i];
-        for (int i = tid; i < nx * nu; i += kGenThreads) s.Bm[i] = io.Bm[((size_t)b * T + t) * nx * nu + i];
+        for (int i = tid; i < nx * nx; i += DT::tpe) s.A[i] = io.A[((size_t)b * T + t) * nx * nx + i];
+        for (int i = tid; i < nx * nu; i += DT::tpe) s.Bm[i] = io.Bm[((size_t)b * T + t) * nx * nu + i];
       } else if (d.dyn != TACD_DYN_LTI) {
-        for (int i = tid; i < nx; i += kGenThreads) s.x[i] = X[t * nx + i];
-        for (int i = tid; i < nu; i += kGenThreads) s.u[i] = U[t * nu + i];
-        __syncthreads();
+        for (int i = tid; i < nx; i += DT::tpe) s.x[i] = X[t * nx + i];
+        for (int i = tid; i < nu; i += DT::tpe) s.u[i] = U[t * nu + i];
+        DT::sync();
         gen_dyn_jac<R>(P, d, s.x, s.u, s.A, s.Bm);
       }
-      __syncthreads();
+      DT::sync();
     };
-    for (int idx = tid; idx < nx * nx; idx += kGenThreads) s.V[idx] = Cp[(size_t)(T - 1) * n * n + (idx / nx) * n + (idx % nx)];
-    for (int i = tid; i < nx; i += kGenThreads) s.v[i] = -gX[(T - 1) * nx + i];
-    __syncthreads();
+    for (int idx = tid; idx < nx * nx; idx += DT::tpe) s.V[idx] = Cp[(size_t)(T - 1) * n * n + (idx / nx) * n + (idx % nx)];
+    for (int i = tid; i < nx; i += DT::tpe) s.v[i] = -gX[(T - 1) * nx + i];
+    DT::sync();
     for (int t = T - 1; t >= 0; --t) {
       const R* Ct = Cp + (size_t)t * n * n;
-      for (int idx = tid; idx < nx * nx; idx += kGenThreads) s.Qxx[idx] = Ct[(idx / nx) * n + (idx % nx)];
-      for (int idx = tid; idx < nx * nu; idx += kGenThreads) s.Qxu[idx] = Ct[(idx / nu) * n + nx + (idx % nu)];
-      for (int idx = tid; idx < nu * nu; idx += kGenThreads) s.Quu[idx] = Ct[(nx + idx / nu) * n + nx + (idx % nu)];
-      for (int i = tid; i < nx; i += kGenThreads) s.qx[i] = -gX[t * nx + i];
-      for (int i = tid; i < nu; i += kGenThreads) s.qu[i] = -gU[t * nu + i];
+      for (int idx = tid; idx < nx * nx; idx += DT::tpe) s.Qxx[idx] = Ct[(idx / nx) * n + (idx % nx)];
+      for (int idx = tid; idx < nx * nu; idx += DT::tpe) s.Qxu[idx] = Ct[(idx / nu) * n + nx + (idx % nu)];
+      for (int idx = tid; idx < nu * nu; idx += DT::tpe) s.Quu[idx] = Ct[(nx + idx / nu) * n + nx + (idx % nu)];
+      for (int i = tid; i < nx; i += DT::tpe) s.qx[i] = -gX[t * nx + i];
+      for (int i = tid; i < nu; i += DT::tpe) s.qu[i] = -gU[t * nu + i];
       load_AB(t);
       gen_value_step<R>(P, d, s, true, tg + (size_t)t * nu, U + (size_t)t * nu);
-      for (int idx = tid; idx < nu * nx; idx += kGenThreads) gK[(size_t)t * nu * nx + idx] = s.Kt[idx];
-      for (int i = tid; i < nu; i += kGenThreads) gk[(size_t)t * nu + i] = s.kt[i];
-      __syncthreads();
+      for (int idx = tid; idx < nu * nx; idx += DT::tpe) gK[(size_t)t * nu * nx + idx] = s.Kt[idx];
+      for (int i = tid; i < nu; i += DT::tpe) gk[(size_t)t * nu + i] = s.kt[i];
+      DT::sync();
     }
     // forward sweep + gradients; s.x = dx_t, s.u = du_t, s.tau = tau_t, s.qx (n entries via ct) = dtau_t
     R* dtau = s.ct;
-    for (int i = tid; i < nx; i += kGenThreads) s.x[i] = 0;
-    if (io.grad_x0) for (int i = tid; i < nx; i += kGenThreads) io.grad_x0[(size_t)b * nx + i] = 0;
-    __syncthreads();
+    for (int i = tid; i < nx; i += DT::tpe) s.x[i] = 0;
+    if (io.grad_x0) for (int i = tid; i < nx; i += DT::tpe) io.grad_x0[(size_t)b * nx + i] = 0;
+    DT::sync();
     for (int t = 0; t <= T; ++t) {
       if (t < T) {
-        for (int i = tid; i < nu; i += kGenThreads) {
+        for (int i = tid; i < nu; i += DT::tpe) {
           R a = 0;
           for (int j = 0; j < nx; ++j) a += gK[(size_t)t * nu * nx + i * nx + j] * s.x[j];
           s.u[i] = a + gk[(size_t)t * nu + i];
         }
       }
-      __syncthreads();
-      for (int i = tid; i < nx; i += kGenThreads) { s.tau[i] = X[t * nx + i] - xr[t * nx + i]; dtau[i] = s.x[i]; }
-      if (t < T) for (int i = tid; i < nu; i += kGenThreads) { s.tau[nx + i] = U[t * nu + i] - ur[t * nu + i]; dtau[nx + i] = s.u[i]; }
-      __syncthreads();
+      DT::sync();
+      for (int i = tid; i < nx; i += DT::tpe) { s.tau[i] = X[t * nx + i] - xr[t * nx + i]; dtau[i] = s.x[i]; }
+      if (t < T) for (int i = tid; i < nu; i += DT::tpe) { s.tau[nx + i] = U[t * nu + i] - ur[t * nu + i]; dtau[nx + i] = s.u[i]; }
+      DT::sync();
       if (t < T) {
         if (io.grad_C)
-          for (int idx = tid; idx < n * n; idx += kGenThreads) {
+          for (int idx = tid; idx < n * n; idx += DT::tpe) {
             const int i = idx / n, j = idx % n;
             const R g = (R)-0.5 * (dtau[i] * s.tau[j] + s.tau[i] * dtau[j]);
             if (P.C_batched) io.grad_C[((size_t)b * T + t) * n * n + idx] = g; else atomicAdd(&io.grad_C[(size_t)t * n * n + idx], g);
           }
         if (io.grad_c)
-          for (int i = tid; i < n; i += kGenThreads) {
+          for (int i = tid; i < n; i += DT::tpe) {
             if (P.C_batched) io.grad_c[((size_t)b * T + t) * n + i] = -dtau[i]; else atomicAdd(&io.grad_c[(size_t)t * n + i], -dtau[i]);
           }
         if (io.grad_uref)
-          for (int i = tid; i < nu; i += kGenThreads) {
+          for (int i = tid; i < nu; i += DT::tpe) {
             if (P.uref_batched) io.grad_uref[(size_t)b * szU + t * nu + i] = s.u[i]; else atomicAdd(&io.grad_uref[t * nu + i], s.u[i]);
           }
-        if (io.dU) for (int i = tid; i < nu; i += kGenThreads) io.dU[(size_t)b * szU + t * nu + i] = s.u[i];
+        if (io.dU) for (int i = tid; i < nu; i += DT::tpe) io.dU[(size_t)b * szU + t * nu + i] = s.u[i];
       } else {
         if (io.grad_Cf)
-          for (int idx = tid; idx < n * n; idx += kGenThreads) {
+          for (int idx = tid; idx < n * n; idx += DT::tpe) {
             const int i = idx / n, j = idx % n;
             const bool in = (i < nx && j < nx);
             const R g = in ? (R)-0.5 * (dtau[i] * s.tau[j] + s.tau[i] * dtau[j]) : (R)0;
             if (P.Cf_batched) io.grad_Cf[(size_t)b * n * n + idx] = g; else if (in) atomicAdd(&io.grad_Cf[idx], g);
           }
         if (io.grad_cf)
-          for (int i = tid; i < n; i += kGenThreads) {
+          for (int i = tid; i < n; i += DT::tpe) {
             const R g = (i < nx) ? -dtau[i] : (R)0;
             if (P.Cf_batched) io.grad_cf[(size_t)b * n + i] = g; else if (i < nx) atomicAdd(&io.grad_cf[i], g);
           }
       }
       if (io.grad_xref)
-        for (int i = tid; i < nx; i += kGenThreads) {
+        for (int i = tid; i < nx; i += DT::tpe) {
           if (P.xref_batched) io.grad_xref[(size_t)b * szX + t * nx + i] = s.x[i]; else atomicAdd(&io.grad_xref[t * nx + i], s.x[i]);
         }
-      if (io.dX) for (int i = tid; i < nx; i += kGenThreads) io.dX[(size_t)b * szX + t * nx + i] = s.x[i];
+      if (io.dX) for (int i = tid; i < nx; i += DT::tpe) io.dX[(size_t)b * szX + t * nx + i] = s.x[i];
       if (t < T) {
-        __syncthreads();
+        DT::sync();
         // dx+ = A dx + B du; the jacobian load clobbers s.x/s.u for non-LTI embedded dynamics, so stash them
-        for (int i = tid; i < nx; i += kGenThreads) s.xa[i] = s.x[i];
-        for (int i = tid; i < nu; i += kGenThreads) s.ua[i] = s.u[i];
-        __syncthreads();
+        for (int i = tid; i < nx; i += DT::tpe) s.xa[i] = s.x[i];
+        for (int i = tid; i < nu; i += DT::tpe) s.ua[i] = s.u[i];
+        DT::sync();
         load_AB(t);
-        for (int i = tid; i < nx; i += kGenThreads) {
+        for (int i = tid; i < nx; i += DT::tpe) {
           R a = 0, a2 = 0;
           for (int j = 0; j < nx; ++j) a += s.A[i * nx + j] * s.xa[j];
           for (int j = 0; j < nu; ++j) a2 += s.Bm[i * nu + j] * s.ua[j];
           s.xan[i] = a + a2;
         }
-        __syncthreads();
-        for (int i = tid; i < nx; i += kGenThreads) s.x[i] = s.xan[i];
+        DT::sync();
+        for (int i = tid; i < nx; i += DT::tpe) s.x[i] = s.xan[i];
       }
-      __syncthreads();
+      DT::sync();
     }
   }
 }
@@ -378,8 +392,8 @@ __global__ void __launch_bounds__(kGenThreads) ilqr_backward_generic(const DevPr
 template <typename R>
 __global__ void __launch_bounds__(kGenThreads) stage_rollout(const DevProblem<R> P, const GenDims<R> d, const R* x0, const R* U, R* X) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  GenSmem<R> s = gen_carve<R>(smem_raw, d.nx, d.nu);
-  const int tid = threadIdx.x, nx = d.nx, nu = d.nu, T = d.T;
+  GenSmem<R> s = gen_carve<R>(smem_raw, d.nx(), d.nu());
+  const int tid = threadIdx.x, nx = d.nx(), nu = d.nu(), T = d.T;
   if (d.dyn == TACD_DYN_LTI) {
     for (int i = tid; i < nx * nx; i += kGenThreads) s.A[i] = P.dyn_A[i];
     for (int i = tid; i < nx * nu; i += kGenThreads) s.Bm[i] = P.dyn_B[i];
@@ -400,7 +414,7 @@ __global__ void __launch_bounds__(kGenThreads) stage_rollout(const DevProblem<R>
 template <typename R>
 __global__ void __launch_bounds__(kGenThreads) stage_linearize(const DevProblem<R> P, const GenDims<R> d, const R* X, const R* U, R* A, R* Bm) {
   // one thread per (b, t)
-  const int nx = d.nx, nu = d.nu, T = d.T;
+  const int nx = d.nx(), nu = d.nu(), T = d.T;
   const size_t total = (size_t)P.B * T;
   for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (size_t)gridDim.x * blockDim.x) {
     const size_t b = w / T, t = w % T;
@@ -419,8 +433,8 @@ template <typename R>
 __global__ void __launch_bounds__(kGenThreads) stage_objective(const DevProblem<R> P, const GenDims<R> d, const R* X, const R* U, const R* C,
                                                                 const R* c, const R* Cf, const R* cf, const R* xref, const R* uref, R* cost) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  GenSmem<R> s = gen_carve<R>(smem_raw, d.nx, d.nu);
-  const int nx = d.nx, nu = d.nu, n = d.n, T = d.T;
+  GenSmem<R> s = gen_carve<R>(smem_raw, d.nx(), d.nu());
+  const int nx = d.nx(), nu = d.nu(), n = d.n(), T = d.T;
   const size_t szX = (size_t)(T + 1) * nx, szU = (size_t)T * nu;
   for (int b = blockIdx.x; b < P.B; b += gridDim.x) {
     const R v = gen_objective<R>(d, s, X + b * szX, U + b * szU, C + (P.C_batched ? (size_t)b * T * n * n : 0),
@@ -436,8 +450,8 @@ __global__ void __launch_bounds__(kGenThreads) stage_riccati(const DevProblem<R>
                                                               const R* lu, const R* lxx, const R* lxu, const R* luu, const R* lxN,
                                                               const R* lxxN, R* K, R* k, uint8_t* flags) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  GenSmem<R> s = gen_carve<R>(smem_raw, d.nx, d.nu);
-  const int tid = threadIdx.x, nx = d.nx, nu = d.nu, T = d.T;
+  GenSmem<R> s = gen_carve<R>(smem_raw, d.nx(), d.nu());
+  const int tid = threadIdx.x, nx = d.nx(), nu = d.nu(), T = d.T;
   for (int b = blockIdx.x; b < P.B; b += gridDim.x) {
     bool nonpd = false;
     for (int i = tid; i < nx * nx; i += kGenThreads) s.V[i] = lxxN[(size_t)b * nx * nx + i];
@@ -465,8 +479,8 @@ __global__ void __launch_bounds__(kGenThreads) stage_linesearch(const DevProblem
                                                                  const R* K, const R* k, const R* C, const R* c, const R* Cf, const R* cf,
                                                                  const R* xref, const R* uref, R* Xc, R* Uc, R* costs) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  GenSmem<R> s = gen_carve<R>(smem_raw, d.nx, d.nu);
-  const int tid = threadIdx.x, nx = d.nx, nu = d.nu, n = d.n, T = d.T, na = P.n_alpha;
+  GenSmem<R> s = gen_carve<R>(smem_raw, d.nx(), d.nu());
+  const int tid = threadIdx.x, nx = d.nx(), nu = d.nu(), n = d.n(), T = d.T, na = P.n_alpha;
   const size_t szX = (size_t)(T + 1) * nx, szU = (size_t)T * nu;
   if (d.dyn == TACD_DYN_LTI) {
     for (int i = tid; i < nx * nx; i += kGenThreads) s.A[i] = P.dyn_A[i];
@@ -530,7 +544,7 @@ __global__ void __launch_bounds__(128) closed_loop_advance(const DevProblem<R> P
                                                            R* xref_win, R* uref_win) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= P.B) return;
-  const int nx = d.nx, nu = d.nu, T = d.T;
+  const int nx = d.nx(), nu = d.nu(), T = d.T;
   R xc[TACD_MAX_NX], xn[TACD_MAX_NX], u[TACD_MAX_NU];
   for (int i = 0; i < nx; ++i) xc[i] = x[(size_t)b * nx + i];
   for (int i = 0; i < nu; ++i) u[i] = U_opt[(size_t)b * T * nu + i];
@@ -625,35 +639,59 @@ static FwdPtrs<R> fwd_ptrs(const tacd_forward_io* io) {
   return f;
 }
 
-template <typename R>
-int launch_forward_generic(const tacd_problem* p, const tacd_forward_io* io, void* ws, size_t ws_bytes, cudaStream_t s) {
+// Sizes of the LTI sweep get kernels with compile-time nx, nu; everything else runs the
+// run-time-dimension instance (NXT = NUT = 0).  TACD_GENERIC_RUNTIME_DIMS=1 forces the latter (A/B measurements).
+#define TACD_GEN_SIZES(X) X(8, 4) X(16, 4) X(16, 8) X(32, 8)
+static bool gen_runtime_dims() { static const bool v = getenv("TACD_GENERIC_RUNTIME_DIMS") != nullptr; return v; }
+
+// Shared memory of one launch: per element slot the matrices and, when enough slots per SM still fit, the element's
+// X, U, K, k (global-memory round trips inside the per-step loops were the bulk of the time otherwise).
+struct GenLaunch { int grid; size_t smem; bool in_smem; };
+template <typename R, int TPE>
+static GenLaunch gen_launch_shape(const tacd_problem* p, size_t slice) {
+  constexpr int per_cta = kGenThreads / TPE;
+  const size_t with_slice = gen_elem_bytes<R>(p->nx, p->nu, slice) * per_cta;
+  GenLaunch L;
+  // CTA-per-element: four CTAs per SM; warp-per-element: two four-element CTAs per SM are enough to cover the barriers
+  L.in_smem = with_slice <= (size_t)device_info().smem_optin / (TPE == 32 ? 2 : 4) && !getenv("TACD_GENERIC_WS");
+  L.smem = L.in_smem ? with_slice : gen_elem_bytes<R>(p->nx, p->nu, 0) * per_cta;
+  L.grid = (gen_slots(p, TPE) + per_cta - 1) / per_cta;
+  return L;
+}
+
+template <typename R, int NXT, int NUT, int TPE>
+static int run_forward_generic(const tacd_problem* p, const tacd_forward_io* io, void* ws, size_t ws_bytes, cudaStream_t s) {
   const size_t slice = gen_slice_scalars(p);
-  const int grid = gen_grid(p);
-  if (ws_bytes < (size_t)grid * slice * sizeof(R)) { set_error("forward workspace too small: %zu < %zu", ws_bytes, (size_t)grid * slice * sizeof(R)); return TACD_EWORKSPACE; }
-  size_t smem = gen_smem_bytes<R>(p->nx, p->nu);
-  auto kernel = ilqr_forward_generic<R>;
-  // the element's X, U, K, k in shared memory when four CTAs per SM still fit (global-memory round trips inside
-  // the per-step loops were the bulk of this kernel's time), else in the workspace slice
-  const size_t smem_slice = gen_smem_bytes_aligned<R>(p->nx, p->nu) + slice * sizeof(R);
-  const bool in_smem = smem_slice <= (size_t)device_info().smem_optin / 4 && !getenv("TACD_GENERIC_WS");
-  if (in_smem) smem = smem_slice;
-  if (int rc = prep_smem(kernel, smem)) return rc;
-  kernel<<<grid, kGenThreads, smem, s>>>(to_dev<R>(p), dims_of<R>(p), fwd_ptrs<R>(io), in_smem ? nullptr : (R*)ws, slice);
+  const GenLaunch L = gen_launch_shape<R, TPE>(p, slice);
+  const size_t need = (size_t)L.grid * (kGenThreads / TPE) * slice * sizeof(R);
+  if (!L.in_smem && ws_bytes < need) { set_error("forward workspace too small: %zu < %zu", ws_bytes, need); return TACD_EWORKSPACE; }
+  auto kernel = ilqr_forward_generic<R, NXT, NUT, TPE>;
+  if (int rc = prep_smem(kernel, L.smem)) return rc;
+  kernel<<<L.grid, kGenThreads, L.smem, s>>>(to_dev<R>(p), dims_of<R, NXT, NUT, TPE>(p), fwd_ptrs<R>(io), L.in_smem ? nullptr : (R*)ws, slice);
   note_launches(1);
   return check_cuda(cudaPeekAtLastError(), "ilqr_forward_generic launch");
 }
 
 template <typename R>
-int launch_backward_generic(const tacd_problem* p, const tacd_backward_io* io, void* ws, size_t ws_bytes, cudaStream_t s) {
+int launch_forward_generic(const tacd_problem* p, const tacd_forward_io* io, void* ws, size_t ws_bytes, cudaStream_t s) {
+  const bool warp = gen_tpe(p) == 32;
+  if (!gen_runtime_dims()) {
+#define X(NX_, NU_) if (p->nx == NX_ && p->nu == NU_) \
+    return warp ? run_forward_generic<R, NX_, NU_, 32>(p, io, ws, ws_bytes, s) : run_forward_generic<R, NX_, NU_, kGenThreads>(p, io, ws, ws_bytes, s);
+    TACD_GEN_SIZES(X)
+#undef X
+  }
+  return warp ? run_forward_generic<R, 0, 0, 32>(p, io, ws, ws_bytes, s) : run_forward_generic<R, 0, 0, kGenThreads>(p, io, ws, ws_bytes, s);
+}
+
+template <typename R, int NXT, int NUT, int TPE>
+static int run_backward_generic(const tacd_problem* p, const tacd_backward_io* io, void* ws, size_t ws_bytes, cudaStream_t s) {
   const size_t slice = gen_slice_scalars(p);
-  const int grid = gen_grid(p);
-  if (ws_bytes < (size_t)grid * slice * sizeof(R)) { set_error("backward workspace too small"); return TACD_EWORKSPACE; }
-  size_t smem = gen_smem_bytes<R>(p->nx, p->nu);
-  auto kernel = ilqr_backward_generic<R>;
-  const size_t smem_slice = gen_smem_bytes_aligned<R>(p->nx, p->nu) + slice * sizeof(R);
-  const bool in_smem = smem_slice <= (size_t)device_info().smem_optin / 4 && !getenv("TACD_GENERIC_WS");
-  if (in_smem) smem = smem_slice;
-  if (int rc = prep_smem(kernel, smem)) return rc;
+  const GenLaunch L = gen_launch_shape<R, TPE>(p, slice);
+  const size_t need = (size_t)L.grid * (kGenThreads / TPE) * slice * sizeof(R);
+  if (!L.in_smem && ws_bytes < need) { set_error("backward workspace too small: %zu < %zu", ws_bytes, need); return TACD_EWORKSPACE; }
+  auto kernel = ilqr_backward_generic<R, NXT, NUT, TPE>;
+  if (int rc = prep_smem(kernel, L.smem)) return rc;
   const size_t T = p->T, nx = p->nx, nu = p->nu, n = nx + nu, szX = (T + 1) * nx, szU = T * nu;
   if (io->grad_C && !p->C_batched) if (int rc = check_cuda(cudaMemsetAsync(io->grad_C, 0, T * n * n * sizeof(R), s), "memset")) return rc;
   if (io->grad_c && !p->C_batched) if (int rc = check_cuda(cudaMemsetAsync(io->grad_c, 0, T * n * sizeof(R), s), "memset")) return rc;
@@ -666,9 +704,21 @@ int launch_backward_generic(const tacd_problem* p, const tacd_backward_io* io, v
   f.A = (const R*)io->A; f.Bm = (const R*)io->Bm; f.gX = (const R*)io->gX; f.gU = (const R*)io->gU; f.tight = io->tight;
   f.grad_C = (R*)io->grad_C; f.grad_c = (R*)io->grad_c; f.grad_Cf = (R*)io->grad_Cf; f.grad_cf = (R*)io->grad_cf;
   f.grad_x0 = (R*)io->grad_x0; f.grad_xref = (R*)io->grad_xref; f.grad_uref = (R*)io->grad_uref; f.dX = (R*)io->dX; f.dU = (R*)io->dU;
-  kernel<<<grid, kGenThreads, smem, s>>>(to_dev<R>(p), dims_of<R>(p), f, in_smem ? nullptr : (R*)ws, slice);
+  kernel<<<L.grid, kGenThreads, L.smem, s>>>(to_dev<R>(p), dims_of<R, NXT, NUT, TPE>(p), f, L.in_smem ? nullptr : (R*)ws, slice);
   note_launches(1);
   return check_cuda(cudaPeekAtLastError(), "ilqr_backward_generic launch");
+}
+
+template <typename R>
+int launch_backward_generic(const tacd_problem* p, const tacd_backward_io* io, void* ws, size_t ws_bytes, cudaStream_t s) {
+  const bool warp = gen_tpe(p) == 32;
+  if (!gen_runtime_dims()) {
+#define X(NX_, NU_) if (p->nx == NX_ && p->nu == NU_) \
+    return warp ? run_backward_generic<R, NX_, NU_, 32>(p, io, ws, ws_bytes, s) : run_backward_generic<R, NX_, NU_, kGenThreads>(p, io, ws, ws_bytes, s);
+    TACD_GEN_SIZES(X)
+#undef X
+  }
+  return warp ? run_backward_generic<R, 0, 0, 32>(p, io, ws, ws_bytes, s) : run_backward_generic<R, 0, 0, kGenThreads>(p, io, ws, ws_bytes, s);
 }
 
 template int launch_forward_generic<float>(const tacd_problem*, const tacd_forward_io*, void*, size_t, cudaStream_t);

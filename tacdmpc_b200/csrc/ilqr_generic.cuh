@@ -15,9 +15,31 @@ namespace tacd {
 
 constexpr int kGenThreads = 128;
 
-template <typename R>
+// Run-time dimensions; NXT / NUT > 0 pin nx / nu at compile time (the whole-solve kernels are instantiated for the
+// sizes of the LTI sweep), which turns the index arithmetic of every matrix loop into immediates
+// and lets the k-loops unroll.
+template <typename R, int NXT = 0, int NUT = 0, int TPE_ = kGenThreads>
 struct GenDims {
-  int nx, nu, n, T, dyn;
+  int nx_, nu_, T, dyn;
+  __host__ __device__ __forceinline__ int nx() const { return NXT > 0 ? NXT : nx_; }
+  __host__ __device__ __forceinline__ int nu() const { return NUT > 0 ? NUT : nu_; }
+  __host__ __device__ __forceinline__ int n() const { return nx() + nu(); }
+  // Threads per element: the whole CTA (kGenThreads) or one warp.  With one warp per element a CTA carries
+  // kGenThreads / 32 independent elements, each with its own shared-memory carve, and every barrier of the
+  // per-step pipeline is a __syncwarp: small systems (nx <= 16) have too few matrix entries to occupy 128 threads
+  // and spent most of their time at CTA barriers (profiles/r1_backward_generic: 54 % of samples).
+  static constexpr int tpe = TPE_;
+  static constexpr int NX = NXT, NU = NUT;
+  static constexpr bool fixed = NXT > 0 && NUT > 0 && NXT % 4 == 0 && NUT % 4 == 0;  // 128-bit tiles are legal
+  static constexpr int per_cta = kGenThreads / TPE_;
+  static_assert(TPE_ == 32 || TPE_ == kGenThreads, "an element is worked on by one warp or by the whole CTA");
+  static __device__ __forceinline__ int tid() { return TPE_ == kGenThreads ? threadIdx.x : (threadIdx.x & (TPE_ - 1)); }
+  static __device__ __forceinline__ int sub() { return TPE_ == kGenThreads ? 0 : threadIdx.x / TPE_; }
+  static __device__ __forceinline__ int slot() { return blockIdx.x * per_cta + sub(); }
+  static __device__ __forceinline__ int nslots() { return gridDim.x * per_cta; }
+  static __device__ __forceinline__ void sync() {
+    if (TPE_ == 32) __syncwarp(); else __syncthreads();
+  }
 };
 
 // ---- run-time-dimension dynamics on one thread (non-LTI plugins are tiny) ----
@@ -54,29 +76,29 @@ __device__ void gen_dyn_jac_scalar(const DevProblem<R>& P, int dyn, const R* x, 
 }
 
 // CTA-parallel x+ = f(x,u) for `na` independent (x,u) pairs laid out [a][nx], [a][nu]
-template <typename R>
-__device__ void gen_dyn_step(const DevProblem<R>& P, const GenDims<R>& d, const R* sA, const R* sB, int na, const R* x, const R* u, R* xn) {
-  const int tid = threadIdx.x;
+template <typename R, typename DT>
+__device__ void gen_dyn_step(const DevProblem<R>& P, const DT& d, const R* sA, const R* sB, int na, const R* x, const R* u, R* xn) {
+  const int tid = DT::tid();
   if (d.dyn == TACD_DYN_LTI) {
-    for (int idx = tid; idx < na * d.nx; idx += kGenThreads) {
-      const int a = idx / d.nx, i = idx % d.nx;
+    for (int idx = tid; idx < na * d.nx(); idx += DT::tpe) {
+      const int a = idx / d.nx(), i = idx % d.nx();
       R s = 0, s2 = 0;
-      for (int j = 0; j < d.nx; ++j) s += sA[i * d.nx + j] * x[a * d.nx + j];
-      for (int j = 0; j < d.nu; ++j) s2 += sB[i * d.nu + j] * u[a * d.nu + j];
-      xn[a * d.nx + i] = s + s2;
+      for (int j = 0; j < d.nx(); ++j) s += sA[i * d.nx() + j] * x[a * d.nx() + j];
+      for (int j = 0; j < d.nu(); ++j) s2 += sB[i * d.nu() + j] * u[a * d.nu() + j];
+      xn[a * d.nx() + i] = s + s2;
     }
   } else {
-    if (tid < na) gen_dyn_step_scalar<R>(P, d.dyn, x + tid * d.nx, u + tid * d.nu, xn + tid * d.nx);
+    if (tid < na) gen_dyn_step_scalar<R>(P, d.dyn, x + tid * d.nx(), u + tid * d.nu(), xn + tid * d.nx());
   }
 }
 
 // A_t, B_t at (x,u) into shared memory (LTI: already resident, nothing to do).
 // LTI + finite differences reproduces A,B up to rounding; the reference's FD mode is
 // unreachable (controller.py:468-471 raises), so LTI always uses the matrices themselves.
-template <typename R>
-__device__ void gen_dyn_jac(const DevProblem<R>& P, const GenDims<R>& d, const R* x, const R* u, R* sA, R* sB) {
+template <typename R, typename DT>
+__device__ void gen_dyn_jac(const DevProblem<R>& P, const DT& d, const R* x, const R* u, R* sA, R* sB) {
   if (d.dyn == TACD_DYN_LTI) return;
-  if (threadIdx.x == 0) gen_dyn_jac_scalar<R>(P, d.dyn, x, u, sA, sB);
+  if (DT::tid() == 0) gen_dyn_jac_scalar<R>(P, d.dyn, x, u, sA, sB);
 }
 
 // ---- single-thread nu x nu factorizations on shared memory -------------------
@@ -143,6 +165,133 @@ __device__ void gen_chol_solve_col(const R* L, int m, R* rhs, int nr, int r) {
     for (int k = i + 1; k < m; ++k) s -= L[k * m + i] * rhs[k * nr + r];
     rhs[i * nr + r] = s / L[i * m + i];
   }
+}
+
+// ---- fixed-size factorizations in registers --------------------------------------------------------------------
+// Same operations in the same order as gen_chol / gen_lu / *_solve_col above, on a fully unrolled register copy: the
+// shared-memory versions serialise ~M^3/3 load -> fma -> store round trips (~30 cycles each) on one thread, which was
+// most of a Riccati step's latency for nu = 8.
+template <typename R, int M>
+__device__ __forceinline__ bool gen_chol_reg(R* Ms) {
+  R a[M][M];
+#pragma unroll
+  for (int i = 0; i < M; ++i)
+#pragma unroll
+    for (int j = 0; j <= i; ++j) a[i][j] = Ms[i * M + j];
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < M; ++j) {
+    R dd = a[j][j];
+#pragma unroll
+    for (int k = 0; k < j; ++k) dd -= a[j][k] * a[j][k];
+    if (!(dd > 0)) ok = false;
+    dd = sqrt_<R>(dd);
+    a[j][j] = dd;
+#pragma unroll
+    for (int i = j + 1; i < M; ++i) {
+      R s = a[i][j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) s -= a[i][k] * a[j][k];
+      a[i][j] = s / dd;
+    }
+  }
+  if (!ok) return false;  // the caller refactorises Q_uu with LU; shared memory still holds the input
+#pragma unroll
+  for (int i = 0; i < M; ++i)
+#pragma unroll
+    for (int j = 0; j <= i; ++j) Ms[i * M + j] = a[i][j];
+  return true;
+}
+template <typename R, int M>
+__device__ __forceinline__ void gen_chol_solve_col_reg(const R* L, R* rhs, int nr, int r) {
+  R x[M];
+#pragma unroll
+  for (int i = 0; i < M; ++i) x[i] = rhs[i * nr + r];
+#pragma unroll
+  for (int i = 0; i < M; ++i) {
+    R s = x[i];
+#pragma unroll
+    for (int k = 0; k < i; ++k) s -= L[i * M + k] * x[k];
+    x[i] = s / L[i * M + i];
+  }
+#pragma unroll
+  for (int i = M - 1; i >= 0; --i) {
+    R s = x[i];
+#pragma unroll
+    for (int k = i + 1; k < M; ++k) s -= L[k * M + i] * x[k];
+    x[i] = s / L[i * M + i];
+  }
+#pragma unroll
+  for (int i = 0; i < M; ++i) rhs[i * nr + r] = x[i];
+}
+template <typename R, int M>
+__device__ __forceinline__ void gen_lu_reg(R* Ms, int* piv) {
+  R a[M][M];
+#pragma unroll
+  for (int i = 0; i < M; ++i)
+#pragma unroll
+    for (int j = 0; j < M; ++j) a[i][j] = Ms[i * M + j];
+#pragma unroll
+  for (int j = 0; j < M; ++j) {
+    int p = j;
+    R best = abs_<R>(a[j][j]);
+#pragma unroll
+    for (int i = j + 1; i < M; ++i) {
+      const R v = abs_<R>(a[i][j]);
+      if (v > best) { best = v; p = i; }
+    }
+    piv[j] = p;
+#pragma unroll
+    for (int i = j + 1; i < M; ++i) {
+      const bool sw = (i == p);
+#pragma unroll
+      for (int k = 0; k < M; ++k) {
+        const R lo = a[j][k], hi = a[i][k];
+        a[j][k] = sw ? hi : lo;
+        a[i][k] = sw ? lo : hi;
+      }
+    }
+    const R dd = a[j][j];
+#pragma unroll
+    for (int i = j + 1; i < M; ++i) {
+      const R f = a[i][j] / dd;
+      a[i][j] = f;
+#pragma unroll
+      for (int k = j + 1; k < M; ++k) a[i][k] -= f * a[j][k];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < M; ++i)
+#pragma unroll
+    for (int j = 0; j < M; ++j) Ms[i * M + j] = a[i][j];
+}
+template <typename R, int M>
+__device__ __forceinline__ void gen_lu_solve_col_reg(const R* Ms, const int* piv, R* rhs, int nr, int r) {
+  R x[M];
+#pragma unroll
+  for (int i = 0; i < M; ++i) x[i] = rhs[i * nr + r];
+#pragma unroll
+  for (int j = 0; j < M; ++j) {
+    const int p = piv[j];
+#pragma unroll
+    for (int i = j + 1; i < M; ++i) {
+      const bool sw = (i == p);
+      const R lo = x[j], hi = x[i];
+      x[j] = sw ? hi : lo;
+      x[i] = sw ? lo : hi;
+    }
+#pragma unroll
+    for (int i = j + 1; i < M; ++i) x[i] -= Ms[i * M + j] * x[j];
+  }
+#pragma unroll
+  for (int i = M - 1; i >= 0; --i) {
+    R s = x[i];
+#pragma unroll
+    for (int k = i + 1; k < M; ++k) s -= Ms[i * M + k] * x[k];
+    x[i] = s / Ms[i * M + i];
+  }
+#pragma unroll
+  for (int i = 0; i < M; ++i) rhs[i * nr + r] = x[i];
 }
 
 // pnqp (utils.py:66-124) on one thread, compacted problem of size m, scratch in `w`
@@ -243,6 +392,11 @@ __host__ __device__ inline size_t gen_smem_bytes(int nx, int nu) {
 }
 template <typename R>
 __host__ __device__ inline size_t gen_smem_bytes_aligned(int nx, int nu) { return (gen_smem_bytes<R>(nx, nu) + 15) & ~(size_t)15; }
+// bytes of one element slot: matrices, then (optionally) its X, U, K, k slice
+template <typename R>
+__host__ __device__ inline size_t gen_elem_bytes(int nx, int nu, size_t slice_scalars) {
+  return (gen_smem_bytes_aligned<R>(nx, nu) + slice_scalars * sizeof(R) + 15) & ~(size_t)15;
+}
 template <typename R>
 __device__ GenSmem<R> gen_carve(unsigned char* raw, int nx, int nu) {
   const int n = nx + nu, na = TACD_MAX_ALPHA;
@@ -262,9 +416,13 @@ __device__ GenSmem<R> gen_carve(unsigned char* raw, int nx, int nu) {
   return s;
 }
 
-// block-wide sum (all threads get the result)
-template <typename R>
+// sum over the threads of one element (all of them get the result)
+template <typename R, typename DT = GenDims<R>>
 __device__ R gen_block_sum(R val, R* red) {
+  if (DT::tpe == 32) {
+    for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+    return val;
+  }
   const int tid = threadIdx.x;
   red[tid] = val;
   __syncthreads();
@@ -278,13 +436,13 @@ __device__ R gen_block_sum(R val, R* red) {
 }
 
 // objective of one trajectory held in global memory (cost.py:37-62), CTA-parallel
-template <typename R>
-__device__ R gen_objective(const GenDims<R>& d, GenSmem<R>& s, const R* X, const R* U, const R* C, const R* c, const R* Cf, const R* cf,
+template <typename R, typename DT>
+__device__ R gen_objective(const DT& d, GenSmem<R>& s, const R* X, const R* U, const R* C, const R* c, const R* Cf, const R* cf,
                            const R* xr, const R* ur) {
-  const int tid = threadIdx.x, nx = d.nx, nu = d.nu, n = d.n, T = d.T;
+  const int tid = DT::tid(), nx = d.nx(), nu = d.nu(), n = d.n(), T = d.T;
   R acc_q = 0, acc_l = 0;
   // work item = (t, i): tau_i * (C_t[i,:] . tau) and c_t[i] tau_i
-  for (int idx = tid; idx < T * n; idx += kGenThreads) {
+  for (int idx = tid; idx < T * n; idx += DT::tpe) {
     const int t = idx / n, i = idx % n;
     const R* Ct = C + (size_t)t * n * n + (size_t)i * n;
     R sdot = 0;
@@ -295,76 +453,146 @@ __device__ R gen_objective(const GenDims<R>& d, GenSmem<R>& s, const R* X, const
     acc_l += c[(size_t)t * n + i] * ti;
   }
   R accN_q = 0, accN_l = 0;
-  for (int i = tid; i < nx; i += kGenThreads) {
+  for (int i = tid; i < nx; i += DT::tpe) {
     R sdot = 0;
     for (int j = 0; j < nx; ++j) sdot += Cf[i * n + j] * (X[T * nx + j] - xr[T * nx + j]);
     const R ti = X[T * nx + i] - xr[T * nx + i];
     accN_q += ti * sdot;
     accN_l += cf[i] * ti;
   }
-  const R q = gen_block_sum<R>(acc_q, s.red), l = gen_block_sum<R>(acc_l, s.red);
-  const R qN = gen_block_sum<R>(accN_q, s.red), lN = gen_block_sum<R>(accN_l, s.red);
+  const R q = gen_block_sum<R, DT>(acc_q, s.red), l = gen_block_sum<R, DT>(acc_l, s.red);
+  const R qN = gen_block_sum<R, DT>(accN_q, s.red), lN = gen_block_sum<R, DT>(accN_l, s.red);
   return ((R)0.5 * q + l) + ((R)0.5 * qN + lN);
+}
+
+// ---- register-tiled products for the fixed-size instances -------------------------------------------------------
+// One thread owns a 1 x 4 tile of the output: per k it reads one left entry and one 128-bit (2 x 128 for double)
+// row segment of the right operand, i.e. 0.5 shared-memory instructions per multiply-add where the entry-per-thread
+// loops need 2.  The sum over k runs in the same (ascending) order, so results are bit-identical to those loops.
+template <typename R>
+struct alignas(16) Quad { R v[4]; };
+// acc[c] += sum_k L(k, i) * Rm[k * ldr + j0 + c];  LT: L is indexed [k][i] (a transposed read), else [i][k]
+template <typename R, int K, bool LT>
+__device__ __forceinline__ void gen_mac4(R (&acc)[4], const R* L, int ldl, int i, const R* Rm, int ldr, int j0) {
+  if (LT) {
+#pragma unroll 8
+    for (int k = 0; k < K; ++k) {
+      const R l = L[k * ldl + i];
+      const Quad<R> r = *reinterpret_cast<const Quad<R>*>(Rm + k * ldr + j0);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[c] += l * r.v[c];
+    }
+  } else {
+    static_assert(K % 4 == 0, "left rows are read four entries at a time");
+#pragma unroll 2
+    for (int k = 0; k < K; k += 4) {
+      const Quad<R> l = *reinterpret_cast<const Quad<R>*>(L + i * ldl + k);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const Quad<R> r = *reinterpret_cast<const Quad<R>*>(Rm + (k + kk) * ldr + j0);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[c] += l.v[kk] * r.v[c];
+      }
+    }
+  }
 }
 
 // One Riccati/KKT value-recursion step on shared memory.  On entry s.Qxx/Qxu/Quu/qx/qu
 // hold the cost blocks, s.A/s.Bm the Jacobians, s.V/s.v the value at t+1.  `kkt`
 // selects the backward-pass variant (box QP for k, LU gain with 1e-8 reg; controller.py:736-767).
-template <typename R>
-__device__ bool gen_value_step(const DevProblem<R>& P, const GenDims<R>& d, GenSmem<R>& s, bool kkt, const uint8_t* tight_t, const R* U_t) {
-  const int tid = threadIdx.x, nx = d.nx, nu = d.nu;
+template <typename R, typename DT>
+__device__ bool gen_value_step(const DevProblem<R>& P, const DT& d, GenSmem<R>& s, bool kkt, const uint8_t* tight_t, const R* U_t) {
+  const int tid = DT::tid(), nx = d.nx(), nu = d.nu();
   const int nr = nx + 1;
   bool nonpd = false;
-  for (int idx = tid; idx < nx * nx; idx += kGenThreads) {
+  if constexpr (DT::fixed) {
+    constexpr int NX = DT::NX, NU = DT::NU;
+    for (int tl = tid; tl < NX * NX / 4; tl += DT::tpe) {
+      const int i = tl / (NX / 4), j0 = (tl % (NX / 4)) * 4;
+      R a[4] = {0, 0, 0, 0};
+      gen_mac4<R, NX, true>(a, s.A, NX, i, s.V, NX, j0);
+      *reinterpret_cast<Quad<R>*>(s.AtV + i * NX + j0) = Quad<R>{{a[0], a[1], a[2], a[3]}};
+    }
+    for (int tl = tid; tl < NU * NX / 4; tl += DT::tpe) {
+      const int i = tl / (NX / 4), j0 = (tl % (NX / 4)) * 4;
+      R a[4] = {0, 0, 0, 0};
+      gen_mac4<R, NX, true>(a, s.Bm, NU, i, s.V, NX, j0);
+      *reinterpret_cast<Quad<R>*>(s.BtV + i * NX + j0) = Quad<R>{{a[0], a[1], a[2], a[3]}};
+    }
+    DT::sync();
+    for (int tl = tid; tl < NX * NX / 4; tl += DT::tpe) {
+      const int i = tl / (NX / 4), j0 = (tl % (NX / 4)) * 4;
+      R a[4] = {0, 0, 0, 0};
+      gen_mac4<R, NX, false>(a, s.AtV, NX, i, s.A, NX, j0);
+      Quad<R>& q = *reinterpret_cast<Quad<R>*>(s.Qxx + i * NX + j0);
+      for (int c = 0; c < 4; ++c) q.v[c] += a[c];
+    }
+    for (int tl = tid; tl < NX * NU / 4; tl += DT::tpe) {
+      const int i = tl / (NU / 4), j0 = (tl % (NU / 4)) * 4;
+      R a[4] = {0, 0, 0, 0};
+      gen_mac4<R, NX, false>(a, s.AtV, NX, i, s.Bm, NU, j0);
+      Quad<R>& q = *reinterpret_cast<Quad<R>*>(s.Qxu + i * NU + j0);
+      for (int c = 0; c < 4; ++c) q.v[c] += a[c];
+    }
+    for (int tl = tid; tl < NU * NU / 4; tl += DT::tpe) {
+      const int i = tl / (NU / 4), j0 = (tl % (NU / 4)) * 4;
+      R a[4] = {0, 0, 0, 0};
+      gen_mac4<R, NX, false>(a, s.BtV, NX, i, s.Bm, NU, j0);
+      Quad<R>& q = *reinterpret_cast<Quad<R>*>(s.Quu + i * NU + j0);
+      for (int c = 0; c < 4; ++c) q.v[c] += a[c] + ((i == j0 + c) ? P.reg : (R)0);
+    }
+  } else {
+  for (int idx = tid; idx < nx * nx; idx += DT::tpe) {
     const int i = idx / nx, j = idx % nx;
     R a = 0;
     for (int k = 0; k < nx; ++k) a += s.A[k * nx + i] * s.V[k * nx + j];
     s.AtV[idx] = a;
   }
-  for (int idx = tid; idx < nu * nx; idx += kGenThreads) {
+  for (int idx = tid; idx < nu * nx; idx += DT::tpe) {
     const int i = idx / nx, j = idx % nx;
     R a = 0;
     for (int k = 0; k < nx; ++k) a += s.Bm[k * nu + i] * s.V[k * nx + j];
     s.BtV[idx] = a;
   }
-  __syncthreads();
-  for (int idx = tid; idx < nx * nx; idx += kGenThreads) {
+  DT::sync();
+  for (int idx = tid; idx < nx * nx; idx += DT::tpe) {
     const int i = idx / nx, j = idx % nx;
     R a = 0;
     for (int k = 0; k < nx; ++k) a += s.AtV[i * nx + k] * s.A[k * nx + j];
     s.Qxx[idx] += a;
   }
-  for (int idx = tid; idx < nx * nu; idx += kGenThreads) {
+  for (int idx = tid; idx < nx * nu; idx += DT::tpe) {
     const int i = idx / nu, j = idx % nu;
     R a = 0;
     for (int k = 0; k < nx; ++k) a += s.AtV[i * nx + k] * s.Bm[k * nu + j];
     s.Qxu[idx] += a;
   }
-  for (int idx = tid; idx < nu * nu; idx += kGenThreads) {
+  for (int idx = tid; idx < nu * nu; idx += DT::tpe) {
     const int i = idx / nu, j = idx % nu;
     R a = 0;
     for (int k = 0; k < nx; ++k) a += s.BtV[i * nx + k] * s.Bm[k * nu + j];
     s.Quu[idx] += a + ((i == j) ? P.reg : (R)0);
   }
-  for (int i = tid; i < nx; i += kGenThreads) {
+  }
+  for (int i = tid; i < nx; i += DT::tpe) {
     R a = 0;
     for (int k = 0; k < nx; ++k) a += s.A[k * nx + i] * s.v[k];
     s.qx[i] += a;
   }
-  for (int i = tid; i < nu; i += kGenThreads) {
+  for (int i = tid; i < nu; i += DT::tpe) {
     R a = 0;
     for (int k = 0; k < nx; ++k) a += s.Bm[k * nu + i] * s.v[k];
     s.qu[i] += a;
   }
-  __syncthreads();
+  DT::sync();
   // rhs = [Q_ux | q_u], L = Q_uu + reg' I
   const R reg2 = kkt ? (R)1e-8 * P.reg : P.reg;
-  for (int idx = tid; idx < nu * nr; idx += kGenThreads) {
+  for (int idx = tid; idx < nu * nr; idx += DT::tpe) {
     const int i = idx / nr, j = idx % nr;
     s.rhs[idx] = (j < nx) ? s.Qxu[j * nu + i] : s.qu[i];
   }
-  for (int idx = tid; idx < nu * nu; idx += kGenThreads) s.L[idx] = s.Quu[idx] + ((idx / nu == idx % nu) ? reg2 : (R)0);
-  __syncthreads();
+  for (int idx = tid; idx < nu * nu; idx += DT::tpe) s.L[idx] = s.Quu[idx] + ((idx / nu == idx % nu) ? reg2 : (R)0);
+  DT::sync();
   // Without input bounds nothing can be tight and the box QP of the KKT pass (utils.py:66-124 with +-inf bounds) is
   // its own first Newton step, x = -H^-1 q, accepted at the first convergence check: k_t is then one more
   // right-hand side of the gain solve below (Q_uu vs Q_uu + 1e-8 reg I: 1e-14 apart) instead of ~3 single-thread
@@ -372,7 +600,7 @@ __device__ bool gen_value_step(const DevProblem<R>& P, const GenDims<R>& d, GenS
   const bool box = P.has_umin || P.has_umax;
   if (tid == 0) {
     if (kkt && !box) {
-      gen_lu<R>(s.L, nu, s.piv);
+      if constexpr (DT::fixed) gen_lu_reg<R, DT::NU>(s.L, s.piv); else gen_lu<R>(s.L, nu, s.piv);
       s.flag[0] = 0;
     } else if (kkt) {
       // k_t: box QP over the free coordinates (compacted, as the reference does)
@@ -396,10 +624,11 @@ __device__ bool gen_value_step(const DevProblem<R>& P, const GenDims<R>& d, GenS
         gen_pnqp<R>(m, Hf, qf, lof, hif, duf, w, idxs);
         for (int i = 0; i < m; ++i) s.kt[freeidx[i]] = duf[i];
       }
-      gen_lu<R>(s.L, nu, s.piv);
+      if constexpr (DT::fixed) gen_lu_reg<R, DT::NU>(s.L, s.piv); else gen_lu<R>(s.L, nu, s.piv);
       s.flag[0] = 0;
     } else {
-      const bool pd = gen_chol<R>(s.L, nu);
+      bool pd;
+      if constexpr (DT::fixed) pd = gen_chol_reg<R, DT::NU>(s.L); else pd = gen_chol<R>(s.L, nu);
       s.flag[0] = pd ? 1 : 0;
       if (!pd) {
         for (int idx = 0; idx < nu * nu; ++idx) s.L[idx] = s.Quu[idx] + ((idx / nu == idx % nu) ? reg2 : (R)0);
@@ -407,31 +636,58 @@ __device__ bool gen_value_step(const DevProblem<R>& P, const GenDims<R>& d, GenS
       }
     }
   }
-  __syncthreads();
+  DT::sync();
   const bool use_chol = s.flag[0] != 0;
   if (!kkt && !use_chol) nonpd = true;
   const int ncols = (kkt && box) ? nx : nr;  // with bounds the KKT pass takes k from the box QP, not from the solve
-  for (int r = tid; r < ncols; r += kGenThreads) {
-    if (use_chol) gen_chol_solve_col<R>(s.L, nu, s.rhs, nr, r);
-    else gen_lu_solve_col<R>(s.L, nu, s.piv, s.rhs, nr, r);
+  for (int r = tid; r < ncols; r += DT::tpe) {
+    if constexpr (DT::fixed) {
+      if (use_chol) gen_chol_solve_col_reg<R, DT::NU>(s.L, s.rhs, nr, r);
+      else gen_lu_solve_col_reg<R, DT::NU>(s.L, s.piv, s.rhs, nr, r);
+    } else {
+      if (use_chol) gen_chol_solve_col<R>(s.L, nu, s.rhs, nr, r);
+      else gen_lu_solve_col<R>(s.L, nu, s.piv, s.rhs, nr, r);
+    }
   }
-  __syncthreads();
-  for (int idx = tid; idx < nu * nx; idx += kGenThreads) s.Kt[idx] = -s.rhs[(idx / nx) * nr + (idx % nx)];
-  if (!kkt || !box) for (int i = tid; i < nu; i += kGenThreads) s.kt[i] = -s.rhs[i * nr + nx];
-  __syncthreads();
-  for (int idx = tid; idx < nu * nx; idx += kGenThreads) {
+  DT::sync();
+  for (int idx = tid; idx < nu * nx; idx += DT::tpe) s.Kt[idx] = -s.rhs[(idx / nx) * nr + (idx % nx)];
+  if (!kkt || !box) for (int i = tid; i < nu; i += DT::tpe) s.kt[i] = -s.rhs[i * nr + nx];
+  DT::sync();
+  for (int idx = tid; idx < nu * nx; idx += DT::tpe) {
     const int i = idx / nx, j = idx % nx;
     R a = 0;
     for (int m = 0; m < nu; ++m) a += s.Quu[i * nu + m] * s.Kt[m * nx + j];
     s.QK[idx] = a;
   }
-  for (int i = tid; i < nu; i += kGenThreads) {
+  for (int i = tid; i < nu; i += DT::tpe) {
     R a = 0;
     for (int m = 0; m < nu; ++m) a += s.Quu[i * nu + m] * s.kt[m];
     s.Qk[i] = a;
   }
-  __syncthreads();
-  for (int idx = tid; idx < nx * nx; idx += kGenThreads) {
+  DT::sync();
+  if constexpr (DT::fixed) {
+    constexpr int NX = DT::NX, NU = DT::NU;
+    for (int tl = tid; tl < NX * NX / 4; tl += DT::tpe) {
+      const int i = tl / (NX / 4), j0 = (tl % (NX / 4)) * 4;
+      R a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0}, c[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int m = 0; m < NU; ++m) {
+        const R ki = s.Kt[m * NX + i], xi = s.Qxu[i * NU + m];
+        const Quad<R> qk = *reinterpret_cast<const Quad<R>*>(s.QK + m * NX + j0);
+        const Quad<R> kj = *reinterpret_cast<const Quad<R>*>(s.Kt + m * NX + j0);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          a[e] += ki * qk.v[e];
+          b[e] += ki * s.Qxu[(j0 + e) * NU + m];
+          c[e] += xi * kj.v[e];
+        }
+      }
+      const Quad<R> q = *reinterpret_cast<const Quad<R>*>(s.Qxx + i * NX + j0);
+      *reinterpret_cast<Quad<R>*>(s.Vn + i * NX + j0) =
+          Quad<R>{{((q.v[0] + a[0]) + b[0]) + c[0], ((q.v[1] + a[1]) + b[1]) + c[1], ((q.v[2] + a[2]) + b[2]) + c[2], ((q.v[3] + a[3]) + b[3]) + c[3]}};
+    }
+  } else {
+  for (int idx = tid; idx < nx * nx; idx += DT::tpe) {
     const int i = idx / nx, j = idx % nx;
     R a = 0, b = 0, c = 0;
     for (int m = 0; m < nu; ++m) {
@@ -441,7 +697,8 @@ __device__ bool gen_value_step(const DevProblem<R>& P, const GenDims<R>& d, GenS
     }
     s.Vn[idx] = ((s.Qxx[idx] + a) + b) + c;
   }
-  for (int i = tid; i < nx; i += kGenThreads) {
+  }
+  for (int i = tid; i < nx; i += DT::tpe) {
     R a = 0, b = 0, c = 0;
     for (int m = 0; m < nu; ++m) {
       a += s.Kt[m * nx + i] * s.Qk[m];
@@ -450,10 +707,10 @@ __device__ bool gen_value_step(const DevProblem<R>& P, const GenDims<R>& d, GenS
     }
     s.vn[i] = ((s.qx[i] + a) + b) + c;
   }
-  __syncthreads();
-  for (int idx = tid; idx < nx * nx; idx += kGenThreads) s.V[idx] = s.Vn[idx];
-  for (int i = tid; i < nx; i += kGenThreads) s.v[i] = s.vn[i];
-  __syncthreads();
+  DT::sync();
+  for (int idx = tid; idx < nx * nx; idx += DT::tpe) s.V[idx] = s.Vn[idx];
+  for (int i = tid; i < nx; i += DT::tpe) s.v[i] = s.vn[i];
+  DT::sync();
   return nonpd;
 }
 
