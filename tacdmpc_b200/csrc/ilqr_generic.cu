@@ -138,19 +138,29 @@ __global__ void __launch_bounds__(kGenThreads, sizeof(R) == 4 ? 4 : 2) ilqr_forw
           s.ua[idx] = ui;
         }
         DT::sync();
+        // the step's cost rows (scoring cost, and the element's own when they differ) and every candidate's tau go
+        // through shared memory: one coalesced read of C_t instead of one row read per (candidate, row) thread
+        for (int idx = tid; idx < n * n; idx += DT::tpe) {
+          s.Ct[idx] = Cl[(size_t)t * n * n + idx];
+          if (lssep) s.Ct2[idx] = Cp[(size_t)t * n * n + idx];
+        }
         for (int idx = tid; idx < na * n; idx += DT::tpe) {
           const int a = idx / n, i = idx % n;
-          const R* Ct = Cl + (size_t)t * n * n + (size_t)i * n;
+          s.taua[idx] = (i < nx) ? (s.xa[a * nx + i] - xr[t * nx + i]) : (s.ua[a * nu + (i - nx)] - ur[t * nu + (i - nx)]);
+        }
+        DT::sync();
+        for (int idx = tid; idx < na * n; idx += DT::tpe) {
+          const int a = idx / n, i = idx % n;
+          const R* Ct = s.Ct + i * n;
+          const R* ta = s.taua + a * n;
           R sd = 0;
-          for (int j = 0; j < nx; ++j) sd += Ct[j] * (s.xa[a * nx + j] - xr[t * nx + j]);
-          for (int j = 0; j < nu; ++j) sd += Ct[nx + j] * (s.ua[a * nu + j] - ur[t * nu + j]);
-          const R ti = (i < nx) ? (s.xa[a * nx + i] - xr[t * nx + i]) : (s.ua[a * nu + (i - nx)] - ur[t * nu + (i - nx)]);
+          for (int j = 0; j < n; ++j) sd += Ct[j] * ta[j];
+          const R ti = ta[i];
           s.part1[idx] += (R)0.5 * (ti * sd) + cl[(size_t)t * n + i] * ti;
           if (lssep) {
-            const R* Co = Cp + (size_t)t * n * n + (size_t)i * n;
+            const R* Co = s.Ct2 + i * n;
             R so = 0;
-            for (int j = 0; j < nx; ++j) so += Co[j] * (s.xa[a * nx + j] - xr[t * nx + j]);
-            for (int j = 0; j < nu; ++j) so += Co[nx + j] * (s.ua[a * nu + j] - ur[t * nu + j]);
+            for (int j = 0; j < n; ++j) so += Co[j] * ta[j];
             s.part2[idx] += (R)0.5 * (ti * so) + cp[(size_t)t * n + i] * ti;
           }
         }

@@ -376,7 +376,7 @@ __device__ int gen_pnqp(int m, const R* H, const R* q, const R* lo, const R* hi,
 template <typename R>
 struct GenSmem {
   R *V, *Vn, *v, *vn, *A, *Bm, *Ct, *ct, *Qxx, *Qxu, *Quu, *qx, *qu, *AtV, *BtV, *Kt, *kt, *L, *rhs, *QK, *Qk, *tau, *x, *u;
-  R *xa, *xan, *ua, *part1, *part2, *red, *scr;
+  R *xa, *xan, *ua, *part1, *part2, *red, *scr, *Ct2, *taua;
   int* piv;
   int* flag;
 };
@@ -384,7 +384,7 @@ __host__ __device__ inline size_t gen_smem_scalars(int nx, int nu) {
   const size_t n = nx + nu, na = TACD_MAX_ALPHA;
   return 2 * nx * nx + 2 * nx + nx * nx + nx * nu + n * n + n + nx * nx + nx * nu + nu * nu + nx + nu + nx * nx + nu * nx + nu * nx + nu +
          nu * nu + nu * (nx + 1) + nu * nx + nu + n + nx + nu +
-         2 * na * nx + na * nu + 2 * na * n + kGenThreads + (2 * nu * nu + 8 * nu + 8);
+         2 * na * nx + na * nu + 2 * na * n + kGenThreads + (2 * nu * nu + 8 * nu + 8) + n * n + na * n;
 }
 template <typename R>
 __host__ __device__ inline size_t gen_smem_bytes(int nx, int nu) {
@@ -411,6 +411,7 @@ __device__ GenSmem<R> gen_carve(unsigned char* raw, int nx, int nu) {
   s.tau = take(n); s.x = take(nx); s.u = take(nu);
   s.xa = take(na * nx); s.xan = take(na * nx); s.ua = take(na * nu);
   s.part1 = take(na * n); s.part2 = take(na * n); s.red = take(kGenThreads); s.scr = take(2 * nu * nu + 8 * nu + 8);
+  s.Ct2 = take(n * n); s.taua = take(na * n);
   s.piv = reinterpret_cast<int*>(p);
   s.flag = s.piv + TACD_MAX_NU;
   return s;

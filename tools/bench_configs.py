@@ -47,8 +47,9 @@ def run(name, spec, inp, ls=None, C_diag=False, Cf_batched=False):
     t_b, _ = timed(bwd)
     it = fw["iters"].float()
     tight = float(fw["tight"].float().mean())
+    nonpd = float((fw["flags"] & 1).float().mean())
     print(f"{name:28s} B={B:6d} T={T:3d} nx={spec.nx:2d} nu={spec.nu:2d}  fwd {t_f:8.3f} ms  bwd {t_b:7.3f} ms  "
-          f"{B / (t_f + t_b) * 1e3:12.4g} solves/s  iters mean {float(it.mean()):5.2f} max {int(it.max()):2d}  tight {tight:.2f}", flush=True)
+          f"{B / (t_f + t_b) * 1e3:12.4g} solves/s  iters mean {float(it.mean()):5.2f} max {int(it.max()):2d}  tight {tight:.2f}  nonpd {nonpd:.3f}", flush=True)
 
 
 def cartpole_inputs(B, T, seed=0):
