@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define TACD_ABI_VERSION 2
+#define TACD_ABI_VERSION 3
 
 #define TACD_MAX_ALPHA 8
 #define TACD_MAX_NU 16
@@ -228,6 +228,54 @@ int tacd_closed_loop_advance(const tacd_problem* p, int32_t k, int32_t n_sim, vo
 int tacd_al_update(int32_t dtype, int32_t B, int32_t T, int32_t nx, const void* X, const void* xref, int32_t xref_batched,
                    const void* x_min, const void* x_max, void* lam_lo, void* lam_hi, double rho, double rho_next,
                    int32_t update_lambda, void* dq, void* dp, void* viol, void* stream);
+/* ---- PPO glue: what ACMPC/training_loop.py does around the MPC solve with Python loops over
+ * environments and time steps, as three batched kernels.  dtype as tacd_dtype; all arrays on the device. ---- */
+
+/* One step of B independent environments whose transition is the problem's dynamics plugin (p->dyn_id, dyn_params,
+ * dt; p->T is ignored) — ACMPC/parallel_env.py:34-54 (the per-environment Python loop), the environments of
+ * examples/02_demo_cartpole_AC.py:78-96 and examples/01_demo_linear_AC.py:30-44, and the reset-on-done of
+ * ACMPC/training_loop.py:103-107:
+ *     a  = clip_action ? clamp(action, p->umin, p->umax) : action
+ *     x' = f(x, a);   steps += 1
+ *     terminated = exists i: |x'_i| > term_limit[i]          (term_limit[i] = +inf: state i is not checked)
+ *     truncated  = steps >= max_steps                        (max_steps <= 0: never)
+ *     reward = -(sum_i w_x[i] s_i^2 + sum_j w_u[j] action_j^2),  s = x' if reward_on_next else x
+ *     obs = x'                                               (what env.step returns)
+ *     next_state = (terminated or truncated) and reset_state ? reset_state : x';  steps = 0 where that happened
+ * The reset states are drawn by the caller (the reference draws them on the host, per environment), which keeps the
+ * random stream the caller's. */
+typedef struct tacd_env_io {
+  const void* state;        /* [B,nx] */
+  const void* action;       /* [B,nu] */
+  const void* reset_state;  /* [B,nx] or NULL */
+  int32_t* steps;           /* [B] in/out, or NULL (then truncated is always 0) */
+  void* obs;                /* [B,nx] out, nullable */
+  void* next_state;         /* [B,nx] out; may alias state */
+  void* reward;             /* [B] out */
+  uint8_t* terminated;      /* [B] out */
+  uint8_t* truncated;       /* [B] out */
+  int32_t max_steps;
+  int32_t clip_action;
+  int32_t reward_on_next;
+  int32_t reserved_;
+  double term_limit[TACD_MAX_NX];
+  double w_x[TACD_MAX_NX];
+  double w_u[TACD_MAX_NU];
+} tacd_env_io;
+int tacd_env_step(const tacd_problem* p, const tacd_env_io* io, void* stream);
+
+/* Generalised advantage estimation over N environments (ACMPC/training_loop.py:30-41 under vmap, :119):
+ *     v_T = values[:, T-1]                                   (the reference bootstraps with the last value)
+ *     delta_t = rewards_t + gamma v_{t+1} - v_t;   adv_t = delta_t + (gamma lam) adv_{t+1};   returns = adv + values
+ * rewards, values, returns, advantages: [N,T].  Evaluated in the reference's operation order without fused
+ * multiply-adds, so fp32 / fp64 results are bit-identical to the reference on the CPU. */
+int tacd_gae(int32_t dtype, int32_t N, int32_t T, const void* rewards, const void* values, double gamma, double lam,
+             void* returns, void* advantages, void* stream);
+/* Value-expansion targets (ACMPC/training_loop.py:162-170):  target_t = rewards_t + gamma target_{t+1},
+ * target_H = bootstrap.   rewards, targets: [N,H];  bootstrap: [N] (NULL = 0).  Same rounding contract as tacd_gae. */
+int tacd_discounted_targets(int32_t dtype, int32_t N, int32_t H, const void* rewards, const void* bootstrap, double gamma,
+                            void* targets, void* stream);
+
 /* batched projected-Newton box QP: H[N,m,m] q[N,m] lo[N,m] hi[N,m] -> x[N,m], iters[N] (nullable) */
 int tacd_pnqp(int32_t dtype, int32_t N, int32_t m, const void* H, const void* q,
               const void* lo, const void* hi, void* x, int32_t* iters, void* stream);

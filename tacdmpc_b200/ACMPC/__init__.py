@@ -1,8 +1,13 @@
-"""The ActorMPC call site of the reference (ACMPC/actor.py) on top of the B200 solve.
+"""The call sites of the reference's ACMPC package on top of the B200 solve.
 
-Only the actor is mirrored: it is the caller of the hot path.  The critic, the PPO loop, the environment
-manager and checkpointing are out of scope.
+``ActorMPC`` (ACMPC/actor.py) is the caller of the hot path; ``DeviceEnvManager`` (ACMPC/parallel_env.py) and
+``compute_gae_and_returns`` / ``mpve_targets`` / ``collect_rollout`` (ACMPC/training_loop.py) are the batched pieces
+around it.  The critic, the optimiser loop and checkpointing are plain torch in the reference and out of scope
+(SURVEY §2 rows 8-18).
 """
 from .actor import ActorMPC
+from .parallel_env import DeviceEnvManager, cartpole_envs, double_integrator_envs, uniform_reset
+from .training_loop import collect_rollout, compute_gae_and_returns, mpve_targets
 
-__all__ = ["ActorMPC"]
+__all__ = ["ActorMPC", "DeviceEnvManager", "cartpole_envs", "double_integrator_envs", "uniform_reset",
+           "collect_rollout", "compute_gae_and_returns", "mpve_targets"]

@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_ALPHA = 8
 MAX_NU = 16
 MAX_NX = 64
@@ -54,6 +54,15 @@ class BackwardIO(C.Structure):
     _fields_ = [(name, C.c_void_p) for name in (
         "X", "U", "C", "Cf", "xref", "uref", "tight", "A", "Bm", "gX", "gU",
         "grad_C", "grad_c", "grad_Cf", "grad_cf", "grad_x0", "grad_xref", "grad_uref", "dX", "dU")]
+
+
+class EnvIO(C.Structure):
+    """tacd_env_io (include/tacd_ilqr.h)."""
+    _fields_ = [("state", C.c_void_p), ("action", C.c_void_p), ("reset_state", C.c_void_p), ("steps", C.c_void_p),
+                ("obs", C.c_void_p), ("next_state", C.c_void_p), ("reward", C.c_void_p), ("terminated", C.c_void_p),
+                ("truncated", C.c_void_p), ("max_steps", C.c_int32), ("clip_action", C.c_int32),
+                ("reward_on_next", C.c_int32), ("reserved_", C.c_int32),
+                ("term_limit", C.c_double * MAX_NX), ("w_x", C.c_double * MAX_NX), ("w_u", C.c_double * MAX_NU)]
 
 
 def make_problem(*, B, T, nx, nu, dtype, dyn_id, dt, reg_eps=1e-6, max_iter=40,

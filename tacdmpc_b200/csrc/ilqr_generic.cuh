@@ -633,7 +633,7 @@ __device__ bool gen_value_step(const DevProblem<R>& P, const DT& d, GenSmem<R>& 
       s.flag[0] = pd ? 1 : 0;
       if (!pd) {
         for (int idx = 0; idx < nu * nu; ++idx) s.L[idx] = s.Quu[idx] + ((idx / nu == idx % nu) ? reg2 : (R)0);
-        gen_lu<R>(s.L, nu, s.piv);
+        if constexpr (DT::fixed) gen_lu_reg<R, DT::NU>(s.L, s.piv); else gen_lu<R>(s.L, nu, s.piv);
       }
     }
   }

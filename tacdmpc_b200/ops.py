@@ -304,3 +304,70 @@ def al_update(X, xref, x_min, x_max, lam_lo, lam_hi, rho: float, rho_next: float
         _lib.check(_lib.lib().tacd_al_update(_DT[dt], B, T1 - 1, nx, *_vp(X, xref), int(xref.shape[0] == B), *_vp(x_min, x_max, lam_lo, lam_hi),
                                              float(rho), float(rho_next), int(update_lambda), *_vp(dq, dp, viol), _stream()), "tacd_al_update")
     return dq, dp, viol
+
+
+# ---- PPO glue ----------------------------------------------------------------------------------
+def env_step(spec: Spec, state, action, *, steps=None, reset_state=None, max_steps: int = 0, term_limit=None,
+             w_x=None, w_u=None, clip_action: bool = False, reward_on_next: bool = True, next_state=None):
+    """One step of ``B`` environments driven by the dynamics plugin of ``spec`` (``tacd_env_step``;
+    ACMPC/parallel_env.py:34-54 without the Python loop).  ``steps`` (int32 [B]) is advanced in place and zeroed
+    where an episode ended and ``reset_state`` supplied the next start.  Returns
+    ``(obs, next_state, reward, terminated, truncated)``; ``next_state`` may be passed in (it may be ``state``)."""
+    _need_cuda(state, action, steps, reset_state)
+    dt, dev = state.dtype, state.device
+    B, nx = state.shape
+    state, action = _prep(state, dt, dev), _prep(action, dt, dev).reshape(B, spec.nu)
+    if reset_state is not None:
+        reset_state = _prep(reset_state, dt, dev)
+    if steps is not None and (steps.dtype != torch.int32 or not steps.is_contiguous()):
+        raise RuntimeError("steps must be a contiguous int32 tensor")
+    obs = torch.empty(B, nx, device=dev, dtype=dt)
+    if next_state is None:
+        next_state = torch.empty(B, nx, device=dev, dtype=dt)
+    reward = torch.empty(B, device=dev, dtype=dt)
+    term = torch.empty(B, device=dev, dtype=torch.uint8)
+    trunc = torch.empty(B, device=dev, dtype=torch.uint8)
+    io = _abi.EnvIO()
+    io.state, io.action, io.reset_state, io.steps = _ptr(state), _ptr(action), _ptr(reset_state), _ptr(steps)
+    io.obs, io.next_state, io.reward, io.terminated, io.truncated = _ptr(obs), _ptr(next_state), _ptr(reward), _ptr(term), _ptr(trunc)
+    io.max_steps, io.clip_action, io.reward_on_next = int(max_steps), int(clip_action), int(reward_on_next)
+    for i in range(_abi.MAX_NX):
+        io.term_limit[i] = float(term_limit[i]) if term_limit is not None and i < len(term_limit) else float("inf")
+        io.w_x[i] = float(w_x[i]) if w_x is not None and i < len(w_x) else 0.0
+    for j in range(_abi.MAX_NU):
+        io.w_u[j] = float(w_u[j]) if w_u is not None and j < len(w_u) else 0.0
+    p = _problem(spec, B, dt)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().tacd_env_step(C.byref(p), C.byref(io), _stream()), "tacd_env_step")
+    return obs, next_state, reward, term.bool(), trunc.bool()
+
+
+def gae(rewards, values, gamma: float = 0.99, lam: float = 1.0):
+    """``(returns, advantages)`` of ACMPC/training_loop.py:30-41 for ``[N, T]`` rewards / values (``tacd_gae``)."""
+    _need_cuda(rewards, values)
+    dt, dev = rewards.dtype, rewards.device
+    if rewards.ndim != 2 or values.shape != rewards.shape:
+        raise RuntimeError(f"rewards, values must be [N, T]; got {tuple(rewards.shape)}, {tuple(values.shape)}")
+    rewards, values = _prep(rewards, dt, dev), _prep(values, dt, dev)
+    N, T = rewards.shape
+    ret, adv = torch.empty_like(rewards), torch.empty_like(rewards)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().tacd_gae(_DT[dt], N, T, *_vp(rewards, values), float(gamma), float(lam), *_vp(ret, adv), _stream()), "tacd_gae")
+    return ret, adv
+
+
+def discounted_targets(rewards, bootstrap=None, gamma: float = 0.99):
+    """``target_t = r_t + gamma target_{t+1}``, ``target_H = bootstrap`` for ``[N, H]`` rewards (``tacd_discounted_targets``;
+    the value-expansion targets of ACMPC/training_loop.py:162-170)."""
+    _need_cuda(rewards, bootstrap)
+    dt, dev = rewards.dtype, rewards.device
+    if rewards.ndim != 2 or (bootstrap is not None and bootstrap.shape != rewards.shape[:1]):
+        raise RuntimeError("rewards must be [N, H] and bootstrap [N]")
+    rewards = _prep(rewards, dt, dev)
+    bootstrap = None if bootstrap is None else _prep(bootstrap, dt, dev)
+    N, H = rewards.shape
+    out = torch.empty_like(rewards)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().tacd_discounted_targets(_DT[dt], N, H, *_vp(rewards, bootstrap), float(gamma), *_vp(out), _stream()),
+                   "tacd_discounted_targets")
+    return out

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for nm in names:
         assert hasattr(L, nm), nm
     assert set(names) == set(_lib.EXPORTS)
-    assert L.tacd_abi_version() == 2
+    assert L.tacd_abi_version() == 3
 
 
 def test_oracle_exports_same_entry_points(oracle):
@@ -40,16 +40,17 @@ def test_struct_layout_matches_header():
 #include <stdio.h>
 #include <stddef.h>
 #include "tacd_ilqr.h"
-int main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(tacd_problem), sizeof(tacd_forward_io), sizeof(tacd_backward_io),
+int main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(tacd_problem), sizeof(tacd_forward_io), sizeof(tacd_backward_io),
  offsetof(tacd_problem, dyn_params), offsetof(tacd_problem, alphas), offsetof(tacd_problem, umax), offsetof(tacd_problem, C_diag),
- offsetof(tacd_problem, compat_exact));return 0;}'''
+ offsetof(tacd_problem, compat_exact), sizeof(tacd_env_io), offsetof(tacd_env_io, max_steps), offsetof(tacd_env_io, w_u));return 0;}'''
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "t.c"), "w").write(prog)
         subprocess.run(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "t.c"), "-o", os.path.join(d, "t")], check=True)
         out = subprocess.run([os.path.join(d, "t")], capture_output=True, text=True, check=True).stdout.split()
     got = [int(v) for v in out]
     exp = [C.sizeof(_abi.Problem), C.sizeof(_abi.ForwardIO), C.sizeof(_abi.BackwardIO), _abi.Problem.dyn_params.offset,
-           _abi.Problem.alphas.offset, _abi.Problem.umax.offset, _abi.Problem.C_diag.offset, _abi.Problem.compat_exact.offset]
+           _abi.Problem.alphas.offset, _abi.Problem.umax.offset, _abi.Problem.C_diag.offset, _abi.Problem.compat_exact.offset,
+           C.sizeof(_abi.EnvIO), _abi.EnvIO.max_steps.offset, _abi.EnvIO.w_u.offset]
     assert got == exp
 
 
