@@ -86,6 +86,8 @@ __global__ void __launch_bounds__(128) gae_scan(int N, int T, const R* __restric
   const R* r = rewards + (size_t)n * T;
   const R* v = values + (size_t)n * T;
   R vnext = v[T - 1], last = 0;
+  // the loads do not depend on the recurrence: unrolled, eight steps of them are in flight ahead of the adds
+#pragma unroll 8
   for (int t = T - 1; t >= 0; --t) {
     const R vt = v[t];
     const R delta = add_rn<R>(add_rn<R>(r[t], mul_rn<R>(gamma, vnext)), -vt);
@@ -103,6 +105,7 @@ __global__ void __launch_bounds__(128) discounted_scan(int N, int H, const R* __
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   R next = bootstrap ? bootstrap[n] : (R)0;
+#pragma unroll 8
   for (int t = H - 1; t >= 0; --t) {
     next = add_rn<R>(rewards[(size_t)n * H + t], mul_rn<R>(gamma, next));
     targets[(size_t)n * H + t] = next;
@@ -149,13 +152,15 @@ int tacd_gae(int32_t dtype, int32_t N, int32_t T, const void* rewards, const voi
   if (N == 0) return TACD_OK;
   if (!rewards || !values || !returns || !advantages) { set_error("tacd_gae: required pointer is null"); return TACD_EINVAL; }
   cudaStream_t s = (cudaStream_t)stream;
-  const int grid = (N + 127) / 128;
+  // one sequential scan per thread: PPO-sized batches (a few thousand rows) are spread one warp per CTA over the SMs
+  const int block = N >= 148 * 128 ? 128 : 32;
+  const int grid = (N + block - 1) / block;
   // gamma * lam is formed in double and rounded once, as the reference's Python float product is (training_loop.py:39)
   if (dtype == TACD_F32)
-    gae_scan<float><<<grid, 128, 0, s>>>(N, T, (const float*)rewards, (const float*)values, (float)gamma, (float)(gamma * lam), (float*)returns,
+    gae_scan<float><<<grid, block, 0, s>>>(N, T, (const float*)rewards, (const float*)values, (float)gamma, (float)(gamma * lam), (float*)returns,
                                          (float*)advantages);
   else
-    gae_scan<double><<<grid, 128, 0, s>>>(N, T, (const double*)rewards, (const double*)values, gamma, gamma * lam, (double*)returns,
+    gae_scan<double><<<grid, block, 0, s>>>(N, T, (const double*)rewards, (const double*)values, gamma, gamma * lam, (double*)returns,
                                           (double*)advantages);
   note_launches(1);
   return check_cuda(cudaPeekAtLastError(), "gae_scan launch");
@@ -167,11 +172,12 @@ int tacd_discounted_targets(int32_t dtype, int32_t N, int32_t H, const void* rew
   if (N == 0) return TACD_OK;
   if (!rewards || !targets) { set_error("tacd_discounted_targets: required pointer is null"); return TACD_EINVAL; }
   cudaStream_t s = (cudaStream_t)stream;
-  const int grid = (N + 127) / 128;
+  const int block = N >= 148 * 128 ? 128 : 32;
+  const int grid = (N + block - 1) / block;
   if (dtype == TACD_F32)
-    discounted_scan<float><<<grid, 128, 0, s>>>(N, H, (const float*)rewards, (const float*)bootstrap, (float)gamma, (float*)targets);
+    discounted_scan<float><<<grid, block, 0, s>>>(N, H, (const float*)rewards, (const float*)bootstrap, (float)gamma, (float*)targets);
   else
-    discounted_scan<double><<<grid, 128, 0, s>>>(N, H, (const double*)rewards, (const double*)bootstrap, gamma, (double*)targets);
+    discounted_scan<double><<<grid, block, 0, s>>>(N, H, (const double*)rewards, (const double*)bootstrap, gamma, (double*)targets);
   note_launches(1);
   return check_cuda(cudaPeekAtLastError(), "discounted_scan launch");
 }

@@ -7,6 +7,7 @@ falls back to PyTorch math: a non-CUDA tensor or a missing library is an error.
 from __future__ import annotations
 
 import ctypes as C
+import functools
 from dataclasses import dataclass, field
 from typing import Optional, Sequence
 
@@ -307,6 +308,14 @@ def al_update(X, xref, x_min, x_max, lam_lo, lam_hi, rho: float, rho_next: float
 
 
 # ---- PPO glue ----------------------------------------------------------------------------------
+@functools.lru_cache(maxsize=64)
+def _env_vecs(term_limit, w_x, w_u):
+    """The fixed-size host arrays of tacd_env_io, built once per environment definition."""
+    def arr(n, vals, fill):
+        return (C.c_double * n)(*[float(vals[i]) if vals is not None and i < len(vals) else fill for i in range(n)])
+    return arr(_abi.MAX_NX, term_limit, float("inf")), arr(_abi.MAX_NX, w_x, 0.0), arr(_abi.MAX_NU, w_u, 0.0)
+
+
 def env_step(spec: Spec, state, action, *, steps=None, reset_state=None, max_steps: int = 0, term_limit=None,
              w_x=None, w_u=None, clip_action: bool = False, reward_on_next: bool = True, next_state=None):
     """One step of ``B`` environments driven by the dynamics plugin of ``spec`` (``tacd_env_step``;
@@ -331,11 +340,8 @@ def env_step(spec: Spec, state, action, *, steps=None, reset_state=None, max_ste
     io.state, io.action, io.reset_state, io.steps = _ptr(state), _ptr(action), _ptr(reset_state), _ptr(steps)
     io.obs, io.next_state, io.reward, io.terminated, io.truncated = _ptr(obs), _ptr(next_state), _ptr(reward), _ptr(term), _ptr(trunc)
     io.max_steps, io.clip_action, io.reward_on_next = int(max_steps), int(clip_action), int(reward_on_next)
-    for i in range(_abi.MAX_NX):
-        io.term_limit[i] = float(term_limit[i]) if term_limit is not None and i < len(term_limit) else float("inf")
-        io.w_x[i] = float(w_x[i]) if w_x is not None and i < len(w_x) else 0.0
-    for j in range(_abi.MAX_NU):
-        io.w_u[j] = float(w_u[j]) if w_u is not None and j < len(w_u) else 0.0
+    io.term_limit, io.w_x, io.w_u = _env_vecs(None if term_limit is None else tuple(term_limit), None if w_x is None else tuple(w_x),
+                                              None if w_u is None else tuple(w_u))
     p = _problem(spec, B, dt)
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().tacd_env_step(C.byref(p), C.byref(io), _stream()), "tacd_env_step")
