@@ -1,0 +1,190 @@
+"""-m gpu: the hot path at BASELINE.json's full size (cart-pole, B = 65 536 per GPU, T = 20 — bench.py's workload),
+checked through properties that do not need the oracle to finish 65 536 solves:
+
+* batch-composition invariance — an element's result does not depend on which batch it is solved in, bit for bit
+  (persistent CTAs, the longest-first work queue and the lane packing must not leak into the numbers);
+* the returned state trajectory is the rollout of the returned inputs; inputs respect the box and the active-set
+  mask says exactly where; the cost never increases over the solve; a solve started from its own answer stops
+  after one iteration and returns that answer;
+* the backward is linear in the incoming gradients, and the shared-cost gradient is the batch sum of the
+  per-element gradients (a checksum of checksums);
+* a random sample of the full batch against the CPU oracle driven along the kernel's own decision trace.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+B_FULL, T, NX, NU, DT = 65536, 20, 4, 1, 0.05
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+
+
+def inputs(B, seed=0, per_element=False):
+    """bench.py::make_inputs, restated so the tests do not import the benchmark."""
+    g = torch.Generator().manual_seed(seed)
+    n = NX + NU
+    C = torch.zeros(T, n, n)
+    C[:, :NX, :NX] = torch.diag(torch.tensor([10.0, 1.0, 100.0, 1.0]))
+    C[:, NX:, NX:] = 0.1
+    c = torch.zeros(T, n)
+    Cf = torch.zeros(n, n)
+    Cf[:NX, :NX] = 10 * C[0, :NX, :NX]
+    cf = torch.zeros(n)
+    x0 = torch.tensor([0.0, 0.0, 0.2, 0.0]) + torch.randn(B, NX, generator=g) * torch.tensor([0.5, 0.5, 0.2, 0.2])
+    if per_element:
+        s = 0.5 + torch.rand(B, 1, 1, 1, generator=g)
+        C, c = (C[None] * s).contiguous(), c[None].expand(B, T, n).contiguous()
+        Cf, cf = (Cf[None] * s[:, 0]).contiguous(), cf[None].expand(B, n).contiguous()
+    d = dict(x0=x0, C=C, c=c, Cf=Cf, cf=cf, xref=torch.zeros(B, T + 1, NX), uref=torch.zeros(B, T, NU), Uinit=torch.zeros(B, T, NU))
+    return {k: v.cuda() for k, v in d.items()}
+
+
+def spec():
+    from tacdmpc_b200 import ops
+    from tacdmpc_b200.dynamics import CartPole
+    f = CartPole()
+    return ops.Spec(nx=NX, nu=NU, T=T, dt=DT, dyn_id=f.dyn_id, dyn_params=f.params, reg_eps=1e-6, max_iter=40, u_min=[-20.0], u_max=[20.0])
+
+
+def solve(d, **kw):
+    from tacdmpc_b200 import ops
+    return ops.ilqr_forward(spec(), d["x0"], d["C"], d["c"], d["Cf"], d["cf"], d["xref"], d["uref"], d["Uinit"], **kw)
+
+
+@pytest.fixture(scope="module")
+def full():
+    d = inputs(B_FULL)
+    return d, solve(d)
+
+
+def take(d, idx):
+    return {k: (v[idx].contiguous() if v.shape[0] == B_FULL else v) for k, v in d.items()}
+
+
+def test_batch_composition_invariance(full):
+    d, fw = full
+    g = torch.Generator().manual_seed(1)
+    for nsub in (1, 6, 517, 4096):
+        idx = torch.randperm(B_FULL, generator=g)[:nsub].cuda()
+        sub = solve(take(d, idx))
+        for k in ("X", "U", "iters", "alpha_trace", "flags", "tight", "cost"):
+            assert torch.equal(sub[k], fw[k][idx]), (nsub, k)
+
+
+def test_solution_invariants(full):
+    from tacdmpc_b200 import ops
+    d, fw = full
+    X, U = fw["X"], fw["U"]
+    assert torch.isfinite(X).all() and torch.isfinite(U).all()
+    # X* is the rollout of U* from x0 (the accepted candidate is rolled out with the same device function)
+    Xr = ops.rollout(spec(), d["x0"], U)
+    assert float((Xr - X).abs().max()) <= 1e-5 * max(1.0, float(X.abs().max()))
+    # input box and active-set mask (controller.py:317-330: isclose to a bound)
+    assert float(U.min()) >= -20.0 and float(U.max()) <= 20.0
+    near = torch.isclose(U, torch.full_like(U, -20.0)) | torch.isclose(U, torch.full_like(U, 20.0))
+    assert torch.equal(fw["tight"].bool(), near)
+    assert 0.0 < float(near.float().mean()) < 0.2          # the workload does exercise the bounds
+    # the solve never ends above the cost it started from, and its reported cost is the objective of (X*, U*)
+    J0 = ops.objective(spec(), ops.rollout(spec(), d["x0"], d["Uinit"]), d["Uinit"], d["C"], d["c"], d["Cf"], d["cf"], d["xref"], d["uref"])
+    J = ops.objective(spec(), X, U, d["C"], d["c"], d["Cf"], d["cf"], d["xref"], d["uref"])
+    assert bool((J <= J0 * (1 + 1e-6)).all())
+    assert float(((J - fw["cost"]).abs() / J.abs().clamp_min(1.0)).max()) < 1e-4
+    it = fw["iters"]
+    assert int(it.min()) >= 1 and int(it.max()) <= 40 and 4.5 < float(it.float().mean()) < 6.5
+
+
+def test_resolve_from_the_answer_is_a_fixed_point(full):
+    d, fw = full
+    again = solve(dict(d, Uinit=fw["U"]))
+    # the first solve stopped because no candidate improved; started there, the first iteration sees the same
+    # trajectory, so it stops too and hands the input back
+    stopped = (fw["flags"] & 2) == 0            # not stopped by max_iter
+    assert float(stopped.float().mean()) > 0.999
+    same = again["iters"][stopped] == 1
+    assert float(same.float().mean()) > 0.995   # (a handful re-improve by one rounding step)
+    sel = stopped.clone()
+    sel[stopped] = same
+    assert torch.equal(again["U"][sel], fw["U"][sel]) and torch.equal(again["X"][sel], fw["X"][sel])
+    assert bool((again["cost"] <= fw["cost"] * (1 + 1e-6)).all())
+
+
+def _backward(d, fw, gX, gU, **kw):
+    from tacdmpc_b200 import ops
+    return ops.ilqr_backward(spec(), fw["X"], fw["U"], d["C"], d["xref"], d["uref"], fw["tight"], gX, gU, **kw)
+
+
+def test_backward_linearity_and_batch_sum(full):
+    d, fw = full
+    g = torch.Generator(device="cuda").manual_seed(2)
+    g1X, g1U = torch.randn(B_FULL, T + 1, NX, device="cuda", generator=g), torch.randn(B_FULL, T, NU, device="cuda", generator=g)
+    g2X, g2U = torch.randn(B_FULL, T + 1, NX, device="cuda", generator=g), torch.randn(B_FULL, T, NU, device="cuda", generator=g)
+    # The KKT pass solves a BOX QP for the input offsets (lo = u_min - U*, hi = u_max - U*; controller.py:736-767), so
+    # it is linear only while no offset reaches the box: incoming gradients are scaled down until they cannot, and
+    # the claim is per element (the few whose U* sits within that distance of a bound without being tight may clamp).
+    eps = 1e-4
+    g1X, g1U, g2X, g2U = (eps * t for t in (g1X, g1U, g2X, g2U))
+    b1, b2 = _backward(d, fw, g1X, g1U), _backward(d, fw, g2X, g2U)
+    b12 = _backward(d, fw, 0.5 * g1X - 2.0 * g2X, 0.5 * g1U - 2.0 * g2U)
+    for k in ("grad_xref", "grad_uref"):
+        ref = 0.5 * b1[k] - 2.0 * b2[k]
+        err = (b12[k] - ref).flatten(1).abs().amax(1)
+        scale = ref.flatten(1).abs().amax(1).clamp_min(1e-12)
+        assert float((err <= 2e-3 * scale).float().mean()) > 0.999, k
+        assert float(scale.median()) > 0          # not vacuous
+    # shared-cost gradients are the batch sum of the per-element ones: same elements, cost passed per element
+    n = NX + NU
+    dpe = dict(d, C=d["C"][None].expand(B_FULL, T, n, n).contiguous())
+    bpe = _backward(dpe, fw, g1X, g1U)
+    for k in ("grad_C", "grad_c"):
+        tot = bpe[k].double().sum(0)
+        scale = max(1.0, float(tot.abs().max()))
+        assert float((b1[k].double() - tot).abs().max()) <= 1e-4 * scale, k
+
+
+def test_full_batch_sample_against_oracle(full, oracle):
+    d, fw = full
+    g = torch.Generator().manual_seed(3)
+    idx = torch.randperm(B_FULL, generator=g)[:384]
+    sub = take(d, idx.cuda())
+    f = spec()
+    sp = dict(nx=NX, nu=NU, T=T, dt=DT, dyn="cartpole", dyn_params=f.dyn_params, reg_eps=1e-6, max_iter=40, u_min=[-20.0], u_max=[20.0])
+    rp = dict(iters=fw["iters"][idx.cuda()].cpu().numpy(), alpha_trace=fw["alpha_trace"][idx.cuda()].cpu().numpy(),
+              flags=fw["flags"][idx.cuda()].cpu().numpy())
+    h = {k: v.cpu().numpy() for k, v in sub.items()}
+    ref = oracle.forward(sp, h["x0"], h["C"], h["c"], h["Cf"], h["cf"], h["xref"], h["uref"], h["Uinit"], replay=rp)
+    X, U = fw["X"][idx.cuda()].cpu().numpy(), fw["U"][idx.cuda()].cpu().numpy()
+    # fp32, tolerance as smoke(): relative to the largest entry, along the same decisions
+    assert np.abs(U - ref["U"]).max() / max(1.0, np.abs(ref["U"]).max()) < 2e-4
+    assert np.abs(X - ref["X"]).max() / max(1.0, np.abs(ref["X"]).max()) < 2e-4
+    assert np.array_equal(fw["tight"][idx.cuda()].cpu().numpy().astype(bool), ref["tight"].astype(bool))
+    # Free-running oracle (its own decisions).  In fp32 the last one or two accept/reject decisions of a solve compare
+    # costs that differ by rounding ("noise margin"), so iteration counts agree only in the mean; what must
+    # agree is where the solves end up: the same cost to 1e-5, the same first input to 1e-2 of its range.
+    free = oracle.forward(sp, h["x0"], h["C"], h["c"], h["Cf"], h["cf"], h["xref"], h["uref"], h["Uinit"])
+    assert abs(free["iters"].mean() - rp["iters"].mean()) < 0.5
+    J = fw["cost"][idx.cuda()].cpu().numpy()
+    assert np.quantile(np.abs(J - free["cost"]) / np.maximum(1.0, np.abs(free["cost"])), 0.99) < 1e-5
+    assert np.quantile(np.abs(U[:, 0] - free["U"][:, 0]), 0.99) < 0.2
+
+
+def test_per_element_layout_full_size():
+    """The per-element cost layout at full size: invariance under batch composition with the shared scoring cost
+    (quirk Q4) held fixed, and compact-diagonal == dense, bit for bit."""
+    d = inputs(B_FULL, per_element=True)
+    ls = (d["C"][0].contiguous(), d["c"][0].contiguous(), d["Cf"][0].contiguous(), d["cf"][0].contiguous())
+    fw = solve(d, ls_cost=ls)
+    idx = torch.randperm(B_FULL, generator=torch.Generator().manual_seed(4))[:1000].cuda()
+    sub = solve(take(d, idx), ls_cost=ls)
+    for k in ("X", "U", "iters", "alpha_trace", "tight"):
+        assert torch.equal(sub[k], fw[k][idx]), k
+    dd = dict(d, C=torch.diagonal(d["C"], dim1=-2, dim2=-1).contiguous(), Cf=torch.diagonal(d["Cf"], dim1=-2, dim2=-1).contiguous())
+    lsd = (torch.diagonal(ls[0], dim1=-2, dim2=-1).contiguous(), ls[1], torch.diagonal(ls[2]).contiguous(), ls[3])
+    fd = solve(dd, ls_cost=lsd, C_diag=True)
+    for k in ("X", "U", "iters", "alpha_trace", "tight"):
+        assert torch.equal(fd[k], fw[k]), k
