@@ -20,9 +20,14 @@ static int gen_tpe(const tacd_problem* p) {
   return p->nx <= 16 ? 32 : kGenThreads;
 }
 // element slots in flight: four CTAs per SM, kGenThreads / tpe elements per CTA
+static int gen_ctas_per_sm() {
+  static const char* e = getenv("TACD_GENERIC_CTAS");
+  const int v = e ? atoi(e) : 4;
+  return v >= 1 && v <= 16 ? v : 4;
+}
 static int gen_slots(const tacd_problem* p, int tpe) {
   const DeviceInfo di = device_info();
-  int g = di.sms * 4 * (kGenThreads / tpe);
+  int g = di.sms * gen_ctas_per_sm() * (kGenThreads / tpe);
   if (g > p->B) g = p->B;
   return g < 1 ? 1 : g;
 }
@@ -31,7 +36,7 @@ size_t generic_forward_ws_bytes(const tacd_problem* p) {
   const size_t es = (p->dtype == TACD_F32) ? 4 : 8;
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-  const size_t g = (size_t)sms * 4 * (kGenThreads / gen_tpe(p));
+  const size_t g = (size_t)sms * gen_ctas_per_sm() * (kGenThreads / gen_tpe(p));
   return g * gen_slice_scalars(p) * es + 256;
 }
 size_t generic_backward_ws_bytes(const tacd_problem* p) { return generic_forward_ws_bytes(p); }
