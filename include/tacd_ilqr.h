@@ -103,7 +103,7 @@ typedef struct tacd_problem {
   /* 0 = reproduce the reference's backward with its quirks Q1-Q3, Q6 (default).  1 = exact implicit
    * differentiation (compat="exact"; Amos et al. 2018): terminal value C_final / -grad_X[T],
    * gains and offsets solved on the free inputs only (no box), grad_x0 = -v_0, grad_xref/uref = C_t dtau_t.
-   * tacd_ilqr_backward, thread-per-element kernel only; needs tacd_backward_io.Cf. */
+   * tacd_ilqr_backward (thread-per-element and run-time-dimension kernels); needs tacd_backward_io.Cf. */
   int32_t compat_exact;
 } tacd_problem;
 

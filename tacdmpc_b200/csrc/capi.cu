@@ -156,7 +156,6 @@ int tacd_ilqr_backward(const tacd_problem* p, const tacd_backward_io* io, void* 
                               : launch_backward_small<double>(p, io, ws, workspace_bytes - 256, s);
   if (rc != TACD_EUNSUPPORTED) return rc;
   if (p->C_diag) { set_error("C_diag: no thread-per-element backward kernel for this (nx, nu, dyn); pass dense costs"); return TACD_EUNSUPPORTED; }
-  if (p->compat_exact) { set_error("compat_exact: no thread-per-element backward kernel for this (nx, nu, dyn)"); return TACD_EUNSUPPORTED; }
   rc = (p->dtype == TACD_F32) ? launch_backward_generic<float>(p, io, ws, workspace_bytes - 256, s)
                               : launch_backward_generic<double>(p, io, ws, workspace_bytes - 256, s);
   return rc;

@@ -313,8 +313,15 @@ __global__ void __launch_bounds__(kGenThreads, sizeof(R) == 4 ? 4 : 2) ilqr_back
       }
       DT::sync();
     };
-    for (int idx = tid; idx < nx * nx; idx += DT::tpe) s.V[idx] = Cp[(size_t)(T - 1) * n * n + (idx / nx) * n + (idx % nx)];
-    for (int i = tid; i < nx; i += DT::tpe) s.v[i] = -gX[(T - 1) * nx + i];
+    const bool exact = P.exact != 0;   // compat="exact" (SURVEY 8f N3): see gen_value_step and tests/exact_ref.py
+    const R* Cfe = exact ? io.Cf + (P.Cf_batched ? (size_t)b * n * n : 0) : nullptr;
+    if (exact) {   // terminal value C_final[:nx,:nx], -grad_X[T] (fixes Q1, Q2)
+      for (int idx = tid; idx < nx * nx; idx += DT::tpe) s.V[idx] = Cfe[(idx / nx) * n + (idx % nx)];
+      for (int i = tid; i < nx; i += DT::tpe) s.v[i] = -gX[T * nx + i];
+    } else {
+      for (int idx = tid; idx < nx * nx; idx += DT::tpe) s.V[idx] = Cp[(size_t)(T - 1) * n * n + (idx / nx) * n + (idx % nx)];
+      for (int i = tid; i < nx; i += DT::tpe) s.v[i] = -gX[(T - 1) * nx + i];
+    }
     DT::sync();
     for (int t = T - 1; t >= 0; --t) {
       const R* Ct = Cp + (size_t)t * n * n;
@@ -332,7 +339,7 @@ __global__ void __launch_bounds__(kGenThreads, sizeof(R) == 4 ? 4 : 2) ilqr_back
     // forward sweep + gradients; s.x = dx_t, s.u = du_t, s.tau = tau_t, s.qx (n entries via ct) = dtau_t
     R* dtau = s.ct;
     for (int i = tid; i < nx; i += DT::tpe) s.x[i] = 0;
-    if (io.grad_x0) for (int i = tid; i < nx; i += DT::tpe) io.grad_x0[(size_t)b * nx + i] = 0;
+    if (io.grad_x0) for (int i = tid; i < nx; i += DT::tpe) io.grad_x0[(size_t)b * nx + i] = exact ? -s.v[i] : (R)0;   // exact: -lambda_0 (Q3)
     DT::sync();
     for (int t = 0; t <= T; ++t) {
       if (t < T) {
@@ -359,7 +366,12 @@ __global__ void __launch_bounds__(kGenThreads, sizeof(R) == 4 ? 4 : 2) ilqr_back
           }
         if (io.grad_uref)
           for (int i = tid; i < nu; i += DT::tpe) {
-            if (P.uref_batched) io.grad_uref[(size_t)b * szU + t * nu + i] = s.u[i]; else atomicAdd(&io.grad_uref[t * nu + i], s.u[i]);
+            R g = s.u[i];
+            if (exact) {   // d loss / d ref_t = C_t dtau_t
+              g = 0;
+              for (int j = 0; j < n; ++j) g += Cp[(size_t)t * n * n + (size_t)(nx + i) * n + j] * dtau[j];
+            }
+            if (P.uref_batched) io.grad_uref[(size_t)b * szU + t * nu + i] = g; else atomicAdd(&io.grad_uref[t * nu + i], g);
           }
         if (io.dU) for (int i = tid; i < nu; i += DT::tpe) io.dU[(size_t)b * szU + t * nu + i] = s.u[i];
       } else {
@@ -378,7 +390,13 @@ __global__ void __launch_bounds__(kGenThreads, sizeof(R) == 4 ? 4 : 2) ilqr_back
       }
       if (io.grad_xref)
         for (int i = tid; i < nx; i += DT::tpe) {
-          if (P.xref_batched) io.grad_xref[(size_t)b * szX + t * nx + i] = s.x[i]; else atomicAdd(&io.grad_xref[t * nx + i], s.x[i]);
+          R g = s.x[i];
+          if (exact) {   // C_t dtau_t for t < T, C_final[:nx,:nx] dx_T at the end
+            g = 0;
+            if (t < T) for (int j = 0; j < n; ++j) g += Cp[(size_t)t * n * n + (size_t)i * n + j] * dtau[j];
+            else for (int j = 0; j < nx; ++j) g += Cfe[i * n + j] * dtau[j];
+          }
+          if (P.xref_batched) io.grad_xref[(size_t)b * szX + t * nx + i] = g; else atomicAdd(&io.grad_xref[t * nx + i], g);
         }
       if (io.dX) for (int i = tid; i < nx; i += DT::tpe) io.dX[(size_t)b * szX + t * nx + i] = s.x[i];
       if (t < T) {
@@ -717,6 +735,7 @@ static int run_backward_generic(const tacd_problem* p, const tacd_backward_io* i
   BwdPtrs<R> f;
   f.X = (const R*)io->X; f.U = (const R*)io->U; f.C = (const R*)io->C; f.xref = (const R*)io->xref; f.uref = (const R*)io->uref;
   f.A = (const R*)io->A; f.Bm = (const R*)io->Bm; f.gX = (const R*)io->gX; f.gU = (const R*)io->gU; f.tight = io->tight;
+  f.Cf = (const R*)io->Cf;
   f.grad_C = (R*)io->grad_C; f.grad_c = (R*)io->grad_c; f.grad_Cf = (R*)io->grad_Cf; f.grad_cf = (R*)io->grad_cf;
   f.grad_x0 = (R*)io->grad_x0; f.grad_xref = (R*)io->grad_xref; f.grad_uref = (R*)io->grad_uref; f.dX = (R*)io->dX; f.dU = (R*)io->dU;
   kernel<<<L.grid, kGenThreads, L.smem, s>>>(to_dev<R>(p), dims_of<R, NXT, NUT, TPE>(p), f, L.in_smem ? nullptr : (R*)ws, slice);

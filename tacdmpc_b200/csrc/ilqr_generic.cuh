@@ -506,6 +506,10 @@ __device__ bool gen_value_step(const DevProblem<R>& P, const DT& d, GenSmem<R>& 
   const int tid = DT::tid(), nx = d.nx(), nu = d.nu();
   const int nr = nx + 1;
   bool nonpd = false;
+  // compat="exact" (tacd_problem.compat_exact, backward only): the KKT system proper — no reg I in Q_uu (the reference
+  // adds it, controller.py:731), active inputs frozen, the free block solved alone for K_t and k_t (fixes Q6)
+  const bool exact = kkt && P.exact;
+  const R quu_reg = exact ? (R)0 : P.reg;
   if constexpr (DT::fixed) {
     constexpr int NX = DT::NX, NU = DT::NU;
     for (int tl = tid; tl < NX * NX / 4; tl += DT::tpe) {
@@ -540,7 +544,7 @@ __device__ bool gen_value_step(const DevProblem<R>& P, const DT& d, GenSmem<R>& 
       R a[4] = {0, 0, 0, 0};
       gen_mac4<R, NX, false>(a, s.BtV, NX, i, s.Bm, NU, j0);
       Quad<R>& q = *reinterpret_cast<Quad<R>*>(s.Quu + i * NU + j0);
-      for (int c = 0; c < 4; ++c) q.v[c] += a[c] + ((i == j0 + c) ? P.reg : (R)0);
+      for (int c = 0; c < 4; ++c) q.v[c] += a[c] + ((i == j0 + c) ? quu_reg : (R)0);
     }
   } else {
   for (int idx = tid; idx < nx * nx; idx += DT::tpe) {
@@ -572,7 +576,7 @@ __device__ bool gen_value_step(const DevProblem<R>& P, const DT& d, GenSmem<R>& 
     const int i = idx / nu, j = idx % nu;
     R a = 0;
     for (int k = 0; k < nx; ++k) a += s.BtV[i * nx + k] * s.Bm[k * nu + j];
-    s.Quu[idx] += a + ((i == j) ? P.reg : (R)0);
+    s.Quu[idx] += a + ((i == j) ? quu_reg : (R)0);
   }
   }
   for (int i = tid; i < nx; i += DT::tpe) {
@@ -590,15 +594,21 @@ __device__ bool gen_value_step(const DevProblem<R>& P, const DT& d, GenSmem<R>& 
   const R reg2 = kkt ? (R)1e-8 * P.reg : P.reg;
   for (int idx = tid; idx < nu * nr; idx += DT::tpe) {
     const int i = idx / nr, j = idx % nr;
-    s.rhs[idx] = (j < nx) ? s.Qxu[j * nu + i] : s.qu[i];
+    const R r = (j < nx) ? s.Qxu[j * nu + i] : s.qu[i];
+    s.rhs[idx] = (exact && tight_t[i]) ? (R)0 : r;
   }
-  for (int idx = tid; idx < nu * nu; idx += DT::tpe) s.L[idx] = s.Quu[idx] + ((idx / nu == idx % nu) ? reg2 : (R)0);
+  for (int idx = tid; idx < nu * nu; idx += DT::tpe) {
+    const int i = idx / nu, j = idx % nu;
+    R l = s.Quu[idx] + ((i == j) ? reg2 : (R)0);
+    if (exact && (tight_t[i] || tight_t[j])) l = (i == j) ? (R)1 : (R)0;
+    s.L[idx] = l;
+  }
   DT::sync();
   // Without input bounds nothing can be tight and the box QP of the KKT pass (utils.py:66-124 with +-inf bounds) is
   // its own first Newton step, x = -H^-1 q, accepted at the first convergence check: k_t is then one more
   // right-hand side of the gain solve below (Q_uu vs Q_uu + 1e-8 reg I: 1e-14 apart) instead of ~3 single-thread
   // LU factorisations per step, which were 55 % of this kernel's instructions (profiles/r1_backward_generic).
-  const bool box = P.has_umin || P.has_umax;
+  const bool box = (P.has_umin || P.has_umax) && !exact;   // exact: k_t is one more column of the masked solve
   if (tid == 0) {
     if (kkt && !box) {
       if constexpr (DT::fixed) gen_lu_reg<R, DT::NU>(s.L, s.piv); else gen_lu<R>(s.L, nu, s.piv);

@@ -21,7 +21,8 @@ def G():
     return gpu_common
 
 
-@pytest.mark.parametrize("name", ["di_f64", "cartpole_shared_f64", "cartpole_actor_f64", "unicycle_tight_f64", "unicycle_loose_f64"])
+@pytest.mark.parametrize("name", ["di_f64", "cartpole_shared_f64", "cartpole_actor_f64", "unicycle_tight_f64", "unicycle_loose_f64",
+                                  "lti8_f64", "lti8_T50_f64", "lti8_mixed_f64"])   # lti8_*: the generic (run-time dimension) kernel
 def test_exact_kernel_matches_numpy_restatement(G, name):
     from tacdmpc_b200 import ops
     g = P.load(name)
@@ -45,7 +46,9 @@ def test_exact_kernel_matches_numpy_restatement(G, name):
         if got.shape != exp.shape:            # shared inputs: the kernel returns the sum over the batch
             exp = exp.sum(0).reshape(got.shape) if got.size * B == exp.size else exp.reshape(got.shape)
         scale = max(np.abs(exp).max(), 1.0)
-        assert np.abs(got - exp).max() / scale <= 1e-9, (nm, np.abs(got - exp).max() / scale)
+        # T = 50 on the (unstable) random LTI system: the value function grows to 1e6 and the two LU orders part at 1e-7
+        tol = 1e-6 if name == "lti8_T50_f64" else 1e-9
+        assert np.abs(got - exp).max() / scale <= tol, (nm, np.abs(got - exp).max() / scale)
     assert float(out["grad_x0"].abs().max()) > 0     # no longer identically zero (quirk Q3)
 
 
