@@ -151,6 +151,41 @@ def test_device_env_manager_and_rollout():
     assert torch.isfinite(ret).all() and (adv <= 0).all()   # rewards are non-positive
 
 
+def test_graphed_policy_replays_on_new_observations():
+    """ActorMPC.graphed: cost network + whole solve + sampling as one CUDA-graph replay; every replay must be a valid
+    policy call on ITS observations (the plan starts at the observation, is the rollout of its own inputs) and agree with
+    the eager call up to what the random 0.01-sigma warm start moves the solution."""
+    from tacdmpc_b200 import ops
+    from tacdmpc_b200.ACMPC import ActorMPC, cartpole_envs, collect_rollout
+    from tacdmpc_b200.dynamics import CartPole
+    torch.manual_seed(0)
+    f = CartPole()
+    actor = ActorMPC(4, 1, 12, 0.05, f_dyn=f, f_dyn_jac=f.jac, device="cuda", grad_method="analytic")
+    pol = actor.graphed(64, deterministic=True)
+    spec = actor.mpc._last_spec
+    for seed in (1, 2, 3):
+        obs = torch.rand(64, 4, device="cuda", generator=torch.Generator(device="cuda").manual_seed(seed)) * 0.45 - 0.2
+        a, lp, Xp, Up = pol(obs)
+        assert a.shape == (64, 1) and lp.shape == (64,) and Xp.shape == (64, 13, 4) and Up.shape == (64, 12, 1)
+        assert torch.equal(Xp[:, 0], obs) and torch.equal(a, Up[:, 0])
+        assert float((ops.rollout(spec, obs, Up) - Xp).abs().max()) < 1e-5
+        with torch.no_grad():
+            ae, _, _, Ue = actor(obs, deterministic=True)
+        assert float((Ue - Up).abs().max()) < 5e-2 * max(1.0, float(Ue.abs().max()))
+    with pytest.raises(RuntimeError, match="captured"):
+        pol(torch.zeros(3, 4, device="cuda"))
+    # an optimiser step between replays is seen (weights are read at replay time)
+    with torch.no_grad():
+        for p_ in actor.cost_map_net.parameters():
+            p_.add_(0.05 * torch.randn_like(p_))
+    a2, _, _, _ = pol(obs)
+    assert not torch.equal(a2, a)
+    # the rollout phase with the graphed policy
+    envs = cartpole_envs(64, "cuda", max_steps=50)
+    buf = collect_rollout(actor.graphed(64), envs, 10)
+    assert buf["states"].shape == (64, 10, 4) and torch.isfinite(buf["rewards"]).all() and buf["pred_actions"].shape == (64, 10, 12, 1)
+
+
 def test_ppo_glue_rejects_cpu_tensors():
     from tacdmpc_b200 import _lib, ops
     with pytest.raises(_lib.TacdError, match="CUDA"):
