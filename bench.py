@@ -407,26 +407,34 @@ def main():
                     slots[slot][k].copy_(pin[k], non_blocking=True)
             ev_up[slot].record(copy_s)
 
-    def step_body(slot):
-        """One public-API step on the inputs of `slot`: solve, loss, backward, read-back of the result."""
+    def step_core(slot):
+        """The device part of one public-API step on the inputs of `slot`: solve, loss, backward, read-back of the
+        actions.  Returns the gradient that is read back (this rank's contribution when sharded)."""
         x0 = slots[slot]["x0"]
         Cd.grad = xr_dev.grad = ur_dev.grad = x0.grad = None
         X, U = mpc(x0, slots[slot]["Uinit"])
         U[:, 0].sum().backward()
-        gC = Cd.grad if args.layout == "shared" else Cd.grad[0]   # per-element: grads stay on the device, read one back
+        act_host.copy_(U.detach()[:, 0], non_blocking=True)
+        return Cd.grad if args.layout == "shared" else Cd.grad[0]   # per-element: grads stay on the device, read one back
+
+    def step_tail(gC):
+        """Cross-rank sum of the shared-cost gradient (the path's only collective) and its read-back."""
         if world > 1:
             sharding.allreduce_sum_([gC])
-        act_host.copy_(U.detach()[:, 0], non_blocking=True)
         gC_host.copy_(gC, non_blocking=True)
+
+    def step_body(slot):
+        step_tail(step_core(slot))
 
     for sl in slots:
         sl["x0"].requires_grad_(True)
     # The solve never synchronises the host and allocates only through torch's allocator, so a whole step
     # (forward, autograd backward, read-back) is CUDA-graph capturable: one graph per input slot removes the
-    # ~0.2 ms of Python / launch gaps per step that the eager loop leaves between kernels.  Single process only
-    # (the NCCL all-reduce of the sharded case stays eager); falls back to eager if capture fails.
+    # ~0.2 ms of Python / launch gaps per step that the eager loop leaves between kernels.  The NCCL all-reduce of the
+    # sharded case and the gradient read-back stay outside the graph (step_tail); falls back to eager if capture fails.
     graphs = None
-    if world == 1 and not os.environ.get("TACD_BENCH_NO_GRAPH"):
+    g_static = [None, None]
+    if not os.environ.get("TACD_BENCH_NO_GRAPH"):
         try:
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(comp_s)
@@ -443,8 +451,9 @@ def main():
             for sl in range(2):
                 g_ = torch.cuda.CUDAGraph()
                 Cd.grad = xr_dev.grad = ur_dev.grad = slots[sl]["x0"].grad = None
-                with torch.cuda.graph(g_):
-                    step_body(sl)
+                # (thread_local: the NCCL watchdog thread of a sharded run may query events while this thread captures)
+                with torch.cuda.graph(g_, capture_error_mode="thread_local"):
+                    g_static[sl] = step_core(sl)
                 graphs.append(g_)
         except Exception as ex:   # noqa: BLE001
             print(f"[bench] CUDA-graph capture of the e2e step failed ({type(ex).__name__}: {ex}); eager loop", file=sys.stderr)
@@ -465,6 +474,7 @@ def main():
             comp_s.wait_event(ev_up[slot])
             if graphs is not None:
                 graphs[slot].replay()
+                step_tail(g_static[slot])
             else:
                 step_body(slot)
             ev_free[slot].record(comp_s)
