@@ -677,6 +677,12 @@ static FwdPtrs<R> fwd_ptrs(const tacd_forward_io* io) {
 #define TACD_GEN_SIZES(X) X(8, 4) X(16, 4) X(16, 8) X(32, 8)
 static bool gen_runtime_dims() { static const bool v = getenv("TACD_GENERIC_RUNTIME_DIMS") != nullptr; return v; }
 
+// one warp per element only if four element slots (matrices alone) fit the CTA's shared memory
+template <typename R>
+static bool gen_warp_mode(const tacd_problem* p) {
+  return gen_tpe(p) == 32 && gen_elem_bytes<R>(p->nx, p->nu, 0) * (kGenThreads / 32) <= (size_t)device_info().smem_optin;
+}
+
 // Shared memory of one launch: per element slot the matrices and, when enough slots per SM still fit, the element's
 // X, U, K, k (global-memory round trips inside the per-step loops were the bulk of the time otherwise).
 struct GenLaunch { int grid; size_t smem; bool in_smem; };
@@ -707,7 +713,7 @@ static int run_forward_generic(const tacd_problem* p, const tacd_forward_io* io,
 
 template <typename R>
 int launch_forward_generic(const tacd_problem* p, const tacd_forward_io* io, void* ws, size_t ws_bytes, cudaStream_t s) {
-  const bool warp = gen_tpe(p) == 32;
+  const bool warp = gen_warp_mode<R>(p);
   if (!gen_runtime_dims()) {
 #define X(NX_, NU_) if (p->nx == NX_ && p->nu == NU_) \
     return warp ? run_forward_generic<R, NX_, NU_, 32>(p, io, ws, ws_bytes, s) : run_forward_generic<R, NX_, NU_, kGenThreads>(p, io, ws, ws_bytes, s);
@@ -745,7 +751,7 @@ static int run_backward_generic(const tacd_problem* p, const tacd_backward_io* i
 
 template <typename R>
 int launch_backward_generic(const tacd_problem* p, const tacd_backward_io* io, void* ws, size_t ws_bytes, cudaStream_t s) {
-  const bool warp = gen_tpe(p) == 32;
+  const bool warp = gen_warp_mode<R>(p);
   if (!gen_runtime_dims()) {
 #define X(NX_, NU_) if (p->nx == NX_ && p->nu == NU_) \
     return warp ? run_backward_generic<R, NX_, NU_, 32>(p, io, ws, ws_bytes, s) : run_backward_generic<R, NX_, NU_, kGenThreads>(p, io, ws, ws_bytes, s);

@@ -126,3 +126,81 @@ def test_non_finite_inputs_terminate(G):
     good[[5, 9]] = False
     assert np.isfinite(U[good]).all() and (it[good] >= 2).all()
     assert (it[~good] <= 40).all() and not np.isfinite(out["cost"].cpu().numpy()[~good]).any()
+
+
+# ---- the run-time-dimension kernels (csrc/ilqr_generic.cu): warp-per-element (nx <= 16) and CTA-per-element modes,
+# compile-time-size instances ((8,4), (16,8), (32,8)) and the run-time fallback (5,2), (20,3), ragged batches that do
+# not fill a four-element CTA, with and without the input box (box QP in the KKT pass)
+GEN_CASES = [
+    # nx, nu, T, B, dtype, per_element, bounds
+    (5, 2, 7, 1, np.float64, False, True),
+    (5, 2, 12, 7, np.float32, True, False),
+    (8, 4, 10, 5, np.float64, True, True),
+    (8, 4, 25, 130, np.float32, False, False),
+    (16, 8, 6, 9, np.float64, False, True),
+    (16, 4, 8, 3, np.float32, True, False),
+    (20, 3, 5, 6, np.float64, True, True),
+    (32, 8, 4, 5, np.float64, False, False),
+    (32, 8, 6, 3, np.float32, True, True),
+]
+
+
+def _lti_problem(nx, nu, T, B, dtype, seed, per_element, bounds):
+    rng = np.random.default_rng(seed)
+    n = nx + nu
+    A = np.eye(nx) * 0.9 + 0.3 * rng.standard_normal((nx, nx)) / np.sqrt(nx)
+    A *= 0.95 / np.abs(np.linalg.eigvals(A)).max()   # spectral radius 0.95: an unstable A over T = 25 is ill-conditioned in
+    #                                                  fp32 to the point where the fp32 and fp64 oracles part by 3-90 % (measured)
+    Bm = 0.3 * rng.standard_normal((nx, nu))
+    w = rng.uniform(0.5, 1.5, n)
+    w[nx:] *= 0.2
+    M = 0.05 * rng.standard_normal((n, n))
+    C = np.tile(np.diag(w) + M @ M.T, (T, 1, 1)) * (1 + 0.02 * np.arange(T))[:, None, None]
+    c = 0.1 * rng.standard_normal((T, n))
+    Cf = np.zeros((n, n))
+    Cf[:nx, :nx] = 3 * C[0, :nx, :nx]
+    cf = np.zeros(n)
+    cf[:nx] = 0.1 * rng.standard_normal(nx)
+    if per_element:
+        s = rng.uniform(0.5, 1.5, (B, 1, 1, 1))
+        C, c = C[None] * s, np.tile(c, (B, 1, 1))
+        Cf, cf = Cf[None] * s[:, 0], np.tile(cf, (B, 1))
+    spec = dict(nx=nx, nu=nu, T=T, dt=0.05, dyn="lti", A=A, B=Bm, reg_eps=1e-6, max_iter=40)
+    if bounds:
+        spec.update(u_min=[-0.4] * nu, u_max=[0.4] * nu)
+    d = dict(x0=rng.standard_normal((B, nx)), C=C, c=c, Cf=Cf, cf=cf, xref=0.1 * rng.standard_normal((B, T + 1, nx)),
+             uref=0.05 * rng.standard_normal((B, T, nu)), Uinit=0.01 * rng.standard_normal((B, T, nu)))
+    return spec, {k: v.astype(dtype) for k, v in d.items()}
+
+
+@pytest.mark.parametrize("case", GEN_CASES, ids=lambda c: f"nx{c[0]}-nu{c[1]}-T{c[2]}-B{c[3]}-{np.dtype(c[4]).name}-pe{int(c[5])}-box{int(c[6])}")
+def test_generic_kernels_against_oracle(G, oracle, case):
+    from tacdmpc_b200 import ops
+    nx, nu, T, B, dtype, per_element, bounds = case
+    spec, d = _lti_problem(nx, nu, T, B, dtype, seed=nx * 1000 + T * 10 + B, per_element=per_element, bounds=bounds)
+    s = G.gpu_spec(spec, dtype)
+    dv = G.dev
+    ls = (d["C"][0], d["c"][0], d["Cf"][0], d["cf"][0]) if per_element else None
+    out = ops.ilqr_forward(s, dv(d["x0"]), dv(d["C"]), dv(d["c"]), dv(d["Cf"]), dv(d["cf"]), dv(d["xref"]), dv(d["uref"]), dv(d["Uinit"]),
+                           ls_cost=None if ls is None else tuple(dv(a) for a in ls))
+    torch.cuda.synchronize()
+    o = {k: v.cpu().numpy() for k, v in out.items()}
+    rp = dict(iters=o["iters"], alpha_trace=o["alpha_trace"], flags=o["flags"])
+    ref = oracle.forward(spec, d["x0"], d["C"], d["c"], d["Cf"], d["cf"], d["xref"], d["uref"], d["Uinit"], ls_cost=ls, replay=rp)
+    tol = 2e-4 if dtype == np.float32 else 1e-9
+    for k in ("X", "U"):
+        scale = max(1.0, np.abs(ref[k]).max())
+        assert np.abs(o[k].astype(np.float64) - ref[k]).max() / scale <= tol, (k, np.abs(o[k] - ref[k]).max())
+    assert np.array_equal(o["tight"].astype(bool), ref["tight"].astype(bool))
+    if bounds:
+        assert o["tight"].any()                       # the box is exercised
+    rng = np.random.default_rng(2)
+    gX, gU = rng.standard_normal(o["X"].shape).astype(dtype), rng.standard_normal(o["U"].shape).astype(dtype)
+    want = ("grad_C", "grad_c", "grad_Cf", "grad_cf", "grad_x0", "grad_xref", "grad_uref")
+    bw = ops.ilqr_backward(s, out["X"], out["U"], dv(d["C"]), dv(d["xref"]), dv(d["uref"]), out["tight"], dv(gX), dv(gU),
+                           Cf_batched=per_element, want=want)
+    rb = oracle.backward(spec, o["X"], o["U"], d["C"], d["xref"], d["uref"], o["tight"], gX, gU, Cf_batched=int(per_element))
+    for nm in want:
+        got, exp = bw[nm].cpu().numpy().astype(np.float64), rb[nm]
+        scale = max(1.0, np.abs(exp).max())
+        assert np.abs(got - exp.reshape(got.shape)).max() / scale <= 50 * tol, (nm, np.abs(got - exp.reshape(got.shape)).max() / scale)
