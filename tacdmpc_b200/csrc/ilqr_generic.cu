@@ -6,6 +6,13 @@
 #include "host_common.h"
 #include "ilqr_generic.cuh"
 
+// The whole-solve kernels are instantiated for 5 sizes x 2 element mappings x 2 dtypes; to keep the build parallel the
+// file is compiled four times (build.py): part 0 = fp32 forward + the stand-alone stages + the C entry points (this
+// file as is), parts 1-3 = fp32 backward / fp64 forward / fp64 backward through ilqr_generic_part{1,2,3}.cu.
+#ifndef TACD_GEN_PART
+#define TACD_GEN_PART 0
+#endif
+
 namespace tacd {
 
 // per-CTA slice of the workspace: X[(T+1)nx] U[T nu] K[T nu nx] k[T nu]
@@ -32,6 +39,7 @@ static int gen_slots(const tacd_problem* p, int tpe) {
   return g < 1 ? 1 : g;
 }
 static int gen_grid(const tacd_problem* p) { return gen_slots(p, kGenThreads); }
+#if TACD_GEN_PART == 0
 size_t generic_forward_ws_bytes(const tacd_problem* p) {
   const size_t es = (p->dtype == TACD_F32) ? 4 : 8;
   int sms = 148;
@@ -40,6 +48,7 @@ size_t generic_forward_ws_bytes(const tacd_problem* p) {
   return g * gen_slice_scalars(p) * es + 256;
 }
 size_t generic_backward_ws_bytes(const tacd_problem* p) { return generic_forward_ws_bytes(p); }
+#endif
 
 template <typename R, int NXT = 0, int NUT = 0, int TPE = kGenThreads>
 static GenDims<R, NXT, NUT, TPE> dims_of(const tacd_problem* p) {
@@ -761,10 +770,17 @@ int launch_backward_generic(const tacd_problem* p, const tacd_backward_io* io, v
   return warp ? run_backward_generic<R, 0, 0, 32>(p, io, ws, ws_bytes, s) : run_backward_generic<R, 0, 0, kGenThreads>(p, io, ws, ws_bytes, s);
 }
 
+#if TACD_GEN_PART == 0
 template int launch_forward_generic<float>(const tacd_problem*, const tacd_forward_io*, void*, size_t, cudaStream_t);
-template int launch_forward_generic<double>(const tacd_problem*, const tacd_forward_io*, void*, size_t, cudaStream_t);
+#elif TACD_GEN_PART == 1
 template int launch_backward_generic<float>(const tacd_problem*, const tacd_backward_io*, void*, size_t, cudaStream_t);
+#elif TACD_GEN_PART == 2
+template int launch_forward_generic<double>(const tacd_problem*, const tacd_forward_io*, void*, size_t, cudaStream_t);
+#else
 template int launch_backward_generic<double>(const tacd_problem*, const tacd_backward_io*, void*, size_t, cudaStream_t);
+#endif
+
+#if TACD_GEN_PART == 0   // stand-alone stages and the C entry points: once
 
 template <typename R>
 static int stage_common(const tacd_problem* p) {
@@ -827,8 +843,10 @@ static int run_linesearch(const tacd_problem* p, const void* x0, const void* X, 
   return check_cuda(cudaPeekAtLastError(), "stage_linesearch launch");
 }
 
+#endif  // TACD_GEN_PART == 0
 }  // namespace tacd
 
+#if TACD_GEN_PART == 0
 using namespace tacd;
 
 #define TACD_DISPATCH(p, fn, ...) ((p)->dtype == TACD_F32 ? fn<float>(__VA_ARGS__) : fn<double>(__VA_ARGS__))
@@ -928,3 +946,4 @@ int tacd_pnqp(int32_t dtype, int32_t N, int32_t m, const void* H, const void* q,
 }
 
 }  // extern "C"
+#endif  // TACD_GEN_PART == 0
