@@ -472,6 +472,25 @@ __device__ R gen_objective(const DT& d, GenSmem<R>& s, const R* X, const R* U, c
 // loops need 2.  The sum over k runs in the same (ascending) order, so results are bit-identical to those loops.
 template <typename R>
 struct alignas(16) Quad { R v[4]; };
+// acc[0..3] += l * r[0..3].  fp32: two packed FFMA2 (sm_100's fma.rn.f32x2; ptxas folds the {l, l} pair into the
+// instruction's scalar-broadcast operand) — the same two IEEE fused multiply-adds per instruction, half the issue slots.
+template <typename R>
+__device__ __forceinline__ void gen_axpy4(R (&acc)[4], R l, const Quad<R>& r) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) acc[c] += l * r.v[c];
+}
+template <>
+__device__ __forceinline__ void gen_axpy4<float>(float (&acc)[4], float l, const Quad<float>& r) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    unsigned long long lb, rb, ab;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(lb) : "f"(l));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(r.v[2 * h]), "f"(r.v[2 * h + 1]));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ab) : "f"(acc[2 * h]), "f"(acc[2 * h + 1]));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(ab) : "l"(lb), "l"(rb));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[2 * h]), "=f"(acc[2 * h + 1]) : "l"(ab));
+  }
+}
 // acc[c] += sum_k L(k, i) * Rm[k * ldr + j0 + c];  LT: L is indexed [k][i] (a transposed read), else [i][k]
 template <typename R, int K, bool LT>
 __device__ __forceinline__ void gen_mac4(R (&acc)[4], const R* L, int ldl, int i, const R* Rm, int ldr, int j0) {
@@ -480,8 +499,7 @@ __device__ __forceinline__ void gen_mac4(R (&acc)[4], const R* L, int ldl, int i
     for (int k = 0; k < K; ++k) {
       const R l = L[k * ldl + i];
       const Quad<R> r = *reinterpret_cast<const Quad<R>*>(Rm + k * ldr + j0);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) acc[c] += l * r.v[c];
+      gen_axpy4<R>(acc, l, r);
     }
   } else {
     static_assert(K % 4 == 0, "left rows are read four entries at a time");
@@ -491,8 +509,7 @@ __device__ __forceinline__ void gen_mac4(R (&acc)[4], const R* L, int ldl, int i
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
         const Quad<R> r = *reinterpret_cast<const Quad<R>*>(Rm + (k + kk) * ldr + j0);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) acc[c] += l.v[kk] * r.v[c];
+        gen_axpy4<R>(acc, l.v[kk], r);
       }
     }
   }
