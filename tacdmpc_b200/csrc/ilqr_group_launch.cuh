@@ -167,7 +167,7 @@ static int run_backward_group(const tacd_problem* p, const tacd_backward_io* io,
   note_launches(1);
   if (int rc = check_cuda(cudaPeekAtLastError(), "ilqr_backward_group launch")) return rc;
   if (reduce) {
-    reduce_shared_grads<R, NX, NU><<<(nacc + 127) / 128, 128, 0, s>>>(dp, f, partials, grid);
+    reduce_shared_grads<R, NX, NU><<<(nacc * kReduceSeg + 127) / 128, 128, 0, s>>>(dp, f, partials, grid);
     note_launches(1);
     return check_cuda(cudaPeekAtLastError(), "reduce_shared_grads launch");
   }
