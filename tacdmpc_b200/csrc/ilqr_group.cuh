@@ -213,7 +213,9 @@ TACD_DEV void load_cost_vec(const R* p, R (&Ct)[N * N], R (&ct)[N]) {
 // e conflict-free), X_t is written over the slot of x_ref[t] once that has been read and leaves as
 // coalesced rows; per-element costs come in the same way, `chunk` time steps at a time: the whole horizon
 // in one piece when the tile fits (one DRAM latency for everything), else double-buffered one chunk ahead.
-__host__ __device__ inline int init_in_words(int T, int nx, int nu) { return ((T + 1) * nx + 2 * T * nu) | 1; }
+// (U_init is read straight from global memory, one step ahead: with it in the tile a cart-pole T=20 CTA needs 17 KB, 13
+// fit an SM, and the 2048 tiles of B = 65 536 take 1.06 waves — the kernel lasted two passes, 45 us; without it 16 fit)
+__host__ __device__ inline int init_in_words(int T, int nx, int nu) { return ((T + 1) * nx + T * nu) | 1; }
 // row stride of a cost tile: chunk steps of [C_t (cw words: n*n dense, n compact diagonal)] then chunk steps of c_t
 __host__ __device__ inline int init_cost_words(int chunk, int nx, int nu, int C_diag) {
   const int n = nx + nu;
@@ -240,7 +242,7 @@ __global__ void __launch_bounds__(128) ilqr_init_rollout(const DevProblem<R> P, 
   const int T = P.T, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int XW = (T + 1) * NX, UW = T * NU, RSI = init_in_words(T, NX, NU), RSC = init_cost_words(chunk, NX, NU, P.C_diag);
   const int cw = P.C_diag ? N : N * N;   // words of C per step (compact diagonal or dense)
-  // row of one element: [x_ref -> X (XW) | u_ref (UW) | U_init (UW)]
+  // row of one element: [x_ref -> X (XW) | u_ref (UW)]
   R* tile = reinterpret_cast<R*>(smem_raw) + (size_t)wid * init_warp_words(T, NX, NU, P.C_batched, P.C_diag, chunk);
   R* ctile = tile + (size_t)32 * RSI;   // [1 or 2][32][RSC]: [C_t0.. (chunk*cw) | c_t0.. (chunk*N)]
   const int nbuf = chunk >= T ? 1 : 2;
@@ -265,9 +267,8 @@ __global__ void __launch_bounds__(128) ilqr_init_rollout(const DevProblem<R> P, 
     R* row = tile + (size_t)r * RSI;
     const R* xr = io.xref + (P.xref_batched ? (size_t)(b0 + r) * XW : 0);
     const R* ur = io.uref + (P.uref_batched ? (size_t)(b0 + r) * UW : 0);
-    const R* ui = io.Uinit + (size_t)(b0 + r) * UW;
     for (int w = lane; w < XW; w += 32) cp_async<R>(&row[w], &xr[w]);
-    for (int w = lane; w < UW; w += 32) { cp_async<R>(&row[XW + w], &ur[w]); cp_async<R>(&row[XW + UW + w], &ui[w]); }
+    for (int w = lane; w < UW; w += 32) cp_async<R>(&row[XW + w], &ur[w]);
   }
   fetch_cost(0);   // group 0: inputs + first cost chunk
   fetch_cost(1);
@@ -278,11 +279,13 @@ __global__ void __launch_bounds__(128) ilqr_init_rollout(const DevProblem<R> P, 
   const R* cfp = io.cf + (P.Cf_batched ? (size_t)b * N : 0);
   R* row = tile + (size_t)(lane < nlive ? lane : nlive - 1) * RSI;
   const R* ur = row + XW;
-  const R* ui = row + XW + UW;
-  R x[NX], u[NU], xn[NX];
+  const R* ui = io.Uinit + (size_t)b * UW;
+  R x[NX], u[NU], un[NU], xn[NX];
   R quad = 0, lin = 0;
 #pragma unroll
   for (int i = 0; i < NX; ++i) x[i] = io.x0[(size_t)b * NX + i];
+#pragma unroll
+  for (int i = 0; i < NU; ++i) un[i] = ui[i];
   for (int c = 0; c < nchunk; ++c) {
     cp_async_wait_group<1>();
     __syncwarp();
@@ -291,7 +294,7 @@ __global__ void __launch_bounds__(128) ilqr_init_rollout(const DevProblem<R> P, 
     for (int t = t0; t < t1; ++t) {
       R tau[N], Ct[N * N], ct[N];
 #pragma unroll
-      for (int i = 0; i < NU; ++i) u[i] = ui[t * NU + i];
+      for (int i = 0; i < NU; ++i) { u[i] = un[i]; un[i] = ui[(t + 1 < T ? t + 1 : t) * NU + i]; }
 #pragma unroll
       for (int i = 0; i < NX; ++i) { tau[i] = x[i] - row[t * NX + i]; row[t * NX + i] = x[i]; }
 #pragma unroll
