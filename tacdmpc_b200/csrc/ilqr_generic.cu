@@ -1,4 +1,4 @@
-// ilqr_generic.cu — CTA-per-element whole-solve kernels for run-time dimensions,
+// ilqr_generic.cu — CTA- / warp-per-element whole-solve kernels for run-time dimensions,
 // plus the stand-alone stage entry points of the C ABI (rollout, linearize,
 // objective, riccati, linesearch, pnqp).  See ilqr_generic.cuh for the layout.
 #include <stdlib.h>

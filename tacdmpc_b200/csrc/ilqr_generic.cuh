@@ -1,13 +1,12 @@
-// ilqr_generic.cuh — run-time-dimension kernels: ONE CTA PER BATCH ELEMENT.
+// ilqr_generic.cuh — run-time-dimension kernels: one CTA (nx > 16) or one warp (nx <= 16) per batch element.
 //
-// Covers every (nx <= 64, nu <= 16, dynamics) the thread-per-element kernels have
-// no instantiation for (config 5: LTI nx in {8,16,32}, nu in {4,8}, T=50) and the
-// stand-alone stage entry points.  Per-step matrices (V, Q*, A, B, C_t, gains) live
-// in shared memory; the trajectory state that must survive between passes
-// (X, U, K, k) lives in a per-CTA slice of the caller's workspace (contiguous, so
-// CTA-wide accesses coalesce and the slice stays L2-resident).  Every matrix
-// product is a CTA-parallel loop over output entries; the nu x nu factorizations
-// and the box QP run on one thread.
+// Covers every (nx <= 64, nu <= 16, dynamics) the small-system kernels have no instantiation for (config 5: LTI
+// nx in {8,16,32}, nu in {4,8}, T=50; Python dynamics with external Jacobians) and the stand-alone stage entry
+// points.  Per-step matrices (V, Q*, A, B, C_t, gains) live in shared memory; the trajectory state that must survive
+// between passes (X, U, K, k) sits right behind them when enough element slots per SM still fit, else in a
+// per-slot slice of the caller's workspace (contiguous, L2-resident).  Every matrix product is a loop over output
+// entries (or, for the compile-time-size instances, over 1x4 register tiles) spread over the element's threads; the
+// nu x nu factorisations and the box QP run on one thread (in registers for the compile-time sizes).
 #pragma once
 #include "tacd_dev.cuh"
 
