@@ -125,57 +125,22 @@ struct BwdPtrs {
   R *grad_C, *grad_c, *grad_Cf, *grad_cf, *grad_x0, *grad_xref, *grad_uref, *dX, *dU;
 };
 
-#ifndef TACD_QUAD_PACKED
-#define TACD_QUAD_PACKED 1
-#endif
-constexpr bool kQuadPacked = TACD_QUAD_PACKED != 0;
 constexpr int kNA = 5;  // line-search candidates rolled out together (the reference has 5 alphas)
 
 // words of shared memory per thread for the forward state
 __host__ __device__ inline int fwd_words(int T, int nx, int nu) { return (T + 1) * nx + T * nu + T * nu * nx + T * nu; }
 __host__ __device__ inline int bwd_words(int T, int nx, int nu) { return T * nu * nx + T * nu; }
 
-// (a0, a1) += s * (c0, c1) as ONE packed fp32 FMA (sm_100 fma.rn.f32x2 / SASS FFMA2; the {s, s} pair folds into the
-// instruction's scalar-broadcast operand): the same two IEEE fused multiply-adds, half the issue slots
-TACD_DEV void ffma2(float& a0, float& a1, float s, float c0, float c1) {
-  unsigned long long sb, cb, ab;
-  asm("mov.b64 %0, {%1, %1};" : "=l"(sb) : "f"(s));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(cb) : "f"(c0), "f"(c1));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(ab) : "f"(a0), "f"(a1));
-  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(ab) : "l"(sb), "l"(cb));
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(ab));
-}
-
 // tau^T C tau and c^T tau with C [N,N] row-major in registers
 template <typename R, int N>
 TACD_DEV void quad_terms(const R (&Ct)[N * N], const R (&ct)[N], const R (&tau)[N], R& quad, R& lin) {
-  if constexpr (sizeof(R) == 4 && kQuadPacked) {
-    // s_i = sum_j C[j][i] tau_j, two i at a time: tau' C tau = tau' C' tau, and for the symmetric C every caller passes
-    // these are the same products accumulated in the same order as the row form below (bit-identical); a non-symmetric
-    // C changes the rounding of the scalar, not its value
-    float s[N + 1];
 #pragma unroll
-    for (int i = 0; i < N + 1; ++i) s[i] = 0.f;
+  for (int i = 0; i < N; ++i) {
+    R s = 0;
 #pragma unroll
-    for (int j = 0; j < N; ++j) {
-#pragma unroll
-      for (int i = 0; i + 1 < N; i += 2) ffma2(s[i], s[i + 1], tau[j], Ct[j * N + i], Ct[j * N + i + 1]);
-      if (N & 1) s[N - 1] += Ct[j * N + N - 1] * tau[j];
-    }
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-      quad += tau[i] * s[i];
-      lin += ct[i] * tau[i];
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-      R s = 0;
-#pragma unroll
-      for (int j = 0; j < N; ++j) s += Ct[i * N + j] * tau[j];
-      quad += tau[i] * s;
-      lin += ct[i] * tau[i];
-    }
+    for (int j = 0; j < N; ++j) s += Ct[i * N + j] * tau[j];
+    quad += tau[i] * s;
+    lin += ct[i] * tau[i];
   }
 }
 
