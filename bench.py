@@ -113,19 +113,26 @@ class ClockSampler:
         self.rows, self.proc, self.index, self.uuid = [], None, index, uuid
         self.samples, self.max_mhz, self.reasons, self._stop, self.th, self.nvml = [], None, set(), False, None, None
 
-    def _nvml_loop(self):
-        n, h = self.nvml, self.handle
+    def sample(self):
+        """One NVML reading (also called from the timed loop itself, while the GPU works through the queued steps: the
+        polling thread alone can be starved by the interpreter lock for most of a 16 ms region)."""
+        n, h = self.nvml, getattr(self, "handle", None)
+        if n is None or h is None:
+            return
         bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
+        try:
+            self.samples.append(float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)))
+            r = int(n.nvmlDeviceGetCurrentClocksEventReasons(h)) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+                else int(n.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+            for name, b in bits.items():
+                if r & b:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def _nvml_loop(self):
         while not self._stop:
-            try:
-                self.samples.append(float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)))
-                r = int(n.nvmlDeviceGetCurrentClocksEventReasons(h)) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
-                    else int(n.nvmlDeviceGetCurrentClocksThrottleReasons(h))
-                for name, b in bits.items():
-                    if r & b:
-                        self.reasons.add(name)
-            except Exception:
-                pass
+            self.sample()
             time.sleep(0.001)
 
     def __enter__(self):
@@ -356,6 +363,8 @@ def main():
             if world > 1 and args.layout == "shared":
                 sharding.allreduce_sum_([bw["grad_C"], bw["grad_c"], bw["grad_Cf"], bw["grad_cf"]])
             ev[i][2].record()
+            if i >= 2:
+                clk.sample()               # the GPU is two or more steps behind the host here: a reading under load
         barrier()
         gpu_launches = int(_lib.lib().tacd_kernel_launches()) - launches0
         mean_iters = float(fw["iters"].float().mean().item())
