@@ -251,6 +251,11 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # Contract: stdout carries ONE JSON line.  Libraries write there too (NCCL prints "NCCL version ..." on the first
+    # communicator), so file descriptor 1 is pointed at stderr for the run and the line goes out through a saved copy.
+    sys.stdout.flush()
+    out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -279,7 +284,7 @@ def main():
                 "gpu_launches": 0,
                 "note": "CPU oracle (C restatement of the reference, OpenMP over the batch); the reference itself is "
                         "pure Python and cannot travel to the GPU box (DESIGN.md)"}
-        print(json.dumps(line))
+        print(json.dumps(line), file=out, flush=True)
         return 0
 
     # ---------------------------------------------------------------- B200 arm
@@ -551,7 +556,7 @@ def main():
                     "ms_per_step": 1e3 * t_e2e / args.steps, "mode": "cuda_graph" if graphs is not None else "eager",
                     "checked_against_device_solve": e2e_checked},
             "gpu_launches": gpu_launches, "roofline": roofline, "cpu_baseline": cpu}
-    print(json.dumps(line))
+    print(json.dumps(line), file=out, flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0
