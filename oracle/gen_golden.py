@@ -455,6 +455,46 @@ def closed_loop_batch_tracking():
     print("closed_loop_batch_tracking       Xs", d["Xs"].shape)
 
 
+def config1_di_closed_loop():
+    """SURVEY 8d config 1 = examples/01_demo_linear.py:94-169 as the script runs it (main() + run_simulation, plotting
+    left out): double integrator, B = 50, T = 20, 150 closed-loop steps, fp64, sinusoid references with amplitude
+    U(5,10) and frequency U(1,2) drawn after torch.manual_seed(0).  Position MSE 0.1296 for analytic and auto_diff
+    (SURVEY 8c "soft KAT")."""
+    torch.set_default_dtype(torch.float64)
+    torch.manual_seed(0)
+    B, DT, H, N_SIM, nx, nu = 50, 0.05, 20, 150, 2, 1
+    Q, R = torch.diag(torch.tensor([100.0, 1.0])), torch.diag(torch.tensor([0.01]))
+    C = torch.zeros(H, nx + nu, nx + nu)
+    C[:, :nx, :nx], C[:, nx:, nx:] = Q, R
+    c = torch.zeros(H, nx + nu)
+    Cf, cf = C[0].clone() * 10, torch.zeros(nx + nu)
+    cm = GeneralQuadCost(nx, nu, C, c, Cf, cf, device="cpu")
+    ref_len = N_SIM + H + 1
+    t_full = torch.arange(ref_len) * DT
+    amp = 5.0 + torch.rand(B, 1) * 5.0
+    om = 1.0 + torch.rand(B, 1) * 1.0
+    xref = torch.stack([amp * torch.sin(om * t_full.unsqueeze(0)), amp * om * torch.cos(om * t_full.unsqueeze(0))], dim=2)
+    uref = torch.zeros(B, ref_len - 1, nu)
+    res = {}
+    for gm, jac in (("analytic", EX1.f_dyn_jac_linear_batched), ("auto_diff", None)):
+        mpc = DifferentiableMPCController(f_dyn=EX1.f_dyn_linear, total_time=H * DT, step_size=DT, horizon=H, cost_module=cm,
+                                          u_min=torch.tensor([-50.0]), u_max=torch.tensor([50.0]), grad_method=gm, f_dyn_jac=jac,
+                                          device="cpu")
+        x = torch.zeros(B, nx)
+        xs, us = [x], []
+        for k in range(N_SIM):
+            mpc.cost_module.set_reference(x_ref=xref[:, k:k + H + 1], u_ref=uref[:, k:k + H])
+            _, U = mpc.forward(x)
+            us.append(U[:, 0, :])
+            x = EX1.f_dyn_linear(x, U[:, 0, :], DT)
+            xs.append(x)
+        Xs, Us = torch.stack(xs, 1), torch.stack(us, 1)
+        res[gm] = (Xs, Us, torch.mean((Xs[:, :, 0] - xref[:, :N_SIM + 1, 0]) ** 2).item())
+    np.savez_compressed(os.path.join(OUT, "config1_di_closed_loop.npz"), amp=_np(amp), om=_np(om), Xs=_np(res["analytic"][0]),
+                        Us=_np(res["analytic"][1]), mse_analytic=res["analytic"][2], mse_auto_diff=res["auto_diff"][2])
+    print("config1_di_closed_loop           MSE analytic", res["analytic"][2], "auto_diff", res["auto_diff"][2])
+
+
 def closed_loop_unicycle_warm():
     """examples/03_demo_unicycle_tracking.py:119-141: two unicycle agents track lemniscates in closed loop, the
     solve warm-started with the previous plan shifted by one step (torch.roll, last input zeroed)."""
@@ -588,6 +628,7 @@ def main():
     run_case("gradcheck_f64", **case_gradcheck())
     closed_loop_batch_tracking()
     closed_loop_unicycle_warm()
+    config1_di_closed_loop()
     pnqp_kats()
 
 

@@ -98,3 +98,32 @@ def test_cartpole_regulation_closed_loop_fp32_large_batch():
     assert X.shape == (B, N + 1, nx) and U.shape == (B, N, nu)
     assert torch.isfinite(X).all() and float(X[:, -1, 2].abs().max()) < 0.05      # pole upright after 3 s
     assert float(U.abs().max()) <= 20.0
+
+
+@pytest.mark.parametrize("grad_method", ["analytic", "auto_diff"])
+def test_config1_double_integrator_demo_known_answer(grad_method):
+    """SURVEY §8d config 1 / §8c soft KAT: examples/01_demo_linear.py as the script runs it (B = 50, T = 20, 150
+    closed-loop steps, fp64, references drawn after torch.manual_seed(0), cold start every step): position MSE 0.1296
+    for both Jacobian modes, and the recorded closed loop of the unmodified reference state for state."""
+    from tacdmpc_b200.DifferentialMPC import DifferentiableMPCController, GeneralQuadCost
+    from tacdmpc_b200.dynamics import DoubleIntegrator
+    g = np.load(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "config1_di_closed_loop.npz"))
+    B, DT, H, N_SIM, nx, nu = 50, 0.05, 20, 150, 2, 1
+    dd = dict(device="cuda", dtype=torch.float64)
+    C = torch.zeros(H, 3, 3, **dd)
+    C[:, 0, 0], C[:, 1, 1], C[:, 2, 2] = 100.0, 1.0, 0.01
+    Cf = C[0].clone() * 10
+    cm = GeneralQuadCost(nx, nu, C, torch.zeros(H, 3, **dd), Cf, torch.zeros(3, **dd), device="cuda")
+    ref_len = N_SIM + H + 1
+    t_full = torch.arange(ref_len, **dd) * DT
+    amp, om = _t(g["amp"]), _t(g["om"])
+    xref = torch.stack([amp * torch.sin(om * t_full[None]), amp * om * torch.cos(om * t_full[None])], dim=2)
+    uref = torch.zeros(B, ref_len - 1, nu, **dd)
+    f = DoubleIntegrator(DT)
+    mpc = DifferentiableMPCController(f, H * DT, DT, H, cm, u_min=torch.tensor([-50.0]), u_max=torch.tensor([50.0]),
+                                      grad_method=grad_method, f_dyn_jac=f.jac if grad_method == "analytic" else None, device="cuda",
+                                      N_sim=N_SIM)
+    Xs, Us = mpc.forward(torch.zeros(B, nx, **dd), x_ref_full=xref, u_ref_full=uref, warm_start=False)
+    mse = float(torch.mean((Xs[:, :, 0] - xref[:, :N_SIM + 1, 0]) ** 2))
+    assert abs(mse - 0.1296) < 5e-5 and abs(mse - float(g["mse_" + grad_method])) < 1e-9
+    assert np.abs(Xs.cpu().numpy() - g["Xs"]).max() < 1e-6 and np.abs(Us.cpu().numpy() - g["Us"]).max() < 1e-5

@@ -141,3 +141,33 @@ def test_finite_difference_jacobians(oracle, tag, dyn):
     tol = 2e-3 if tag == "f32" else 1e-9   # fp32 central differences with eps=1e-4 are noise-limited
     assert np.abs(A[:, 0] - g[f"{dyn}_{tag}_A"]).max() <= tol
     assert np.abs(Bm[:, 0] - g[f"{dyn}_{tag}_B"]).max() <= tol
+
+
+def test_config1_double_integrator_demo_known_answer(oracle):
+    """SURVEY §8d config 1 / §8c soft KAT (examples/01_demo_linear.py as the script runs it): the oracle driven in
+    closed loop for 150 cold-started solves of 50 agents reproduces the reference's recorded states and its
+    position MSE of 0.1296."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "config1_di_closed_loop.npz"))
+    B, DT, H, N_SIM, nx, nu = 50, 0.05, 20, 150, 2, 1
+    C = np.zeros((H, 3, 3))
+    C[:, 0, 0], C[:, 1, 1], C[:, 2, 2] = 100.0, 1.0, 0.01
+    c, Cf, cf = np.zeros((H, 3)), C[0] * 10, np.zeros(3)
+    ref_len = N_SIM + H + 1
+    t_full = np.arange(ref_len) * DT
+    pos = g["amp"] * np.sin(g["om"] * t_full[None])
+    vel = g["amp"] * g["om"] * np.cos(g["om"] * t_full[None])
+    xref = np.stack([pos, vel], axis=2)
+    A, Bm = np.array([[1.0, DT], [0.0, 1.0]]), np.array([[0.0], [DT]])
+    spec = dict(nx=nx, nu=nu, T=H, dt=DT, dyn="lti", A=A, B=Bm, reg_eps=1e-6, max_iter=40, u_min=[-50.0], u_max=[50.0])
+    x = np.zeros((B, nx))
+    Xs = [x]
+    for k in range(N_SIM):
+        out = oracle.forward(spec, x, C, c, Cf, cf, np.ascontiguousarray(xref[:, k:k + H + 1]), np.zeros((B, H, nu)),
+                             np.zeros((B, H, nu)), want_AB=False)
+        x = x @ A.T + out["U"][:, 0] @ Bm.T
+        Xs.append(x)
+    Xs = np.stack(Xs, 1)
+    mse = np.mean((Xs[:, :, 0] - xref[:, :N_SIM + 1, 0]) ** 2)
+    assert abs(mse - 0.1296) < 5e-5 and abs(mse - float(g["mse_analytic"])) < 1e-9
+    assert np.abs(Xs - g["Xs"]).max() < 1e-6
