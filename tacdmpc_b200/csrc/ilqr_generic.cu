@@ -701,7 +701,7 @@ static GenLaunch gen_launch_shape(const tacd_problem* p, size_t slice) {
   const size_t with_slice = gen_elem_bytes<R>(p->nx, p->nu, slice) * per_cta;
   GenLaunch L;
   // CTA-per-element: four CTAs per SM; warp-per-element: two four-element CTAs per SM are enough to cover the barriers
-  L.in_smem = with_slice <= (size_t)device_info().smem_optin / (TPE == 32 ? 2 : 4) && !getenv("TACD_GENERIC_WS");
+  L.in_smem = with_slice <= (size_t)device_info().smem_optin / (TPE == 32 ? 2 : gen_ctas_per_sm()) && !getenv("TACD_GENERIC_WS");
   L.smem = L.in_smem ? with_slice : gen_elem_bytes<R>(p->nx, p->nu, 0) * per_cta;
   L.grid = (gen_slots(p, TPE) + per_cta - 1) / per_cta;
   return L;
