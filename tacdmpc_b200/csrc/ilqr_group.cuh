@@ -223,7 +223,7 @@ __host__ __device__ inline int init_cost_words(int chunk, int nx, int nu, int C_
 }
 __host__ __device__ inline size_t init_warp_words(int T, int nx, int nu, int C_batched, int C_diag, int chunk) {
   return (size_t)32 * init_in_words(T, nx, nu) +
-         (C_batched ? (size_t)(chunk >= T ? 32 : 64) * init_cost_words(chunk, nx, nu, C_diag) : 0);
+         (C_batched && chunk > 0 ? (size_t)(chunk >= T ? 32 : 64) * init_cost_words(chunk, nx, nu, C_diag) : 0);
 }
 
 template <typename R, int NX, int NU, int DYN>
@@ -249,9 +249,14 @@ __global__ void __launch_bounds__(128) ilqr_init_rollout(const DevProblem<R> P, 
   const int b0 = (blockIdx.x * (blockDim.x >> 5) + wid) * 32;
   if (b0 >= P.B) return;
   const int nlive = P.B - b0 < 32 ? P.B - b0 : 32;
+  // chunk == 0: per-element costs are read straight from global memory, each thread its own element's 2n or n*n + n
+  // consecutive words per step (every byte of the touched sectors is used and stays in L1 for the next loads); no
+  // cost tile, so the CTA keeps the 13 KB footprint of the shared-cost case
+  const bool direct = chunk == 0;
+  if (direct) chunk = T;
   const int nchunk = (T + chunk - 1) / chunk;
   auto fetch_cost = [&](int c) {
-    if (P.C_batched && c < nchunk) {
+    if (P.C_batched && !direct && c < nchunk) {
       const int t0 = c * chunk, nst = (T - t0 < chunk) ? T - t0 : chunk;
       R* buf = ctile + (size_t)(c & (nbuf - 1)) * 32 * RSC;
       for (int r = 0; r < nlive; ++r) {
@@ -299,7 +304,19 @@ __global__ void __launch_bounds__(128) ilqr_init_rollout(const DevProblem<R> P, 
       for (int i = 0; i < NX; ++i) { tau[i] = x[i] - row[t * NX + i]; row[t * NX + i] = x[i]; }
 #pragma unroll
       for (int i = 0; i < NU; ++i) tau[NX + i] = u[i] - ur[t * NU + i];
-      if (P.C_diag) {   // expanded to dense: same arithmetic as the dense layout (diag_embed, actor.py:74)
+      if (direct) {
+        const R* Cg = io.C + ((size_t)b * T + t) * cw;
+        const R* cg = io.c + ((size_t)b * T + t) * N;
+        if (P.C_diag) {
+#pragma unroll
+          for (int i = 0; i < N * N; ++i) Ct[i] = (i / N == i % N) ? Cg[i / N] : (R)0;
+        } else {
+#pragma unroll
+          for (int i = 0; i < N * N; ++i) Ct[i] = Cg[i];
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) ct[i] = cg[i];
+      } else if (P.C_diag) {   // expanded to dense: same arithmetic as the dense layout (diag_embed, actor.py:74)
 #pragma unroll
         for (int i = 0; i < N * N; ++i) Ct[i] = (i / N == i % N) ? cbuf[(t - t0) * N + i / N] : (R)0;
 #pragma unroll
