@@ -5,9 +5,9 @@
 around it.  The critic, the optimiser loop and checkpointing are plain torch in the reference and out of scope
 (SURVEY §2 rows 8-18).
 """
-from .actor import ActorMPC, GraphedPolicy
+from .actor import ActorMPC, GraphedPolicy, GraphedUpdate
 from .parallel_env import DeviceEnvManager, cartpole_envs, double_integrator_envs, uniform_reset
 from .training_loop import collect_rollout, compute_gae_and_returns, mpve_targets
 
-__all__ = ["ActorMPC", "GraphedPolicy", "DeviceEnvManager", "cartpole_envs", "double_integrator_envs", "uniform_reset",
+__all__ = ["ActorMPC", "GraphedPolicy", "GraphedUpdate", "DeviceEnvManager", "cartpole_envs", "double_integrator_envs", "uniform_reset",
            "collect_rollout", "compute_gae_and_returns", "mpve_targets"]

@@ -75,18 +75,23 @@ class ActorMPC(nn.Module):
         log_prob = dist.log_prob(action).sum(dim=-1)
         return action, log_prob, predicted_states, predicted_actions
 
+    def graphed_update(self, loss_fn, obs, actions, *extras) -> "GraphedUpdate":
+        """``evaluate_actions`` + ``loss_fn`` + backward for the mini-batch shape of the example tensors as ONE
+        CUDA-graph replay — see ``GraphedUpdate``."""
+        return GraphedUpdate(self, loss_fn, obs, actions, *extras)
+
     def graphed(self, batch_size: int, deterministic: bool = False) -> "GraphedPolicy":
         """The rollout-phase policy call (no gradient) for a fixed batch size as ONE CUDA-graph replay — see
         ``GraphedPolicy``."""
         return GraphedPolicy(self, batch_size, deterministic)
 
-    def evaluate_actions(self, x: Tensor, actions: Tensor) -> Tuple[Tensor, Tensor]:
+    def evaluate_actions(self, x: Tensor, actions: Tensor, *, _validate_args=None) -> Tuple[Tensor, Tensor]:
         if x.ndim == 1:
             x = x.unsqueeze(0)
         self._update_cost_module(x)
         U_init = torch.zeros(x.shape[0], self.horizon, self.nu, device=self.device, dtype=self.dtype)
         _, predicted_actions = self.mpc(x[:, :self.nx], U_init)
-        dist = Normal(predicted_actions[:, 0], self.log_std.exp())
+        dist = Normal(predicted_actions[:, 0], self.log_std.exp(), validate_args=_validate_args)
         return dist.log_prob(actions).sum(dim=-1), dist.entropy().sum(dim=-1)
 
 
@@ -122,3 +127,52 @@ class GraphedPolicy:
         self._obs.copy_(obs)
         self._graph.replay()
         return tuple(t.clone() for t in self._out)
+
+
+class GraphedUpdate:
+    """The PPO update's device work for a fixed mini-batch shape — ``log_probs, entropy = actor.evaluate_actions(obs,
+    actions)``, ``loss = loss_fn(log_probs, entropy, *extras)``, ``loss.backward()`` (``training_loop.py:140-183``) — as one
+    CUDA-graph replay.  The forward solve, the autograd backward through ``ILQRSolve`` and the cost network are all
+    capturable (no host synchronisation, torch-allocator memory only), and at the reference's mini-batch of 512 the
+    eager step is host-bound (≈ 2 ms around ≈ 0.5 ms of kernels).
+
+    After a call the gradients are in the actor parameters' ``.grad`` (the graph's static output tensors, attached on
+    every call, so an ``optimizer.zero_grad(set_to_none=True)`` in between is harmless); the optimiser step stays with
+    the caller.  Weights are read at replay time.  Gradients are overwritten, not accumulated.  As for any whole-step
+    CUDA-graph capture in PyTorch, build it before eager backward passes have run on the default stream (their autograd
+    state is bound to that stream and a capture may not depend on it); eager steps afterwards are fine.
+    """
+
+    def __init__(self, actor: ActorMPC, loss_fn, obs: Tensor, actions: Tensor, *extras: Tensor):
+        self.actor, self.loss_fn = actor, loss_fn
+        self._in = [t.detach().clone() for t in (obs, actions, *extras)]
+        self._params = [p for p in actor.parameters() if p.requires_grad]
+        side = torch.cuda.Stream(device=actor.device)
+        side.wait_stream(torch.cuda.current_stream(actor.device))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                self._step()
+        torch.cuda.current_stream(actor.device).wait_stream(side)
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._loss, self._grads = self._step()
+
+    def _step(self):
+        log_probs, entropy = self.actor.evaluate_actions(self._in[0], self._in[1], _validate_args=False)
+        loss = self.loss_fn(log_probs, entropy, *self._in[2:])
+        # torch.autograd.grad, not loss.backward(): no AccumulateGrad nodes take part, so gradient accumulators left
+        # over from eager steps on the default stream cannot pull that stream into the capture
+        grads = torch.autograd.grad(loss, self._params, allow_unused=True)
+        return loss.detach(), grads
+
+    def __call__(self, obs: Tensor, actions: Tensor, *extras: Tensor) -> Tensor:
+        new = (obs, actions, *extras)
+        if len(new) != len(self._in) or any(a.shape != b.shape for a, b in zip(new, self._in)):
+            raise RuntimeError("graphed update was captured for inputs of shapes " + str([tuple(t.shape) for t in self._in]))
+        with torch.no_grad():
+            for dst, src in zip(self._in, new):
+                dst.copy_(src)
+        self._graph.replay()
+        for p, g in zip(self._params, self._grads):
+            p.grad = g
+        return self._loss.clone()

@@ -186,6 +186,42 @@ def test_graphed_policy_replays_on_new_observations():
     assert buf["states"].shape == (64, 10, 4) and torch.isfinite(buf["rewards"]).all() and buf["pred_actions"].shape == (64, 10, 12, 1)
 
 
+def test_graphed_update_matches_eager_update():
+    """ActorMPC.graphed_update: evaluate_actions + PPO-style loss + backward as one CUDA-graph replay gives the eager
+    step's loss and parameter gradients on new mini-batches, also after an optimiser step and a zero_grad(None)."""
+    from tacdmpc_b200.ACMPC import ActorMPC
+    from tacdmpc_b200.dynamics import CartPole
+    torch.manual_seed(0)
+    f = CartPole()
+    actor = ActorMPC(4, 1, 10, 0.05, f_dyn=f, f_dyn_jac=f.jac, device="cuda", grad_method="analytic")
+    opt = torch.optim.SGD(actor.parameters(), lr=1e-3)
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    mk = lambda: (torch.rand(48, 4, device="cuda", generator=gen) * 0.45 - 0.2, torch.randn(48, 1, device="cuda", generator=gen),
+                  torch.randn(48, device="cuda", generator=gen), torch.randn(48, device="cuda", generator=gen) - 1.0)
+
+    def loss_fn(log_probs, entropy, adv, old_lp):                 # training_loop.py:142-147
+        ratio = torch.exp(log_probs - old_lp)
+        return -torch.min(ratio * adv, torch.clamp(ratio, 0.8, 1.2) * adv).mean() - 0.01 * entropy.mean()
+
+    upd = actor.graphed_update(loss_fn, *mk())                 # (captured before any eager backward, see GraphedUpdate)
+    for it in range(3):
+        obs, act, adv, old = mk()
+        opt.zero_grad(set_to_none=True)
+        lp, ent = actor.evaluate_actions(obs, act)
+        le = loss_fn(lp, ent, adv, old)
+        le.backward()
+        ge = [p.grad.clone() for p in actor.parameters()]
+        opt.zero_grad(set_to_none=True)
+        lg = upd(obs, act, adv, old)
+        gg = [p.grad for p in actor.parameters()]
+        assert abs(float(lg) - float(le.detach())) <= 1e-5 * max(1.0, abs(float(le.detach())))
+        for a, b in zip(gg, ge):
+            assert float((a - b).abs().max()) <= 1e-4 * max(1e-3, float(b.abs().max()))
+        opt.step()                                              # weights change between replays
+    with pytest.raises(RuntimeError, match="captured"):
+        upd(*[t[:3] for t in mk()])
+
+
 def test_ppo_glue_rejects_cpu_tensors():
     from tacdmpc_b200 import _lib, ops
     with pytest.raises(_lib.TacdError, match="CUDA"):

@@ -39,6 +39,10 @@ for T in (20, 15):
         for B in (512, 4096):
             obs = torch.rand(B, 4, device=dev) * 0.45 - 0.2          # U(-0.2, 0.25)^4, examples/02_demo_cartpole_AC.py:100
             acts = torch.randn(B, 1, device=dev)
+            if B == 512:   # graph captures first (before any eager backward on the default stream)
+                graphed = {b_: (actor.graphed(b_), actor.graphed_update(lambda lp, ent: -(lp.mean()) - 0.01 * ent.mean(),
+                                                                         torch.zeros(b_, 4, device=dev), torch.zeros(b_, 1, device=dev)))
+                           for b_ in (512, 4096)}
 
             def rollout_call():
                 with torch.no_grad():
@@ -50,13 +54,14 @@ for T in (20, 15):
                 (-(lp.mean()) - 0.01 * ent.mean()).backward()
 
             t_roll = timed(rollout_call)
-            pol = actor.graphed(B)
+            pol, upd = graphed[B]
             t_graph = timed(lambda: pol(obs))
             t_upd = timed(update_step)
+            t_gupd = timed(lambda: upd(obs, acts))
             n0 = _lib.lib().tacd_kernel_launches()
             update_step()
             launches = _lib.lib().tacd_kernel_launches() - n0
             it = float(actor.mpc.iters_last.float().mean())
             print(f"T={T} {'compact-diagonal' if fused else 'dense           '} B={B:5d}: policy call {t_roll:7.3f} ms, graphed {t_graph:6.3f} ms ({B / t_graph / 1e3:7.3f} M obs/s)   "
-                  f"PPO update step {t_upd:7.3f} ms ({B / t_upd / 1e3:7.3f} M samples/s)   mean iters {it:5.2f}   library launches/step {launches}",
+                  f"PPO update step {t_upd:7.3f} ms, graphed {t_gupd:6.3f} ms ({B / t_gupd / 1e3:7.3f} M samples/s)   mean iters {it:5.2f}   library launches/step {launches}",
                   flush=True)
