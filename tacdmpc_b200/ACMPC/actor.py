@@ -139,8 +139,9 @@ class GraphedUpdate:
     After a call the gradients are in the actor parameters' ``.grad`` (the graph's static output tensors, attached on
     every call, so an ``optimizer.zero_grad(set_to_none=True)`` in between is harmless); the optimiser step stays with
     the caller.  Weights are read at replay time.  Gradients are overwritten, not accumulated.  As for any whole-step
-    CUDA-graph capture in PyTorch, build it before eager backward passes have run on the default stream (their autograd
-    state is bound to that stream and a capture may not depend on it); eager steps afterwards are fine.
+    CUDA-graph capture in PyTorch, build it before eager backward passes through THIS actor's parameters have run on the
+    default stream (their autograd state is bound to that stream and a capture may not depend on it); eager steps
+    afterwards are fine.
     """
 
     def __init__(self, actor: ActorMPC, loss_fn, obs: Tensor, actions: Tensor, *extras: Tensor):
