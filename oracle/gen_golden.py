@@ -36,6 +36,7 @@ OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
 for _m in ["matplotlib", "matplotlib.pyplot", "gym", "gymnasium", "gym.spaces", "gymnasium.spaces"]:
     sys.modules.setdefault(_m, MagicMock())
 sys.path.insert(0, REF)
+sys.path.insert(0, HERE)
 warnings.filterwarnings("ignore")
 
 from DifferentialMPC import DifferentiableMPCController, GeneralQuadCost, pnqp  # noqa: E402
@@ -267,37 +268,7 @@ def run_case(name, *, nx, nu, T, dt, f_dyn, f_dyn_jac, grad_method, dtype, x0, C
 # ----------------------------------------------------------------------------
 # configurations
 # ----------------------------------------------------------------------------
-def quad_cost(Q, R, T, final_scale=10.0, final_full=True):
-    nx, nu = Q.shape[0], R.shape[0]
-    n = nx + nu
-    C = torch.zeros(T, n, n)
-    C[:, :nx, :nx] = Q
-    C[:, nx:, nx:] = R
-    c = torch.zeros(T, n)
-    if final_full:
-        Cf = C[0].clone() * final_scale
-    else:
-        Cf = torch.zeros(n, n)
-        Cf[:nx, :nx] = Q * final_scale
-    cf = torch.zeros(n)
-    return C, c, Cf, cf
-
-
-def case_di(dtype, B=6, seed=0):
-    g = torch.Generator().manual_seed(seed)
-    nx, nu, T, dt = 2, 1, 20, 0.05
-    C, c, Cf, cf = quad_cost(torch.diag(torch.tensor([100.0, 1.0])), torch.diag(torch.tensor([0.01])), T)
-    t = torch.arange(T + 1) * dt
-    amp = 5.0 + torch.rand(B, 1, generator=g) * 5.0
-    om = 1.0 + torch.rand(B, 1, generator=g)
-    ph = torch.rand(B, 1, generator=g) * 3.0
-    xref = torch.stack([amp * torch.sin(om * t + ph), amp * om * torch.cos(om * t + ph)], dim=2)
-    uref = torch.zeros(B, T, nu)
-    x0 = torch.randn(B, nx, generator=g) * torch.tensor([2.0, 1.0])
-    return dict(nx=nx, nu=nu, T=T, dt=dt, f_dyn=EX1.f_dyn_linear, f_dyn_jac=EX1.f_dyn_jac_linear_batched,
-                grad_method="analytic", dtype=dtype, x0=x0, C=C, c=c, Cf=Cf, cf=cf, xref=xref, uref=uref,
-                Uinit=torch.zeros(B, T, nu), u_min=torch.tensor([-50.0]), u_max=torch.tensor([50.0]),
-                spec_extra=dict(dyn="lti", lti_A=np.array([[1.0, dt], [0.0, 1.0]]), lti_B=np.array([[0.0], [dt]])))
+from golden_inputs import CASES, make as make_inputs, quad_cost  # noqa: E402  (seeded input generators, torch only)
 
 
 def cartpole_fns():
@@ -305,107 +276,40 @@ def cartpole_fns():
             lambda x, u, dt: EX2.f_cartpole_jac_batched(x, u, dt, CP_PARAMS))
 
 
-def case_cartpole_shared(dtype, B=32, seed=0, grad_method="analytic", T=20):
-    g = torch.Generator().manual_seed(seed)
-    nx, nu, dt = 4, 1, 0.05
-    C, c, Cf, cf = quad_cost(torch.diag(torch.tensor([10.0, 1.0, 100.0, 1.0])), torch.diag(torch.tensor([0.1])), T,
-                             final_full=False)
-    x0 = torch.tensor([0.0, 0.0, 0.2, 0.0]) + torch.randn(B, nx, generator=g) * torch.tensor([0.5, 0.5, 0.2, 0.2])
-    f, fj = cartpole_fns()
-    return dict(nx=nx, nu=nu, T=T, dt=dt, f_dyn=f, f_dyn_jac=fj if grad_method == "analytic" else None,
-                grad_method=grad_method, dtype=dtype, x0=x0, C=C, c=c, Cf=Cf, cf=cf,
-                xref=torch.zeros(B, T + 1, nx), uref=torch.zeros(B, T, nu), Uinit=torch.zeros(B, T, nu),
-                u_min=torch.tensor([-20.0]), u_max=torch.tensor([20.0]),
-                spec_extra=dict(dyn="cartpole", dyn_params=np.array([1.0, 0.1, 0.5, 9.8])))
+def attach_dynamics(case):
+    """golden_inputs case (tensors only) -> run_case keyword arguments: the reference's shipped example dynamics."""
+    case = dict(case)
+    kind = case.pop("dyn_kind")
+    if kind == "di":
+        f, fj = EX1.f_dyn_linear, EX1.f_dyn_jac_linear_batched
+    elif kind == "cartpole":
+        f, fj = cartpole_fns()
+    elif kind == "unicycle":
+        f, fj = EX3.f_dyn_unicycle, EX3.f_dyn_jac_unicycle
+    elif kind == "unicycle_wrapped":
+        f, fj = EX3AC.f_dyn_torch, EX3AC.f_dyn_jac_torch
+    elif kind == "lti":
+        A, Bm = case.pop("lti")
 
+        def f(x, u, dt, A=A, Bm=Bm):
+            return x @ A.to(x.dtype).T + u @ Bm.to(x.dtype).T
 
-def case_cartpole_actor(dtype, B=16, seed=1, T=20):
-    """ActorMPC-shaped problem (ACMPC/actor.py:58-81): per-element diagonal C, c; C_final=C[:,-1];
-    reg_eps=1e-2; no bounds; U_init = 0.01 randn.  Exercises quirk Q4."""
-    g = torch.Generator().manual_seed(seed)
-    nx, nu, dt = 4, 1, 0.05
-    n = nx + nu
-    q = torch.nn.functional.softplus(torch.randn(B, T, n, generator=g)) + 1e-2
-    C = torch.diag_embed(q)
-    c = 0.3 * torch.randn(B, T, n, generator=g)
-    Cf, cf = C[:, -1].clone(), c[:, -1].clone()
-    x0 = torch.rand(B, nx, generator=g) * 0.45 - 0.2
-    f, fj = cartpole_fns()
-    return dict(nx=nx, nu=nu, T=T, dt=dt, f_dyn=f, f_dyn_jac=fj, grad_method="analytic", dtype=dtype,
-                x0=x0, C=C, c=c, Cf=Cf, cf=cf, xref=torch.zeros(B, T + 1, nx), uref=torch.zeros(B, T, nu),
-                Uinit=0.01 * torch.randn(B, T, nu, generator=g), reg_eps=1e-2,
-                spec_extra=dict(dyn="cartpole", dyn_params=np.array([1.0, 0.1, 0.5, 9.8])))
-
-
-def case_unicycle(dtype, B=8, seed=2, tight=True, wrapped=False, T=30):
-    g = torch.Generator().manual_seed(seed)
-    nx, nu, dt = 3, 2, 0.1
-    C, c, Cf, cf = quad_cost(torch.diag(torch.tensor([20.0, 20.0, 5.0])), torch.diag(torch.tensor([0.1, 0.1])), T)
-    ph = torch.rand(B, 1, generator=g) * 2 * torch.pi
-    amp = 3.0 + 2.0 * torch.rand(B, 1, generator=g)
-    tt = ph + torch.arange(T + 1) * dt * 0.5
-    xr = amp * torch.sin(tt)
-    yr = amp * torch.sin(tt) * torch.cos(tt)
-    dxr = amp * torch.cos(tt)
-    dyr = amp * torch.cos(2 * tt)
-    th = torch.atan2(dyr, dxr)
-    xref = torch.stack([xr, yr, th], dim=2)
-    uref = torch.zeros(B, T, nu)
-    x0 = xref[:, 0] + torch.randn(B, nx, generator=g) * torch.tensor([1.0, 1.0, 0.5])
-    if tight:
-        umin, umax = torch.tensor([-2.0, -1.0]), torch.tensor([2.0, 1.0])
+        def fj(x, u, dt, A=A, Bm=Bm):
+            N = x.shape[0]
+            return A.to(x.dtype).unsqueeze(0).expand(N, -1, -1), Bm.to(x.dtype).unsqueeze(0).expand(N, -1, -1)
+    elif kind == "gradcheck":
+        def f(x, u, dt):
+            return x + dt * u
+        fj = None
     else:
-        umin, umax = torch.tensor([-10.0, -2 * np.pi]), torch.tensor([10.0, 2 * np.pi])
-    f = EX3AC.f_dyn_torch if wrapped else EX3.f_dyn_unicycle
-    fj = EX3AC.f_dyn_jac_torch if wrapped else EX3.f_dyn_jac_unicycle
-    return dict(nx=nx, nu=nu, T=T, dt=dt, f_dyn=f, f_dyn_jac=fj, grad_method="analytic", dtype=dtype,
-                x0=x0, C=C, c=c, Cf=Cf, cf=cf, xref=xref, uref=uref, Uinit=torch.zeros(B, T, nu),
-                u_min=umin, u_max=umax, spec_extra=dict(dyn="unicycle_wrapped" if wrapped else "unicycle"))
+        raise KeyError(kind)
+    case["f_dyn"] = f
+    case["f_dyn_jac"] = fj if case["grad_method"] == "analytic" else None
+    return case
 
 
-def case_lti(dtype, nx=8, nu=4, T=50, B=4, seed=0, mixed=False):
-    """config 5: shared LTI dynamics, per-element diagonal costs."""
-    g = torch.Generator().manual_seed(seed)
-    n = nx + nu
-    A = torch.eye(nx) + 0.1 * torch.randn(nx, nx, generator=g) / np.sqrt(nx)
-    Bm = 0.1 * torch.randn(nx, nu, generator=g)
-    d = 0.5 + torch.rand(B, T, n, generator=g)
-    d[..., nx:] *= 0.1
-    C = torch.diag_embed(d)
-    c = 0.1 * torch.randn(B, T, n, generator=g)
-    Cf, cf = C[:, -1].clone(), c[:, -1].clone()
-    if mixed:  # shared running cost, per-element terminal cost
-        C, c = C[0].clone(), c[0].clone()
-    x0 = torch.randn(B, nx, generator=g)
-
-    def f(x, u, dt, A=A, Bm=Bm):
-        return x @ A.to(x.dtype).T + u @ Bm.to(x.dtype).T
-
-    def fj(x, u, dt, A=A, Bm=Bm):
-        N = x.shape[0]
-        return A.to(x.dtype).unsqueeze(0).expand(N, -1, -1), Bm.to(x.dtype).unsqueeze(0).expand(N, -1, -1)
-
-    return dict(nx=nx, nu=nu, T=T, dt=0.1, f_dyn=f, f_dyn_jac=fj, grad_method="analytic", dtype=dtype,
-                x0=x0, C=C, c=c, Cf=Cf, cf=cf, xref=torch.zeros(B, T + 1, nx), uref=torch.zeros(B, T, nu),
-                Uinit=torch.zeros(B, T, nu), spec_extra=dict(dyn="lti", lti_A=A.numpy().astype(np.float64),
-                                                             lti_B=Bm.numpy().astype(np.float64)))
-
-
-def case_gradcheck():
-    """tests/test_gradcheck.py:7-51 adapted to the current API: nx=nu=1, H=4, all-zero cost, f = x + dt u."""
-    nx = nu = 1
-    T, dt = 4, 0.1
-    torch.manual_seed(0)
-    x0 = torch.randn(1, nx, dtype=torch.float64)
-    n = nx + nu
-
-    def f(x, u, dt):
-        return x + dt * u
-
-    return dict(nx=nx, nu=nu, T=T, dt=dt, f_dyn=f, f_dyn_jac=None, grad_method="auto_diff", dtype=torch.float64,
-                x0=x0, C=torch.zeros(T, n, n), c=torch.zeros(T, n), Cf=torch.zeros(n, n), cf=torch.zeros(n),
-                xref=torch.zeros(1, T + 1, nx), uref=torch.zeros(1, T, nu), Uinit=torch.zeros(1, T, nu),
-                spec_extra=dict(dyn="lti", lti_A=np.array([[1.0]]), lti_B=np.array([[dt]])))
+def solve_case(name):
+    return run_case(name, **attach_dynamics(make_inputs(name)))
 
 
 def closed_loop_batch_tracking():
@@ -538,6 +442,7 @@ def closed_loop_unicycle_warm():
 
 
 def pnqp_kats():
+    torch.set_default_dtype(torch.float64)   # (0.3 * torch.eye(m) below is formed in the default dtype)
     d = {}
     for dtype, tag in ((torch.float64, "f64"), (torch.float32, "f32")):
         g = torch.Generator().manual_seed(7)
@@ -599,37 +504,38 @@ def check_shipped_dynamics_match_example_variants():
     assert torch.allclose(a, b, rtol=0, atol=1e-15), (a - b).abs().max()
 
 
-def main():
-    torch.manual_seed(0)
+SOLVE_ORDER = ["di_f64", "di_f32", "cartpole_shared_f32", "cartpole_shared_f64", "cartpole_actor_f32", "cartpole_actor_f64",
+               "cartpole_ad_f64", "unicycle_tight_f32", "unicycle_tight_f64", "unicycle_loose_f64", "unicycle_loose_f32",
+               "unicycle_wrapped_f64", "lti8_f32", "lti8_T20_f32", "lti8_f64", "lti8_T50_f64", "lti8_mixed_f64", "lti16_f32",
+               "lti32_f32", "gradcheck_f64"]
+EXTRA = {"fd_jacobian_kat": fd_jacobian_kats, "closed_loop_batch_tracking": closed_loop_batch_tracking,
+         "closed_loop_unicycle_warm": closed_loop_unicycle_warm, "config1_di_closed_loop": config1_di_closed_loop,
+         "pnqp_kat": pnqp_kats}
+
+
+def main(argv=None):
+    """python oracle/gen_golden.py [--only NAME ...] [--out DIR]: every fixture can be regenerated on its own; the inputs
+    do not depend on which cases ran before (golden_inputs.CASES fixes the dtype they are drawn in)."""
+    import argparse
+    global OUT
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", nargs="*", default=None)
+    ap.add_argument("--out", default=OUT)
+    a = ap.parse_args(argv)
+    OUT = a.out
+    assert set(SOLVE_ORDER) == set(CASES)
+    names = a.only if a.only else SOLVE_ORDER + list(EXTRA)
     torch.set_num_threads(4)
     os.makedirs(OUT, exist_ok=True)
     check_shipped_dynamics_match_example_variants()
-    F32, F64 = torch.float32, torch.float64
-    run_case("di_f64", **case_di(F64))
-    run_case("di_f32", **case_di(F32))
-    run_case("cartpole_shared_f32", **case_cartpole_shared(F32))
-    run_case("cartpole_shared_f64", **case_cartpole_shared(F64, B=16))
-    run_case("cartpole_actor_f32", **case_cartpole_actor(F32))
-    run_case("cartpole_actor_f64", **case_cartpole_actor(F64, B=8))
-    fd_jacobian_kats()
-    run_case("cartpole_ad_f64", **case_cartpole_shared(F64, B=4, grad_method="auto_diff"))
-    run_case("unicycle_tight_f32", **case_unicycle(F32))
-    run_case("unicycle_tight_f64", **case_unicycle(F64))
-    run_case("unicycle_loose_f64", **case_unicycle(F64, B=4, tight=False))
-    run_case("unicycle_loose_f32", **case_unicycle(F32, B=8, tight=False, seed=5, T=20))
-    run_case("unicycle_wrapped_f64", **case_unicycle(F64, B=4, tight=True, wrapped=True, T=15))
-    run_case("lti8_f32", **case_lti(F32))
-    run_case("lti8_T20_f32", **case_lti(F32, T=20, B=4, seed=3))
-    run_case("lti8_f64", **case_lti(F64, T=20))
-    run_case("lti8_T50_f64", **case_lti(F64, T=50, B=2, seed=4))
-    run_case("lti8_mixed_f64", **case_lti(F64, T=12, mixed=True))
-    run_case("lti16_f32", **case_lti(F32, nx=16, nu=4, T=20, B=2))
-    run_case("lti32_f32", **case_lti(F32, nx=32, nu=8, T=10, B=2))
-    run_case("gradcheck_f64", **case_gradcheck())
-    closed_loop_batch_tracking()
-    closed_loop_unicycle_warm()
-    config1_di_closed_loop()
-    pnqp_kats()
+    for nm in names:
+        torch.manual_seed(0)
+        torch.set_default_dtype(torch.float32)
+        if nm in CASES:
+            solve_case(nm)
+        else:
+            EXTRA[nm]()
+    torch.set_default_dtype(torch.float32)
 
 
 if __name__ == "__main__":
