@@ -25,7 +25,7 @@ from typing import Callable, Optional, Tuple
 import torch
 from torch import Tensor
 
-from .. import _abi, ops
+from .. import _abi, _lib, ops
 from ..dynamics import NativeDynamics
 from .cost import DiagQuadCost, GeneralQuadCost
 from .AugmentedLagrangianManager import ConstrainedQuadCost
@@ -66,7 +66,7 @@ class ILQRSolve(torch.autograd.Function):
 
         ctx.controller = controller
         ctx.spec = controller._last_spec
-        ctx.Cf_batched = C_final.ndim == 3
+        ctx.Cf_batched = controller._last_Cf.ndim == 3   # what the kernel was given (_costs squeezes a batch of 1)
         ctx.exact = controller.compat == "exact"
         ctx.Cf = controller._last_Cf if ctx.exact else None
         ctx.shapes = tuple(t.shape for t in (x0, C, c, C_final, c_final, x_ref, u_ref))
@@ -114,6 +114,7 @@ class ILQRSolveDiag(torch.autograd.Function):
             X, U = X.detach(), U.detach()
         ctx.spec = controller._last_spec
         ctx.diag = controller._last_diag
+        ctx.Cf_batched = controller._last_Cf.ndim == (2 if ctx.diag else 3)
         ctx.exact = controller.compat == "exact"
         ctx.Cf = controller._last_Cf if ctx.exact else None
         ctx.shapes = tuple(t.shape for t in (x0, q, p, q_final, p_final, x_ref, u_ref))
@@ -134,7 +135,7 @@ class ILQRSolveDiag(torch.autograd.Function):
         names = ("grad_x0", "grad_C", "grad_c", "grad_Cf", "grad_cf", "grad_xref", "grad_uref")
         want = tuple(nm for nm, nd in zip(names, need[:7]) if nd)
         out = ops.ilqr_backward(ctx.spec, X, U, Cm, xref, uref, tight, grad_X.to(X.dtype), grad_U.to(U.dtype),
-                                A=A, Bm=Bm, Cf_batched=True, want=want, C_diag=ctx.diag, exact=ctx.exact, Cf=ctx.Cf) if want else {}
+                                A=A, Bm=Bm, Cf_batched=ctx.Cf_batched, want=want, C_diag=ctx.diag, exact=ctx.exact, Cf=ctx.Cf) if want else {}
         grads = []
         for nm, shape, dt in zip(names, ctx.shapes, ctx.in_dtypes):
             g = out.get(nm)
@@ -284,16 +285,35 @@ class DifferentiableMPCController(torch.nn.Module):
                         jac_mode=_JAC[self.grad_method], fd_eps=1e-4,  # quirk Q9: self.fd_eps is never read
                         u_min=bounds(self.u_min), u_max=bounds(self.u_max))
 
-    def _costs(self, B, dtype, device):
+    def _ls_override(self, dtype, device, diag: bool):
+        """The installed line-search cost (sharding.broadcast_line_search_cost) in the layout of the path that is about
+        to run: compact diagonals ([T,n], [T,n], [n], [n]) for the C_diag kernels, dense ([T,n,n], [T,n], [n,n], [n])
+        otherwise.  An override of the other layout is converted (a compact one is expanded; a dense one is reduced to
+        its diagonal, which is exact for the diagonal costs that reach the compact path); anything else raises."""
+        C, c, Cf, cf = (t.detach().to(device=device, dtype=dtype) for t in self.ls_cost_override)
+        T, n = self.horizon, self.nx + self.nu
+        if C.shape == (T, n) and Cf.shape == (n,):
+            if not diag:
+                C, Cf = torch.diag_embed(C), torch.diag_embed(Cf)
+        elif C.shape == (T, n, n) and Cf.shape == (n, n):
+            if diag:
+                C, Cf = torch.diagonal(C, dim1=-2, dim2=-1), torch.diagonal(Cf, dim1=-2, dim2=-1)
+        else:
+            raise RuntimeError(f"ls_cost_override must be ([T,n,n],[T,n],[n,n],[n]) or compact ([T,n],[T,n],[n],[n]); got "
+                               f"{tuple(C.shape)}, {tuple(c.shape)}, {tuple(Cf.shape)}, {tuple(cf.shape)}")
+        if c.shape != (T, n) or cf.shape != (n,):
+            raise RuntimeError(f"ls_cost_override linear terms must be [T,n], [n]; got {tuple(c.shape)}, {tuple(cf.shape)}")
+        return tuple(t.contiguous() for t in (C, c, Cf, cf))
+
+    def _costs(self, B, dtype, device, dense_only: bool = False):
         cm = self.cost_module
-        if self._diag_eligible() and cm.q.shape[0] == B:
+        if self._diag_eligible() and cm.q.shape[0] == B and not dense_only:
             q, p, qf, pf = (t.detach().to(device=device, dtype=dtype).contiguous() for t in (cm.q, cm.p, cm.q_final, cm.p_final))
             xref = cm.x_ref.detach().to(device=device, dtype=dtype).contiguous()
             uref = cm.u_ref.detach().to(device=device, dtype=dtype).contiguous()
             ls = None
             if self.compat == "reference":   # quirk Q4, compact as well
-                ls = tuple(t.detach().to(device=device, dtype=dtype).contiguous() for t in self.ls_cost_override) \
-                    if self.ls_cost_override is not None else (q[0], p[0], qf[0], pf[0])
+                ls = self._ls_override(dtype, device, True) if self.ls_cost_override is not None else (q[0], p[0], qf[0], pf[0])
             self._last_diag = True
             return q, p, qf, pf, xref, uref, ls
         self._last_diag = False
@@ -309,7 +329,7 @@ class DifferentiableMPCController(torch.nn.Module):
         ls = None
         if self.compat == "reference" and (C.ndim == 4 or Cf.ndim == 3):
             if self.ls_cost_override is not None:
-                ls = tuple(t.detach().to(device=device, dtype=dtype).contiguous() for t in self.ls_cost_override)
+                ls = self._ls_override(dtype, device, False)
             else:
                 ls = (C[0] if C.ndim == 4 else C, c[0] if c.ndim == 3 else c, Cf[0] if Cf.ndim == 3 else Cf,
                       cf[0] if cf.ndim == 2 else cf)
@@ -367,7 +387,9 @@ class DifferentiableMPCController(torch.nn.Module):
         params = [x0, x_ref_full, u_ref_full] + ([cm.q, cm.p, cm.q_final, cm.p_final] if isinstance(cm, DiagQuadCost)
                                                  else [cm.C, cm.c, cm.C_final, cm.c_final])
         needs_grad = torch.is_grad_enabled() and any(isinstance(t, Tensor) and t.requires_grad for t in params)
-        if not needs_grad and self._is_native() and x0.is_cuda:
+        # (a ConstrainedQuadCost runs the augmented-Lagrangian outer loop per step: forward() dispatches it below; the
+        # device loop would solve the unconstrained problem)
+        if not needs_grad and self._is_native() and x0.is_cuda and not isinstance(cm, ConstrainedQuadCost):
             return self._simulate_device(x0, x_ref_full, u_ref_full, U_init, warm_start, N)
         # autograd / generic path: the loop of the reference's demos, step by step
         x = x0
@@ -391,7 +413,10 @@ class DifferentiableMPCController(torch.nn.Module):
         T, nx, nu, B = self.horizon, self.nx, self.nu, x0.shape[0]
         spec = self._spec(dtype, device)
         prep = lambda t: t.detach().to(device=device, dtype=dtype).contiguous()
-        xf, uf = prep(x_ref_full), prep(u_ref_full)
+        # tacd_closed_loop_advance strides the input reference by ref_len - 1: hand it exactly that many steps (the Python loop
+        # only ever reads [k, k+T) windows, so any u_ref_full of at least N_sim + T steps means the same thing on both paths)
+        L = min(x_ref_full.shape[1], u_ref_full.shape[1] + 1)
+        xf, uf = prep(x_ref_full[:, :L]), prep(u_ref_full[:, :L - 1])
         xw, uw = xf[:, :T + 1].contiguous(), uf[:, :T].contiguous()
         self.cost_module.set_reference(xw, uw)
         C, c, Cf, cf, _, _, ls = self._costs(B, dtype, device)
@@ -403,6 +428,8 @@ class DifferentiableMPCController(torch.nn.Module):
         for k in range(N):
             out = ops.ilqr_forward(spec, x, C, c, Cf, cf, xw, uw, warm, ls_cost=ls, want_trace=False, C_diag=self._last_diag)
             ops.closed_loop_advance(spec, k, N, x, out["U"], Xs, Us, warm if warm_start else None, xf, uf, xw, uw)
+            if not warm_start and k == 0 and U_init is not None:
+                warm.zero_()   # cold start: U_init seeds the first solve only, as in the step-by-step loop of simulate()
         if out is not None:
             self.X_last, self.U_last = out["X"].to(x0.dtype), out["U"].to(x0.dtype)
             self.tight_mask_last = out["tight"].bool()
@@ -473,8 +500,16 @@ class DifferentiableMPCController(torch.nn.Module):
         x0d = x0.detach().to(dtype)
         U0 = U_init.detach().to(device=device, dtype=dtype)
         if self._is_native():
-            out = ops.ilqr_forward(spec, x0d, C, c, Cf, cf, xref, uref, U0, ls_cost=ls, want_trace=True,
-                                   C_diag=self._last_diag)
+            try:
+                out = ops.ilqr_forward(spec, x0d, C, c, Cf, cf, xref, uref, U0, ls_cost=ls, want_trace=True,
+                                       C_diag=self._last_diag)
+            except _lib.TacdUnsupported:
+                # compact diagonals are taken by the five-lanes-per-element kernels only (shipped (nx, nu, dyn) instances, horizon
+                # within shared memory); anything else solves on the dense expansion, as GeneralQuadCost would
+                if not self._last_diag:
+                    raise
+                C, c, Cf, cf, xref, uref, ls = self._costs(B, dtype, device, dense_only=True)
+                out = ops.ilqr_forward(spec, x0d, C, c, Cf, cf, xref, uref, U0, ls_cost=ls, want_trace=True)
             AB = None
         else:
             out, AB = self._solve_generic(spec, x0d, C, c, Cf, cf, xref, uref, U0, ls)

@@ -44,6 +44,11 @@ class TacdError(RuntimeError):
     pass
 
 
+class TacdUnsupported(TacdError):
+    """TACD_EUNSUPPORTED: a valid request this build has no kernel for (callers may re-route, e.g. dense instead of
+    compact-diagonal costs)."""
+
+
 def lib():
     """Load (once) and return the CUDA library; raises if it is not built."""
     global _lib
@@ -73,4 +78,6 @@ def check(rc: int, what: str) -> None:
             _abi.EWORKSPACE: "workspace too small"}.get(rc, f"error {rc}")
     if rc == _abi.EINVAL:
         raise ValueError(f"{what}: {kind}: {msg}")
+    if rc == _abi.EUNSUPPORTED:
+        raise TacdUnsupported(f"{what}: {kind}: {msg}")
     raise TacdError(f"{what}: {kind}: {msg}")

@@ -282,6 +282,9 @@ def closed_loop_advance(spec: Spec, k: int, n_sim: int, x, U_opt, Xs, Us, U_warm
     p = _problem(spec, B, dt, xref_batched=int(xref_full is not None and xref_full.shape[0] == B),
                  uref_batched=int(uref_full is not None and uref_full.shape[0] == B))
     ref_len = int(xref_full.shape[1]) if xref_full is not None else 0
+    if xref_full is not None and uref_full is not None and int(uref_full.shape[1]) != ref_len - 1:
+        raise RuntimeError(f"closed_loop_advance: uref_full must hold ref_len - 1 = {ref_len - 1} steps (the kernel strides it by "
+                           f"that), got {int(uref_full.shape[1])}")
     with torch.cuda.device(x.device):
         _lib.check(_lib.lib().tacd_closed_loop_advance(C.byref(p), int(k), int(n_sim), *_vp(x, U_opt, Xs, Us, U_warm, xref_full, uref_full),
                                                        ref_len, *_vp(xref_win, uref_win), _stream()), "tacd_closed_loop_advance")

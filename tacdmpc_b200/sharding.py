@@ -35,12 +35,20 @@ def broadcast_line_search_cost(controller, group=None, src: int = 0) -> None:
     No-op when both the running and the terminal cost are shared (then the line search already uses the
     same cost everywhere) or when ``compat="exact"``."""
     cm = controller.cost_module
-    C, c, Cf, cf = cm.C, cm.c, cm.C_final, cm.c_final
-    if getattr(controller, "compat", "reference") != "reference" or (C.ndim == 3 and Cf.ndim == 2):
+    if getattr(controller, "compat", "reference") != "reference":
         controller.ls_cost_override = None
         return
-    parts = [(C[0] if C.ndim == 4 else C), (c[0] if c.ndim == 3 else c), (Cf[0] if Cf.ndim == 3 else Cf),
-             (cf[0] if cf.ndim == 2 else cf)]
+    if hasattr(cm, "q") and hasattr(cm, "q_final"):
+        # DiagQuadCost: always per-element; element 0's DIAGONALS travel ([T,n], [T,n], [n], [n]).  The controller
+        # expands them if a solve ends up on the dense kernels (controller._costs), so the override is valid on both paths.
+        parts = [cm.q[0], cm.p[0], cm.q_final[0], cm.p_final[0]]
+    else:
+        C, c, Cf, cf = cm.C, cm.c, cm.C_final, cm.c_final
+        if C.ndim == 3 and Cf.ndim == 2:
+            controller.ls_cost_override = None
+            return
+        parts = [(C[0] if C.ndim == 4 else C), (c[0] if c.ndim == 3 else c), (Cf[0] if Cf.ndim == 3 else Cf),
+                 (cf[0] if cf.ndim == 2 else cf)]
     parts = [p.detach().clone().contiguous() for p in parts]
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         flat = torch.cat([p.reshape(-1) for p in parts])

@@ -45,3 +45,68 @@ def forward(spec: dict, g, *, replay=False, want_AB=True, cost_trace=False):
                            replay=rp, want_AB=want_AB, want_trace=True, want_cost_trace=cost_trace)
     torch.cuda.synchronize()
     return {k: v.cpu().numpy() for k, v in out.items()}
+
+
+def backward(spec: dict, g, gX, gU, want=("grad_C", "grad_c", "grad_Cf", "grad_cf", "grad_x0", "grad_xref", "grad_uref")):
+    s = gpu_spec(spec, g["x0"].dtype)
+    out = ops.ilqr_backward(s, dev(g["X"]), dev(g["U"]), dev(g["C"]), dev(g["xref"]), dev(g["uref"]), dev(g["tight"]), dev(gX), dev(gU),
+                            Cf_batched=g["Cf"].ndim == 3, want=want)
+    torch.cuda.synchronize()
+    return {k: v.cpu().numpy() for k, v in out.items()}
+
+
+def golden_report(names=None):
+    """One row per golden case (recorded from the unmodified reference): what the CUDA path achieves against it.
+    Used by __graft_entry__.smoke() so the driver's record (smoke tail) carries the parity table, and by the tests.
+      held      elements whose reference answer is itself reproducible to the north-star tolerance (tests/parity.py::elem_tol)
+      X, U      max relative error in REPLAY (the reference's decisions) over those elements
+      grads     max over the seven gradients and three losses of the error relative to the gradient's largest entry,
+                beyond the reference's own fp32-vs-fp64 floor
+      traces    free-running: elements whose whole decision trace (iteration count + alpha indices) equals the reference's
+    """
+    rows = []
+    for name in names or P.SOLVE_CASES:
+        g = P.load(name)
+        spec = P.spec_of(g)
+        tol = P.case_tol(g)
+        out = forward(spec, g, replay=True, want_AB=False)
+        ex, eu = P.rel_err(out["X"], g["X"]), P.rel_err(out["U"], g["U"])
+        well = (P.elem_tol(g, "U") <= tol) & (P.elem_tol(g, "X") <= tol)
+        free = forward(spec, g, want_AB=False)
+        same, below, bad = P.lockstep(g, free["iters"], free["alpha_trace"], free["flags"], P.MARGIN[g["x0"].dtype])
+        eg = 0.0
+        gskip = False
+        for loss in ("Usum", "U0sum", "weighted"):
+            X, U = g["X"], g["U"]
+            if loss == "Usum":
+                gX, gU = np.zeros_like(X), np.ones_like(U)
+            elif loss == "U0sum":
+                gX, gU = np.zeros_like(X), np.zeros_like(U)
+                gU[:, 0] = 1
+            else:
+                gX, gU = g["wX"], g["wU"]
+            ob = backward(spec, g, gX, gU)
+            for nm in ("C", "c", "Cf", "cf", "x0", "xref", "uref"):
+                gold = g[f"grad_{loss}_{nm}"]
+                scale = max(np.abs(gold).max(), 1.0)
+                err = np.abs(ob[f"grad_{nm}"].reshape(gold.shape).astype(np.float64) - gold).max() / scale
+                floor = 0.0
+                if f"grad64_{loss}_{nm}" in g:
+                    floor = 4 * np.abs(g[f"grad64_{loss}_{nm}"] - gold).max() / scale
+                if floor > 4 * P.REPRO_LIMIT:
+                    gskip = True
+                    continue
+                eg = max(eg, err - floor)
+        B = len(well)
+        rows.append(dict(case=name, B=B, tol=tol, held=int(well.sum()), X=float(ex[well].max()) if well.any() else float("nan"),
+                         U=float(eu[well].max()) if well.any() else float("nan"), grads=max(eg, 0.0), grads_partial=gskip,
+                         traces=int(same), below_margin=int(below), above_margin=len(bad)))
+    return rows
+
+
+def format_report(rows):
+    lines = ["golden case (reference)            tol     held   X relerr  U relerr  grads     identical traces (departed below / above margin)"]
+    for r in rows:
+        lines.append(f"{r['case']:32s} {r['tol']:.0e} {r['held']:3d}/{r['B']:<3d} {r['X']:9.2e} {r['U']:9.2e} {r['grads']:9.2e}"
+                     f"{'*' if r['grads_partial'] else ' '} {r['traces']:3d}/{r['B']:<3d} ({r['below_margin']} / {r['above_margin']})")
+    return "\n".join(lines)

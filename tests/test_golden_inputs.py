@@ -2,16 +2,12 @@
 generators (oracle/golden_inputs.py, torch only — the reference is not needed) produce for that case, bit for bit.
 oracle/gen_golden.py feeds the same generators to the unmodified reference, so a fixture whose inputs match was
 produced by the committed script on the committed configuration (VERDICT r1 weak #3: lti8_T50_f64 was not)."""
-import os
-import sys
-
 import numpy as np
 import pytest
 
 import parity as P
 
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
-import golden_inputs as GI  # noqa: E402
+from oracle import golden_inputs as GI  # noqa: E402
 
 
 def test_every_solve_case_has_a_generator():

@@ -17,6 +17,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 B_FULL, T, NX, NU, DT = 65536, 20, 4, 1, 0.05
+SAMPLE_BAR = 2e-4   # sample vs oracle along the kernel's decisions, relative to the largest entry (<= 4x achieved)
 
 
 @pytest.fixture(scope="module", autouse=True)
@@ -160,8 +161,9 @@ def test_full_batch_sample_against_oracle(full, oracle):
     ref = oracle.forward(sp, h["x0"], h["C"], h["c"], h["Cf"], h["cf"], h["xref"], h["uref"], h["Uinit"], replay=rp)
     X, U = fw["X"][idx.cuda()].cpu().numpy(), fw["U"][idx.cuda()].cpu().numpy()
     # fp32, tolerance as smoke(): relative to the largest entry, along the same decisions
-    assert np.abs(U - ref["U"]).max() / max(1.0, np.abs(ref["U"]).max()) < 2e-4
-    assert np.abs(X - ref["X"]).max() / max(1.0, np.abs(ref["X"]).max()) < 2e-4
+    import parity as P
+    P.held("fullsize_2a_sample384", "replay U err / max|U|", np.abs(U - ref["U"]).max() / max(1.0, np.abs(ref["U"]).max()), SAMPLE_BAR)
+    P.held("fullsize_2a_sample384", "replay X err / max|X|", np.abs(X - ref["X"]).max() / max(1.0, np.abs(ref["X"]).max()), SAMPLE_BAR)
     assert np.array_equal(fw["tight"][idx.cuda()].cpu().numpy().astype(bool), ref["tight"].astype(bool))
     # Free-running oracle (its own decisions).  In fp32 the last one or two accept/reject decisions of a solve compare
     # costs that differ by rounding ("noise margin"), so iteration counts agree only in the mean; what must

@@ -10,6 +10,13 @@ import parity as P
 
 pytestmark = pytest.mark.gpu
 
+# Multipliers on the north-star tolerance (1e-5 fp32 / 1e-9 fp64).  Each is at most 4x what the kernels achieve on the worst
+# golden case (the ledger tests/conftest.py prints; DESIGN.md 5 has the table).
+COST_K = 10.0         # replay: final objective, in units of the element's value tolerance
+FREE_COST_K = 200.0   # free-running final objective
+GRAD_K = 50.0         # gradients, beyond the reference's own fp32-vs-fp64 floor
+PNQP_ITERS_FRAC = 0.8
+
 
 @pytest.fixture(scope="module")
 def G():
@@ -52,10 +59,20 @@ def test_forward_replay_matches_reference(G, name, fwd_kernel):
     well = (tu <= tol) & (tx <= tol)
     print(f"{name}: {well.sum()}/{len(well)} elements held to {tol:g}; max err X {ex[well].max() if well.any() else 0:.2e} "
           f"U {eu[well].max() if well.any() else 0:.2e}")
+    tag = f"{name}[{fwd_kernel}]"
+    P.record(tag, "replay elems held to north-star tol", float(well.mean()), note=f"({int(well.sum())}/{len(well)} at {tol:g})")
+    if well.any():
+        P.record(tag, "replay max relerr X (held elems)", float(ex[well].max()), tol)
+        P.record(tag, "replay max relerr U (held elems)", float(eu[well].max()), tol)
+    if rep.any():
+        P.record(tag, "replay max relerr/elem_tol (all reproducible)", float(np.maximum(ex / tx, eu / tu)[rep].max()), 1.0)
     assert (P.rel_err(out["A"], g["A"])[rep] <= np.maximum(tx, tu)[rep]).all()
     assert (P.rel_err(out["Bm"], g["Bm"])[rep] <= np.maximum(tx, tu)[rep]).all()
     assert np.array_equal(out["tight"][well], g["tight"][well])
-    assert (P.rel_err(out["cost"][:, None], g["cost"][:, None])[rep] <= 10 * np.maximum(tx, tu)[rep]).all()
+    ce = P.rel_err(out["cost"][:, None], g["cost"][:, None])
+    if rep.any():
+        P.record(tag, "replay cost relerr/elem_tol", float((ce / np.maximum(tx, tu))[rep].max()), COST_K)
+    assert (ce[rep] <= COST_K * np.maximum(tx, tu)[rep]).all()
     print(f"{name}: {rep.sum()}/{len(rep)} elements reproducible in the reference itself")
 
 
@@ -74,7 +91,10 @@ def test_forward_lockstep_decisions(G, name, fwd_kernel):
     well = tu <= P.case_tol(g)
     scale = np.maximum(np.abs(g["cost"].astype(np.float64)), 1.0)
     cerr = np.abs(out["cost"].astype(np.float64) - g["cost"]) / scale
-    assert (cerr[well] <= 200 * P.case_tol(g)).all(), cerr
+    if well.any():
+        P.record(f"{name}[{fwd_kernel}]", "free-run cost relerr / tol", float(cerr[well].max() / P.case_tol(g)), FREE_COST_K)
+    P.record(f"{name}[{fwd_kernel}]", "free-run identical trace frac", same / B, note="(recorded, not a bar)")
+    assert (cerr[well] <= FREE_COST_K * P.case_tol(g)).all(), cerr
     assert np.isfinite(out["cost"][P.reproducible(g)]).all()
     idx = [b for b in range(B) if out["iters"][b] == g["iters"][b]
            and np.array_equal(out["alpha_trace"][b, :g["alpha_trace"].shape[1]], g["alpha_trace"][b])]
@@ -192,10 +212,13 @@ def test_backward_matches_reference(G, oracle, name, loss, bwd_kernel):
             floor = 4 * np.abs(g[f"grad64_{loss}_{nm}"] - gold).max() / scale
         if floor > 4 * P.REPRO_LIMIT:
             continue   # the reference's own fp32 gradient has lost its digits against fp64: nothing to pin
-        assert err <= 50 * tol + floor, (nm, err, floor)
+        tag = f"{name}[{bwd_kernel}]"
+        P.record(tag, f"bwd {loss} grad_{nm} vs reference: (err - floor)/tol", max(err - floor, 0.0) / tol, GRAD_K)
+        assert err <= GRAD_K * tol + floor, (nm, err, floor)
         # and against the oracle
         eo = np.abs(got.astype(np.float64) - ref[f"grad_{nm}"].reshape(gold.shape)).max() / scale
-        assert eo <= 50 * tol + floor, ("oracle", nm, eo)
+        P.record(tag, f"bwd {loss} grad_{nm} vs oracle: (err - floor)/tol", max(eo - floor, 0.0) / tol, GRAD_K)
+        assert eo <= GRAD_K * tol + floor, ("oracle", nm, eo)
     assert np.all(out["grad_x0"] == 0)  # quirk Q3
 
 
@@ -227,7 +250,10 @@ def test_pnqp_known_answers(G, tag, m):
     tol = 1e-5 if tag == "f32" else 1e-8
     ref = g[f"{tag}_m{m}_x"]
     assert np.abs(x.cpu().numpy() - ref).max() <= tol * max(1.0, np.abs(ref).max())
-    assert (iters.cpu().numpy() == g[f"{tag}_m{m}_iters"]).mean() >= 0.8
+    frac = float((iters.cpu().numpy() == g[f"{tag}_m{m}_iters"]).mean())
+    P.record(f"pnqp_{tag}_m{m}", "x max abs err / tol", float(np.abs(x.cpu().numpy() - ref).max() / (tol * max(1.0, np.abs(ref).max()))), 1.0)
+    P.record(f"pnqp_{tag}_m{m}", "iteration counts equal frac", frac, PNQP_ITERS_FRAC)
+    assert frac >= PNQP_ITERS_FRAC
 
 
 @pytest.mark.parametrize("tag", ["f32", "f64"])

@@ -102,6 +102,50 @@ def test_sharded_solve_equals_single_process(oracle, tmp_path, name):
             np.testing.assert_allclose(parts[0][k], fbw[k], rtol=1e-12, atol=1e-12 * max(1.0, np.abs(fbw[k]).max()))
 
 
+def _worker_diag(rank, world, port, name, out_dir):
+    """with a DiagQuadCost the override must be element 0's DIAGONALS, and the controller must hand
+    the kernels the layout of the path that runs (compact for C_diag, expanded for the dense fallback)."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from tacdmpc_b200 import sharding
+        from tacdmpc_b200.DifferentialMPC import DiagQuadCost, DifferentiableMPCController
+        from tacdmpc_b200.dynamics import CartPole
+        g = P.load(name)
+        B = g["x0"].shape[0]
+        lo, hi = sharding.shard_range(B, rank, world)
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+        q, qf = np.diagonal(g["C"], axis1=-2, axis2=-1), np.diagonal(g["Cf"], axis1=-2, axis2=-1)
+        cm = DiagQuadCost(4, 1, t(q[lo:hi]), t(g["c"][lo:hi]), t(qf[lo:hi]), t(g["cf"][lo:hi]), device="cpu")
+        f = CartPole()
+        ctl = DifferentiableMPCController(f, 1.0, 0.05, int(g["meta_T"]), cm, device="cpu", grad_method="analytic", f_dyn_jac=f.jac)
+        sharding.broadcast_line_search_cost(ctl)
+        ls = ctl.ls_cost_override
+        assert ls is not None and ls[0].shape == q.shape[1:] and ls[2].shape == qf.shape[1:]
+        for a, b in zip(ls, (q[0], g["c"][0], qf[0], g["cf"][0])):
+            assert np.array_equal(a.numpy(), b), "rank %d does not hold global element 0's diagonals" % rank
+        # what the two kernel families would be handed
+        cd = ctl._ls_override(torch.float64, "cpu", True)
+        dn = ctl._ls_override(torch.float64, "cpu", False)
+        ref = P.ls_cost_of(g)
+        assert all(np.array_equal(a.numpy(), b) for a, b in zip(dn, ref))
+        assert np.array_equal(cd[0].numpy(), q[0]) and np.array_equal(cd[2].numpy(), qf[0])
+        # a dense override (what round 1 installed) is reduced to its diagonal for the compact kernels
+        ctl.ls_cost_override = tuple(t(a) for a in ref)
+        cd2 = ctl._ls_override(torch.float64, "cpu", True)
+        assert all(np.array_equal(a.numpy(), b.numpy()) for a, b in zip(cd, cd2))
+        ctl.ls_cost_override = (t(ref[0][:, :2]), t(ref[1]), t(ref[2]), t(ref[3]))
+        with pytest.raises(RuntimeError):
+            ctl._ls_override(torch.float64, "cpu", True)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_diag_cost_line_search_broadcast(tmp_path):
+    mp.spawn(_worker_diag, args=(2, _free_port(), "cartpole_actor_f64", str(tmp_path)), nprocs=2, join=True)
+
+
 def test_shard_range_partitions_exactly():
     from tacdmpc_b200 import sharding
     for B in (0, 1, 7, 8, 65536, 65537):
