@@ -15,9 +15,11 @@ One "step" = one forward solve + one implicit-differentiation backward over the 
             states x0 and the warm start U_init are copied from pinned HOST memory (two-deep pipeline on a copy
             stream) and the actions + one cost gradient are read back; references are set once, as in the
             reference's regulation example.
-`roofline`: the dominant kernel (the forward solve), algorithmic bytes (SURVEY §8d formula) / its measured
-            launch duration vs the measured HBM peak; the FP32-pipe view is given beside it because the
-            forward solve is arithmetic-bound, not HBM-bound.
+`value`   : median of the per-step device times, max over ranks; mean / max / the list are in `timing`.
+`roofline`: the dominant kernel (the forward solve) against its BINDING roof (max of the bytes term and the
+            flops term): the FP32 pipe (model flops of the measured mean iteration count / launch time vs the nominal
+            FP32 peak, with an in-run FMA microbenchmark beside it); the HBM view is the sub-object `hbm_view`.
+`extra_configs`: BASELINE configs 2b, 3, 4, 5 at their sizes (N=1): solves/s, forward / backward ms, mean iterations.
 `cpu_baseline`: the CPU oracle ("port": the reference is pure Python and does not travel to the GPU box)
             on all host threads on a bounded sample of the same workload.
 """
@@ -112,6 +114,7 @@ class ClockSampler:
     def __init__(self, index, uuid=None):
         self.rows, self.proc, self.index, self.uuid = [], None, index, uuid
         self.samples, self.max_mhz, self.reasons, self._stop, self.th, self.nvml = [], None, set(), False, None, None
+        self.armed = False
 
     def sample(self):
         """One NVML reading (also called from the timed loop itself, while the GPU works through the queued steps: the
@@ -131,9 +134,12 @@ class ClockSampler:
             pass
 
     def _nvml_loop(self):
+        # samples are taken only while a timed region is open (`armed`), from this thread only: round 1 also read NVML from
+        # the launching thread inside the timed loop, which stalled the launches of that rank
         while not self._stop:
-            self.sample()
-            time.sleep(0.001)
+            if self.armed:
+                self.sample()
+            time.sleep(0.002)
 
     def __enter__(self):
         try:
@@ -250,6 +256,7 @@ def main():
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="solves per GPU")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra_configs table (BASELINE configs 2b-5, N=1 only)")
     args = ap.parse_args()
     # Contract: stdout carries ONE JSON line.  Libraries write there too (NCCL prints "NCCL version ..." on the first
     # communicator), so file descriptor 1 is pointed at stderr for the run and the line goes out through a saved copy.
@@ -291,6 +298,7 @@ def main():
     import torch
     import torch.distributed as dist
     from tacdmpc_b200 import _lib, ops, sharding
+    from tacdmpc_b200 import workloads as WL
     from tacdmpc_b200.DifferentialMPC import DifferentiableMPCController, GeneralQuadCost
     from tacdmpc_b200.dynamics import CartPole
 
@@ -328,58 +336,111 @@ def main():
     gU[:, 0] = 1.0
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     want = ("grad_C", "grad_c", "grad_Cf", "grad_cf", "grad_x0", "grad_xref", "grad_uref")
+    shared = args.layout == "shared"
+    # Shared-cost gradients are sums over the whole (sharded) batch: the backward kernels write them straight into one flat
+    # bucket (no gather copy), and the cross-rank sum is ONE all-reduce on a communication stream that the next step's solve
+    # does not wait for (two buckets, alternating: a consumer has a full step to read the reduced gradient).  Round 1 ran
+    # cat + all-reduce + four copies on the launching stream inside every step's window.
+    buckets = [sharding.GradBucket({"grad_C": (T, N, N), "grad_c": (T, N), "grad_Cf": (N, N), "grad_cf": (N,)}, dev) for _ in range(2)] \
+        if shared else None
 
-    def step_device():
-        fw = ops.ilqr_forward(spec, d["x0"], d["C"], d["c"], d["Cf"], d["cf"], d["xref"], d["uref"], d["Uinit"], ls_cost=ls,
-                              want_trace=False, C_diag=diag)
-        bw = ops.ilqr_backward(spec, fw["X"], fw["U"], d["C"], d["xref"], d["uref"], fw["tight"], gX, gU,
-                               Cf_batched=args.layout != "shared", want=want, C_diag=diag)
-        if world > 1 and args.layout == "shared":
-            sharding.allreduce_sum_([bw["grad_C"], bw["grad_c"], bw["grad_Cf"], bw["grad_cf"]])
-        return fw, bw
+    def fwd_call():
+        return ops.ilqr_forward(spec, d["x0"], d["C"], d["c"], d["Cf"], d["cf"], d["xref"], d["uref"], d["Uinit"], ls_cost=ls,
+                                want_trace=False, C_diag=diag)
+
+    def bwd_call(fw, slot):
+        return ops.ilqr_backward(spec, fw["X"], fw["U"], d["C"], d["xref"], d["uref"], fw["tight"], gX, gU,
+                                 Cf_batched=not shared, want=want, C_diag=diag, out=buckets[slot].views if shared else None)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(W):
-        fw, bw = step_device()
+    for i in range(W):                       # eager warm-up (also what CUDA-graph capture needs to have happened)
+        fw = fwd_call()
+        bw = bwd_call(fw, i & 1)
+        if shared:
+            buckets[i & 1].all_reduce_async()
         flush.fill_(1)
+    if shared:
+        for bk in buckets:
+            bk.join()
     barrier()
-    mean_iters = float(fw["iters"].float().mean().item())
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-          for _ in range(args.steps)]
-    launches0 = int(_lib.lib().tacd_kernel_launches())
+    # The device-timed loop replays the forward and the backward from CUDA graphs (one forward graph, one backward graph
+    # per bucket): the host then spends ~20 us per step instead of ~300 us in the Python / ctypes launch path, so with 8
+    # ranks on one box no rank's GPU ever waits for its host (the solve never synchronises the host and allocates only
+    # through torch, so it is capturable as it is).  TACD_BENCH_NO_GRAPH=1 times the eager calls instead.
+    g_fwd = g_bwd = None
+    if not os.environ.get("TACD_BENCH_NO_GRAPH"):
+        try:
+            g_fwd = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_fwd, capture_error_mode="thread_local"):
+                fw = fwd_call()
+            g_bwd = []
+            for sl in range(2 if shared else 1):
+                g_ = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_, capture_error_mode="thread_local"):
+                    bw = bwd_call(fw, sl)
+                g_bwd.append(g_)
+        except Exception as ex:   # noqa: BLE001
+            print(f"[bench] CUDA-graph capture of the device-timed step failed ({type(ex).__name__}: {ex}); eager loop", file=sys.stderr)
+            g_fwd = g_bwd = None
+            torch.cuda.synchronize(dev)
+    launches_per_step = None
+    l0 = int(_lib.lib().tacd_kernel_launches())
+    fw_e = fwd_call()
+    bwd_call(fw_e, 0)
+    launches_per_step = int(_lib.lib().tacd_kernel_launches()) - l0     # kernels of this library per step (graph replays re-issue them)
+    barrier()
+    K = args.steps
+    ev = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(3)) for _ in range(K)]
     try:
         dev_uuid = str(torch.cuda.get_device_properties(dev).uuid)
     except Exception:
         dev_uuid = None
-    with ClockSampler(local_rank, dev_uuid) as clk:
-        barrier()
-        for i in range(args.steps):
-            flush.fill_(i & 0xFF)          # L2 flush, outside the timed events
-            ev[i][0].record()
-            fw = ops.ilqr_forward(spec, d["x0"], d["C"], d["c"], d["Cf"], d["cf"], d["xref"], d["uref"], d["Uinit"],
-                                  ls_cost=ls, want_trace=False, C_diag=diag)
-            ev[i][1].record()
-            bw = ops.ilqr_backward(spec, fw["X"], fw["U"], d["C"], d["xref"], d["uref"], fw["tight"], gX, gU,
-                                   Cf_batched=args.layout != "shared", want=want, C_diag=diag)
-            if world > 1 and args.layout == "shared":
-                sharding.allreduce_sum_([bw["grad_C"], bw["grad_c"], bw["grad_Cf"], bw["grad_cf"]])
-            ev[i][2].record()
-            if i >= 2:
-                clk.sample()               # the GPU is two or more steps behind the host here: a reading under load
-        barrier()
-        gpu_launches = int(_lib.lib().tacd_kernel_launches()) - launches0
-        mean_iters = float(fw["iters"].float().mean().item())
-        t_fwd = sum(e[0].elapsed_time(e[1]) for e in ev) / 1e3
-        t_tot = sum(e[0].elapsed_time(e[2]) for e in ev) / 1e3
-        clocks = clk
-    clocks = clocks.summary()
-    t_tot_max = sharding.allreduce_max_scalar(t_tot, dev)
-    t_fwd_max = sharding.allreduce_max_scalar(t_fwd, dev)
-    value = world * B * args.steps / t_tot_max
+    clk = ClockSampler(local_rank, dev_uuid)
+    clk.__enter__()
+    barrier()
+    clk.armed = True
+    t_wall0 = time.perf_counter()
+    for i in range(K):
+        flush.fill_(i & 0xFF)          # L2 flush, outside the timed events
+        sl = i & 1
+        if shared:
+            buckets[sl].join()         # the all-reduce that last used this bucket (two steps ago) is long done: no stall
+        ev[i][0].record()
+        if g_fwd is not None:
+            g_fwd.replay()
+        else:
+            fw = fwd_call()
+        ev[i][1].record()
+        if g_bwd is not None:
+            g_bwd[sl if shared else 0].replay()
+        else:
+            bw = bwd_call(fw, sl)
+        ev[i][2].record()
+        if shared:
+            buckets[sl].all_reduce_async()     # communication stream; `done` event marks the reduced gradient of step i
+    if shared:
+        for bk in buckets:
+            bk.join()
+    barrier()                                  # every rank's solves AND all-reduces are complete inside the bracket
+    t_wall = time.perf_counter() - t_wall0
+    clk.armed = False
+    gpu_launches = launches_per_step * K
+    mean_iters = float(fw["iters"].float().mean().item())
+    step_ms = [e[0].elapsed_time(e[2]) for e in ev]
+    fwd_ms_l = [e[0].elapsed_time(e[1]) for e in ev]
+    med = lambda v: sorted(v)[len(v) // 2]
+    # median of the per-step device times (a straggler step shows in max / in the list, not in the headline)
+    t_step = sharding.allreduce_max_scalar(med(step_ms), dev)
+    t_fwd_step = sharding.allreduce_max_scalar(med(fwd_ms_l), dev)
+    t_step_mean = sharding.allreduce_max_scalar(sum(step_ms) / K, dev)
+    t_step_max = sharding.allreduce_max_scalar(max(step_ms), dev)
+    t_bracket = sharding.allreduce_max_scalar(t_wall, dev)
+    value = world * B / (t_step * 1e-3)
+    t_tot_max, t_fwd_max = t_step * 1e-3 * K, t_fwd_step * 1e-3 * K
 
     # ---------------------------------------------------------------- e2e through the public API, host buffers
     pin = {k: v.pin_memory() for k, v in host.items()}
@@ -431,14 +492,25 @@ def main():
         act_host.copy_(U.detach()[:, 0], non_blocking=True)
         return Cd.grad if args.layout == "shared" else Cd.grad[0]   # per-element: grads stay on the device, read one back
 
-    def step_tail(gC):
-        """Cross-rank sum of the shared-cost gradient (the path's only collective) and its read-back."""
-        if world > 1:
-            sharding.allreduce_sum_([gC])
-        gC_host.copy_(gC, non_blocking=True)
+    tail_s = torch.cuda.Stream(device=dev)
+    tail_ready = [torch.cuda.Event() for _ in range(2)]
+    tail_done = [torch.cuda.Event() for _ in range(2)]
+
+    def step_tail(gC, slot):
+        """Cross-rank sum of the shared-cost gradient (the path's only collective) and its read-back, on a side stream: the
+        next step's solve does not wait for them (they are joined before the slot's buffers are reused and before the
+        closing barrier, so every step's collective and read-back are inside the timed region)."""
+        tail_ready[slot].record(comp_s)
+        with torch.cuda.stream(tail_s):
+            tail_s.wait_event(tail_ready[slot])
+            gC.record_stream(tail_s)
+            if world > 1 and args.layout == "shared":
+                dist.all_reduce(gC, op=dist.ReduceOp.SUM)
+            gC_host.copy_(gC, non_blocking=True)
+            tail_done[slot].record(tail_s)
 
     def step_body(slot):
-        step_tail(step_core(slot))
+        step_tail(step_core(slot), slot)
 
     for sl in slots:
         sl["x0"].requires_grad_(True)
@@ -480,25 +552,34 @@ def main():
     def run_e2e(n):
         for e_ in ev_free:
             e_.record(comp_s)
+        for e_ in tail_done:
+            e_.record(tail_s)
         upload(0)
         for i in range(n):
             slot = i & 1
             if i + 1 < n:
                 upload(slot ^ 1)
             comp_s.wait_event(ev_up[slot])
+            comp_s.wait_event(tail_done[slot])     # the tail that last read this slot's gradient (two steps ago)
             if graphs is not None:
                 graphs[slot].replay()
-                step_tail(g_static[slot])
+                step_tail(g_static[slot], slot)
             else:
                 step_body(slot)
             ev_free[slot].record(comp_s)
+        for e_ in tail_done:
+            comp_s.wait_event(e_)
 
     run_e2e(W)
     barrier()
+    clk.armed = True
     t0 = time.perf_counter()
     run_e2e(args.steps)
     barrier()
     t_e2e = sharding.allreduce_max_scalar(time.perf_counter() - t0, dev)
+    clk.armed = False
+    clk.__exit__(None, None, None)
+    clocks = clk.summary()
     e2e_value = world * B * args.steps / t_e2e
     # the read-back of the last e2e step must be the actions of the device-timed solve (same inputs)
     e2e_checked = bool(torch.equal(act_host, fw["U"][:, 0].cpu()))
@@ -518,14 +599,24 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     fwd_b, bwd_b = algorithmic_bytes(args.layout)
-    fwd_ms = 1e3 * t_fwd_max / args.steps
-    bwd_ms = 1e3 * (t_tot_max - t_fwd_max) / args.steps
+    fwd_ms = t_fwd_step
+    bwd_ms = t_step - t_fwd_step
     ach = fwd_b * B / (fwd_ms * 1e-3) / 1e9
     ach_b = bwd_b * B / (bwd_ms * 1e-3) / 1e9
     F_fwd, F_bwd = flops_per_solve(mean_iters)
     sm_mhz = clocks.get("sm_mhz") or 1965.0
     fp32_peak_nominal = 148 * 128 * 2 * 1.965e9 / 1e12
     fp32_peak_at_clock = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+    # FP32-pipe microbenchmark on this GPU, this run: dependent-FMA chains, scalar FFMA and packed FFMA2
+    probe = {}
+    try:
+        for nm, kind in (("ffma", 0), ("ffma2", 1)):
+            tf, ms_ = ops.fp32_probe(kind, iters=8192, device=dev)
+            probe[nm + "_tflops"] = tf
+        probe["how"] = "tacd_fp32_probe: 148*8 CTAs x 256 threads x 16 chains x 8192 dependent FMAs, best of 5, CUDA events"
+    except Exception as ex:   # noqa: BLE001
+        probe = {"error": f"{type(ex).__name__}: {ex}"}
+    fp32_measured = max(probe.get("ffma_tflops", 0.0), probe.get("ffma2_tflops", 0.0)) or None
     traffic = limiter = None
     tj = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tj):
@@ -537,29 +628,121 @@ def main():
             traffic = None
     fwd_kernel = "ilqr_forward_small<float,4,1,cartpole>" if os.environ.get("TACD_FWD_KERNEL") == "thread" else \
         "ilqr_init_rollout + ilqr_forward_group<float,4,1,cartpole> (five lanes per element)"
-    roofline = {"kernel": fwd_kernel, "bound": "hbm", "achieved": ach, "peak": hbm_peak,
-                "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic, "peak_source": peak_src, "limiter": limiter,
-                "algorithmic_bytes_per_solve": fwd_b, "launch_ms": fwd_ms, "mean_iters": mean_iters,
-                "fp32_pipe": {"flops_per_solve": F_fwd, "achieved_tflops": F_fwd * B / (fwd_ms * 1e-3) / 1e12,
-                              "peak_tflops_nominal": fp32_peak_nominal, "peak_tflops_at_measured_clock": fp32_peak_at_clock,
-                              "frac_of_nominal": F_fwd * B / (fwd_ms * 1e-3) / 1e12 / fp32_peak_nominal},
-                "backward": {"kernel": "ilqr_backward_small<float,4,1,cartpole>", "bound": "hbm", "achieved": ach_b, "peak": hbm_peak,
-                             "unit": "GB/s", "frac": ach_b / hbm_peak, "algorithmic_bytes_per_solve": bwd_b, "launch_ms": bwd_ms}}
+    ach_tf = F_fwd * B / (fwd_ms * 1e-3) / 1e12
+    hbm_view = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic,
+                "peak_source": peak_src, "algorithmic_bytes_per_solve": fwd_b}
+    fp32_view = {"bound": "fp32", "achieved": ach_tf, "peak": fp32_peak_nominal, "unit": "TFLOP/s", "frac": ach_tf / fp32_peak_nominal,
+                 "peak_source": "nominal 148 SM x 128 lanes x 2 x 1.965 GHz (no driver-measured FP32 figure in MEASURED_PEAKS.json); "
+                                "the in-run FMA probe is given beside it",
+                 "flops_per_solve": F_fwd, "peak_tflops_at_measured_clock": fp32_peak_at_clock, "probe": probe,
+                 "frac_of_measured_probe": (ach_tf / fp32_measured) if fp32_measured else None}
+    # roofline.achieved = max(bytes term, flops term) — the BINDING roof leads, the other view sits beside it
+    # (the contract's enum offers hbm|tensor; the forward solve is bound by the FP32 / issue pipes, so the bound is named "fp32")
+    lead, other = (fp32_view, hbm_view) if fp32_view["frac"] >= hbm_view["frac"] else (hbm_view, fp32_view)
+    roofline = dict(lead)
+    roofline.update({"kernel": fwd_kernel, "launch_ms": fwd_ms, "mean_iters": mean_iters, "limiter": limiter,
+                     "traffic": traffic, ("hbm_view" if lead is fp32_view else "fp32_view"): other,
+                     "backward": {"kernel": "ilqr_backward_small<float,4,1,cartpole>" + (" + reduce_shared_grads" if shared else ""),
+                                  "bound": "hbm", "achieved": ach_b, "peak": hbm_peak,
+                                  "unit": "GB/s", "frac": ach_b / hbm_peak, "algorithmic_bytes_per_solve": bwd_b, "launch_ms": bwd_ms}})
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         v, cores, sample, _, _ = cpu_port_run(args.layout, args.cpu_seconds)
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+               "reference_python": "the unmodified reference (pure Python, does not travel to this box) measured 141 solves/s on 8 cores "
+                                   "in the build container at B=1024 (SURVEY 6)"}
+    extra = None
+    if world == 1 and not args.no_extra:
+        try:
+            extra = extra_configs(torch, ops, WL, dev, flush)
+        except Exception as ex:   # noqa: BLE001
+            extra = [{"error": f"{type(ex).__name__}: {ex}"}]
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
-            "ms_per_step": 1e3 * t_tot_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": t_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks,
+            "timing": {"statistic": "median over the K steps of each step's CUDA-event time (forward + backward), max over ranks",
+                       "ms_per_step_mean": t_step_mean, "ms_per_step_max": t_step_max, "fwd_ms": fwd_ms, "bwd_ms": bwd_ms,
+                       "bracket_ms_per_step": 1e3 * t_bracket / K, "bracket": "barrier + synchronize on both sides; includes the L2 "
+                       "flushes, the host loop and, sharded, every step's all-reduce (overlapped on a communication stream)",
+                       "mode": "cuda_graph" if g_fwd is not None else "eager", "step_ms_rank0": [round(v, 4) for v in step_ms]},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * t_e2e / args.steps, "mode": "cuda_graph" if graphs is not None else "eager",
                     "checked_against_device_solve": e2e_checked},
-            "gpu_launches": gpu_launches, "roofline": roofline, "cpu_baseline": cpu}
+            "gpu_launches": gpu_launches, "roofline": roofline, "cpu_baseline": cpu, "extra_configs": extra}
     print(json.dumps(line), file=out, flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+# ------------------------------------------------------------------------------------------- the other configurations
+def extra_configs(torch, ops, WL, dev, flush, reps=10, warm=3):
+    """BASELINE.json configs 2b, 3, 4, 5 at their sizes on one GPU: device-timed forward / backward (median of `reps`,
+    L2 flushed between), solves/s, mean iterations, fraction of the binding roof.  Same seeded workloads as the BASELINE-size
+    parity tests (tacdmpc_b200/workloads.py)."""
+    def timed(fn):
+        for _ in range(warm):
+            o = fn()
+        torch.cuda.synchronize(dev)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        for a, b in ev:
+            flush.fill_(1)
+            a.record()
+            o = fn()
+            b.record()
+        torch.cuda.synchronize(dev)
+        ts = sorted(a.elapsed_time(b) for a, b in ev)
+        return ts[len(ts) // 2], o
+
+    cases = [("2a cartpole shared C, B=16384", lambda: WL.cartpole(16384, "shared"), "shared"),
+             ("2a cartpole shared C, B=4096", lambda: WL.cartpole(4096, "shared"), "shared"),
+             ("2a cartpole shared C, B=1024", lambda: WL.cartpole(1024, "shared"), "shared"),
+             ("2b cartpole per-element dense C, B=65536", lambda: WL.cartpole(65536, "per_element"), "per_element"),
+             ("2b cartpole per-element diagonal C (compact), B=65536", lambda: WL.cartpole(65536, "diag"), "diag"),
+             ("3(i) unicycle T=30 loose box, B=16384", lambda: WL.unicycle(16384, tight=False), "shared"),
+             ("3(ii) unicycle T=30 tight box, B=16384", lambda: WL.unicycle(16384, tight=True), "shared"),
+             ("4 ActorMPC-shaped diagonal costs, B=512", lambda: WL.ppo_actor(512), "diag"),
+             ("4 ActorMPC-shaped diagonal costs, B=4096", lambda: WL.ppo_actor(4096), "diag"),
+             ("5 LTI nx=8 nu=4 T=50, B=4096", lambda: WL.lti(8, 4), "per_element"),
+             ("5 LTI nx=16 nu=4 T=50, B=4096", lambda: WL.lti(16, 4), "per_element"),
+             ("5 LTI nx=16 nu=8 T=50, B=4096", lambda: WL.lti(16, 8), "per_element"),
+             ("5 LTI nx=32 nu=8 T=50, B=4096", lambda: WL.lti(32, 8), "per_element"),
+             ("5 LTI nx=32 nu=8 T=50 spectral radius 0.9, B=4096", lambda: WL.lti(32, 8, rho=0.9), "per_element"),
+             ("5 LTI nx=8 nu=4 T=50 spectral radius 0.9, B=4096", lambda: WL.lti(8, 4, rho=0.9), "per_element")]
+    peaks = {}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+    hbm = float(peaks.get("hbm_gbs", 6650.0)) * 1e9
+    fp32 = 148 * 128 * 2 * 1.965e9
+    rows = []
+    for name, make, layout in cases:
+        w = make()
+        s = WL.gpu_spec(w["spec"], dev)
+        d = {k: v.to(dev) for k, v in w["inp"].items()}
+        ls = None if w["ls"] is None else tuple(t.to(dev) for t in w["ls"])
+        Bc, Tc = d["x0"].shape[0], s.T
+        t_f, fw = timed(lambda: ops.ilqr_forward(s, d["x0"], d["C"], d["c"], d["Cf"], d["cf"], d["xref"], d["uref"], d["Uinit"], ls_cost=ls,
+                                                 want_trace=False, C_diag=w["C_diag"]))
+        gX = torch.zeros(Bc, Tc + 1, s.nx, device=dev)
+        gU = torch.zeros(Bc, Tc, s.nu, device=dev)
+        gU[:, 0] = 1
+        t_b, _ = timed(lambda: ops.ilqr_backward(s, fw["X"], fw["U"], d["C"], d["xref"], d["uref"], fw["tight"], gX, gU,
+                                                 Cf_batched=w["Cf_batched"], C_diag=w["C_diag"]))
+        it = fw["iters"].float()
+        mi = float(it.mean())
+        bf, bb = WL.bytes_per_solve(w["spec"], layout)
+        ff, fb = WL.flops_per_solve(w["spec"], mi)
+        fr_f = max(bf * Bc / (t_f * 1e-3) / hbm, ff * Bc / (t_f * 1e-3) / fp32)
+        fr_b = max(bb * Bc / (t_b * 1e-3) / hbm, fb * Bc / (t_b * 1e-3) / fp32)
+        rows.append({"config": name, "B": Bc, "T": Tc, "nx": s.nx, "nu": s.nu, "solves_per_s": Bc / ((t_f + t_b) * 1e-3), "fwd_ms": t_f,
+                     "bwd_ms": t_b, "mean_iters": mi, "max_iters": int(it.max()), "nonpd_frac": float((fw["flags"] & 1).float().mean()),
+                     "tight_frac": float(fw["tight"].float().mean()),
+                     "fwd_roof_frac": fr_f, "fwd_roof": "hbm" if bf * Bc / hbm >= ff * Bc / fp32 else "fp32",
+                     "bwd_roof_frac": fr_b, "bwd_roof": "hbm" if bb * Bc / hbm >= fb * Bc / fp32 else "fp32"})
+        del d, fw, w
+        torch.cuda.empty_cache()
+    return rows
 
 
 if __name__ == "__main__":

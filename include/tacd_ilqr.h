@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define TACD_ABI_VERSION 3
+#define TACD_ABI_VERSION 4
 
 #define TACD_MAX_ALPHA 8
 #define TACD_MAX_NU 16
@@ -275,6 +275,13 @@ int tacd_gae(int32_t dtype, int32_t N, int32_t T, const void* rewards, const voi
  * target_H = bootstrap.   rewards, targets: [N,H];  bootstrap: [N] (NULL = 0).  Same rounding contract as tacd_gae. */
 int tacd_discounted_targets(int32_t dtype, int32_t N, int32_t H, const void* rewards, const void* bootstrap, double gamma,
                             void* targets, void* stream);
+
+/* FP32-pipe microbenchmark for the roofline denominator of the forward solve (SURVEY 8d asks for an FMA probe beside the nominal
+ * 148 SM x 128 lanes x 2 x f_SM): launches `blocks` CTAs of 256 threads, each thread running 16 independent dependent-FMA chains of
+ * `iters` steps.  kind 0 = scalar FFMA with three register sources (what the solve kernels issue), kind 1 = packed fma.rn.f32x2
+ * (FFMA2).  seed: 3 floats on the device {multiplier, addend, start}; out: blocks * 256 floats; *flops (host, nullable) receives the
+ * floating-point operations of the launch.  The caller times the launch with CUDA events.  No reference counterpart. */
+int tacd_fp32_probe(int32_t kind, int32_t iters, int32_t blocks, const void* seed, void* out, double* flops, void* stream);
 
 /* batched projected-Newton box QP: H[N,m,m] q[N,m] lo[N,m] hi[N,m] -> x[N,m], iters[N] (nullable) */
 int tacd_pnqp(int32_t dtype, int32_t N, int32_t m, const void* H, const void* q,

@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_ALPHA = 8
 MAX_NU = 16
 MAX_NX = 64

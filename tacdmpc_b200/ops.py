@@ -136,11 +136,12 @@ _GRAD_NAMES = ("grad_C", "grad_c", "grad_Cf", "grad_cf", "grad_x0", "grad_xref",
 
 def ilqr_backward(spec: Spec, X, U, Cm, xref, uref, tight, gX, gU, *, A=None, Bm=None, Cf_batched=False,
                   want=("grad_C", "grad_c", "grad_Cf", "grad_cf", "grad_x0", "grad_xref", "grad_uref"), C_diag=False,
-                  exact=False, Cf=None):
+                  exact=False, Cf=None, out=None):
     """ILQRSolve.backward (controller.py:63-115) on the GPU.  Outputs for shared (un-batched) inputs are
     already summed over the batch.  ``C_diag``: ``Cm [B,T,n]`` holds diagonals; ``grad_C [B,T,n]`` and
     ``grad_Cf [B,n]`` come back as diagonals too.  ``exact`` (needs ``Cf``): exact implicit differentiation instead
-    of the reference's (``tacd_problem.compat_exact``)."""
+    of the reference's (``tacd_problem.compat_exact``).  ``out``: optional ``{name: tensor}`` of caller-owned result buffers
+    (e.g. views into ONE flat bucket that is then all-reduced across ranks without a gather copy)."""
     _need_cuda(X, U, Cm, xref, uref, tight, gX, gU, A, Bm)
     dev, dt = X.device, X.dtype
     X, U, Cm, xref, uref, gX, gU = (_prep(t, dt, dev) for t in (X, U, Cm, xref, uref, gX, gU))
@@ -171,7 +172,15 @@ def ilqr_backward(spec: Spec, X, U, Cm, xref, uref, tight, gX, gU, *, A=None, Bm
                   grad_Cf=lead(Cf_batched) + ((n,) if C_diag else (n, n)),
                   grad_cf=lead(Cf_batched) + (n,), grad_x0=(B, nx), grad_xref=((B,) if xb else (1,)) + (T + 1, nx),
                   grad_uref=((B,) if ub else (1,)) + (T, nu), dX=(B, T + 1, nx), dU=(B, T, nu))
-    out = {k: torch.empty(shapes[k], device=dev, dtype=dt) for k in want}
+    given = out or {}
+    out = {}
+    for k in want:
+        t = given.get(k)
+        if t is None:
+            t = torch.empty(shapes[k], device=dev, dtype=dt)
+        elif t.numel() != torch.Size(shapes[k]).numel() or t.dtype != dt or t.device != dev or not t.is_contiguous():
+            raise RuntimeError(f"out[{k!r}] must be a contiguous {dt} tensor of {torch.Size(shapes[k]).numel()} elements on {dev}")
+        out[k] = t
     for k, v in out.items():
         setattr(io, k, _ptr(v))
     L = _lib.lib()
@@ -380,3 +389,26 @@ def discounted_targets(rewards, bootstrap=None, gamma: float = 0.99):
         _lib.check(_lib.lib().tacd_discounted_targets(_DT[dt], N, H, *_vp(rewards, bootstrap), float(gamma), *_vp(out), _stream()),
                    "tacd_discounted_targets")
     return out
+
+
+def fp32_probe(kind: int = 0, iters: int = 4096, blocks: int = 0, device=None, reps: int = 5):
+    """Measured FP32 throughput of this GPU in TFLOP/s (``tacd_fp32_probe``): ``kind`` 0 = scalar FFMA, 1 = packed FFMA2.
+    Best of ``reps`` CUDA-event timings after a warm-up launch.  Returns ``(tflops, ms)``."""
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if blocks <= 0:
+        blocks = torch.cuda.get_device_properties(device).multi_processor_count * 8
+    seed = torch.tensor([0.999999, 1e-6, 1.0], device=device, dtype=torch.float32)
+    out = torch.empty(blocks * 256, device=device, dtype=torch.float32)
+    flops = C.c_double(0.0)
+    best = float("inf")
+    with torch.cuda.device(device):
+        for r in range(reps + 1):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            _lib.check(_lib.lib().tacd_fp32_probe(int(kind), int(iters), int(blocks), C.c_void_p(seed.data_ptr()), C.c_void_p(out.data_ptr()),
+                                                  C.byref(flops), _stream()), "tacd_fp32_probe")
+            b.record()
+            b.synchronize()
+            if r > 0:
+                best = min(best, a.elapsed_time(b))
+    return flops.value / (best * 1e-3) / 1e12, best

@@ -43,6 +43,9 @@ SMALL_CASES = [c for c in SOLVE_CASES if not c.startswith("lti")]
 # recursion amplifies rounding by ~1e9 (in fp64 two correct implementations agree to ~1e-6 on K and ~3e-9
 # on U; in fp32 nothing survives, see REPRO_LIMIT below).  The tolerance of such a case is scaled.
 CASE_SLACK = {"lti8_T50_f64": 1e3}
+# ... but X*, U* of that case are reproduced far better than its gains: achieved 1.05e-9 relative in replay, so the VALUES are
+# held to 4e-9 (round 1 held them to 1e-6 with the blanket slack above, which now only covers gains / gradients / margins)
+VALUE_SLACK = {"lti8_T50_f64": 4.0}
 
 
 def load(name):
@@ -51,8 +54,9 @@ def load(name):
     return g
 
 
-def case_tol(g):
-    return TOL[g["x0"].dtype] * CASE_SLACK.get(str(g.get("__name__", "")), 1.0)
+def case_tol(g, values=False):
+    slack = (VALUE_SLACK if values else CASE_SLACK).get(str(g.get("__name__", "")), 1.0)
+    return TOL[g["x0"].dtype] * slack
 
 
 def spec_of(g):
@@ -93,7 +97,7 @@ def elem_tol(g, what="U", k=8.0):
     that — measured by gen_golden.py as (1) how far the reference's answer moves when x0 moves by one ulp
     with decisions held fixed (noise_*), and (2) for fp32 cases, how far the reference's fp32 answer is from
     the same decision sequence carried out in fp64 (X64/U64)."""
-    tol = case_tol(g)
+    tol = case_tol(g, values=True)
     floor = np.asarray(g["noise_" + what], np.float64)
     if what + "64" in g:
         floor = np.maximum(floor, rel_err(g[what], g[what + "64"]))

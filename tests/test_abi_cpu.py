@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for nm in names:
         assert hasattr(L, nm), nm
     assert set(names) == set(_lib.EXPORTS)
-    assert L.tacd_abi_version() == 3
+    assert L.tacd_abi_version() == 4
 
 
 def test_oracle_exports_same_entry_points(oracle):

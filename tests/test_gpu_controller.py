@@ -8,6 +8,10 @@ import parity as P
 
 pytestmark = pytest.mark.gpu
 
+# multipliers on the north-star tolerance, <= 4x achieved (ledger in the pytest summary); round 1 allowed 200 for both
+CTRL_COST_K = 200.0
+CTRL_GRAD_K = 200.0
+
 
 @pytest.fixture(scope="module", autouse=True)
 def _cuda():
@@ -70,7 +74,10 @@ def test_controller_forward_and_autograd(name):
     # end-to-end objective agreement where the reference itself is reproducible
     ok = np.maximum(P.elem_tol(g, "U"), P.elem_tol(g, "X")) <= P.case_tol(g)
     scale = np.maximum(np.abs(g["cost"].astype(np.float64)), 1.0)
-    assert ((np.abs(mpc.cost_last.cpu().numpy() - g["cost"]) / scale)[ok] <= 200 * P.case_tol(g)).all()
+    ce = (np.abs(mpc.cost_last.cpu().numpy() - g["cost"]) / scale)[ok]
+    if ok.any():
+        P.record("controller:" + name, "free-run cost relerr / tol", float(ce.max() / P.case_tol(g)), CTRL_COST_K)
+    assert (ce <= CTRL_COST_K * P.case_tol(g)).all()
     loss = (U * torch.from_numpy(g["wU"]).cuda()).sum() + (X * torch.from_numpy(g["wX"]).cuda()).sum()
     loss.backward()
     assert lv["x0"].grad is not None and float(lv["x0"].grad.abs().max()) == 0.0   # quirk Q3
@@ -81,7 +88,8 @@ def test_controller_forward_and_autograd(name):
             ref = g[f"grad_weighted_{nm}"]
             scale = max(np.abs(ref).max(), 1.0)
             err = np.abs(lv[nm].grad.cpu().numpy().astype(np.float64) - ref).max() / scale
-            assert err <= 200 * P.case_tol(g), (nm, err)
+            P.record("controller:" + name, f"autograd grad_{nm} relerr / tol", err / P.case_tol(g), CTRL_GRAD_K)
+            assert err <= CTRL_GRAD_K * P.case_tol(g), (nm, err)
 
 
 @pytest.mark.parametrize("name,mode", [("cartpole_shared_f64", "analytic"), ("cartpole_ad_f64", "auto_diff"),
@@ -99,7 +107,8 @@ def test_generic_path_with_python_callable(name, mode):
     X, U = mpc(lv["x0"], torch.from_numpy(g["Uinit"]).cuda())
     scale = np.maximum(np.abs(g["cost"]), 1.0)
     cerr = np.abs(mpc.cost_last.cpu().numpy() - g["cost"]) / scale
-    assert cerr.max() <= (1e-4 if mode == "finite_diff" else 200 * P.case_tol(g))
+    P.record(f"generic-path:{name}:{mode}", "free-run cost relerr / tol", float(cerr.max() / P.case_tol(g)), 1e-4 / P.case_tol(g) if mode == "finite_diff" else CTRL_COST_K)
+    assert cerr.max() <= (1e-4 if mode == "finite_diff" else CTRL_COST_K * P.case_tol(g))
     if mode != "finite_diff":
         iters = mpc.iters_last.cpu().numpy()
         same, below, bad = P.lockstep(g, iters, mpc.alpha_trace_last.cpu().numpy(), mpc.flags_last.cpu().numpy(), P.MARGIN[dt])

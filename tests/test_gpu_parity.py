@@ -12,10 +12,12 @@ pytestmark = pytest.mark.gpu
 
 # Multipliers on the north-star tolerance (1e-5 fp32 / 1e-9 fp64).  Each is at most 4x what the kernels achieve on the worst
 # golden case (the ledger tests/conftest.py prints; DESIGN.md 5 has the table).
-COST_K = 10.0         # replay: final objective, in units of the element's value tolerance
-FREE_COST_K = 200.0   # free-running final objective
-GRAD_K = 50.0         # gradients, beyond the reference's own fp32-vs-fp64 floor
-PNQP_ITERS_FRAC = 0.8
+COST_K = 1.0          # replay: final objective, in units of the element's value tolerance (achieved 0.19; round 1 allowed 10)
+FREE_COST_K = 1.0     # free-running final objective, in units of the north-star tolerance (achieved 0.19; round 1 allowed 200)
+GRAD_K = 2.0          # gradients beyond the reference's own fp32-vs-fp64 floor (achieved <= 0.49 on 16 of 18 cases; round 1: 50)
+# the two cases whose one-sample floor underestimates the spread of fp32 answers (achieved 7.0 and 35.4)
+GRAD_K_CASE = {"unicycle_loose_f32": 28.0, "lti16_f32": 50.0}
+PNQP_ITERS_FRAC = 0.85   # achieved 0.896 (m = 4): the stop test max|dx| < 1e-5 is decided by rounding on a few problems
 
 
 @pytest.fixture(scope="module")
@@ -48,7 +50,7 @@ def test_forward_replay_matches_reference(G, name, fwd_kernel):
     _skip_dup(name, fwd_kernel)
     g = P.load(name)
     spec = P.spec_of(g)
-    tol = P.case_tol(g)
+    tol = P.case_tol(g, values=True)
     out = G.forward(spec, g, replay=True)
     assert np.array_equal(out["iters"], g["iters"])
     assert np.array_equal(out["alpha_trace"][:, :g["alpha_trace"].shape[1]], g["alpha_trace"])
@@ -213,12 +215,13 @@ def test_backward_matches_reference(G, oracle, name, loss, bwd_kernel):
         if floor > 4 * P.REPRO_LIMIT:
             continue   # the reference's own fp32 gradient has lost its digits against fp64: nothing to pin
         tag = f"{name}[{bwd_kernel}]"
-        P.record(tag, f"bwd {loss} grad_{nm} vs reference: (err - floor)/tol", max(err - floor, 0.0) / tol, GRAD_K)
-        assert err <= GRAD_K * tol + floor, (nm, err, floor)
+        GK = GRAD_K_CASE.get(name, GRAD_K)
+        P.record(tag, f"bwd {loss} grad_{nm} vs reference: (err - floor)/tol", max(err - floor, 0.0) / tol, GK)
+        assert err <= GK * tol + floor, (nm, err, floor)
         # and against the oracle
         eo = np.abs(got.astype(np.float64) - ref[f"grad_{nm}"].reshape(gold.shape)).max() / scale
-        P.record(tag, f"bwd {loss} grad_{nm} vs oracle: (err - floor)/tol", max(eo - floor, 0.0) / tol, GRAD_K)
-        assert eo <= GRAD_K * tol + floor, ("oracle", nm, eo)
+        P.record(tag, f"bwd {loss} grad_{nm} vs oracle: (err - floor)/tol", max(eo - floor, 0.0) / tol, GK)
+        assert eo <= GK * tol + floor, ("oracle", nm, eo)
     assert np.all(out["grad_x0"] == 0)  # quirk Q3
 
 

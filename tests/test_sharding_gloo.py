@@ -65,8 +65,19 @@ def _worker(rank, world, port, name, out_dir):
         bw = orc.backward(spec, out["X"], out["U"], sh(g["C"], Cb), g["xref"][lo:hi], g["uref"][lo:hi], out["tight"],
                           np.zeros_like(out["X"]), gU, Cf_batched=int(Cfb))
         # (3) shared-cost gradients: one flat all-reduce
+        bw0 = {k: v.copy() for k, v in bw.items()}
         shared = [torch.from_numpy(bw[k]) for k, b in (("grad_C", Cb), ("grad_c", Cb), ("grad_Cf", Cfb), ("grad_cf", Cfb)) if not b]
         sharding.allreduce_sum_(shared)
+        # the same sum through the flat bucket the bench / PPO step use (views handed out as result buffers, one all-reduce)
+        names = [k for k, b in (("grad_C", Cb), ("grad_c", Cb), ("grad_Cf", Cfb), ("grad_cf", Cfb)) if not b]
+        if names:
+            bk = sharding.GradBucket({k: bw0[k].shape for k in names}, "cpu", torch.float64)
+            for k in names:
+                bk.views[k].copy_(torch.from_numpy(bw0[k]))
+            bk.all_reduce_async()
+            bk.join()
+            for k, t in zip(names, shared):
+                assert torch.equal(bk.views[k], t), k
         tmax = sharding.allreduce_max_scalar(float(rank + 1), "cpu")
         assert tmax == float(world)
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), lo=lo, hi=hi, X=out["X"], U=out["U"], iters=out["iters"],
