@@ -171,6 +171,8 @@ int tacd_abi_version(void);
 const char* tacd_last_error(void);
 /* diagnostic: kernels of this library enqueued by the calling process so far (all entry points) */
 unsigned long long tacd_kernel_launches(void);
+/* The library caches its TACD_* experiment knobs (environment variables) on first use; call this after changing one. */
+void tacd_refresh_env(void);
 
 /* bytes of device scratch tacd_ilqr_forward / tacd_ilqr_backward need */
 size_t tacd_forward_workspace_bytes(const tacd_problem* p);

@@ -12,7 +12,8 @@ import threading
 from . import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtacd_ilqr.so")
+# TACD_LIB=path loads an experiment build of the same ABI instead (python -m tacdmpc_b200.build -DX=.. --out=path); A/B runs only
+LIB_PATH = os.environ.get("TACD_LIB") or os.path.join(_HERE, "libtacd_ilqr.so")
 _lock = threading.Lock()
 _lib = None
 
@@ -21,6 +22,7 @@ _SIGS = {
     "tacd_abi_version": (C.c_int, []),
     "tacd_last_error": (C.c_char_p, []),
     "tacd_kernel_launches": (C.c_ulonglong, []),
+    "tacd_refresh_env": (None, []),
     "tacd_forward_workspace_bytes": (C.c_size_t, [C.POINTER(_abi.Problem)]),
     "tacd_backward_workspace_bytes": (C.c_size_t, [C.POINTER(_abi.Problem)]),
     "tacd_ilqr_forward": (C.c_int, [C.POINTER(_abi.Problem), C.POINTER(_abi.ForwardIO), _VP, C.c_size_t, _VP]),

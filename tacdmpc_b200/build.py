@@ -42,11 +42,14 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in _deps())
 
 
-def build_extension(force: bool = False, verbose: bool = False) -> str:
-    if not force and not is_stale():
+def build_extension(force: bool = False, verbose: bool = False, defines=(), out: str | None = None, sources=None) -> str:
+    """Compile the library.  `defines` / `out` build an experiment variant (e.g. ("-DTACD_GROUP_MAXW=16",) into
+    tacdmpc_b200/variants/x.so, selected at run time with TACD_LIB=path); the default call builds the product."""
+    variant = bool(defines) or out is not None
+    if not variant and not force and not is_stale():
         return LIB
     nvcc = _nvcc()
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build" if not variant else "build_" + os.path.splitext(os.path.basename(out or "variant"))[0])
     os.makedirs(objdir, exist_ok=True)
     env = dict(os.environ)
     # the image exports CC=/opt/gcc/bin/gcc; nvcc wants the system g++
@@ -54,7 +57,7 @@ def build_extension(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(src):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, *ccbin, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *defines, *ccbin, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True, env=env)
@@ -66,12 +69,16 @@ def build_extension(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [nvcc, "-shared", *ccbin, "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs]
+    target = out or LIB
+    os.makedirs(os.path.dirname(target), exist_ok=True)
+    cmd = [nvcc, "-shared", *ccbin, "-gencode", "arch=compute_100a,code=sm_100a", "-o", target, *objs]
     r = subprocess.run(cmd, capture_output=True, text=True, env=env)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    return LIB
+    return target
 
 
 if __name__ == "__main__":
-    print(build_extension(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = tuple(a for a in sys.argv[1:] if a.startswith("-D"))
+    outs = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build_extension(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, out=outs[0] if outs else None))

@@ -1,6 +1,7 @@
 // capi.cu — the C ABI of include/tacd_ilqr.h: argument validation, dispatch
 // between the thread-per-element kernels (shipped small plugins) and the generic
 // CTA-per-element kernels, error reporting.  Nothing here synchronises the host.
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -21,6 +22,18 @@ void set_error(const char* fmt, ...) {
 // number of kernels of this library enqueued by the process (diagnostic; read by bench.py for gpu_launches)
 static std::atomic<unsigned long long> g_launches{0};
 void note_launches(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+static std::atomic<int> g_env_gen{0};
+int env_generation() { return g_env_gen.load(std::memory_order_relaxed); }
+void env_read(EnvKnob& k) {
+  const char* e = getenv(k.name);
+  k.set = e != nullptr;
+  k.ival = e ? atoi(e) : 0;
+  k.sval[0] = 0;
+  if (e) { strncpy(k.sval, e, sizeof(k.sval) - 1); k.sval[sizeof(k.sval) - 1] = 0; }
+  k.gen = env_generation();
+}
+bool env_is(EnvKnob& k, const char* value) { const EnvKnob& e = env_get(k); return e.set && !strcmp(e.sval, value); }
 
 int check_cuda(cudaError_t e, const char* what) {
   if (e == cudaSuccess) return TACD_OK;
@@ -80,12 +93,15 @@ extern "C" {
 int tacd_abi_version(void) { return TACD_ABI_VERSION; }
 const char* tacd_last_error(void) { return g_err; }
 unsigned long long tacd_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }
+void tacd_refresh_env(void) { g_env_gen.fetch_add(1, std::memory_order_relaxed); }
 
 // forward workspace: [0, kFwdHead) queue counter + bucket counters + longest-first order of the
 // thread-per-element kernel; the generic kernel's per-CTA slices follow
 static size_t fwd_head_bytes(const tacd_problem* p) {
   size_t b = 16384 + (((size_t)p->B * 4 + 255) / 256) * 256;
   b += (((size_t)p->B * 8 + 255) / 256) * 256;   // initial cost of every element (group kernel)
+  b += ((group_forward_scratch_bytes(p) + 255) / 256) * 256;   // the line-search candidates' state tiles (group kernel)
+  b += (((size_t)p->B * 4 + 255) / 256) * 256;   // hand-over list of the two-phase solve
   if (p->C_batched) {
     // lane-slot copy of the per-element (C, c): one slot per resident thread, bounded by shared memory
     const size_t es = p->dtype == TACD_F32 ? 4 : 8, n = p->nx + p->nu, T = p->T;

@@ -13,6 +13,24 @@ void set_error(const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);
 void note_launches(int n);
 
+// Experiment knobs (TACD_* environment variables: A/B measurements and the alternative-kernel parity runs).  Each is read
+// from the environment ONCE and cached at its call site; tacd_refresh_env() invalidates the caches (the tests flip
+// knobs inside one process).  Production leaves them unset: a launch costs no getenv() calls.
+struct EnvKnob {
+  const char* name;
+  int gen;
+  bool set;
+  int ival;
+  char sval[24];
+};
+int env_generation();
+void env_read(EnvKnob& k);
+inline const EnvKnob& env_get(EnvKnob& k) { if (k.gen != env_generation()) env_read(k); return k; }
+#define TACD_KNOB(var, NAME) static ::tacd::EnvKnob var = {NAME, -1, false, 0, {0}}
+inline int env_int(EnvKnob& k, int dflt) { const EnvKnob& e = env_get(k); return e.set ? e.ival : dflt; }
+inline bool env_set(EnvKnob& k) { return env_get(k).set; }
+bool env_is(EnvKnob& k, const char* value);
+
 struct DeviceInfo { int sms; int smem_optin; };
 DeviceInfo device_info();
 
@@ -48,12 +66,16 @@ inline DevProblem<R> to_dev(const tacd_problem* p) {
 
 // small-system (thread-per-element) launchers; return TACD_EUNSUPPORTED when
 // (nx, nu, dyn) has no instantiation or the per-thread state does not fit shared memory
-template <typename R> int launch_forward_small(const tacd_problem* p, const tacd_forward_io* io, void* ws, size_t ws_bytes, cudaStream_t s);
+// hand-over buffers of the two-phase solve (all in the caller's workspace); nullptr = the thread kernel runs every solve to its end
+struct FwdHandover { int cap_iters; unsigned int* count; int32_t* list; void* cost; };
+template <typename R> int launch_forward_small(const tacd_problem* p, const tacd_forward_io* io, void* ws, size_t ws_bytes, cudaStream_t s,
+                                               const FwdHandover* ho = nullptr);
 template <typename R> int launch_backward_small(const tacd_problem* p, const tacd_backward_io* io, void* ws, size_t ws_bytes, cudaStream_t s);
 size_t small_backward_ws_bytes(const tacd_problem* p);
 // five-lanes-per-element forward kernel (ilqr_group.cuh); TACD_EUNSUPPORTED when not eligible
 template <typename R> int launch_forward_group(const tacd_problem* p, const tacd_forward_io* io, void* ws, size_t ws_bytes, cudaStream_t s);
 template <typename R> int launch_backward_group(const tacd_problem* p, const tacd_backward_io* io, void* ws, size_t ws_bytes, cudaStream_t s);
+size_t group_forward_scratch_bytes(const tacd_problem* p);
 
 // generic (CTA-per-element, run-time dimensions) launchers
 template <typename R> int launch_forward_generic(const tacd_problem* p, const tacd_forward_io* io, void* ws, size_t ws_bytes, cudaStream_t s);

@@ -22,14 +22,14 @@ static inline size_t gen_slice_scalars(const tacd_problem* p) {
 }
 // Threads per element (GenDims::tpe): one warp for systems up to nx = 16, the whole CTA above.
 static int gen_tpe(const tacd_problem* p) {
-  static const char* e = getenv("TACD_GENERIC_TPE");
-  if (e) return atoi(e) == 32 ? 32 : kGenThreads;
+  TACD_KNOB(k, "TACD_GENERIC_TPE");
+  if (env_set(k)) return env_int(k, 0) == 32 ? 32 : kGenThreads;
   return p->nx <= 16 ? 32 : kGenThreads;
 }
 // element slots in flight: four CTAs per SM, kGenThreads / tpe elements per CTA
 static int gen_ctas_per_sm() {
-  static const char* e = getenv("TACD_GENERIC_CTAS");
-  const int v = e ? atoi(e) : 4;
+  TACD_KNOB(k, "TACD_GENERIC_CTAS");
+  const int v = env_int(k, 4);
   return v >= 1 && v <= 16 ? v : 4;
 }
 static int gen_slots(const tacd_problem* p, int tpe) {
@@ -684,7 +684,8 @@ static FwdPtrs<R> fwd_ptrs(const tacd_forward_io* io) {
 // Sizes of the LTI sweep get kernels with compile-time nx, nu; everything else runs the
 // run-time-dimension instance (NXT = NUT = 0).  TACD_GENERIC_RUNTIME_DIMS=1 forces the latter (A/B measurements).
 #define TACD_GEN_SIZES(X) X(8, 4) X(16, 4) X(16, 8) X(32, 8)
-static bool gen_runtime_dims() { static const bool v = getenv("TACD_GENERIC_RUNTIME_DIMS") != nullptr; return v; }
+static bool gen_force_ws() { TACD_KNOB(k, "TACD_GENERIC_WS"); return env_set(k); }
+static bool gen_runtime_dims() { TACD_KNOB(k, "TACD_GENERIC_RUNTIME_DIMS"); return env_set(k); }
 
 // one warp per element only if four element slots (matrices alone) fit the CTA's shared memory
 template <typename R>
@@ -701,7 +702,7 @@ static GenLaunch gen_launch_shape(const tacd_problem* p, size_t slice) {
   const size_t with_slice = gen_elem_bytes<R>(p->nx, p->nu, slice) * per_cta;
   GenLaunch L;
   // CTA-per-element: four CTAs per SM; warp-per-element: two four-element CTAs per SM are enough to cover the barriers
-  L.in_smem = with_slice <= (size_t)device_info().smem_optin / (TPE == 32 ? 2 : gen_ctas_per_sm()) && !getenv("TACD_GENERIC_WS");
+  L.in_smem = with_slice <= (size_t)device_info().smem_optin / (TPE == 32 ? 2 : gen_ctas_per_sm()) && !gen_force_ws();
   L.smem = L.in_smem ? with_slice : gen_elem_bytes<R>(p->nx, p->nu, 0) * per_cta;
   L.grid = (gen_slots(p, TPE) + per_cta - 1) / per_cta;
   return L;

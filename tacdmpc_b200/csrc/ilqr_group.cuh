@@ -13,9 +13,13 @@
 //                  per element with 128-bit accesses.  Jacobians are evaluated five time steps at a time
 //                  (lane j takes step t - j) in compact form (6 numbers for the cart-pole, 4 for the
 //                  unicycle) and broadcast with shuffles; the structural zeros / ones of F are skipped.
-//   line search    lane a rolls out candidate alpha_a and keeps its trajectory in its own shared-memory
-//                  buffer (6 buffers per element: nominal + 5 candidates), so accepting a candidate is a
-//                  buffer-index swap — there is no re-rollout pass.
+//   line search    lane a rolls out candidate alpha_a.  Its INPUTS go to its own shared-memory buffer (6 input buffers per
+//                  element: nominal + 5 candidates, accepting = buffer-index swap), its STATES go to a per-warp scratch
+//                  tile in global memory, [word][lane] so that every store is one coalesced 128-byte line; the tile is
+//                  rewritten every iteration and stays in L2.  Only the winner's states are read back (84 words per
+//                  element and iteration), so shared memory holds ONE state trajectory per element instead of six:
+//                  1.3 KB per element instead of 3.0 KB, 20 resident warps per SM instead of 12 (round 2; round 1's
+//                  kernel issued 70 % of its slots with 3 warps per scheduler, profiles/r1_forward_group_v6).
 //   queue          groups pull elements from a global counter; the initial rollout + cost of every element
 //                  is done up front by ilqr_init_rollout (thread per element), so a refill is two coalesced
 //                  copies and all six groups of a warp stay in the same phase.
@@ -30,8 +34,24 @@ namespace tacd {
 
 constexpr int kG = 5;              // lanes per element = line-search candidates rolled out together
 constexpr int kEPW = 32 / kG;      // elements per warp
-constexpr int kNBUF = kG + 1;      // trajectory buffers per element (nominal + one per candidate)
-constexpr int kNSLOT = kNBUF + 1;  // + the element's references (x_ref, u_ref) in the same layout
+constexpr int kNBUF = kG + 1;      // INPUT (U) buffers per element (nominal + one per candidate)
+// Shared-memory layout of one warp (6 element slots), all [word][slot][element-in-warp] so that consecutive lanes of
+// different groups hit consecutive banks:
+//   X part   (T+1) nx words x {nominal X, x_ref}             stride kXS between words
+//   U part   T nu words     x {6 input buffers, u_ref}       stride kUS between words
+//   V part   6 x (nx+1) x 4 words: value-function exchange
+constexpr int kXS = 2 * kEPW;
+constexpr int kUS = (kNBUF + 1) * kEPW;
+constexpr int kURef = kNBUF * kEPW;     // slot offset of u_ref in the U part
+#ifndef TACD_GROUP_MAXW
+// resident warps per SM (fp32) = __launch_bounds__(32 MAXW, 1).  Shared memory would allow 28; measured at B = 65536 (forward ms,
+// registers): 12 -> 0.658 (148), 16 -> 0.626 (127), 20 -> 0.672 (96), 24 -> 0.660 (80): beyond 16 the register cap costs more
+// instructions (+20 % at 80 registers: constants re-loaded, values re-materialised) than the extra warps hide latency.
+#define TACD_GROUP_MAXW 16
+#endif
+constexpr int kGroupMaxWarps = TACD_GROUP_MAXW;
+// resident warps per SM by scalar type: fp64 needs two registers per value (12 warps: 168 registers, no spills)
+template <typename R> constexpr int group_max_warps() { return sizeof(R) == 4 ? kGroupMaxWarps : 12; }
 
 // ---- structured Jacobians ---------------------------------------------------------------------------------
 // F = [A | B] (NX x N) of the shipped plugins in compact form: jc[NJ] holds the entries that depend on (x,u);
@@ -149,15 +169,18 @@ TACD_DEV R pick(const R* a, int i) {
 
 template <typename R> struct alignas(16) Row4 { R v[4]; };
 
-// shared-memory words of one warp's region (6 element slots)
-__host__ __device__ inline int group_traj_words(int T, int nx, int nu) { return (T + 1) * nx + T * nu; }
-// offset of the value-function exchange block (16-byte aligned) and size of the whole region
+// shared-memory words of one warp's region (6 element slots): offsets of the U part and of the value-function exchange
+// block (16-byte aligned), size of the whole region
+__host__ __device__ inline int group_uoff_words(int T, int nx) { return (T + 1) * nx * kXS; }
 __host__ __device__ inline int group_voff_words(int T, int nx, int nu) {
-  return (group_traj_words(T, nx, nu) * kNSLOT * kEPW + 3) & ~3;
+  return (group_uoff_words(T, nx) + T * nu * kUS + 3) & ~3;
 }
 __host__ __device__ inline int group_warp_words(int T, int nx, int nu) {
   return group_voff_words(T, nx, nu) + kEPW * (nx + 1) * 4;
 }
+// global-memory scratch of one warp: the candidates' states X_1..X_T, [word][lane]
+__host__ __device__ inline size_t group_xscratch_words(int T, int nx) { return (size_t)T * nx * 32; }
+template <typename R> TACD_DEV R ld_cg(const R* p) { return __ldcg(p); }
 // CTA-shared staging of the un-batched costs (+ the separate line-search cost) and the LTI matrices.
 // Running cost of step t: [C_t (n*n) | c_t (n) | pad] at stride group_cost_stride(n) (multiple of 4 words, so the
 // line search reads it with 128-bit loads); terminal cost: [C_final | c_final | pad].
@@ -370,7 +393,7 @@ __global__ void __launch_bounds__(128) ilqr_init_rollout(const DevProblem<R> P, 
 // DIAG (only with per-element costs, CSH = false): tacd_problem.C_diag — C, C_final (and the line-search cost)
 // are compact diagonals, the ActorMPC layout (ACMPC/actor.py:58-81); 2n instead of n*n + n words per step.
 template <typename R, int NX, int NU, int DYN, bool LSSEP, bool CSH, bool DIAG>
-__global__ void __launch_bounds__(384, 1) ilqr_forward_group(const DevProblem<R> P, const FwdPtrs<R> io, const R* cost0) {
+__global__ void __launch_bounds__(group_max_warps<R>() * 32, 1) ilqr_forward_group(const DevProblem<R> P, const FwdPtrs<R> io, const R* cost0) {
   constexpr int N = NX + NU;
   static_assert(N <= kG, "one lane per row of the Q-function");
   static_assert(NX <= 4, "value-function rows travel as one 4-word vector");
@@ -380,7 +403,6 @@ __global__ void __launch_bounds__(384, 1) ilqr_forward_group(const DevProblem<R>
   constexpr int CW = DIAG ? N : N * N;         // words of C per step / of C_final in global memory
   constexpr int NJ = GD::NJ;
   constexpr unsigned FULL = 0xffffffffu;
-  constexpr int WS = kNSLOT * kEPW;            // words between consecutive trajectory words of one buffer
   constexpr int CS = (N * N + N + 3) & ~3;     // staged cost stride per step
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int T = P.T;
@@ -390,7 +412,7 @@ __global__ void __launch_bounds__(384, 1) ilqr_forward_group(const DevProblem<R>
   const int j = valid ? lane - e * kG : kG;    // position in the group
   const int base = e * kG;                     // first lane of the group (shuffle source)
   const int jj = j < N ? j : N - 1;            // row of the Q-function this lane computes
-  const int XW = (T + 1) * NX, W = XW + T * NU;
+  const int XW = (T + 1) * NX, UW = T * NU;
   const size_t szX = (size_t)XW, szU = (size_t)T * NU;
 
   // ---- shared memory: CTA-wide cost staging, then one region per warp
@@ -444,12 +466,14 @@ __global__ void __launch_bounds__(384, 1) ilqr_forward_group(const DevProblem<R>
   const bool constOwn = __syncthreads_and(same_own ? 1 : 0) != 0 && CSH;
   const bool constLs = __syncthreads_and(same_ls ? 1 : 0) != 0 && LSSEP;
   R* wreg = sm + (size_t)wid * group_warp_words(T, NX, NU);
-  R* ebuf = wreg + e;                                              // [word][slot][e], slot kNBUF = references
-  const R* refp = ebuf + kNBUF * kEPW;                             // x_ref word w at refp[w * WS], u_ref after XW words
+  R* xb = wreg + e;                                   // nominal X word w at xb[w * kXS], x_ref word w at xb[w * kXS + kEPW]
+  R* ub = wreg + group_uoff_words(T, NX) + e;         // input buffer s, word w at ub[w * kUS + s * kEPW]; u_ref: slot kNBUF
   // The gains have no storage of their own: between the reverse pass that produces them and the line search
-  // that consumes them the five non-nominal buffers are dead, and candidate a overwrites X_{t+1} / U_t of its
-  // buffer only at the end of step t.  K_t[m][:] lives in the X_{t+1} slot of the m-th dead buffer, k_t in
-  // the U_t slot of the first one; the line search reads them at the top of step t.
+  // that consumes them the five non-nominal input buffers are dead, and candidate a overwrites U_t of its
+  // buffer only at the end of step t.  K_t[m][i] lives in the U_t[m] slot of the i-th dead buffer, k_t[m] in
+  // that of the NX-th one ((NX + 1) NU words needed, 5 NU there: NX <= 4); the line search reads them at the top of step t.
+  // The candidates' states go to the warp's global-memory scratch tile, word w = X_{t+1}[i] of lane l at scr[(t NX + i) 32 + l].
+  R* scr = io.xscratch + ((size_t)blockIdx.x * (blockDim.x >> 5) + wid) * group_xscratch_words(T, NX);
   R* myV = wreg + group_voff_words(T, NX, NU) + (size_t)e * (NX + 1) * 4;   // [e][NX+1][4]: rows of V, then v
   // Dyn<> (LTI) wants A and B separately: straight from global memory (uniform, cached)
   const R* sA = P.dyn_A;
@@ -466,7 +490,7 @@ __global__ void __launch_bounds__(384, 1) ilqr_forward_group(const DevProblem<R>
 
   // group state, replicated in the lanes of the group
   bool has = false, exhausted = !valid;
-  int b = 0, it = 0, nom = 0;
+  int b = 0, it = 0;
   unsigned flg = 0;
   R best = 0;
   const R *Cp = io.C, *cp = io.c, *Cfp = io.Cf, *cfp = io.cf;
@@ -479,9 +503,11 @@ __global__ void __launch_bounds__(384, 1) ilqr_forward_group(const DevProblem<R>
       if (need && j == 0) nb = atomicAdd(io.counter, 1u);
       nb = __shfl_sync(FULL, nb, base);
       if (need) {
-        if (nb < (unsigned)P.B) {
+        if (nb < (io.n_dev ? *io.n_dev : (unsigned)P.B)) {
           b = io.order ? io.order[nb] : (int)nb;
-          has = true; it = 0; flg = 0; nom = 0;
+          has = true;
+          it = io.resume ? io.iters[b] : 0;               // resume: the thread-per-element kernel ran the first iterations
+          flg = io.resume ? (unsigned)io.flags[b] : 0u;
           Cp = io.C + (P.C_batched ? (size_t)b * T * CW : 0);
           cp = io.c + (P.C_batched ? (size_t)b * T * N : 0);
           Cfp = io.Cf + (P.Cf_batched ? (size_t)b * CW : 0);
@@ -494,11 +520,10 @@ __global__ void __launch_bounds__(384, 1) ilqr_forward_group(const DevProblem<R>
           const R* ur = io.uref + (P.uref_batched ? (size_t)b * szU : 0);
           const R* Xi = io.X + (size_t)b * szX;
           const R* Ui = io.Uinit + (size_t)b * szU;
-          R* rp = ebuf + kNBUF * kEPW;
-          for (int w = j; w < XW; w += kG) { ebuf[(size_t)w * WS] = Xi[w]; rp[(size_t)w * WS] = xr[w]; }
-          for (int w = j; w < W - XW; w += kG) { ebuf[(size_t)(XW + w) * WS] = Ui[w]; rp[(size_t)(XW + w) * WS] = ur[w]; }
+          for (int w = j; w < XW; w += kG) { xb[w * kXS] = Xi[w]; xb[w * kXS + kEPW] = xr[w]; }
+          for (int w = j; w < UW; w += kG) { ub[w * kUS] = Ui[w]; ub[w * kUS + kURef] = ur[w]; }   // nominal inputs: buffer 0
           best = cost0[b];
-          if (io.alpha_trace)
+          if (io.alpha_trace && !io.resume)
             for (int w = j; w < P.max_iter; w += kG) io.alpha_trace[(size_t)b * P.max_iter + w] = 0xFF;
         } else {
           exhausted = true;
@@ -512,10 +537,12 @@ __global__ void __launch_bounds__(384, 1) ilqr_forward_group(const DevProblem<R>
     if (run && replay) run = it < io.replay_iters[b];
     bool improved = false;
     if (__ballot_sync(FULL, run) != 0u) {
-      const R* nomp = ebuf + nom * kEPW;   // nominal trajectory: word w at nomp[w * WS]
-      int dK[NU];                          // offset of the m-th non-nominal buffer relative to the nominal one
-#pragma unroll
-      for (int m = 0; m < NU; ++m) dK[m] = (m + (m >= nom ? 1 : 0) - nom) * kEPW;
+      // The nominal inputs always sit in buffer 0 (the winner's inputs are copied there on acceptance: 20 words per
+      // iteration), candidate a writes buffer a + 1, gain word k lives in buffer k + 1 — every shared-memory access of the
+      // two passes has a compile-time offset from one running pointer (an index swap instead of the copy cost ~25 integer
+      // instructions per step in address arithmetic).
+      constexpr int nomo = 0;
+      const int dKj = ((j < NX ? j : NX) + 1) * kEPW;   // the dead buffer this lane stores its share of the gains into
       // terminal cost of this element: staged or global (generic pointers; read twice per pass)
       const R* Cfo = ownCf_sh ? sCf : Cfp;
       const R* cfo = ownCf_sh ? sCf + N * N : cfp;
@@ -526,7 +553,7 @@ __global__ void __launch_bounds__(384, 1) ilqr_forward_group(const DevProblem<R>
         {
           R tauN[NX];
 #pragma unroll
-          for (int i = 0; i < NX; ++i) tauN[i] = nomp[(size_t)(T * NX + i) * WS] - refp[(size_t)(T * NX + i) * WS];
+          for (int i = 0; i < NX; ++i) tauN[i] = xb[(T * NX + i) * kXS] - xb[(T * NX + i) * kXS + kEPW];
 #pragma unroll
           for (int i = 0; i < NX; ++i) {
             R s = 0;
@@ -543,14 +570,10 @@ __global__ void __launch_bounds__(384, 1) ilqr_forward_group(const DevProblem<R>
 #pragma unroll
         for (int m = 0; m < NJ; ++m) jcm[m] = 0;
         // running pointers of step t (all decremented once per step)
-        const R* px = nomp + (size_t)(T - 1) * NX * WS;
-        const R* pu = nomp + (size_t)(XW + (T - 1) * NU) * WS;
-        R* gx = const_cast<R*>(px) + NX * WS;   // X_{t+1} slot (nominal buffer); + dK[m] = m-th dead buffer
-        R* gu = const_cast<R*>(pu);             // U_t slot
+        const R* px = xb + (T - 1) * NX * kXS;   // X_t (nominal), x_ref_t at + kEPW
+        R* pu = ub + (T - 1) * NU * kUS;         // U_t: word i of buffer s at pu[i * kUS + s * kEPW]
         const R* pCrow = CSH ? sC + (size_t)(T - 1) * CS + jj * N : DIAG ? Cp + (size_t)(T - 1) * N + jj : Cp + ((size_t)(T - 1) * N + jj) * N;
         const R* pcj = CSH ? sC + (size_t)(T - 1) * CS + N * N + jj : cp + (size_t)(T - 1) * N + jj;
-        const R* pxr = refp + (size_t)(T - 1) * NX * WS;
-        const R* pur = refp + (size_t)(XW + (T - 1) * NU) * WS;
         R Crow[N], cj;        // row jj of C_t and c_t[jj]; loaded once when the running cost is time-invariant
         if (DIAG) {
           const R qd = pCrow[0];
@@ -565,13 +588,13 @@ __global__ void __launch_bounds__(384, 1) ilqr_forward_group(const DevProblem<R>
         for (int t = T - 1; t >= 0; --t) {
           if (GD::kHasJac && s_in_blk == 0) {
             const int back = (j <= t) ? j : t;      // lane j evaluates step t - j (clamped at 0)
-            const R* qx = px - (size_t)back * NX * WS;
-            const R* qu = pu - (size_t)back * NU * WS;
+            const R* qx = px - back * NX * kXS;
+            const R* qu = pu - back * NU * kUS + nomo;
             R xj[NX], uj[NU];
 #pragma unroll
-            for (int i = 0; i < NX; ++i) xj[i] = qx[i * WS];
+            for (int i = 0; i < NX; ++i) xj[i] = qx[i * kXS];
 #pragma unroll
-            for (int i = 0; i < NU; ++i) uj[i] = qu[i * WS];
+            for (int i = 0; i < NU; ++i) uj[i] = qu[i * kUS];
             GD::jac(P, xj, uj, jcm);
           }
           R jc[NJ];
@@ -585,9 +608,9 @@ __global__ void __launch_bounds__(384, 1) ilqr_forward_group(const DevProblem<R>
           s_in_blk = (s_in_blk == kG - 1) ? 0 : s_in_blk + 1;
           R tau[N];
 #pragma unroll
-          for (int i = 0; i < NX; ++i) tau[i] = px[i * WS] - pxr[i * WS];
+          for (int i = 0; i < NX; ++i) tau[i] = px[i * kXS] - px[i * kXS + kEPW];
 #pragma unroll
-          for (int i = 0; i < NU; ++i) tau[NX + i] = pu[i * WS] - pur[i * WS];
+          for (int i = 0; i < NU; ++i) tau[NX + i] = pu[i * kUS + nomo] - pu[i * kUS + kURef];
           // row jj of C_t, l_j = C_t[j,:] tau + c_t[j]
           R Qrow[N], qj;
           {
@@ -641,9 +664,9 @@ __global__ void __launch_bounds__(384, 1) ilqr_forward_group(const DevProblem<R>
           if (run && npd) flg |= TACD_FLAG_NONPD;
           if (j < NX) {
 #pragma unroll
-            for (int m = 0; m < NU; ++m) gx[dK[m] + j * WS] = pick<NX, R>(&Kt[m * NX], j);
+            for (int m = 0; m < NU; ++m) pu[m * kUS + dKj] = pick<NX, R>(&Kt[m * NX], j);
           } else if (j < N) {
-            gu[dK[0] + (j - NX) * WS] = pick<NU, R>(kt, j - NX);
+            pu[(j - NX) * kUS + dKj] = pick<NU, R>(kt, j - NX);
           }
           // row i = j of the value update (controller.py:573-574), association as value_update<>
           {
@@ -702,7 +725,7 @@ __global__ void __launch_bounds__(384, 1) ilqr_forward_group(const DevProblem<R>
             for (int c = 0; c < NX; ++c) v[c] = r.v[c];
           }
           __syncwarp();
-          px -= NX * WS; pu -= NU * WS; pxr -= NX * WS; pur -= NU * WS; gx -= NX * WS; gu -= NU * WS;
+          px -= NX * kXS; pu -= NU * kUS;
           pCrow -= CSH ? CS : CW; pcj -= CSH ? CS : N;
         }
       }
@@ -710,39 +733,35 @@ __global__ void __launch_bounds__(384, 1) ilqr_forward_group(const DevProblem<R>
       // evaluate_alphas (controller.py:589-620); the candidate trajectory goes to this lane's buffer
       R cost_ls, cost_own;
       {
-        const int cb = j + (j >= nom ? 1 : 0);   // the five buffers that are not the nominal one
-        R* cbp = ebuf + (valid ? cb : nom) * kEPW;
+        const int cbo = (j + 1) * kEPW;          // this candidate's input buffer
         R x[NX], q1 = 0, l1 = 0, q2 = 0, l2 = 0;
 #pragma unroll
-        for (int i = 0; i < NX; ++i) { x[i] = nomp[i * WS]; if (valid) cbp[i * WS] = x[i]; }
-        const R* px = nomp;
-        const R* pu = nomp + (size_t)XW * WS;
-        R* cx = cbp + NX * WS;                   // candidate X_{t+1}
-        R* cu = cbp + (size_t)XW * WS;           // candidate U_t
+        for (int i = 0; i < NX; ++i) x[i] = xb[i * kXS];
+        const R* px = xb;
+        R* pu = ub;
+        R* sx = scr + lane;                      // candidate X_{t+1}[i] -> sx[(t NX + i) 32]
         const R* pCl = sCl;                      // staged line-search cost of step t
         const R* pCo = CSH ? sC : Cp;            // own cost of step t (staged block or global C_t)
         const R* pco = cp;
-        const R* pxr = refp;
-        const R* pur = refp + (size_t)XW * WS;
         R Ct[N * N], ct[N], Cl[LSSEP ? N * N : 1], cl[LSSEP ? N : 1];
         if (CSH) load_cost_vec<R, N>(pCo, Ct, ct);
         if constexpr (LSSEP) load_cost_vec<R, N>(pCl, Cl, cl);
         for (int t = 0; t < T; ++t) {
           R u[NU], tau[N], dx[NX], xn[NX];
 #pragma unroll
-          for (int k = 0; k < NX; ++k) dx[k] = x[k] - px[k * WS];
+          for (int k = 0; k < NX; ++k) dx[k] = x[k] - px[k * kXS];
 #pragma unroll
           for (int i = 0; i < NU; ++i) {
             R s = 0;
 #pragma unroll
-            for (int k = 0; k < NX; ++k) s += px[NX * WS + dK[i] + k * WS] * dx[k];
-            R ui = pu[i * WS] + (alpha * pu[dK[0] + i * WS] + s);
+            for (int k = 0; k < NX; ++k) s += pu[i * kUS + (k + 1) * kEPW] * dx[k];
+            R ui = pu[i * kUS + nomo] + (alpha * pu[i * kUS + (NX + 1) * kEPW] + s);
             ui = tmin<R>(tmax<R>(ui, ulo[i]), uhi[i]);
             u[i] = ui;
-            tau[NX + i] = ui - pur[i * WS];
+            tau[NX + i] = ui - pu[i * kUS + kURef];
           }
 #pragma unroll
-          for (int i = 0; i < NX; ++i) tau[i] = x[i] - pxr[i * WS];
+          for (int i = 0; i < NX; ++i) tau[i] = x[i] - px[i * kXS + kEPW];
           if constexpr (LSSEP) {
             if (!constLs) load_cost_vec<R, N>(pCl, Cl, cl);
             quad_terms<R, N>(Cl, cl, tau, q1, l1);
@@ -776,17 +795,17 @@ __global__ void __launch_bounds__(384, 1) ilqr_forward_group(const DevProblem<R>
           __syncwarp();   // every lane of the group has read K_t, k_t from the slots overwritten below
           if (valid) {
 #pragma unroll
-            for (int i = 0; i < NU; ++i) cu[i * WS] = u[i];
+            for (int i = 0; i < NU; ++i) pu[i * kUS + cbo] = u[i];
 #pragma unroll
-            for (int i = 0; i < NX; ++i) cx[i * WS] = xn[i];
+            for (int i = 0; i < NX; ++i) sx[i * 32] = xn[i];
           }
 #pragma unroll
           for (int i = 0; i < NX; ++i) x[i] = xn[i];
-          px += NX * WS; pu += NU * WS; pxr += NX * WS; pur += NU * WS; cx += NX * WS; cu += NU * WS;
+          px += NX * kXS; pu += NU * kUS; sx += NX * 32;
         }
         R tauN[NX];
 #pragma unroll
-        for (int i = 0; i < NX; ++i) tauN[i] = x[i] - pxr[i * WS];
+        for (int i = 0; i < NX; ++i) tauN[i] = x[i] - px[i * kXS + kEPW];
         R qN = 0, lN = 0, qN2 = 0, lN2 = 0;
 #pragma unroll
         for (int i = 0; i < NX; ++i) {
@@ -821,26 +840,30 @@ __global__ void __launch_bounds__(384, 1) ilqr_forward_group(const DevProblem<R>
       }
       if (run && replay) ai = io.replay_alpha[(size_t)b * P.max_iter + it];
       if constexpr (LSSEP) {
-        // Acceptance cost (controller.py:298): the element's OWN cost of the chosen candidate only.  Its
-        // trajectory sits in shared memory, so the five lanes split the evaluation by rows of C_t — lane i
-        // accumulates sum_t tau_i (C_t[i,:] tau) and sum_t c_t[i] tau_i — instead of every candidate lane
-        // reading the whole per-element C_t at every step of the line search (30 global words per step and
-        // lane; 6 here, 2 for a compact diagonal).  The partial sums are combined in lane order.
-        __syncwarp();                       // candidate buffers are complete
-        const R* wp = ebuf + (ai + (ai >= nom ? 1 : 0)) * kEPW;
+        // Acceptance cost (controller.py:298): the element's OWN cost of the chosen candidate only.  Its inputs
+        // sit in shared memory and its states in the warp's scratch tile (L2), so the five lanes split the
+        // evaluation by rows of C_t — lane i accumulates sum_t tau_i (C_t[i,:] tau) and sum_t c_t[i] tau_i —
+        // instead of every candidate lane reading the whole per-element C_t at every step of the line search
+        // (30 global words per step and lane; 6 here, 2 for a compact diagonal).  Partial sums combine in lane order.
+        __syncwarp();                       // the candidates' inputs and states are complete and visible to the group
         const R* prow = DIAG ? Cp + jj : Cp + jj * N;
         const R* pc = cp + jj;
-        const R* wx = wp;
-        const R* wu = wp + (size_t)XW * WS;
-        const R* rx = refp;
-        const R* ru = refp + (size_t)XW * WS;
+        const R* wsx = scr + base + ai;     // the winner's column of the scratch tile
+        const R* rx = xb;
+        const int wbo = (ai + 1) * kEPW;    // the winner's input buffer
+        const R* wu = ub;
         R quad = 0, lin = 0;
+        R wxv[NX];                          // the winner's X_t (X_0 is the common start state)
+#pragma unroll
+        for (int i = 0; i < NX; ++i) wxv[i] = xb[i * kXS];
         for (int t = 0; t < T; ++t) {
           R tau[N];
 #pragma unroll
-          for (int i = 0; i < NX; ++i) tau[i] = wx[i * WS] - rx[i * WS];
+          for (int i = 0; i < NX; ++i) tau[i] = wxv[i] - rx[i * kXS + kEPW];
 #pragma unroll
-          for (int i = 0; i < NU; ++i) tau[NX + i] = wu[i * WS] - ru[i * WS];
+          for (int i = 0; i < NU; ++i) tau[NX + i] = wu[i * kUS + wbo] - wu[i * kUS + kURef];
+#pragma unroll
+          for (int i = 0; i < NX; ++i) wxv[i] = ld_cg<R>(wsx + i * 32);
           const R tj = pick<N, R>(tau, jj);
           R s = 0;
           if (DIAG) {
@@ -854,7 +877,7 @@ __global__ void __launch_bounds__(384, 1) ilqr_forward_group(const DevProblem<R>
           }
           quad += tj * s;
           lin += pc[0] * tj;
-          wx += NX * WS; wu += NU * WS; rx += NX * WS; ru += NU * WS; prow += CW; pc += N;
+          wsx += NX * 32; wu += NU * kUS; rx += NX * kXS; prow += CW; pc += N;
         }
         R qsum = 0, lsum = 0;
 #pragma unroll
@@ -864,7 +887,7 @@ __global__ void __launch_bounds__(384, 1) ilqr_forward_group(const DevProblem<R>
         }
         R tauN[NX], qN2 = 0, lN2 = 0;
 #pragma unroll
-        for (int i = 0; i < NX; ++i) tauN[i] = wx[i * WS] - rx[i * WS];
+        for (int i = 0; i < NX; ++i) tauN[i] = wxv[i] - rx[i * kXS + kEPW];
 #pragma unroll
         for (int i = 0; i < NX; ++i) {
           R s2 = 0;
@@ -889,26 +912,32 @@ __global__ void __launch_bounds__(384, 1) ilqr_forward_group(const DevProblem<R>
           ctr[P.n_alpha + 1] = best;
         }
       }
+      if constexpr (!LSSEP) __syncwarp();   // the candidates' states (global scratch) are visible to the whole group
       if (run) {
         it += 1;
         if (improved) {
+          // accept: the winner's inputs are copied into the nominal buffer, its states come back from the scratch tile
+          // into the one state trajectory shared memory holds (X_0 is common to all candidates)
           best = newc;
-          nom = ai + (ai >= nom ? 1 : 0);
+          const R* wsx = scr + base + ai;
+          const R* wu = ub + (ai + 1) * kEPW;
+          for (int w = j; w < T * NX; w += kG) xb[(NX + w) * kXS] = ld_cg<R>(wsx + w * 32);
+          for (int w = j; w < UW; w += kG) ub[w * kUS] = wu[w * kUS];
         }
       }
-      __syncwarp();   // candidate buffers written by one lane are read by the whole group from here on
+      __syncwarp();   // inputs / states written by one lane are read by the whole group from here on
     }
     // -------------------------------------------------------------------- finalise
     // outputs + final re-linearisation (controller.py:311-314) + active set (636-642)
     const bool keep_going = run && improved && it < P.max_iter;
     if (has && !keep_going) {
       if (run && improved) flg |= TACD_FLAG_MAXITER;
-      const R* nomp = ebuf + nom * kEPW;
+      const R* nomu = ub;
       R* Xo = io.X + (size_t)b * szX;
       R* Uo = io.U + (size_t)b * szU;
-      for (int w = j; w < XW; w += kG) Xo[w] = nomp[(size_t)w * WS];
-      for (int w = j; w < W - XW; w += kG) {
-        const R ui = nomp[(size_t)(XW + w) * WS];
+      for (int w = j; w < XW; w += kG) Xo[w] = xb[w * kXS];
+      for (int w = j; w < UW; w += kG) {
+        const R ui = nomu[w * kUS];
         Uo[w] = ui;
         const int i = w % NU;
         bool m = false;
@@ -920,9 +949,9 @@ __global__ void __launch_bounds__(384, 1) ilqr_forward_group(const DevProblem<R>
         for (int t = j; t < T; t += kG) {
           R x[NX], u[NU], A[NX * NX], Bm[NX * NU];
 #pragma unroll
-          for (int i = 0; i < NX; ++i) x[i] = nomp[(size_t)(t * NX + i) * WS];
+          for (int i = 0; i < NX; ++i) x[i] = xb[(t * NX + i) * kXS];
 #pragma unroll
-          for (int i = 0; i < NU; ++i) u[i] = nomp[(size_t)(XW + t * NU + i) * WS];
+          for (int i = 0; i < NU; ++i) u[i] = nomu[(t * NU + i) * kUS];
           D::jac(P, sA, sB, x, u, A, Bm);
           if (io.A)
 #pragma unroll

@@ -10,28 +10,46 @@
 
 namespace tacd {
 
+// workspace offsets shared by the forward kernels of the small plugins (capi.cu::fwd_head_bytes sizes them):
+// [0,4) queue counter | [8,12) hand-over count | [16,20) queue counter of the resumed solves | [256, +8K) bucket counters |
+// [16K, +4B) longest-first order | initial / hand-over cost of every element (8 B each) | state tiles | hand-over list (4 B each)
+struct GroupWs { size_t order, cost0, scratch, list, end; };
+template <typename R>
+static GroupWs group_ws(const tacd_problem* p) {
+  GroupWs w;
+  w.order = 16384;
+  w.cost0 = w.order + (((size_t)p->B * 4 + 255) / 256) * 256;
+  w.scratch = w.cost0 + (((size_t)p->B * 8 + 255) / 256) * 256;
+  w.list = w.scratch + ((group_forward_scratch_bytes(p) + 255) / 256) * 256;
+  w.end = w.list + (((size_t)p->B * 4 + 255) / 256) * 256;
+  return w;
+}
+
+// resume = the second phase of the two-phase solve: the queue holds the solves the thread-per-element kernel handed over
 template <typename R, int NX, int NU, int DYN, bool LSSEP, bool CSH, bool DIAG>
-static int run_forward_group(const tacd_problem* p, const tacd_forward_io* io, void* ws, size_t ws_bytes, cudaStream_t s) {
+static int run_forward_group(const tacd_problem* p, const tacd_forward_io* io, void* ws, size_t ws_bytes, cudaStream_t s, bool resume = false) {
   auto kernel = ilqr_forward_group<R, NX, NU, DYN, LSSEP, CSH, DIAG>;
   const DeviceInfo di = device_info();
   const size_t cost_b = (size_t)group_cost_words(p->T, NX, NU, p->C_batched, p->Cf_batched, LSSEP ? 1 : 0, DYN == TACD_DYN_LTI) * sizeof(R);
   const size_t warp_b = (size_t)group_warp_words(p->T, NX, NU) * sizeof(R);
   if (cost_b + warp_b > (size_t)di.smem_optin) return TACD_EUNSUPPORTED;   // horizon too long for 6 buffers per element
   int nw = (int)(((size_t)di.smem_optin - cost_b) / warp_b);
-  if (nw > 12) nw = 12;   // __launch_bounds__(384, 1)
-  if (const char* e = getenv("TACD_GROUP_WARPS")) { const int v = atoi(e); if (v >= 1 && v < nw) nw = v; }
-  // small batches: spread the elements over all SMs before stacking warps on one
-  const int spread = (p->B + di.sms * kEPW - 1) / (di.sms * kEPW);
+  if (nw > group_max_warps<R>()) nw = group_max_warps<R>();   // __launch_bounds__(group_max_warps<R>() * 32, 1)
+  { TACD_KNOB(k, "TACD_GROUP_WARPS"); const int v = env_int(k, 0); if (v >= 1 && v < nw) nw = v; }
+  // small batches: spread the elements over all SMs before stacking warps on one (resumed solves: the long tail of the
+  // iteration-count distribution, a few percent of the batch; their number is only known on the device)
+  const int expect = resume ? (p->B + 15) / 16 : p->B;
+  const int spread = (expect + di.sms * kEPW - 1) / (di.sms * kEPW);
   if (nw > spread) nw = spread < 1 ? 1 : spread;
   const size_t smem = cost_b + warp_b * nw;
   if (int rc = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr")) return rc;
-  int grid = (p->B + nw * kEPW - 1) / (nw * kEPW);
+  int grid = (expect + nw * kEPW - 1) / (nw * kEPW);
   if (grid > di.sms) grid = di.sms;
   if (grid < 1) grid = 1;
-  // workspace: [0,4) queue counter | ... | [16K + order, +B*sizeof(R)) initial cost of every element
-  const size_t order_bytes = 16384 + (((size_t)p->B * 4 + 255) / 256) * 256;
-  if (ws_bytes < order_bytes + (size_t)p->B * sizeof(R)) { set_error("forward workspace too small for the initial costs"); return TACD_EWORKSPACE; }
-  R* cost0 = (R*)((char*)ws + order_bytes);
+  const GroupWs wo = group_ws<R>(p);
+  const size_t scratch_bytes = (size_t)grid * nw * group_xscratch_words(p->T, NX) * sizeof(R);
+  if (ws_bytes < wo.end || wo.scratch + scratch_bytes > wo.list) { set_error("forward workspace too small for the initial costs / state tiles"); return TACD_EWORKSPACE; }
+  R* cost0 = (R*)((char*)ws + wo.cost0);
   FwdPtrs<R> f;
   memset(&f, 0, sizeof(f));
   f.x0 = (const R*)io->x0; f.C = (const R*)io->C; f.c = (const R*)io->c; f.Cf = (const R*)io->Cf; f.cf = (const R*)io->cf;
@@ -43,14 +61,29 @@ static int run_forward_group(const tacd_problem* p, const tacd_forward_io* io, v
   f.cost = (R*)io->cost; f.cost_trace = (R*)io->cost_trace;
   f.counter = (unsigned int*)ws;
   f.order = nullptr;
+  f.xscratch = (R*)((char*)ws + wo.scratch);
   const DevProblem<R> dp = to_dev<R>(p);
+  if (resume) {
+    // the nominal trajectories, costs, iteration counts and flags of the handed-over solves are where the first phase left
+    // them: io->X, io->U, cost0, io->iters, io->flags
+    f.Uinit = (const R*)io->U;
+    f.order = (const int32_t*)((char*)ws + wo.list);
+    f.counter = (unsigned int*)((char*)ws + 16);
+    f.n_dev = (const unsigned int*)((char*)ws + 8);
+    f.resume = 1;
+    kernel<<<grid, nw * 32, smem, s>>>(dp, f, cost0);
+    note_launches(1);
+    return check_cuda(cudaPeekAtLastError(), "ilqr_forward_group (resume) launch");
+  }
   // longest-first queue order (ilqr_small.cuh): with more than one wave of elements the long chains must
   // not be popped last (profiles/r1_forward_group_v4: schedulers idle 13 % of the kernel in the tail)
-  const bool lpt = (long)p->B > (long)grid * nw * kEPW && !getenv("TACD_NO_LPT");
+  TACD_KNOB(k_nolpt, "TACD_NO_LPT");
+  TACD_KNOB(k_nofork, "TACD_NO_FORK");
+  const bool lpt = (long)p->B > (long)grid * nw * kEPW && !env_set(k_nolpt);
   // the queue order (3 small launches) and the initial rollout are independent: they run side by side, the
   // order on a helper stream that forks from / joins back into the caller's stream before the solve kernel
   SideStream ss = side_stream();
-  const bool fork = lpt && ss.ok && !getenv("TACD_NO_FORK");
+  const bool fork = lpt && ss.ok && !env_set(k_nofork);
   cudaStream_t s2 = s;
   if (fork) {
     if (int rc = check_cuda(cudaEventRecord(ss.fork, s), "fork record")) return rc;
@@ -84,12 +117,12 @@ static int run_forward_group(const tacd_problem* p, const tacd_forward_io* io, v
     // dense per-element costs: no cost tile, each thread reads its element's rows straight from global memory (chunk 0;
     // measured 2 % faster end to end than the whole-horizon tile, which leaves 2 CTAs per SM; compact diagonals: 1.5 % slower)
     if (p->C_batched && !p->C_diag) chunk = 0;
-    if (const char* e = getenv("TACD_INIT_CHUNK")) { const int v = atoi(e); if (p->C_batched && v >= 0 && v <= p->T) chunk = v; }
+    { TACD_KNOB(k, "TACD_INIT_CHUNK"); const int v = env_int(k, -1); if (p->C_batched && v >= 0 && v <= p->T) chunk = v; }
     const size_t tile_b = init_warp_words(p->T, NX, NU, p->C_batched, p->C_diag, chunk) * sizeof(R);
     // one warp per CTA: the finest granularity for the last wave (2048 warps over 148 SMs at B = 65536)
     if (tile_b > (size_t)di.smem_optin) return TACD_EUNSUPPORTED;
     int iw = 1;
-    if (const char* e = getenv("TACD_INIT_WARPS")) { const int v = atoi(e); if (v >= 1 && v <= 4 && tile_b * v <= (size_t)di.smem_optin) iw = v; }
+    { TACD_KNOB(k, "TACD_INIT_WARPS"); const int v = env_int(k, 0); if (v >= 1 && v <= 4 && tile_b * v <= (size_t)di.smem_optin) iw = v; }
     if (int rc = check_cuda(cudaFuncSetAttribute(init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(tile_b * iw)), "smem attr")) return rc;
     const int nwarp = (p->B + 31) / 32;
     init<<<(nwarp + iw - 1) / iw, iw * 32, tile_b * iw, s>>>(dp, f, cost0, chunk);
@@ -105,6 +138,27 @@ static int run_forward_group(const tacd_problem* p, const tacd_forward_io* io, v
   return check_cuda(cudaPeekAtLastError(), "ilqr_forward_group launch");
 }
 
+// Two-phase solve (EXPERIMENT, off by default: TACD_HYBRID_CAP=k).  Phase 1: the thread-per-element kernel (1.7x cheaper in issue
+// slots per element-step: no redundant gains / tau / shuffles) runs every solve for at most k iterations; phase 2: this file's
+// kernel resumes the few percent that are still improving (2.4 % of the bench workload at k = 8).  Round 1 attributed the thread
+// kernel's 0.81 ms to its tail (iteration counts span 2..19, a thread's iteration is a 5x longer serial chain).  MEASURED in round
+// 2 (B = 65536): the forward takes 0.82-0.85 ms for every k in 5..10, the same as the thread kernel alone — that kernel is
+// latency-bound at 8 warps per SM (28 % of the issue slots), not tail-bound, so capping its chains buys nothing.  Kept, with the
+// hand-over / resume plumbing, as the starting point for a thread kernel with twice the resident warps.
+template <typename R, int NX, int NU, int DYN, bool LSSEP, bool CSH>
+static int run_forward_hybrid(const tacd_problem* p, const tacd_forward_io* io, void* ws, size_t ws_bytes, cudaStream_t s, int cap) {
+  const GroupWs wo = group_ws<R>(p);
+  if (ws_bytes < wo.end) { set_error("forward workspace too small for the two-phase solve"); return TACD_EWORKSPACE; }
+  if (int rc = check_cuda(cudaMemsetAsync((char*)ws + 8, 0, 16, s), "memset hand-over counters")) return rc;
+  FwdHandover ho;
+  ho.cap_iters = cap;
+  ho.count = (unsigned int*)((char*)ws + 8);
+  ho.list = (int32_t*)((char*)ws + wo.list);
+  ho.cost = (char*)ws + wo.cost0;
+  if (int rc = launch_forward_small<R>(p, io, ws, wo.cost0, s, &ho)) return rc;
+  return run_forward_group<R, NX, NU, DYN, LSSEP, CSH, false>(p, io, ws, ws_bytes, s, true);
+}
+
 // (nx, nu, dyn) combinations with an instantiation: the shipped plugins (n = nx + nu <= kG)
 #define TACD_GROUP_FWD(X) \
   X(1, 1, TACD_DYN_LTI) X(2, 1, TACD_DYN_LTI) X(4, 1, TACD_DYN_CARTPOLE) X(3, 2, TACD_DYN_UNICYCLE) X(3, 2, TACD_DYN_UNICYCLE_WRAPPED)
@@ -114,9 +168,18 @@ static int run_forward_group(const tacd_problem* p, const tacd_forward_io* io, v
 template <typename R>
 int launch_forward_group(const tacd_problem* p, const tacd_forward_io* io, void* ws, size_t ws_bytes, cudaStream_t s) {
   if (p->jac_mode == TACD_JAC_FINITE_DIFF || p->n_alpha > kG) return TACD_EUNSUPPORTED;
-  if (const char* e = getenv("TACD_FWD_KERNEL")) if (!strcmp(e, "thread")) return TACD_EUNSUPPORTED;
+  { TACD_KNOB(k, "TACD_FWD_KERNEL"); if (env_is(k, "thread")) return TACD_EUNSUPPORTED; }
+  // two-phase solve (experiment, see run_forward_hybrid): shared running cost, batch of at least TACD_HYBRID_MIN_B solves,
+  // TACD_HYBRID_CAP iterations in the first phase (default 0 = off)
+  int cap = 0, min_b = 32768;
+  { TACD_KNOB(k, "TACD_HYBRID_CAP"); cap = env_int(k, cap); }
+  { TACD_KNOB(k, "TACD_HYBRID_MIN_B"); min_b = env_int(k, min_b); }
+  const bool hybrid = cap > 0 && cap < p->max_iter && p->B >= min_b && !p->C_diag && !p->C_batched && !io->replay_iters && !io->cost_trace;
 #define X(NX_, NU_, DYN_)                                                                      \
   if (p->nx == NX_ && p->nu == NU_ && p->dyn_id == DYN_) {                                     \
+    if (hybrid)                                                                                \
+      return p->ls_cost_shared ? run_forward_hybrid<R, NX_, NU_, DYN_, true, true>(p, io, ws, ws_bytes, s, cap)    \
+                               : run_forward_hybrid<R, NX_, NU_, DYN_, false, true>(p, io, ws, ws_bytes, s, cap);  \
     if (p->C_diag)                                                                             \
       return p->ls_cost_shared ? run_forward_group<R, NX_, NU_, DYN_, true, false, true>(p, io, ws, ws_bytes, s)   \
                                : run_forward_group<R, NX_, NU_, DYN_, false, false, true>(p, io, ws, ws_bytes, s); \
@@ -145,7 +208,7 @@ static int run_backward_group(const tacd_problem* p, const tacd_backward_io* io,
   if (stage_b + warp_b > (size_t)di.smem_optin) return TACD_EUNSUPPORTED;
   int nw = (int)(((size_t)di.smem_optin - stage_b) / warp_b);
   if (nw > 16) nw = 16;
-  if (const char* e = getenv("TACD_GROUP_WARPS")) { const int v = atoi(e); if (v >= 1 && v < nw) nw = v; }
+  { TACD_KNOB(k, "TACD_GROUP_WARPS"); const int v = env_int(k, 0); if (v >= 1 && v < nw) nw = v; }
   const int spread = (p->B + di.sms * kEPW - 1) / (di.sms * kEPW);
   if (nw > spread) nw = spread < 1 ? 1 : spread;
   const size_t smem = stage_b + warp_b * nw;
@@ -187,8 +250,7 @@ static int run_backward_group(const tacd_problem* p, const tacd_backward_io* io,
 template <typename R>
 int launch_backward_group(const tacd_problem* p, const tacd_backward_io* io, void* ws, size_t ws_bytes, cudaStream_t s) {
   if (p->compat_exact || p->dyn_id == TACD_DYN_EXTERNAL) return TACD_EUNSUPPORTED;
-  const char* sel = getenv("TACD_BWD_KERNEL");
-  if (!sel || strcmp(sel, "group")) return TACD_EUNSUPPORTED;
+  { TACD_KNOB(k, "TACD_BWD_KERNEL"); if (!env_is(k, "group")) return TACD_EUNSUPPORTED; }
 #define X(NX_, NU_, DYN_)                                                                      \
   if (p->nx == NX_ && p->nu == NU_ && p->dyn_id == DYN_) {                                     \
     if (p->C_diag) return run_backward_group<R, NX_, NU_, DYN_, false, true>(p, io, ws, ws_bytes, s);   \

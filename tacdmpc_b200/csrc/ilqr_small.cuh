@@ -33,9 +33,18 @@ struct FwdPtrs {
   R* cost_trace;
   unsigned int* counter;  // work queue head; set to first_wave before launch
   const int32_t* order;   // longest-first permutation of the batch (nullable = identity)
+  R* xscratch;            // five-lanes-per-element kernel: the candidates' states, one [T nx][32] tile per resident warp
   R* cscratch;            // per-element costs only: lane-slot copy of (C, c), [word][lane] (nullable)
   size_t cstride;         // number of lane slots (= grid * block)
   unsigned int first_wave;  // queue positions [0, first_wave) are dealt statically, one 32-segment per warp
+  // Two-phase solve (ilqr_group_launch.cuh::run_forward_hybrid): the thread-per-element kernel hands a solve that is still
+  // improving after cap_iters iterations over to the five-lanes-per-element kernel, which resumes it.
+  int cap_iters;                 // thread kernel: > 0 = hand over after this many iterations
+  unsigned int* resume_count;    // thread kernel: number of handed-over elements (device counter)
+  int32_t* resume_list;          // thread kernel: their batch indices
+  R* resume_cost;                // thread kernel: best cost of every handed-over element, [B]
+  const unsigned int* n_dev;     // five-lane kernel: number of queue entries, read on the device (nullable = P.B)
+  int resume;                    // five-lane kernel: elements continue from (io.X, io.Uinit, cost0, io.iters, io.flags)
 };
 
 // ---------------------------------------------------------------------------
@@ -476,6 +485,22 @@ __global__ void __launch_bounds__(256, 1) ilqr_forward_small(const DevProblem<R>
         }
         stop = (it >= P.max_iter);
         if (stop) flg |= TACD_FLAG_MAXITER;
+        if (!stop && io.cap_iters > 0 && it >= io.cap_iters) {
+          // Hand-over: this solve is in the long tail of the iteration-count distribution.  A thread's iteration is one
+          // serial chain of ~26 k instructions, so a kernel that kept it could not end before max(iters) such chains
+          // (round 1: 0.68 of 0.85 ms); the five-lanes-per-element kernel resumes it with a 5x shorter chain.
+          for (int t = 0; t <= T; ++t)
+#pragma unroll
+            for (int i = 0; i < NX; ++i) io.X[(size_t)b * szX + t * NX + i] = SX(t, i);
+          for (int t = 0; t < T; ++t)
+#pragma unroll
+            for (int i = 0; i < NU; ++i) io.U[(size_t)b * szU + t * NU + i] = SU(t, i);
+          io.iters[b] = it;
+          io.flags[b] = (uint8_t)flg;
+          io.resume_cost[b] = best;
+          io.resume_list[atomicAdd(io.resume_count, 1u)] = b;
+          has = false;
+        }
       }
     }
     if (stop) {

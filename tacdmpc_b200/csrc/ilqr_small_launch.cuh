@@ -2,6 +2,7 @@
 // Included by ilqr_small_f32.cu / ilqr_small_f64.cu, which instantiate it for one scalar type each.
 #pragma once
 #include <stdlib.h>
+#include <string.h>
 
 #include "host_common.h"
 
@@ -16,7 +17,7 @@ static int pick_block(K kernel, SmemFn smem_of, int* blocks_per_sm, size_t* smem
   size_t best_smem = 0;
   // experiment knobs (profiling only): cap the block size / resident blocks
   int nt_max = 256;
-  if (const char* e = getenv("TACD_NT_MAX")) { const int v = atoi(e); if (v >= 32 && v <= 256) nt_max = v - v % 32; }
+  { TACD_KNOB(k, "TACD_NT_MAX"); const int v = env_int(k, 0); if (v >= 32 && v <= 256) nt_max = v - v % 32; }
   for (int nt = nt_max; nt >= 32; nt -= 32) {
     const size_t smem = smem_of(nt);
     if (smem > (size_t)di.smem_optin) continue;
@@ -26,14 +27,14 @@ static int pick_block(K kernel, SmemFn smem_of, int* blocks_per_sm, size_t* smem
     if (max_blocks > 0 && nb > max_blocks) nb = max_blocks;
     if (nb * nt > best_blocks * best_nt) { best_nt = nt; best_blocks = nb; best_smem = smem; }
   }
-  if (const char* e = getenv("TACD_BLOCKS_MAX")) { const int v = atoi(e); if (v >= 1 && v < best_blocks) best_blocks = v; }
+  { TACD_KNOB(k, "TACD_BLOCKS_MAX"); const int v = env_int(k, 0); if (v >= 1 && v < best_blocks) best_blocks = v; }
   *blocks_per_sm = best_blocks;
   *smem_out = best_smem;
   return best_nt;
 }
 
 template <typename R, int NX, int NU, int DYN, bool LSSEP>
-static int run_forward_small(const tacd_problem* p, const tacd_forward_io* io, void* ws, size_t ws_bytes, cudaStream_t s) {
+static int run_forward_small(const tacd_problem* p, const tacd_forward_io* io, void* ws, size_t ws_bytes, cudaStream_t s, const FwdHandover* ho) {
   auto kernel = ilqr_forward_small<R, NX, NU, DYN, LSSEP>;
   int bps = 0;
   size_t smem = 0;
@@ -47,6 +48,8 @@ static int run_forward_small(const tacd_problem* p, const tacd_forward_io* io, v
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
   FwdPtrs<R> f;
+  memset(&f, 0, sizeof(f));
+  if (ho) { f.cap_iters = ho->cap_iters; f.resume_count = ho->count; f.resume_list = ho->list; f.resume_cost = (R*)ho->cost; }
   f.x0 = (const R*)io->x0; f.C = (const R*)io->C; f.c = (const R*)io->c; f.Cf = (const R*)io->Cf; f.cf = (const R*)io->cf;
   f.C_ls = (const R*)io->C_ls; f.c_ls = (const R*)io->c_ls; f.Cf_ls = (const R*)io->Cf_ls; f.cf_ls = (const R*)io->cf_ls;
   f.xref = (const R*)io->xref; f.uref = (const R*)io->uref; f.Uinit = (const R*)io->Uinit;
@@ -63,13 +66,15 @@ static int run_forward_small(const tacd_problem* p, const tacd_forward_io* io, v
   f.cscratch = nullptr;
   f.cstride = (size_t)lanes;
   const size_t order_bytes = 16384 + (((size_t)p->B * 4 + 255) / 256) * 256;
-  if (LSSEP && p->C_batched && !getenv("TACD_NO_CSCRATCH")) {
+  TACD_KNOB(k_nocs, "TACD_NO_CSCRATCH");
+  if (LSSEP && p->C_batched && !env_set(k_nocs)) {
     const size_t need = order_bytes + (size_t)lanes * ((size_t)p->T * (NX + NU) * (NX + NU) + (size_t)p->T * (NX + NU)) * sizeof(R);
     if (ws_bytes >= need) f.cscratch = (R*)((char*)ws + order_bytes);
   }
   queue_init<<<1, 1, 0, s>>>(f.counter, first_wave);
   note_launches(1);
-  const bool lpt = (unsigned)p->B > lanes && !getenv("TACD_NO_LPT");   // more than one wave: order matters
+  TACD_KNOB(k_nolpt, "TACD_NO_LPT");
+  const bool lpt = (unsigned)p->B > lanes && !env_set(k_nolpt);   // more than one wave: order matters
   if (lpt) {
     unsigned int* hist = (unsigned int*)((char*)ws + 256);
     int32_t* order = (int32_t*)((char*)ws + 16384);
@@ -151,11 +156,11 @@ static int run_backward_small(const tacd_problem* p, const tacd_backward_io* io,
   TACD_SMALL_FWD(X) X(1, 1, TACD_DYN_EXTERNAL) X(2, 1, TACD_DYN_EXTERNAL) X(4, 1, TACD_DYN_EXTERNAL) X(3, 2, TACD_DYN_EXTERNAL)
 
 template <typename R>
-int launch_forward_small(const tacd_problem* p, const tacd_forward_io* io, void* ws, size_t ws_bytes, cudaStream_t s) {
+int launch_forward_small(const tacd_problem* p, const tacd_forward_io* io, void* ws, size_t ws_bytes, cudaStream_t s, const FwdHandover* ho) {
 #define X(NX_, NU_, DYN_)                                                                      \
   if (p->nx == NX_ && p->nu == NU_ && p->dyn_id == DYN_)                                       \
-    return p->ls_cost_shared ? run_forward_small<R, NX_, NU_, DYN_, true>(p, io, ws, ws_bytes, s)       \
-                             : run_forward_small<R, NX_, NU_, DYN_, false>(p, io, ws, ws_bytes, s);
+    return p->ls_cost_shared ? run_forward_small<R, NX_, NU_, DYN_, true>(p, io, ws, ws_bytes, s, ho)       \
+                             : run_forward_small<R, NX_, NU_, DYN_, false>(p, io, ws, ws_bytes, s, ho);
   TACD_SMALL_FWD(X)
 #undef X
   return TACD_EUNSUPPORTED;

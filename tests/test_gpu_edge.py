@@ -10,6 +10,13 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
+def _refresh_knobs(request):
+    """The library caches its TACD_* knobs; re-read them now and again when monkeypatch has restored the environment."""
+    from tacdmpc_b200 import _lib
+    _lib.lib().tacd_refresh_env()
+    request.addfinalizer(lambda: _lib.lib().tacd_refresh_env())
+
+
 @pytest.fixture(scope="module")
 def G():
     import gpu_common
@@ -71,13 +78,14 @@ CASES = [
 
 @pytest.mark.parametrize("kernel", ["group", "thread"])
 @pytest.mark.parametrize("case", CASES, ids=lambda c: f"{c[0]}-T{c[1]}-B{c[2]}-{np.dtype(c[3]).name}-pe{int(c[4])}-a{c[5]}-it{c[6]}")
-def test_solve_and_backward_against_oracle(G, oracle, monkeypatch, case, kernel):
+def test_solve_and_backward_against_oracle(G, oracle, monkeypatch, request, case, kernel):
     from tacdmpc_b200 import ops
     dyn, T, B, dtype, per_element, n_alpha, max_iter = case
     if kernel == "thread":
         monkeypatch.setenv("TACD_FWD_KERNEL", "thread")
     else:
         monkeypatch.delenv("TACD_FWD_KERNEL", raising=False)
+    _refresh_knobs(request)
     spec, d = _problem(dyn, T, B, dtype, seed=T * 131 + B, per_element=per_element, n_alpha=n_alpha, max_iter=max_iter)
     s = G.gpu_spec(spec, dtype)
     s.alphas = spec["alphas"]

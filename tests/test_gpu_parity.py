@@ -10,6 +10,13 @@ import parity as P
 
 pytestmark = pytest.mark.gpu
 
+
+def _refresh_knobs(request):
+    """The library caches its TACD_* knobs; re-read them now and again when monkeypatch has restored the environment."""
+    from tacdmpc_b200 import _lib
+    _lib.lib().tacd_refresh_env()
+    request.addfinalizer(lambda: _lib.lib().tacd_refresh_env())
+
 # Multipliers on the north-star tolerance (1e-5 fp32 / 1e-9 fp64).  Each is at most 4x what the kernels achieve on the worst
 # golden case (the ledger tests/conftest.py prints; DESIGN.md 5 has the table).
 COST_K = 1.0          # replay: final objective, in units of the element's value tolerance (achieved 0.19; round 1 allowed 10)
@@ -37,6 +44,7 @@ def fwd_kernel(request, monkeypatch):
         monkeypatch.setenv("TACD_FWD_KERNEL", "thread")
     else:
         monkeypatch.delenv("TACD_FWD_KERNEL", raising=False)
+    _refresh_knobs(request)
     return request.param
 
 
@@ -169,6 +177,7 @@ def bwd_kernel(request, monkeypatch):
         monkeypatch.setenv("TACD_BWD_KERNEL", "group")
     else:
         monkeypatch.delenv("TACD_BWD_KERNEL", raising=False)
+    _refresh_knobs(request)
     return request.param
 
 
