@@ -124,7 +124,8 @@ static size_t bwd_partials_bytes(const tacd_problem* p) {
   const size_t nacc = T * (n * n + n + nx + nu) + nx * nx + 2 * nx;
   const DeviceInfo di = device_info();
   const size_t sms = di.sms > 0 ? di.sms : 148;
-  return sms * 32 * nacc * 8;
+  // + the gains of the thread-per-element KKT pass: T nu (nx + 1) words for each of 2 x 256 thread slots per SM
+  return sms * 32 * nacc * 8 + 256 + sms * 2 * 256 * (T * nu * (nx + 1)) * 8;
 }
 size_t tacd_backward_workspace_bytes(const tacd_problem* p) {
   if (validate(p)) return 0;

@@ -749,6 +749,7 @@ static int run_backward_generic(const tacd_problem* p, const tacd_backward_io* i
   if (io->grad_xref && !p->xref_batched) if (int rc = check_cuda(cudaMemsetAsync(io->grad_xref, 0, szX * sizeof(R), s), "memset")) return rc;
   if (io->grad_uref && !p->uref_batched) if (int rc = check_cuda(cudaMemsetAsync(io->grad_uref, 0, szU * sizeof(R), s), "memset")) return rc;
   BwdPtrs<R> f;
+  f.kscratch = nullptr;
   f.X = (const R*)io->X; f.U = (const R*)io->U; f.C = (const R*)io->C; f.xref = (const R*)io->xref; f.uref = (const R*)io->uref;
   f.A = (const R*)io->A; f.Bm = (const R*)io->Bm; f.gX = (const R*)io->gX; f.gU = (const R*)io->gU; f.tight = io->tight;
   f.Cf = (const R*)io->Cf;

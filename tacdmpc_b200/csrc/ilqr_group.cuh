@@ -175,11 +175,22 @@ __host__ __device__ inline int group_uoff_words(int T, int nx) { return (T + 1) 
 __host__ __device__ inline int group_voff_words(int T, int nx, int nu) {
   return (group_uoff_words(T, nx) + T * nu * kUS + 3) & ~3;
 }
-__host__ __device__ inline int group_warp_words(int T, int nx, int nu) {
-  return group_voff_words(T, nx, nu) + kEPW * (nx + 1) * 4;
+// + (stage > 0) the per-element cost blocks [C_b (T cw) | c_b (T n)] of the 6 element slots and their 6 mbarriers
+__host__ __device__ inline int group_coff_words(int T, int nx, int nu) { return group_voff_words(T, nx, nu) + kEPW * (nx + 1) * 4; }
+__host__ __device__ inline int group_warp_words(int T, int nx, int nu, int stage = 0) {
+  return group_coff_words(T, nx, nu) + (stage > 0 ? kEPW * stage + 16 : 0);   // 16 words: 6 x 8-byte mbarriers, 16-byte aligned
 }
-// global-memory scratch of one warp: the candidates' states X_1..X_T, [word][lane]
-__host__ __device__ inline size_t group_xscratch_words(int T, int nx) { return (size_t)T * nx * 32; }
+// words of one element's staged cost block (multiple of 4), or 0 if the blocks cannot be bulk-copied: cp.async.bulk needs
+// 16-byte aligned addresses and sizes, i.e. T cw and T n multiples of 16 bytes (cart-pole T = 20: 2000 + 400 bytes)
+__host__ __device__ inline int group_stage_words(int T, int n, int cw, size_t es) {
+  const size_t bc = (size_t)T * cw * es, bl = (size_t)T * n * es;
+  if (bc % 16 != 0 || bl % 16 != 0) return 0;
+  return (int)((bc + bl) / es) + ((cw + n + 3) & ~3);   // + the element's terminal cost [C_final | c_final] (plain loads)
+}
+// global-memory scratch of one warp: the candidates' states X_1..X_T, [word][lane]; TWO tiles, alternating with the iteration
+// parity, so that the nominal states (the winner of the previous iteration) can be restored after a rejected step
+__host__ __device__ inline size_t group_xtile_words(int T, int nx) { return (size_t)T * nx * 32; }
+__host__ __device__ inline size_t group_xscratch_words(int T, int nx) { return 2 * group_xtile_words(T, nx); }
 template <typename R> TACD_DEV R ld_cg(const R* p) { return __ldcg(p); }
 // CTA-shared staging of the un-batched costs (+ the separate line-search cost) and the LTI matrices.
 // Running cost of step t: [C_t (n*n) | c_t (n) | pad] at stride group_cost_stride(n) (multiple of 4 words, so the
@@ -278,8 +289,9 @@ __global__ void __launch_bounds__(128) ilqr_init_rollout(const DevProblem<R> P, 
   const bool direct = chunk == 0;
   if (direct) chunk = T;
   const int nchunk = (T + chunk - 1) / chunk;
+  const bool want_cost = cost0 != nullptr;   // nullptr: roll out only (the solve kernel evaluates the initial cost itself)
   auto fetch_cost = [&](int c) {
-    if (P.C_batched && !direct && c < nchunk) {
+    if (want_cost && P.C_batched && !direct && c < nchunk) {
       const int t0 = c * chunk, nst = (T - t0 < chunk) ? T - t0 : chunk;
       R* buf = ctile + (size_t)(c & (nbuf - 1)) * 32 * RSC;
       for (int r = 0; r < nlive; ++r) {
@@ -327,7 +339,12 @@ __global__ void __launch_bounds__(128) ilqr_init_rollout(const DevProblem<R> P, 
       for (int i = 0; i < NX; ++i) { tau[i] = x[i] - row[t * NX + i]; row[t * NX + i] = x[i]; }
 #pragma unroll
       for (int i = 0; i < NU; ++i) tau[NX + i] = u[i] - ur[t * NU + i];
-      if (direct) {
+      if (!want_cost) {
+#pragma unroll
+        for (int i = 0; i < N * N; ++i) Ct[i] = 0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) ct[i] = 0;
+      } else if (direct) {
         const R* Cg = io.C + ((size_t)b * T + t) * cw;
         const R* cg = io.c + ((size_t)b * T + t) * N;
         if (P.C_diag) {
@@ -355,7 +372,7 @@ __global__ void __launch_bounds__(128) ilqr_init_rollout(const DevProblem<R> P, 
 #pragma unroll
         for (int i = 0; i < N; ++i) ct[i] = cp[(size_t)t * N + i];
       }
-      quad_terms<R, N>(Ct, ct, tau, quad, lin);
+      if (want_cost) quad_terms<R, N>(Ct, ct, tau, quad, lin);
       D::step(P, sA, sB, x, u, xn);
 #pragma unroll
       for (int i = 0; i < NX; ++i) x[i] = xn[i];
@@ -372,12 +389,12 @@ __global__ void __launch_bounds__(128) ilqr_init_rollout(const DevProblem<R> P, 
     for (int i = 0; i < NX; ++i) {
       R s = 0;
 #pragma unroll
-      for (int j = 0; j < NX; ++j) s += (P.C_diag ? ((i == j) ? Cfp[i] : (R)0) : Cfp[i * N + j]) * tauN[j];
+      for (int j = 0; j < NX; ++j) s += want_cost ? (P.C_diag ? ((i == j) ? Cfp[i] : (R)0) : Cfp[i * N + j]) * tauN[j] : (R)0;
       qN += tauN[i] * s;
-      lN += cfp[i] * tauN[i];
+      lN += want_cost ? cfp[i] * tauN[i] : (R)0;
     }
   }
-  if (lane < nlive) cost0[b] = ((R)0.5 * quad + lin) + ((R)0.5 * qN + lN);
+  if (want_cost && lane < nlive) cost0[b] = ((R)0.5 * quad + lin) + ((R)0.5 * qN + lN);
   cp_async_wait_all();
   __syncwarp();
   for (int r = 0; r < nlive; ++r) {
@@ -465,7 +482,17 @@ __global__ void __launch_bounds__(group_max_warps<R>() * 32, 1) ilqr_forward_gro
   // shared by four schedulers), and those reads were a third of its traffic.
   const bool constOwn = __syncthreads_and(same_own ? 1 : 0) != 0 && CSH;
   const bool constLs = __syncthreads_and(same_ls ? 1 : 0) != 0 && LSSEP;
-  R* wreg = sm + (size_t)wid * group_warp_words(T, NX, NU);
+  // per-element costs bulk-copied into shared memory (io.stage_words > 0; never with CSH)
+  const int SW = CSH ? 0 : io.stage_words;
+  R* wreg = sm + (size_t)wid * group_warp_words(T, NX, NU, SW);
+  R* sCe = wreg + group_coff_words(T, NX, NU) + (size_t)e * SW;                                      // this element's [C_b | c_b]
+  unsigned long long* cbar = reinterpret_cast<unsigned long long*>(wreg + group_coff_words(T, NX, NU) + (size_t)kEPW * SW) + e;
+  unsigned cphase = 0;
+  if (SW > 0) {
+    if (lane < kEPW) mbar_init(reinterpret_cast<unsigned long long*>(wreg + group_coff_words(T, NX, NU) + (size_t)kEPW * SW) + lane, 1);
+    mbar_fence_init();
+    __syncwarp();
+  }
   R* xb = wreg + e;                                   // nominal X word w at xb[w * kXS], x_ref word w at xb[w * kXS + kEPW]
   R* ub = wreg + group_uoff_words(T, NX) + e;         // input buffer s, word w at ub[w * kUS + s * kEPW]; u_ref: slot kNBUF
   // The gains have no storage of their own: between the reverse pass that produces them and the line search
@@ -473,7 +500,8 @@ __global__ void __launch_bounds__(group_max_warps<R>() * 32, 1) ilqr_forward_gro
   // buffer only at the end of step t.  K_t[m][i] lives in the U_t[m] slot of the i-th dead buffer, k_t[m] in
   // that of the NX-th one ((NX + 1) NU words needed, 5 NU there: NX <= 4); the line search reads them at the top of step t.
   // The candidates' states go to the warp's global-memory scratch tile, word w = X_{t+1}[i] of lane l at scr[(t NX + i) 32 + l].
-  R* scr = io.xscratch + ((size_t)blockIdx.x * (blockDim.x >> 5) + wid) * group_xscratch_words(T, NX);
+  R* scr0 = io.xscratch + ((size_t)blockIdx.x * (blockDim.x >> 5) + wid) * group_xscratch_words(T, NX);
+  const size_t tileW = group_xtile_words(T, NX);
   R* myV = wreg + group_voff_words(T, NX, NU) + (size_t)e * (NX + 1) * 4;   // [e][NX+1][4]: rows of V, then v
   // Dyn<> (LTI) wants A and B separately: straight from global memory (uniform, cached)
   const R* sA = P.dyn_A;
@@ -490,13 +518,75 @@ __global__ void __launch_bounds__(group_max_warps<R>() * 32, 1) ilqr_forward_gro
 
   // group state, replicated in the lanes of the group
   bool has = false, exhausted = !valid;
-  int b = 0, it = 0;
+  int b = 0, it = 0, ai_prev = -1;   // ai_prev: winner of the previous iteration (-1: the nominal states are the hand-over io.X)
   unsigned flg = 0;
   R best = 0;
   const R *Cp = io.C, *cp = io.c, *Cfp = io.Cf, *cfp = io.cf;
 
+  // The element's OWN cost (cost.py:37-62) of the trajectory (nominal states, inputs of buffer slot wbo), the five lanes
+  // splitting the evaluation by rows of C_t: lane i accumulates sum_t tau_i (C_t[i,:] tau) and sum_t c_t[i] tau_i, the partial
+  // sums are combined in lane order.  Used with per-element costs scored by a separate line-search cost (quirk Q4): for the
+  // acceptance cost of the winner (controller.py:298) and for the initial cost of a new element — instead of every candidate
+  // lane reading the whole per-element C_t at every step of the line search (30 words per step and lane; 6 here, 2 for a
+  // compact diagonal).  Every lane of the warp must call it (full-mask shuffles); all lanes of a group get the same value.
+  auto own_cost_rows = [&](int wbo) -> R {
+    const R* Cfo = ownCf_sh ? sCf : Cfp;
+    const R* cfo = ownCf_sh ? sCf + N * N : cfp;
+    // (t runs downwards, as in the reverse pass, which accumulates the same sums for the nominal trajectory)
+    const R* prow = (DIAG ? Cp + jj : Cp + jj * N) + (size_t)(T - 1) * CW;
+    const R* pc = cp + jj + (size_t)(T - 1) * N;
+    const R* rx = xb + (T - 1) * NX * kXS;
+    const R* wu = ub + (T - 1) * NU * kUS;
+    R tauN[NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) tauN[i] = rx[(NX + i) * kXS] - rx[(NX + i) * kXS + kEPW];
+    R quad = 0, lin = 0;
+    for (int t = T - 1; t >= 0; --t) {
+      R tau[N];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) tau[i] = rx[i * kXS] - rx[i * kXS + kEPW];
+#pragma unroll
+      for (int i = 0; i < NU; ++i) tau[NX + i] = wu[i * kUS + wbo] - wu[i * kUS + kURef];
+      const R tj = pick<N, R>(tau, jj);
+      R s = 0;
+      if (DIAG) {
+        // q_j tau_j plus the exact zeros the dense row would add (NaN if some tau_k is not finite)
+#pragma unroll
+        for (int k = 0; k < N; ++k) s += tau[k] * (R)0;
+        s += prow[0] * tj;
+      } else {
+#pragma unroll
+        for (int k = 0; k < N; ++k) s += prow[k] * tau[k];
+      }
+      quad += tj * s;
+      lin += pc[0] * tj;
+      rx -= NX * kXS; wu -= NU * kUS; prow -= CW; pc -= N;
+    }
+    R qsum = 0, lsum = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      qsum += __shfl_sync(FULL, quad, base + i);
+      lsum += __shfl_sync(FULL, lin, base + i);
+    }
+    R qN2 = 0, lN2 = 0;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      R s2 = 0;
+#pragma unroll
+      for (int k = 0; k < NX; ++k) s2 += (DIAG ? ((i == k) ? Cfo[i] : (R)0) : Cfo[i * N + k]) * tauN[k];
+      qN2 += tauN[i] * s2;
+      lN2 += cfo[i] * tauN[i];
+    }
+    return ((R)0.5 * qsum + lsum) + ((R)0.5 * qN2 + lN2);
+  };
+  // with per-element costs and a separate scoring cost the initial cost of an element is evaluated here (row-split, from the
+  // staged cost block) and ilqr_init_rollout only rolls the initial inputs out: a thread per element walking its own 2.4 KB of
+  // costs took 176 us of the 1.06 ms forward at B = 65536 (profiles/r2_launches_per_element.csv)
+  constexpr bool kOwnInit = LSSEP && !CSH;
+
   while (true) {
     // ------------------------------------------------------------------ refill (queue pop by the group leader)
+    bool fresh = false;
     {
       const bool need = !has && !exhausted;
       unsigned nb = 0xffffffffu;
@@ -506,10 +596,32 @@ __global__ void __launch_bounds__(group_max_warps<R>() * 32, 1) ilqr_forward_gro
         if (nb < (io.n_dev ? *io.n_dev : (unsigned)P.B)) {
           b = io.order ? io.order[nb] : (int)nb;
           has = true;
+          ai_prev = -1;
           it = io.resume ? io.iters[b] : 0;               // resume: the thread-per-element kernel ran the first iterations
           flg = io.resume ? (unsigned)io.flags[b] : 0u;
           Cp = io.C + (P.C_batched ? (size_t)b * T * CW : 0);
           cp = io.c + (P.C_batched ? (size_t)b * T * N : 0);
+          if (SW > 0) {
+            // The element's running cost, [T, cw] + [T, n] contiguous in global memory, comes in with two bulk asynchronous
+            // copies (cp.async.bulk -> UBLKCP, completion on this slot's mbarrier) and is then read from shared memory for the
+            // rest of the solve: ~10 passes over it (reverse pass + acceptance cost of every iteration) that round 1 served
+            // from L2 with six scalar loads per step and lane (1.6 GB of L2 -> SM traffic per forward at B = 65536).
+            if (j == 0) {
+              fence_proxy_async();          // the previous element's reads of this slot (generic proxy) are ordered before the copy
+              mbar_expect_tx(cbar, (unsigned)((T * CW + T * N) * sizeof(R)));
+              bulk_g2s(sCe, Cp, (unsigned)(T * CW * sizeof(R)), cbar);
+              bulk_g2s(sCe + T * CW, cp, (unsigned)(T * N * sizeof(R)), cbar);
+            }
+            Cp = sCe;
+            cp = sCe + T * CW;
+            if (P.Cf_batched) {   // the 30 (10) words of the terminal cost: 100-byte blocks are not 16-byte aligned, plain loads
+              R* sf = sCe + T * CW + T * N;
+              for (int w = j; w < CW; w += kG) sf[w] = Cfp[w];
+              for (int w = j; w < N; w += kG) sf[CW + w] = cfp[w];
+              Cfp = sf;
+              cfp = sf + CW;
+            }
+          }
           Cfp = io.Cf + (P.Cf_batched ? (size_t)b * CW : 0);
           cfp = io.cf + (P.Cf_batched ? (size_t)b * N : 0);
           // nominal trajectory (initial rollout) and references: global -> shared, once per element.  The
@@ -522,7 +634,9 @@ __global__ void __launch_bounds__(group_max_warps<R>() * 32, 1) ilqr_forward_gro
           const R* Ui = io.Uinit + (size_t)b * szU;
           for (int w = j; w < XW; w += kG) { xb[w * kXS] = Xi[w]; xb[w * kXS + kEPW] = xr[w]; }
           for (int w = j; w < UW; w += kG) { ub[w * kUS] = Ui[w]; ub[w * kUS + kURef] = ur[w]; }   // nominal inputs: buffer 0
-          best = cost0[b];
+          if (!kOwnInit || io.resume) best = cost0[b];
+          else fresh = true;
+          if (SW > 0) { mbar_wait(cbar, cphase); cphase ^= 1u; }   // the cost block has landed
           if (io.alpha_trace && !io.resume)
             for (int w = j; w < P.max_iter; w += kG) io.alpha_trace[(size_t)b * P.max_iter + w] = 0xFF;
         } else {
@@ -536,7 +650,16 @@ __global__ void __launch_bounds__(group_max_warps<R>() * 32, 1) ilqr_forward_gro
     bool run = has && it < P.max_iter;
     if (run && replay) run = it < io.replay_iters[b];
     bool improved = false;
+    if constexpr (kOwnInit) {
+      // a new element that runs no iteration at all (max_iter = 0) still reports its initial cost
+      if (__ballot_sync(FULL, fresh && !run) != 0u) {
+        const R c0 = own_cost_rows(0);
+        if (fresh && !run) best = c0;
+      }
+    }
     if (__ballot_sync(FULL, run) != 0u) {
+      // this iteration's tile of candidate states (the second tile only serves the restore after a rejected step: LSSEP)
+      R* scr = LSSEP ? scr0 + (size_t)(it & 1) * tileW : scr0;
       // The nominal inputs always sit in buffer 0 (the winner's inputs are copied there on acceptance: 20 words per
       // iteration), candidate a writes buffer a + 1, gain word k lives in buffer k + 1 — every shared-memory access of the
       // two passes has a compile-time offset from one running pointer (an index swap instead of the copy cost ~25 integer
@@ -550,6 +673,9 @@ __global__ void __launch_bounds__(group_max_warps<R>() * 32, 1) ilqr_forward_gro
       // quadraticize (cost.py:64-100) + linearize (controller.py:448-471) + backward_lqr (546-578)
       {
         R V[NX * NX], v[NX];
+        // (kOwnInit) the element's own cost of the nominal trajectory, accumulated row by row next to the quadraticisation —
+        // the same sums own_cost_rows() forms; it is the initial `best` of an element on its first iteration
+        R rq = 0, rl = 0, rqN = 0, rlN = 0;
         {
           R tauN[NX];
 #pragma unroll
@@ -564,6 +690,7 @@ __global__ void __launch_bounds__(group_max_warps<R>() * 32, 1) ilqr_forward_gro
               s += cik * tauN[k];
             }
             v[i] = s + cfo[i];
+            if constexpr (kOwnInit) { rqN += tauN[i] * s; rlN += cfo[i] * tauN[i]; }
           }
         }
         R jcm[NJ];   // compact Jacobian of the step this lane evaluated in the current block of kG steps
@@ -631,6 +758,11 @@ __global__ void __launch_bounds__(group_max_warps<R>() * 32, 1) ilqr_forward_gro
               s += Crow[k] * tau[k];
             }
             qj = s + cj;   // l = C tau + c (cost.py:86-88)
+            if constexpr (kOwnInit) {
+              const R tj = pick<N, R>(tau, jj);
+              rq += tj * s;
+              rl += cj * tj;
+            }
           }
           // row jj of F' V F and element jj of F' v
           {
@@ -727,6 +859,17 @@ __global__ void __launch_bounds__(group_max_warps<R>() * 32, 1) ilqr_forward_gro
           __syncwarp();
           px -= NX * kXS; pu -= NU * kUS;
           pCrow -= CSH ? CS : CW; pcj -= CSH ? CS : N;
+        }
+        if constexpr (kOwnInit) {
+          if (__ballot_sync(FULL, fresh) != 0u) {   // some group of this warp is on the first iteration of a new element
+            R qsum = 0, lsum = 0;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+              qsum += __shfl_sync(FULL, rq, base + i);
+              lsum += __shfl_sync(FULL, rl, base + i);
+            }
+            if (fresh) best = ((R)0.5 * qsum + lsum) + ((R)0.5 * rqN + rlN);
+          }
         }
       }
       // ---------------------------------------------------------------- line search: lane a = candidate a
@@ -840,63 +983,17 @@ __global__ void __launch_bounds__(group_max_warps<R>() * 32, 1) ilqr_forward_gro
       }
       if (run && replay) ai = io.replay_alpha[(size_t)b * P.max_iter + it];
       if constexpr (LSSEP) {
-        // Acceptance cost (controller.py:298): the element's OWN cost of the chosen candidate only.  Its inputs
-        // sit in shared memory and its states in the warp's scratch tile (L2), so the five lanes split the
-        // evaluation by rows of C_t — lane i accumulates sum_t tau_i (C_t[i,:] tau) and sum_t c_t[i] tau_i —
-        // instead of every candidate lane reading the whole per-element C_t at every step of the line search
-        // (30 global words per step and lane; 6 here, 2 for a compact diagonal).  Partial sums combine in lane order.
+        // Acceptance cost (controller.py:298): the element's OWN cost of the chosen candidate only.  Its states come back
+        // from the scratch tile into the state trajectory shared memory holds BEFORE the step is judged (one round of 17
+        // independent L2 loads per lane instead of a dependent load per step of the cost loop); a rejected step — the last
+        // iteration of every solve — restores the nominal states from the other tile (the previous iteration's winner).
         __syncwarp();                       // the candidates' inputs and states are complete and visible to the group
-        const R* prow = DIAG ? Cp + jj : Cp + jj * N;
-        const R* pc = cp + jj;
-        const R* wsx = scr + base + ai;     // the winner's column of the scratch tile
-        const R* rx = xb;
-        const int wbo = (ai + 1) * kEPW;    // the winner's input buffer
-        const R* wu = ub;
-        R quad = 0, lin = 0;
-        R wxv[NX];                          // the winner's X_t (X_0 is the common start state)
-#pragma unroll
-        for (int i = 0; i < NX; ++i) wxv[i] = xb[i * kXS];
-        for (int t = 0; t < T; ++t) {
-          R tau[N];
-#pragma unroll
-          for (int i = 0; i < NX; ++i) tau[i] = wxv[i] - rx[i * kXS + kEPW];
-#pragma unroll
-          for (int i = 0; i < NU; ++i) tau[NX + i] = wu[i * kUS + wbo] - wu[i * kUS + kURef];
-#pragma unroll
-          for (int i = 0; i < NX; ++i) wxv[i] = ld_cg<R>(wsx + i * 32);
-          const R tj = pick<N, R>(tau, jj);
-          R s = 0;
-          if (DIAG) {
-            // q_j tau_j plus the exact zeros the dense row would add (NaN if some tau_k is not finite)
-#pragma unroll
-            for (int k = 0; k < N; ++k) s += tau[k] * (R)0;
-            s += prow[0] * tj;
-          } else {
-#pragma unroll
-            for (int k = 0; k < N; ++k) s += prow[k] * tau[k];
-          }
-          quad += tj * s;
-          lin += pc[0] * tj;
-          wsx += NX * 32; wu += NU * kUS; rx += NX * kXS; prow += CW; pc += N;
+        if (run) {
+          const R* wsx = scr + base + ai;
+          for (int w = j; w < T * NX; w += kG) xb[(NX + w) * kXS] = ld_cg<R>(wsx + w * 32);
         }
-        R qsum = 0, lsum = 0;
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-          qsum += __shfl_sync(FULL, quad, base + i);
-          lsum += __shfl_sync(FULL, lin, base + i);
-        }
-        R tauN[NX], qN2 = 0, lN2 = 0;
-#pragma unroll
-        for (int i = 0; i < NX; ++i) tauN[i] = wxv[i] - rx[i * kXS + kEPW];
-#pragma unroll
-        for (int i = 0; i < NX; ++i) {
-          R s2 = 0;
-#pragma unroll
-          for (int k = 0; k < NX; ++k) s2 += (DIAG ? ((i == k) ? Cfo[i] : (R)0) : Cfo[i * N + k]) * tauN[k];
-          qN2 += tauN[i] * s2;
-          lN2 += cfo[i] * tauN[i];
-        }
-        cost_own = ((R)0.5 * qsum + lsum) + ((R)0.5 * qN2 + lN2);
+        __syncwarp();
+        cost_own = own_cost_rows((ai + 1) * kEPW);
       }
       const R newc = LSSEP ? cost_own : __shfl_sync(FULL, cost_own, base + ai);
       improved = newc < best;
@@ -919,10 +1016,19 @@ __global__ void __launch_bounds__(group_max_warps<R>() * 32, 1) ilqr_forward_gro
           // accept: the winner's inputs are copied into the nominal buffer, its states come back from the scratch tile
           // into the one state trajectory shared memory holds (X_0 is common to all candidates)
           best = newc;
-          const R* wsx = scr + base + ai;
           const R* wu = ub + (ai + 1) * kEPW;
-          for (int w = j; w < T * NX; w += kG) xb[(NX + w) * kXS] = ld_cg<R>(wsx + w * 32);
+          if constexpr (!LSSEP) {
+            const R* wsx = scr + base + ai;
+            for (int w = j; w < T * NX; w += kG) xb[(NX + w) * kXS] = ld_cg<R>(wsx + w * 32);
+          }
           for (int w = j; w < UW; w += kG) ub[w * kUS] = wu[w * kUS];
+          ai_prev = ai;
+        } else if constexpr (LSSEP) {
+          // rejected: the nominal states were overwritten by the candidate's for the acceptance cost; they are the previous
+          // iteration's winner (the other scratch tile) or, on an element's first iteration, the hand-over trajectory io.X
+          const R* src = ai_prev >= 0 ? scr0 + (size_t)(it & 1) * tileW + base + ai_prev : io.X + (size_t)b * szX + NX;
+          const int st = ai_prev >= 0 ? 32 : 1;
+          for (int w = j; w < T * NX; w += kG) xb[(NX + w) * kXS] = ld_cg<R>(src + (size_t)w * st);
         }
       }
       __syncwarp();   // inputs / states written by one lane are read by the whole group from here on

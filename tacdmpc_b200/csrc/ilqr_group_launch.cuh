@@ -31,8 +31,26 @@ static int run_forward_group(const tacd_problem* p, const tacd_forward_io* io, v
   auto kernel = ilqr_forward_group<R, NX, NU, DYN, LSSEP, CSH, DIAG>;
   const DeviceInfo di = device_info();
   const size_t cost_b = (size_t)group_cost_words(p->T, NX, NU, p->C_batched, p->Cf_batched, LSSEP ? 1 : 0, DYN == TACD_DYN_LTI) * sizeof(R);
-  const size_t warp_b = (size_t)group_warp_words(p->T, NX, NU) * sizeof(R);
-  if (cost_b + warp_b > (size_t)di.smem_optin) return TACD_EUNSUPPORTED;   // horizon too long for 6 buffers per element
+  // Per-element costs are staged in shared memory by bulk asynchronous copies when the blocks are 16-byte aligned AND the staged
+  // blocks do not cost resident warps.  Measured at B = 65536, cart-pole T = 20 (forward ms, staged / read through L2): compact
+  // diagonals 0.780 / 0.800 at 16 warps either way; dense [T,5,5] blocks 1.066 / 1.043 — 2.4 KB per element leave 10 warps per SM
+  // instead of 16 and the lost latency hiding outweighs the saved L2 reads, so dense blocks stay in L2 (TACD_STAGE=1 forces staging).
+  int stage = 0;
+  if (!CSH && p->C_batched) {
+    TACD_KNOB(k_nostage, "TACD_NO_STAGE");
+    TACD_KNOB(k_stage, "TACD_STAGE");
+    stage = group_stage_words(p->T, NX + NU, DIAG ? NX + NU : (NX + NU) * (NX + NU), sizeof(R));
+    if (((uintptr_t)io->C | (uintptr_t)io->c) % 16 != 0 || env_set(k_nostage)) stage = 0;
+    if (stage > 0) {
+      const size_t avail = (size_t)di.smem_optin - cost_b;
+      size_t w0 = avail / ((size_t)group_warp_words(p->T, NX, NU, 0) * sizeof(R)), w1 = avail / ((size_t)group_warp_words(p->T, NX, NU, stage) * sizeof(R));
+      if (w0 > (size_t)group_max_warps<R>()) w0 = group_max_warps<R>();
+      if (w1 > (size_t)group_max_warps<R>()) w1 = group_max_warps<R>();
+      if (w1 < 1 || (w1 < w0 && !env_set(k_stage))) stage = 0;
+    }
+  }
+  const size_t warp_b = (size_t)group_warp_words(p->T, NX, NU, stage) * sizeof(R);
+  if (cost_b + warp_b > (size_t)di.smem_optin) return TACD_EUNSUPPORTED;   // horizon too long for the per-element buffers
   int nw = (int)(((size_t)di.smem_optin - cost_b) / warp_b);
   if (nw > group_max_warps<R>()) nw = group_max_warps<R>();   // __launch_bounds__(group_max_warps<R>() * 32, 1)
   { TACD_KNOB(k, "TACD_GROUP_WARPS"); const int v = env_int(k, 0); if (v >= 1 && v < nw) nw = v; }
@@ -62,6 +80,7 @@ static int run_forward_group(const tacd_problem* p, const tacd_forward_io* io, v
   f.counter = (unsigned int*)ws;
   f.order = nullptr;
   f.xscratch = (R*)((char*)ws + wo.scratch);
+  f.stage_words = stage;
   const DevProblem<R> dp = to_dev<R>(p);
   if (resume) {
     // the nominal trajectories, costs, iteration counts and flags of the handed-over solves are where the first phase left
@@ -112,12 +131,16 @@ static int run_forward_group(const tacd_problem* p, const tacd_forward_io* io, v
     // a horizon whose tile does not fit goes to the thread-per-element kernel
     // per-element costs: the whole horizon in one tile when one warp's tile stays under ~1/2 of shared memory
     // (two resident warps per SM keep enough bytes in flight), else four steps at a time, double-buffered
+    // per-element costs scored by a separate line-search cost: the solve kernel evaluates the initial cost itself (row-split
+    // over five lanes, from its staged cost block); here the inputs are only rolled out
+    constexpr bool own_init = LSSEP && !CSH;
     int chunk = p->T;
     if (p->C_batched && init_warp_words(p->T, NX, NU, 1, p->C_diag, chunk) * sizeof(R) > (size_t)di.smem_optin / 2) chunk = p->T < 4 ? p->T : 4;
     // dense per-element costs: no cost tile, each thread reads its element's rows straight from global memory (chunk 0;
     // measured 2 % faster end to end than the whole-horizon tile, which leaves 2 CTAs per SM; compact diagonals: 1.5 % slower)
     if (p->C_batched && !p->C_diag) chunk = 0;
     { TACD_KNOB(k, "TACD_INIT_CHUNK"); const int v = env_int(k, -1); if (p->C_batched && v >= 0 && v <= p->T) chunk = v; }
+    if (own_init) chunk = 0;
     const size_t tile_b = init_warp_words(p->T, NX, NU, p->C_batched, p->C_diag, chunk) * sizeof(R);
     // one warp per CTA: the finest granularity for the last wave (2048 warps over 148 SMs at B = 65536)
     if (tile_b > (size_t)di.smem_optin) return TACD_EUNSUPPORTED;
@@ -125,7 +148,7 @@ static int run_forward_group(const tacd_problem* p, const tacd_forward_io* io, v
     { TACD_KNOB(k, "TACD_INIT_WARPS"); const int v = env_int(k, 0); if (v >= 1 && v <= 4 && tile_b * v <= (size_t)di.smem_optin) iw = v; }
     if (int rc = check_cuda(cudaFuncSetAttribute(init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(tile_b * iw)), "smem attr")) return rc;
     const int nwarp = (p->B + 31) / 32;
-    init<<<(nwarp + iw - 1) / iw, iw * 32, tile_b * iw, s>>>(dp, f, cost0, chunk);
+    init<<<(nwarp + iw - 1) / iw, iw * 32, tile_b * iw, s>>>(dp, f, own_init ? (R*)nullptr : cost0, chunk);
     note_launches(1);
   }
   if (int rc = check_cuda(cudaPeekAtLastError(), "ilqr_init_rollout launch")) return rc;
@@ -225,6 +248,7 @@ static int run_backward_group(const tacd_problem* p, const tacd_backward_io* io,
     if (io->grad_cf && !p->Cf_batched) if (int rc = check_cuda(cudaMemsetAsync(io->grad_cf, 0, n * sizeof(R), s), "memset")) return rc;
   }
   BwdPtrs<R> f;
+  f.kscratch = nullptr;
   f.X = (const R*)io->X; f.U = (const R*)io->U; f.C = (const R*)io->C; f.Cf = (const R*)io->Cf; f.xref = (const R*)io->xref; f.uref = (const R*)io->uref;
   f.A = (const R*)io->A; f.Bm = (const R*)io->Bm; f.gX = (const R*)io->gX; f.gU = (const R*)io->gU; f.tight = io->tight;
   f.grad_C = (R*)io->grad_C; f.grad_c = (R*)io->grad_c; f.grad_Cf = (R*)io->grad_Cf; f.grad_cf = (R*)io->grad_cf;

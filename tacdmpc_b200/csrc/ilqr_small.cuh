@@ -34,6 +34,7 @@ struct FwdPtrs {
   unsigned int* counter;  // work queue head; set to first_wave before launch
   const int32_t* order;   // longest-first permutation of the batch (nullable = identity)
   R* xscratch;            // five-lanes-per-element kernel: the candidates' states, one [T nx][32] tile per resident warp
+  int stage_words;        // five-lanes-per-element kernel: > 0 = per-element (C, c) are bulk-copied into shared memory, this many words per element
   R* cscratch;            // per-element costs only: lane-slot copy of (C, c), [word][lane] (nullable)
   size_t cstride;         // number of lane slots (= grid * block)
   unsigned int first_wave;  // queue positions [0, first_wave) are dealt statically, one 32-segment per warp
@@ -132,6 +133,9 @@ struct BwdPtrs {
   const R *X, *U, *C, *Cf, *xref, *uref, *A, *Bm, *gX, *gU;
   const uint8_t* tight;
   R *grad_C, *grad_c, *grad_Cf, *grad_cf, *grad_x0, *grad_xref, *grad_uref, *dX, *dU;
+  // thread-per-element backward: the gains K_t, k_t of the KKT pass, [word][thread slot] in the caller's workspace (L2-resident,
+  // coalesced) instead of 400 bytes of shared memory per thread; nullptr = shared memory
+  R* kscratch;
 };
 
 constexpr int kNA = 5;  // line-search candidates rolled out together (the reference has 5 alphas)
@@ -568,7 +572,7 @@ struct BwdLayout {
 };
 
 template <typename R, int NX, int NU, int DYN, bool DIAG, bool EXACT>
-__global__ void __launch_bounds__(256, 1) ilqr_backward_small(const DevProblem<R> P, const BwdPtrs<R> io, R* partials, int reduce, int vnt) {
+__global__ void __launch_bounds__(256, 2) ilqr_backward_small(const DevProblem<R> P, const BwdPtrs<R> io, R* partials, int reduce, int vnt) {
   constexpr int N = NX + NU;
   using L = BwdLayout<NX, NU>;
   using D = Dyn<R, NX, NU, (DYN == TACD_DYN_EXTERNAL ? TACD_DYN_LTI : DYN)>;
@@ -576,9 +580,16 @@ __global__ void __launch_bounds__(256, 1) ilqr_backward_small(const DevProblem<R
   const int NT = blockDim.x, tid = threadIdx.x;
   const int T = P.T;
   const int lane = tid & 31, wid = tid >> 5, nw = NT >> 5;
-  R* sK = reinterpret_cast<R*>(smem_raw);
-  R* sk = sK + (size_t)T * NU * NX * NT;
-  R* sA = sk + (size_t)T * NU * NT;
+  // Gains of the KKT pass: one [word][slot] column per thread.  Round 1 kept them in shared memory (400 bytes per thread for the
+  // cart-pole, T = 20), which with the reduction tiles left ONE 8-warp CTA per SM — the kernel issued 38 % of its slots and waited
+  // on latencies (profiles/r1_backward_v6).  In the workspace the column is a coalesced, L2-resident stream and shared memory
+  // holds only the tiles: two CTAs (16 warps) per SM at 128 registers.
+  const bool kglob = io.kscratch != nullptr;
+  const size_t kst = kglob ? (size_t)gridDim.x * NT : (size_t)NT;
+  R* smem0 = reinterpret_cast<R*>(smem_raw);
+  R* sK = kglob ? io.kscratch + (size_t)blockIdx.x * NT + tid : smem0 + tid;
+  R* sk = sK + (size_t)T * NU * NX * kst;
+  R* sA = kglob ? smem0 : smem0 + (size_t)T * NU * (NX + 1) * NT;
   R* sB = sA + NX * NX;
   R* tile = sB + NX * NU;                                    // [nw][32][TW]      (only when reduce)
   R* acc = tile + (size_t)nw * L::TILE;                      // [nw][nacc]
@@ -595,8 +606,8 @@ __global__ void __launch_bounds__(256, 1) ilqr_backward_small(const DevProblem<R
   const bool redC = reduce && io.grad_C && !P.C_batched, redc = reduce && io.grad_c && !P.C_batched;
   const bool redCf = reduce && io.grad_Cf && !P.Cf_batched, redcf = reduce && io.grad_cf && !P.Cf_batched;
   const bool redx = reduce && io.grad_xref && !P.xref_batched, redu = reduce && io.grad_uref && !P.uref_batched;
-#define SK(t, i) sK[((size_t)(t) * NU * NX + (i)) * NT + tid]
-#define Sk(t, i) sk[((size_t)(t) * NU + (i)) * NT + tid]
+#define SK(t, i) sK[((size_t)(t) * NU * NX + (i)) * kst]
+#define Sk(t, i) sk[((size_t)(t) * NU + (i)) * kst]
   const size_t szX = (size_t)(T + 1) * NX, szU = (size_t)T * NU;
   // vnt (multiple of 32, <= NT) threads of every CTA take one element per wave, so that all CTAs — and with
   // them all SMs — carry the same load in every wave; the remaining warps of the CTA stay out of the loop

@@ -103,11 +103,19 @@ static int run_backward_small(const tacd_problem* p, const tacd_backward_io* io,
   int bps = 0;
   size_t smem = 0;
   const size_t wpt = (size_t)bwd_words(p->T, NX, NU);
+  // the gains go to the workspace (coalesced [word][thread slot] columns) when it has room for two 256-thread CTAs per SM
+  TACD_KNOB(k_ksmem, "TACD_BWD_K_SMEM");
+  const size_t partial_cap = (size_t)device_info().sms * 2 * nacc * sizeof(R);
+  const size_t kscratch_need = (size_t)device_info().sms * 2 * 256 * wpt * sizeof(R);
+  // Measured at B = 65536, cart-pole (backward ms, gains in the workspace + 2 CTAs per SM / gains in shared memory + 1 CTA): shared
+  // cost 0.123 / 0.138 (round 1) — taken; per-element dense 0.231 / 0.215 and compact diagonal 0.163 / 0.144 — not taken: those
+  // layouts stream 2-6 KB of gradients per element to HBM and the extra 26 MB of gain traffic costs more than the second CTA hides.
+  const bool kglob = reduce && !env_set(k_ksmem) && ws && ws_bytes >= ((partial_cap + 255) / 256) * 256 + kscratch_need;
   const int nt = pick_block(kernel, [&](int n) {
-    size_t w = wpt * n + NX * NX + NX * NU + (size_t)(n / 32) * L::TILE;   // gains + LTI matrices + one tile per warp
+    size_t w = (kglob ? 0 : wpt * n) + NX * NX + NX * NU + (size_t)(n / 32) * L::TILE;   // [gains +] LTI matrices + one tile per warp
     if (reduce) w += (size_t)(n / 32) * nacc;                                   // per-warp accumulators
     return w * sizeof(R);
-  }, &bps, &smem, 1);   // one CTA per SM: two smaller ones measured 15 % slower (compact-diagonal variant, 149 registers)
+  }, &bps, &smem, kglob ? 2 : 1);
   if (nt == 0 || bps == 0) return TACD_EUNSUPPORTED;
   if (int rc = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr")) return rc;
   const DeviceInfo di = device_info();
@@ -137,6 +145,7 @@ static int run_backward_small(const tacd_problem* p, const tacd_backward_io* io,
   f.A = (const R*)io->A; f.Bm = (const R*)io->Bm; f.gX = (const R*)io->gX; f.gU = (const R*)io->gU; f.tight = io->tight;
   f.grad_C = (R*)io->grad_C; f.grad_c = (R*)io->grad_c; f.grad_Cf = (R*)io->grad_Cf; f.grad_cf = (R*)io->grad_cf;
   f.grad_x0 = (R*)io->grad_x0; f.grad_xref = (R*)io->grad_xref; f.grad_uref = (R*)io->grad_uref; f.dX = (R*)io->dX; f.dU = (R*)io->dU;
+  f.kscratch = kglob ? (R*)((char*)ws + ((partial_cap + 255) / 256) * 256) : nullptr;
   const DevProblem<R> dp = to_dev<R>(p);
   kernel<<<grid, nt, smem, s>>>(dp, f, partials, reduce ? 1 : 0, vnt);
   note_launches(1);
