@@ -285,6 +285,15 @@ int tacd_discounted_targets(int32_t dtype, int32_t N, int32_t H, const void* rew
  * floating-point operations of the launch.  The caller times the launch with CUDA events.  No reference counterpart. */
 int tacd_fp32_probe(int32_t kind, int32_t iters, int32_t blocks, const void* seed, void* out, double* flops, void* stream);
 
+/* Tensor-core decision probe for n_x >= 16 (BASELINE north_star: "tensor cores only if ncu shows a batched-GEMM formulation beats
+ * the register-resident path"): evaluates the Riccati step's dominant product  Q_b = C_b + F' V_b F  (controller.py:551-558;
+ * F = [A | B] shared by the batch, as for the LTI plugin of config 5) `reps` times per element, fp32.
+ * kind 0 = CTA per element, 1 x 4 register tiles from shared memory (the round-1 generic kernel's scheme);
+ * kind 1 = warp per element, lane-per-row operands in registers; kind 2 = warp per element, mma.sync TF32 with the 3-term split.
+ * V [B,nx,nx], F [nx,nx+nu], C [B,n,n] in; Q [B,n,n] out (device pointers).  (nx, nu) in {(32, 8), (16, 8)}. */
+int tacd_probe_fvf(int32_t kind, int32_t nx, int32_t nu, int32_t B, int32_t reps, const void* V, const void* F, const void* C,
+                   void* Q, void* stream);
+
 /* batched projected-Newton box QP: H[N,m,m] q[N,m] lo[N,m] hi[N,m] -> x[N,m], iters[N] (nullable) */
 int tacd_pnqp(int32_t dtype, int32_t N, int32_t m, const void* H, const void* q,
               const void* lo, const void* hi, void* x, int32_t* iters, void* stream);

@@ -85,12 +85,33 @@ class ActorMPC(nn.Module):
         ``GraphedPolicy``."""
         return GraphedPolicy(self, batch_size, deterministic)
 
-    def evaluate_actions(self, x: Tensor, actions: Tensor, *, _validate_args=None) -> Tuple[Tensor, Tensor]:
+    def _line_search_cost_of(self, x0: Tensor):
+        """The cost the network assigns to ONE observation, as the controller's line-search override (quirk Q4: under
+        ``compat="reference"`` every element's candidates are scored with batch element 0's cost).  A rank that holds a
+        shard of a mini-batch evaluates the network on GLOBAL element 0's observation itself — same weights on every
+        rank — instead of waiting for a broadcast of 2(T+1)n numbers inside the step."""
+        n = self.nx + self.nu
+        with torch.no_grad():
+            params = self.cost_map_net(x0.reshape(1, -1))
+            q_raw, p_raw = params.split([self.horizon * n, self.horizon * n], dim=-1)
+            q = (F.softplus(q_raw) + 1e-2).view(self.horizon, n)
+            p = p_raw.view(self.horizon, n)
+        return (q, p, q[-1].clone(), p[-1].clone())
+
+    def evaluate_actions(self, x: Tensor, actions: Tensor, *, ls_state: Optional[Tensor] = None, _validate_args=None) -> Tuple[Tensor, Tensor]:
+        """``ls_state`` (not in the reference): observation of the GLOBAL mini-batch's element 0 when ``x`` is one rank's
+        shard of it (``ShardedPPOUpdate``); None = ``x[0]``, the reference's behaviour."""
         if x.ndim == 1:
             x = x.unsqueeze(0)
         self._update_cost_module(x)
         U_init = torch.zeros(x.shape[0], self.horizon, self.nu, device=self.device, dtype=self.dtype)
-        _, predicted_actions = self.mpc(x[:, :self.nx], U_init)
+        if ls_state is not None:
+            self.mpc.ls_cost_override = self._line_search_cost_of(ls_state)
+        try:
+            _, predicted_actions = self.mpc(x[:, :self.nx], U_init)
+        finally:
+            if ls_state is not None:
+                self.mpc.ls_cost_override = None
         dist = Normal(predicted_actions[:, 0], self.log_std.exp(), validate_args=_validate_args)
         return dist.log_prob(actions).sum(dim=-1), dist.entropy().sum(dim=-1)
 

@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtacd_ilqr.so")
 SOURCES = ["capi.cu", "ilqr_small_f32.cu", "ilqr_small_f64.cu", "ilqr_group_f32.cu", "ilqr_group_f64.cu", "ilqr_generic.cu", "ilqr_generic_part1.cu", "ilqr_generic_part2.cu", "ilqr_generic_part3.cu",
-           "ppo_glue.cu", "probe.cu"]
+           "ppo_glue.cu", "probe.cu", "probe_fvf.cu", "ilqr_lti_f32.cu", "ilqr_lti_f64.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

@@ -115,7 +115,8 @@ static size_t fwd_head_bytes(const tacd_problem* p) {
 }
 size_t tacd_forward_workspace_bytes(const tacd_problem* p) {
   if (validate(p)) return 0;
-  return fwd_head_bytes(p) + generic_forward_ws_bytes(p);
+  const size_t g = generic_forward_ws_bytes(p), l = lti_ws_bytes(p);
+  return fwd_head_bytes(p) + (g > l ? g : l);
 }
 // backward workspace: per-CTA partial sums of the shared-input gradients (thread-per-element kernel)
 // or the generic kernel's per-CTA slices, whichever is larger
@@ -129,7 +130,7 @@ static size_t bwd_partials_bytes(const tacd_problem* p) {
 }
 size_t tacd_backward_workspace_bytes(const tacd_problem* p) {
   if (validate(p)) return 0;
-  const size_t a = bwd_partials_bytes(p), b = generic_backward_ws_bytes(p);
+  const size_t a = bwd_partials_bytes(p), g = generic_backward_ws_bytes(p), l = lti_ws_bytes(p), b = g > l ? g : l;
   return 256 + (a > b ? a : b);
 }
 
@@ -150,6 +151,9 @@ int tacd_ilqr_forward(const tacd_problem* p, const tacd_forward_io* io, void* wo
   rc = (p->dtype == TACD_F32) ? launch_forward_small<float>(p, io, workspace, head, s) : launch_forward_small<double>(p, io, workspace, head, s);
   if (rc != TACD_EUNSUPPORTED) return rc;
   char* ws = (char*)workspace + head;
+  rc = (p->dtype == TACD_F32) ? launch_forward_lti<float>(p, io, ws, workspace_bytes - head, s)
+                              : launch_forward_lti<double>(p, io, ws, workspace_bytes - head, s);
+  if (rc != TACD_EUNSUPPORTED) return rc;
   rc = (p->dtype == TACD_F32) ? launch_forward_generic<float>(p, io, ws, workspace_bytes - head, s)
                               : launch_forward_generic<double>(p, io, ws, workspace_bytes - head, s);
   return rc;
@@ -173,6 +177,9 @@ int tacd_ilqr_backward(const tacd_problem* p, const tacd_backward_io* io, void* 
                               : launch_backward_small<double>(p, io, ws, workspace_bytes - 256, s);
   if (rc != TACD_EUNSUPPORTED) return rc;
   if (p->C_diag) { set_error("C_diag: no thread-per-element backward kernel for this (nx, nu, dyn); pass dense costs"); return TACD_EUNSUPPORTED; }
+  rc = (p->dtype == TACD_F32) ? launch_backward_lti<float>(p, io, ws, workspace_bytes - 256, s)
+                              : launch_backward_lti<double>(p, io, ws, workspace_bytes - 256, s);
+  if (rc != TACD_EUNSUPPORTED) return rc;
   rc = (p->dtype == TACD_F32) ? launch_backward_generic<float>(p, io, ws, workspace_bytes - 256, s)
                               : launch_backward_generic<double>(p, io, ws, workspace_bytes - 256, s);
   return rc;

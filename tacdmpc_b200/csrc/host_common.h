@@ -81,6 +81,10 @@ size_t group_forward_scratch_bytes(const tacd_problem* p);
 template <typename R> int launch_forward_generic(const tacd_problem* p, const tacd_forward_io* io, void* ws, size_t ws_bytes, cudaStream_t s);
 template <typename R> int launch_backward_generic(const tacd_problem* p, const tacd_backward_io* io, void* ws, size_t ws_bytes, cudaStream_t s);
 size_t generic_forward_ws_bytes(const tacd_problem* p);
+// warp-per-element kernels of the LTI sweep (ilqr_lti.cuh); TACD_EUNSUPPORTED when not eligible
+template <typename R> int launch_forward_lti(const tacd_problem* p, const tacd_forward_io* io, void* ws, size_t ws_bytes, cudaStream_t s);
+template <typename R> int launch_backward_lti(const tacd_problem* p, const tacd_backward_io* io, void* ws, size_t ws_bytes, cudaStream_t s);
+size_t lti_ws_bytes(const tacd_problem* p);
 size_t generic_backward_ws_bytes(const tacd_problem* p);
 
 }  // namespace tacd
