@@ -294,6 +294,13 @@ int tacd_fp32_probe(int32_t kind, int32_t iters, int32_t blocks, const void* see
 int tacd_probe_fvf(int32_t kind, int32_t nx, int32_t nu, int32_t B, int32_t reps, const void* V, const void* F, const void* C,
                    void* Q, void* stream);
 
+/* The gain solve of the warp-per-element LTI kernels (csrc/ilqr_lti.cuh::gains) in isolation, for unit parity against LAPACK:
+ * x = -(Q + reg' I)^-1 r for n problems, fp32, nu in {4, 8}.  kkt = 0: the forward pass's solve (controller.py:557-566: Cholesky of
+ * Q + reg I, LU with partial pivoting when that fails -> nonpd[i] = 1); kkt = 1: the backward pass's (LU of Q + 1e-8 reg I, :766).
+ * Quu [n,nu,nu], rhs [n,nu,2] (two right-hand sides) in; K [n,nu], k [n,nu] = the two solutions, nonpd [n] out. */
+int tacd_probe_lti_gains(int32_t dtype, int32_t nu, int32_t kkt, int32_t n, double reg, const void* Quu, const void* rhs, void* K,
+                         void* k, uint8_t* nonpd, void* stream);
+
 /* batched projected-Newton box QP: H[N,m,m] q[N,m] lo[N,m] hi[N,m] -> x[N,m], iters[N] (nullable) */
 int tacd_pnqp(int32_t dtype, int32_t N, int32_t m, const void* H, const void* q,
               const void* lo, const void* hi, void* x, int32_t* iters, void* stream);

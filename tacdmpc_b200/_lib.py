@@ -38,6 +38,7 @@ _SIGS = {
     "tacd_gae": (C.c_int, [C.c_int32] * 3 + [_VP, _VP, C.c_double, C.c_double, _VP, _VP, _VP]),
     "tacd_discounted_targets": (C.c_int, [C.c_int32] * 3 + [_VP, _VP, C.c_double, _VP, _VP]),
     "tacd_fp32_probe": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _VP, _VP, C.POINTER(C.c_double), _VP]),
+    "tacd_probe_lti_gains": (C.c_int, [C.c_int32] * 4 + [C.c_double] + [_VP] * 6),
     "tacd_probe_fvf": (C.c_int, [C.c_int32] * 5 + [_VP] * 5),
     "tacd_closed_loop_advance": (C.c_int, [C.POINTER(_abi.Problem), C.c_int32, C.c_int32] + [_VP] * 7 + [C.c_int32] + [_VP] * 3),
 }

@@ -139,11 +139,17 @@ __device__ void gen_lu(R* M, int m, int* piv) {
   }
 }
 // solve with the factors above for column r of rhs [m, nr] (one thread per column)
+// (LAPACK getrs: gen_lu swaps WHOLE rows, so the stored multipliers are in their final row order and every interchange has to
+// be applied to the right-hand side before the forward substitution starts.  Round 1 interleaved the two — correct only while at
+// most one interchange touches a row, i.e. always for nu <= 2 and for diagonally dominant Q_uu; found in round 2 by
+// tests/test_gpu_lti.py::test_gain_solve_against_lapack: 0.2-0.9 median relative error on indefinite 4 x 4 / 8 x 8 systems.)
 template <typename R>
 __device__ void gen_lu_solve_col(const R* M, int m, const int* piv, R* rhs, int nr, int r) {
   for (int j = 0; j < m; ++j) {
     const int p = piv[j];
     if (p != j) { const R t = rhs[j * nr + r]; rhs[j * nr + r] = rhs[p * nr + r]; rhs[p * nr + r] = t; }
+  }
+  for (int j = 0; j < m; ++j) {
     for (int i = j + 1; i < m; ++i) rhs[i * nr + r] -= M[i * m + j] * rhs[j * nr + r];
   }
   for (int i = m - 1; i >= 0; --i) {
@@ -270,7 +276,7 @@ __device__ __forceinline__ void gen_lu_solve_col_reg(const R* Ms, const int* piv
 #pragma unroll
   for (int i = 0; i < M; ++i) x[i] = rhs[i * nr + r];
 #pragma unroll
-  for (int j = 0; j < M; ++j) {
+  for (int j = 0; j < M; ++j) {   // all interchanges first (see gen_lu_solve_col)
     const int p = piv[j];
 #pragma unroll
     for (int i = j + 1; i < M; ++i) {
@@ -279,6 +285,9 @@ __device__ __forceinline__ void gen_lu_solve_col_reg(const R* Ms, const int* piv
       x[j] = sw ? hi : lo;
       x[i] = sw ? lo : hi;
     }
+  }
+#pragma unroll
+  for (int j = 0; j < M; ++j) {
 #pragma unroll
     for (int i = j + 1; i < M; ++i) x[i] -= Ms[i * M + j] * x[j];
   }

@@ -50,6 +50,33 @@ TACD_DEV void stv(R* p, const R (&s)[W]) {
   *reinterpret_cast<LVec<R, W>*>(p) = t;
 }
 
+// acc[0..W) += l * r[0..W).  fp32: packed fma.rn.f32x2 (SASS FFMA2, sm_100): two IEEE fused multiply-adds per issue slot; the
+// {l, l} pair is the instruction's scalar-broadcast operand, r comes out of a 64/128-bit shared-memory load as an aligned pair
+// and the accumulators live in pairs.  Same roundings as W scalar FFMAs.
+template <int W, typename R>
+TACD_DEV void axpyv(R (&acc)[W], R l, const R (&r)[W]) {
+#pragma unroll
+  for (int c = 0; c < W; ++c) acc[c] += l * r[c];
+}
+template <int W>
+TACD_DEV void axpyv_f32x2(float (&acc)[W], float l, const float (&r)[W]) {
+  static_assert(W % 2 == 0, "pairs");
+#pragma unroll
+  for (int h = 0; h < W / 2; ++h) {
+    unsigned long long lb, rb, ab;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(lb) : "f"(l));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(r[2 * h]), "f"(r[2 * h + 1]));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ab) : "f"(acc[2 * h]), "f"(acc[2 * h + 1]));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(ab) : "l"(lb), "l"(rb));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[2 * h]), "=f"(acc[2 * h + 1]) : "l"(ab));
+  }
+}
+#ifndef TACD_LTI_NO_FFMA2
+template <> TACD_DEV void axpyv<2, float>(float (&acc)[2], float l, const float (&r)[2]) { axpyv_f32x2<2>(acc, l, r); }
+template <> TACD_DEV void axpyv<4, float>(float (&acc)[4], float l, const float (&r)[4]) { axpyv_f32x2<4>(acc, l, r); }
+template <> TACD_DEV void axpyv<8, float>(float (&acc)[8], float l, const float (&r)[8]) { axpyv_f32x2<8>(acc, l, r); }
+#endif
+
 // a[i] for a run-time i < M with a in registers
 template <int M, typename R>
 TACD_DEV R lti_pick(const R* a, int i) {
@@ -133,34 +160,221 @@ struct LtiWarp {
     ldv<UQ>(c.quu, Ct + (size_t)(NX + m) * N + NX + mq);
   }
 
+  // Everything one step of the reverse pass reads from global memory, in registers: the cost tile, the rows >= NX of C_t for
+  // l_u (entry e0 / e1 of every row), c_t and the two operands of tau.  With PF the loads of step t-1 are issued before the
+  // arithmetic of step t (small systems are a latency chain: one DRAM / L2 round trip per step was ~1 us of a ~1.6 us step at
+  // n_x = 8); at n_x = 32 the 69 registers are not there and the loads are issued at the top of the step instead.
+  static constexpr bool PF = NX <= 16;
+  struct StepIn { CTile c; R lu0[NU], lu1[N > 32 ? NU : 1]; R cx[RW], cu, ta0, tb0, ta1, tb1; };
+  // FWD: quadraticisation inputs (tau = a - b, c_t); else the KKT pass: lv = -grad
+  template <bool FWD>
+  TACD_DEV void load_step(StepIn& s, int t, const R* Cp, const R* cp, const R* Xn, const R* Un, const R* xr, const R* ur) const {
+    const R* Ct = Cp + (size_t)t * N * N;
+    load_ctile(s.c, Ct);
+    if (FWD) {
+#pragma unroll
+      for (int mm = 0; mm < NU; ++mm) {
+        s.lu0[mm] = Ct[(size_t)(NX + mm) * N + e0];
+        if (N > 32) s.lu1[mm] = Ct[(size_t)(NX + mm) * N + e1];
+      }
+      const R* ct = cp + (size_t)t * N;
+#pragma unroll
+      for (int a = 0; a < RW; ++a) s.cx[a] = ct[rr * RW + a];
+      s.cu = ct[NX + m];
+      s.ta0 = (e0 < NX) ? Xn[(size_t)t * NX + e0] : Un[(size_t)t * NU + e0 - NX];
+      s.tb0 = (e0 < NX) ? xr[(size_t)t * NX + e0] : ur[(size_t)t * NU + e0 - NX];
+      if (N > 32) { s.ta1 = Un[(size_t)t * NU + e1 - NX]; s.tb1 = ur[(size_t)t * NU + e1 - NX]; }
+    } else {
+      // Xn = grad_X, Un = grad_U
+      s.ta0 = (e0 < NX) ? Xn[(size_t)t * NX + e0] : Un[(size_t)t * NU + e0 - NX];
+      if (N > 32) s.ta1 = Un[(size_t)t * NU + e1 - NX];
+    }
+  }
+  TACD_DEV void store_tau(const StepIn& s) const {
+    if (lane < N) tau()[e0] = s.ta0 - s.tb0;
+    if (N > 32 && has1) tau()[e1] = s.ta1 - s.tb1;
+  }
   // l = C_t tau + c_t (cost.py:86-88) -> lv[0..N): rows < NX from the tile (partial sums over the lane's columns, reduced over
-  // cc), rows >= NX by the whole warp, one coalesced row read each.  tau must be in shared memory.
-  TACD_DEV void cost_linear(const CTile& c, const R* Ct, const R* ct) const {
+  // cc), rows >= NX by the whole warp (entry e0 / e1 of the row per lane).  tau must be in shared memory.
+  TACD_DEV void cost_linear(const StepIn& s) const {
     const R* t = tau();
     R tw[CW], tm[MS];
     ldv<CW>(tw, t + cc * CW);
     ldv<MS>(tm, t + NX + cc * MS);
 #pragma unroll
     for (int a = 0; a < RW; ++a) {
-      R s = 0;
+      R acc = 0;
 #pragma unroll
-      for (int e = 0; e < CW; ++e) s += c.qxx[a][e] * tw[e];
+      for (int e = 0; e < CW; ++e) acc += s.c.qxx[a][e] * tw[e];
 #pragma unroll
-      for (int e = 0; e < MS; ++e) s += c.qxu[a][e] * tm[e];
+      for (int e = 0; e < MS; ++e) acc += s.c.qxu[a][e] * tm[e];
 #pragma unroll
-      for (int o = 1; o < NCH; o <<= 1) s += __shfl_xor_sync(FULL, s, o);
-      if (cc == 0) lv()[rr * RW + a] = s + ct[rr * RW + a];
+      for (int o = 1; o < NCH; o <<= 1) acc += __shfl_xor_sync(FULL, acc, o);
+      if (cc == 0) lv()[rr * RW + a] = acc + s.cx[a];
     }
     const R t0 = t[e0], t1 = t[e1];
 #pragma unroll
     for (int mm = 0; mm < NU; ++mm) {
-      const R* row = Ct + (size_t)(NX + mm) * N;
-      R s = (lane < N) ? row[e0] * t0 : (R)0;
-      if (N > 32) s += has1 ? row[e1] * t1 : (R)0;
+      R acc = (lane < N) ? s.lu0[mm] * t0 : (R)0;
+      if (N > 32) acc += has1 ? s.lu1[mm] * t1 : (R)0;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
-      if (lane == 0) lv()[NX + mm] = s + ct[NX + mm];
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+      if (lane == mm) lv()[NX + mm] = acc + s.cu;
     }
+  }
+
+  // The gain solve.  Q_uu + reg I is factorised ONCE per warp with its rows distributed over the lanes (row = lane % NU; the
+  // 32 / NU lane groups are replicas, so every shuffle source is valid): right-looking Cholesky — the same subtractions in the
+  // same order as the left-looking dot products of ilqr_generic.cuh::gen_chol — and, when that fails (or in the KKT pass), LU with
+  // partial pivoting (first maximum, whole rows swapped, as LAPACK getrf / the reference's linalg.solve).  The factors go through
+  // shared memory; every lane then solves ITS column of [Q_ux | q_u] with the triangular factors in registers.  Round 2's first
+  // version factorised redundantly on every lane in registers: 64 + 64 live values, select chains for the row swaps and 1.8 k of
+  // a step's 9.5 k instructions (profiles/r2_lti_fwd_nx32_v1).  Divisions are correctly rounded (div_rn_): with the 1-ulp div_ the
+  // accept / reject decisions of the unstable sweep moved (mean iterations 1.0 -> 2.5 at n_x = 32: measured).
+  template <bool KKT>
+  TACD_DEV bool gains(const DevProblem<R>& P, R (&Kc)[NU], R (&kt)[NU], R (&Qxi)[NU], R (&qu)[NU]) const {
+    const R reg2 = KKT ? (R)1e-8 * P.reg : P.reg;
+    R* Ls = GxT();                       // factors, row-major [NU][NU] (Gx^T is dead after the Q phase)
+    R* LTs = Ls + NU * NU;               // Cholesky: L transposed
+    int* perm = reinterpret_cast<int*>(LTs + NU * NU);
+    const int li = li_();
+    R a[NU];
+    auto load_row = [&]() {
+      ldv<NU>(a, Quu() + m * NU);
+#pragma unroll
+      for (int k = 0; k < NU; ++k) a[k] += (k == m) ? reg2 : (R)0;
+    };
+    load_row();
+    bool chol = false;
+#ifdef TACD_LTI_OLD_CHOL
+    if (!KKT) {
+      R Lf[NU * NU];
+#pragma unroll
+      for (int i = 0; i < NU * NU; i += 4) {
+        R t4[4];
+        ldv<4>(t4, Quu() + i);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) Lf[i + e] = t4[e] + (((i + e) / NU == (i + e) % NU) ? reg2 : (R)0);
+      }
+      chol = gen_chol_reg<R, NU>(Lf);
+      if (chol) {
+#pragma unroll
+        for (int i = 0; i < NU; ++i)
+#pragma unroll
+          for (int k = 0; k < NU; ++k)
+            if (i == m) { Ls[i * NU + k] = (k <= i) ? Lf[i * NU + k] : (R)0; LTs[k * NU + i] = (k <= i) ? Lf[i * NU + k] : (R)0; }
+      }
+    }
+#else
+    if (!KKT) {
+      bool ok = true;
+      R lrow[NU];
+#pragma unroll
+      for (int j = 0; j < NU; ++j) {
+        const R d = __shfl_sync(FULL, a[j], j);
+        if (!(d > 0)) ok = false;
+        const R dd = sqrt_<R>(d);
+        R l = div_rn_<R>(a[j], dd);
+        l = (m == j) ? dd : l;
+        lrow[j] = (m >= j) ? l : (R)0;
+#pragma unroll
+        for (int k = j + 1; k < NU; ++k) {
+          const R lk = __shfl_sync(FULL, l, k);
+          a[k] -= l * lk;
+        }
+      }
+      chol = ok;
+      if (ok) {
+        stv<NU>(Ls + m * NU, lrow);
+#pragma unroll
+        for (int k = 0; k < NU; ++k) LTs[k * NU + m] = lrow[k];
+      }
+    }
+#endif
+    if (!chol) {
+      if (!KKT) load_row();
+      int rowid = m;
+#pragma unroll
+      for (int j = 0; j < NU; ++j) {
+        R v = (m >= j) ? abs_<R>(a[j]) : (R)-1;
+        int idx = m;
+#pragma unroll
+        for (int o = 1; o < NU; o <<= 1) {
+          const R v2 = __shfl_xor_sync(FULL, v, o);
+          const int i2 = __shfl_xor_sync(FULL, idx, o);
+          const bool take = (v2 > v) || (v2 == v && i2 < idx);
+          v = take ? v2 : v;
+          idx = take ? i2 : idx;
+        }
+        const int src = (m == j) ? idx : ((m == idx) ? j : m);
+#pragma unroll
+        for (int k = 0; k < NU; ++k) a[k] = __shfl_sync(FULL, a[k], src);
+        rowid = __shfl_sync(FULL, rowid, src);
+        const R pj = __shfl_sync(FULL, a[j], j);
+        const R f = div_rn_<R>(a[j], pj);
+        if (m > j) a[j] = f;
+#pragma unroll
+        for (int k = j + 1; k < NU; ++k) {
+          const R pk = __shfl_sync(FULL, a[k], j);
+          if (m > j) a[k] -= f * pk;
+        }
+      }
+      stv<NU>(Ls + m * NU, a);
+      perm[m] = rowid;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int mm = 0; mm < NU; ++mm) Qxi[mm] = Qux()[mm * NX + li];
+    ldv<NU>(qu, qv() + NX);
+    R y[NU], yk[NU];
+    if (chol) {
+#pragma unroll
+      for (int i = 0; i < NU; ++i) {
+        R row[NU];
+        ldv<NU>(row, Ls + i * NU);
+        R s = Qxi[i], sk = qu[i];
+#pragma unroll
+        for (int k = 0; k < i; ++k) { s -= row[k] * y[k]; sk -= row[k] * yk[k]; }
+        y[i] = div_rn_<R>(s, row[i]);
+        yk[i] = div_rn_<R>(sk, row[i]);
+      }
+#pragma unroll
+      for (int i = NU - 1; i >= 0; --i) {
+        R row[NU];
+        ldv<NU>(row, LTs + i * NU);
+        R s = y[i], sk = yk[i];
+#pragma unroll
+        for (int k = i + 1; k < NU; ++k) { s -= row[k] * y[k]; sk -= row[k] * yk[k]; }
+        y[i] = div_rn_<R>(s, row[i]);
+        yk[i] = div_rn_<R>(sk, row[i]);
+      }
+    } else {
+      int pr[NU];
+      ldv<NU>(pr, perm);
+#pragma unroll
+      for (int i = 0; i < NU; ++i) {
+        R row[NU];
+        ldv<NU>(row, Ls + i * NU);
+        R s = Qux()[pr[i] * NX + li], sk = qv()[NX + pr[i]];
+#pragma unroll
+        for (int k = 0; k < i; ++k) { s -= row[k] * y[k]; sk -= row[k] * yk[k]; }
+        y[i] = s;
+        yk[i] = sk;
+      }
+#pragma unroll
+      for (int i = NU - 1; i >= 0; --i) {
+        R row[NU];
+        ldv<NU>(row, Ls + i * NU);
+        R s = y[i], sk = yk[i];
+#pragma unroll
+        for (int k = i + 1; k < NU; ++k) { s -= row[k] * y[k]; sk -= row[k] * yk[k]; }
+        y[i] = div_rn_<R>(s, row[i]);
+        yk[i] = div_rn_<R>(sk, row[i]);
+      }
+    }
+#pragma unroll
+    for (int mm = 0; mm < NU; ++mm) { Kc[mm] = -y[mm]; kt[mm] = -yk[mm]; }
+    return !KKT && !chol;
   }
 
   // One step of the value recursion.  In: Vs, vs (value at t+1), lv (linear cost terms; KKT: the negated incoming gradients),
@@ -184,13 +398,10 @@ struct LtiWarp {
         ldv<CW>(aw, sF + k * N + cc * CW);
         ldv<RW>(vd, Vs() + k * LDV + rr * RW);
 #pragma unroll
-        for (int a = 0; a < RW; ++a)
-#pragma unroll
-          for (int e = 0; e < CW; ++e) gx[a][e] += aw[e] * vd[a];
+        for (int a = 0; a < RW; ++a) axpyv<CW, R>(gx[a], vd[a], aw);
         const R bm = sF[k * N + NX + m];
         ldv<UC>(vu, Vs() + k * LDV + ju0);
-#pragma unroll
-        for (int e = 0; e < UC; ++e) gu[e] += bm * vu[e];
+        axpyv<UC, R>(gu, bm, vu);
         const R vk = vs()[k];
         fv0 += sF[k * N + e0] * vk;
         if (N > 32) fv1 += sF[k * N + e1] * vk;
@@ -224,10 +435,8 @@ struct LtiWarp {
         ldv<MS>(bw, sF + k * N + NX + cc * MS);
 #pragma unroll
         for (int a = 0; a < RW; ++a) {
-#pragma unroll
-          for (int e = 0; e < CW; ++e) axx[a][e] += gd[a] * aw[e];
-#pragma unroll
-          for (int e = 0; e < MS; ++e) axu[a][e] += gd[a] * bw[e];
+          axpyv<CW, R>(axx[a], gd[a], aw);
+          axpyv<MS, R>(axu[a], gd[a], bw);
         }
         const R gum = GuT()[k * NU + m];
         ldv<UQ>(bq, sF + k * N + NX + mq);
@@ -245,6 +454,7 @@ struct LtiWarp {
       for (int e = 0; e < UQ; ++e) Quu()[m * NU + mq + e] = c.quu[e] + (auu[e] + ((m == mq + e) ? P.reg : (R)0));   // + reg I (:554)
     }
     __syncwarp();
+#ifdef TACD_LTI_GAINS_V1
     // ---- gains: every lane factorises, lane i solves column i of [Q_ux | q_u]
     bool nonpd = false;
     const int li = lane < NX ? lane : NX - 1;
@@ -279,6 +489,12 @@ struct LtiWarp {
 #pragma unroll
       for (int mm = 0; mm < NU; ++mm) { Kc[mm] = -Kc[mm]; kt[mm] = -kt[mm]; }
     }
+#else
+    // ---- gains: K_t, k_t = -(Q_uu + reg I)^-1 [Q_ux | q_u]  (:557-566)
+    const int li = li_();
+    R Kc[NU], kt[NU], Qxi[NU], qu[NU];
+    const bool nonpd = gains<KKT>(P, Kc, kt, Qxi, qu);
+#endif
     {
       // Q_uu K (column li), Q_uu k, the new v_li (:574)
       R QKc[NU], Qk[NU];
@@ -324,9 +540,7 @@ struct LtiWarp {
           ldv<RW>(ld_, Lm + mm * NX + rr * RW);
           ldv<CW>(rw, Rm + mm * NX + cc * CW);
 #pragma unroll
-          for (int a = 0; a < RW; ++a)
-#pragma unroll
-            for (int e = 0; e < CW; ++e) acc[a][e] += ld_[a] * rw[e];
+          for (int a = 0; a < RW; ++a) axpyv<CW, R>(acc[a], ld_[a], rw);
         }
 #pragma unroll
         for (int a = 0; a < RW; ++a)
@@ -348,13 +562,11 @@ struct LtiWarp {
   TACD_DEV R* taua() const { return sm + C::otaua; }                        // [cand][N]
   TACD_DEV R* dxa() const { return sm + C::odx; }                           // [cand][NX]
 
-  // quad[a] += sum over this lane's block of tau_a[r] C[r][c] tau_a[c];  lin[a] += c_t[e] tau_a[e] (entries e0, e1)
-  template <int NC>
-  TACD_DEV void cost_block(const R* Ct, const R* ct, R (&quad)[NC], R (&lin)[NC]) const {
+  // This lane's block of the step's cost, in registers: rows r0.., columns c0.. of C_t and entries e0 / e1 of c_t
+  struct CostIn { R cb[C::CR][C::CC]; R cl0, cl1; };
+  TACD_DEV void load_cost(CostIn& ci, const R* Ct, const R* ct) const {
     constexpr int CR = C::CR, CC = C::CC, CV = C::CV;
     const int r0 = C::BLK ? (lane / 4) * CR : e0, c0 = C::BLK ? (lane % 4) * CC : 0;
-    const bool live = C::BLK || lane < N;
-    R cb[CR][CC];
 #pragma unroll
     for (int r = 0; r < CR; ++r)
 #pragma unroll
@@ -362,9 +574,17 @@ struct LtiWarp {
         R t[CV];
         ldv<CV>(t, Ct + (size_t)(r0 + r) * N + c0 + q);
 #pragma unroll
-        for (int e = 0; e < CV; ++e) cb[r][q + e] = t[e];
+        for (int e = 0; e < CV; ++e) ci.cb[r][q + e] = t[e];
       }
-    const R cl0 = ct[e0], cl1 = ct[e1];
+    ci.cl0 = ct[e0];
+    ci.cl1 = ct[e1];
+  }
+  // quad[a] += sum over this lane's block of tau_a[r] C[r][c] tau_a[c];  lin[a] += c_t[e] tau_a[e] (entries e0, e1)
+  template <int NC>
+  TACD_DEV void cost_block(const CostIn& ci, R (&quad)[NC], R (&lin)[NC]) const {
+    constexpr int CR = C::CR, CC = C::CC, CV = C::CV;
+    const int r0 = C::BLK ? (lane / 4) * CR : e0, c0 = C::BLK ? (lane % 4) * CC : 0;
+    const bool live = C::BLK || lane < N;
 #pragma unroll
     for (int a = 0; a < NC; ++a) {
       const R* ta = taua() + a * N;
@@ -380,11 +600,11 @@ struct LtiWarp {
       for (int r = 0; r < CR; ++r) {
         R s = 0;
 #pragma unroll
-        for (int q = 0; q < CC; ++q) s += cb[r][q] * tc[q];
+        for (int q = 0; q < CC; ++q) s += ci.cb[r][q] * tc[q];
         if (live) quad[a] += ta[r0 + r] * s;
       }
-      if (lane < N) lin[a] += cl0 * ta[e0];
-      if (N > 32 && has1) lin[a] += cl1 * ta[e1];
+      if (lane < N) lin[a] += ci.cl0 * ta[e0];
+      if (N > 32 && has1) lin[a] += ci.cl1 * ta[e1];
     }
   }
   // terminal terms (cost.py:52-58): lane i < NX owns row i of C_final[:nx, :nx]; tauN in taua()[a][0..NX)
@@ -407,6 +627,21 @@ struct LtiWarp {
     return v;
   }
 
+  // Everything one step of a rollout reads from global memory (prefetched one step ahead when PF)
+  struct RollIn { R xt, kr[UC], un, kk, rf0, rf1; CostIn ci; };
+  template <bool COST>
+  TACD_DEV void load_roll(RollIn& r, int t, const R* Xn, const R* Un, const R* gK, const R* gk, const R* xr, const R* ur, const R* Cq,
+                          const R* cq) const {
+    r.xt = Xn[(size_t)t * NX + li_()];
+    ldv<UC>(r.kr, gK + (size_t)t * NU * NX + m * NX + ju0);
+    r.un = Un[(size_t)t * NU + m];
+    r.kk = gk[(size_t)t * NU + m];
+    if (COST) {
+      r.rf0 = (e0 < NX) ? xr[(size_t)t * NX + e0] : ur[(size_t)t * NU + (e0 - NX)];
+      r.rf1 = ur[(size_t)t * NU + (e1 - NX < 0 ? 0 : e1 - NX)];
+      load_cost(r.ci, Cq + (size_t)t * N * N, cq + (size_t)t * N);
+    }
+  }
   // Roll NC candidates out along the gains (controller.py:598-612): u = clamp(U_t + alpha k_t + K_t (x - X_t)), x+ = A x + B u,
   // cost of every candidate with (Cq, cq, Cfq, cfq) when COST.  STORE (NC = 1): the trajectory goes to Xo / Uo.
   template <int NC, bool STORE, bool COST>
@@ -424,20 +659,18 @@ struct LtiWarp {
     }
     __syncwarp();
     const int jp = lane / NU;
+    RollIn ri, rn;
+    if (PF) load_roll<COST>(ri, 0, Xn, Un, gK, gk, xr, ur, Cq, cq);
     for (int t = 0; t < T; ++t) {
+      if (!PF) load_roll<COST>(ri, t, Xn, Un, gK, gk, xr, ur, Cq, cq);
+      else if (t + 1 < T) load_roll<COST>(rn, t + 1, Xn, Un, gK, gk, xr, ur, Cq, cq);
       const R* z = za(cur);
       R* zn = za(cur ^ 1);
       // dx_a = x_a - X_t
       if (lane < NX) {
-        const R xt = Xn[(size_t)t * NX + lane];
 #pragma unroll
-        for (int a = 0; a < NC; ++a) dxa()[a * NX + lane] = z[a * N + lane] - xt;
+        for (int a = 0; a < NC; ++a) dxa()[a * NX + lane] = z[a * N + lane] - ri.xt;
       }
-      R kr[UC];
-      ldv<UC>(kr, gK + (size_t)t * NU * NX + m * NX + ju0);
-      const R un = Un[(size_t)t * NU + m], kk = gk[(size_t)t * NU + m];
-      const R rf0 = (e0 < NX) ? xr[(size_t)t * NX + e0] : ur[(size_t)t * NU + (e0 - NX)];
-      const R rf1 = ur[(size_t)t * NU + (e1 - NX < 0 ? 0 : e1 - NX)];
       __syncwarp();
 #pragma unroll
       for (int a = 0; a < NC; ++a) {
@@ -445,11 +678,11 @@ struct LtiWarp {
         ldv<UC>(dv, dxa() + a * NX + ju0);
         R s = 0;
 #pragma unroll
-        for (int e = 0; e < UC; ++e) s += kr[e] * dv[e];
+        for (int e = 0; e < UC; ++e) s += ri.kr[e] * dv[e];
 #pragma unroll
         for (int o = NU; o < 32; o <<= 1) s += __shfl_xor_sync(FULL, s, o);
         if (jp == 0) {
-          R ui = un + (alpha[a] * kk + s);
+          R ui = ri.un + (alpha[a] * ri.kk + s);
           if (P.has_umin) ui = tmax<R>(ui, P.umin[m]);
           if (P.has_umax) ui = tmin<R>(ui, P.umax[m]);
           za(cur)[a * N + NX + m] = ui;
@@ -460,8 +693,8 @@ struct LtiWarp {
       if (COST) {
 #pragma unroll
         for (int a = 0; a < NC; ++a) {
-          if (lane < N) taua()[a * N + e0] = z[a * N + e0] - rf0;
-          if (N > 32 && has1) taua()[a * N + e1] = z[a * N + e1] - rf1;
+          if (lane < N) taua()[a * N + e0] = z[a * N + e0] - ri.rf0;
+          if (N > 32 && has1) taua()[a * N + e1] = z[a * N + e1] - ri.rf1;
         }
       }
       // x+ = A x + B u: lane i owns row i (read from F^T, conflict-free)
@@ -502,8 +735,9 @@ struct LtiWarp {
         }
       }
       __syncwarp();
-      if (COST) cost_block<NC>(Cq + (size_t)t * N * N, cq + (size_t)t * N, quad, lin);
+      if (COST) cost_block<NC>(ri.ci, quad, lin);
       cur ^= 1;
+      if (PF && t + 1 < T) ri = rn;
     }
     if (COST) {
       __syncwarp();
@@ -531,7 +765,9 @@ struct LtiWarp {
       if (lane < N) taua()[e0] = (e0 < NX) ? X[(size_t)t * NX + e0] - xr[(size_t)t * NX + e0] : U[(size_t)t * NU + e0 - NX] - ur[(size_t)t * NU + e0 - NX];
       if (N > 32 && has1) taua()[e1] = U[(size_t)t * NU + e1 - NX] - ur[(size_t)t * NU + e1 - NX];
       __syncwarp();
-      cost_block<1>(Cq + (size_t)t * N * N, cq + (size_t)t * N, quad, lin);
+      CostIn ci;
+      load_cost(ci, Cq + (size_t)t * N * N, cq + (size_t)t * N);
+      cost_block<1>(ci, quad, lin);
       __syncwarp();
     }
     if (lane < NX) taua()[lane] = X[(size_t)T * NX + lane] - xr[(size_t)T * NX + lane];
@@ -637,17 +873,17 @@ __global__ void __launch_bounds__(lti_warps<NX, NU, R>() * 32, 1) ilqr_forward_l
           w.vs()[lane] = a + cfp[lane];
         }
         __syncwarp();
+        typename W::StepIn si, sn;
+        if (W::PF) w.template load_step<true>(si, T - 1, Cp, cp, Xn, Un, xr, ur);
         for (int t = T - 1; t >= 0; --t) {
-          typename W::CTile ct;
-          const R* Ct = Cp + (size_t)t * N * N;
-          w.load_ctile(ct, Ct);
-          if (lane < N) w.tau()[w.e0] = (w.e0 < NX) ? Xn[(size_t)t * NX + w.e0] - xr[(size_t)t * NX + w.e0]
-                                                    : Un[(size_t)t * NU + w.e0 - NX] - ur[(size_t)t * NU + w.e0 - NX];
-          if (N > 32 && w.has1) w.tau()[w.e1] = Un[(size_t)t * NU + w.e1 - NX] - ur[(size_t)t * NU + w.e1 - NX];
+          if (!W::PF) w.template load_step<true>(si, t, Cp, cp, Xn, Un, xr, ur);
+          else if (t > 0) w.template load_step<true>(sn, t - 1, Cp, cp, Xn, Un, xr, ur);
+          w.store_tau(si);
           __syncwarp();
-          w.cost_linear(ct, Ct, cp + (size_t)t * N);
+          w.cost_linear(si);
           __syncwarp();
-          if (w.template value_step<false>(P, ct, gK + (size_t)t * NU * NX, gk + (size_t)t * NU)) flg |= TACD_FLAG_NONPD;
+          if (w.template value_step<false>(P, si.c, gK + (size_t)t * NU * NX, gk + (size_t)t * NU)) flg |= TACD_FLAG_NONPD;
+          if (W::PF && t > 0) si = sn;
         }
       }
       // ---- all line-search candidates (evaluate_alphas, controller.py:589-620)
@@ -760,13 +996,16 @@ __global__ void __launch_bounds__(lti_warps<NX, NU, R>() * 32, 1) ilqr_backward_
       w.Vs()[(idx / NX) * C::LDV + (idx % NX)] = Cp[(size_t)(T - 1) * N * N + (size_t)(idx / NX) * N + (idx % NX)];
     if (lane < NX) w.vs()[lane] = -gX[(size_t)(T - 1) * NX + lane];
     __syncwarp();
+    typename W::StepIn si, sn;
+    if (W::PF) w.template load_step<false>(si, T - 1, Cp, nullptr, gX, gU, nullptr, nullptr);
     for (int t = T - 1; t >= 0; --t) {
-      typename W::CTile ct;
-      w.load_ctile(ct, Cp + (size_t)t * N * N);
-      if (lane < N) w.lv()[w.e0] = (w.e0 < NX) ? -gX[(size_t)t * NX + w.e0] : -gU[(size_t)t * NU + w.e0 - NX];
-      if (N > 32 && w.has1) w.lv()[w.e1] = -gU[(size_t)t * NU + w.e1 - NX];
+      if (!W::PF) w.template load_step<false>(si, t, Cp, nullptr, gX, gU, nullptr, nullptr);
+      else if (t > 0) w.template load_step<false>(sn, t - 1, Cp, nullptr, gX, gU, nullptr, nullptr);
+      if (lane < N) w.lv()[w.e0] = -si.ta0;
+      if (N > 32 && w.has1) w.lv()[w.e1] = -si.ta1;
       __syncwarp();
-      w.template value_step<true>(P, ct, gK + (size_t)t * NU * NX, gk + (size_t)t * NU);
+      w.template value_step<true>(P, si.c, gK + (size_t)t * NU * NX, gk + (size_t)t * NU);
+      if (W::PF && t > 0) si = sn;
     }
     // ---- forward sweep dx+ = A dx + B du, du = K dx + k, and the gradients (controller.py:769-788, 100-115)
     if (io.grad_x0 && lane < NX) io.grad_x0[(size_t)b * NX + lane] = (R)0;   // quirk Q3

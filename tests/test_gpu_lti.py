@@ -1,0 +1,151 @@
+"""Config 5 (LTI sweep) on the warp-per-element kernels (csrc/ilqr_lti.cuh) against the run-time-dimension kernels
+(csrc/ilqr_generic.cu, TACD_LTI_KERNEL=0): two independent CUDA implementations of controller.py:275-315 / 546-620 /
+63-115, free-running on BASELINE's workload generator.  The golden and oracle parity of both paths is in
+test_gpu_parity.py / test_gpu_baseline_sizes.py; this file pins what those cannot at B = 4096: that the two paths take the
+SAME decisions (iteration counts, line-search choices, non-PD flags) — on this open-loop-unstable sweep accept / reject is a
+comparison of two rounded sums, and a kernel whose divisions are 1 ulp off runs 2.5x the iterations (measured in round 2)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _fresh_env(request):
+    from tacdmpc_b200 import _lib
+    _lib.lib().tacd_refresh_env()
+    request.addfinalizer(lambda: _lib.lib().tacd_refresh_env())
+
+
+def _run(w, monkeypatch, generic, dtype=torch.float32, backward=True):
+    from tacdmpc_b200 import _lib, ops, workloads
+    if generic:
+        monkeypatch.setenv("TACD_LTI_KERNEL", "0")
+    else:
+        monkeypatch.delenv("TACD_LTI_KERNEL", raising=False)
+    _lib.lib().tacd_refresh_env()
+    dev = torch.device("cuda")
+    spec = workloads.gpu_spec(w["spec"], dev, dtype)
+    d = {k: v.to(device=dev, dtype=dtype) for k, v in w["inp"].items()}
+    ls = tuple(t.to(device=dev, dtype=dtype) for t in w["ls"])
+    n0 = _lib.lib().tacd_kernel_launches()
+    out = ops.ilqr_forward(spec, d["x0"], d["C"], d["c"], d["Cf"], d["cf"], d["xref"], d["uref"], d["Uinit"], ls_cost=ls, want_trace=True)
+    res = {k: out[k].clone() for k in ("X", "U", "iters", "flags", "alpha_trace", "cost")}
+    if backward:
+        gX = torch.zeros_like(out["X"])
+        gU = torch.zeros_like(out["U"])
+        gU[:, 0] = 1.0
+        bw = ops.ilqr_backward(spec, out["X"], out["U"], d["C"], d["xref"], d["uref"], out["tight"], gX, gU, Cf_batched=True)
+        res.update({k: v.clone() for k, v in bw.items() if v is not None and k.startswith("grad")})
+    torch.cuda.synchronize()
+    assert _lib.lib().tacd_kernel_launches() > n0
+    return res
+
+
+@pytest.mark.parametrize("nx,nu", [(8, 4), (16, 4), (16, 8), (32, 8)])
+def test_lti_kernels_take_the_generic_kernels_decisions(monkeypatch, nx, nu):
+    from tacdmpc_b200 import workloads
+    w = workloads.lti(nx, nu, B=1024, T=50, seed=3)
+    a = _run(w, monkeypatch, generic=False)
+    b = _run(w, monkeypatch, generic=True)
+    same = (a["iters"] == b["iters"]) & (a["alpha_trace"] == b["alpha_trace"]).all(dim=1) & (a["flags"] == b["flags"])
+    frac = float(same.float().mean())
+    print(f"lti {nx}x{nu}: identical decision traces {frac:.4f}, mean iters {float(a['iters'].float().mean()):.3f} / {float(b['iters'].float().mean()):.3f}")
+    # fp32, open-loop-unstable systems: the five candidate costs of an iteration near convergence differ by rounding, so two
+    # correct kernels with different summation orders part ways on a fraction of the elements (measured: 0.99 / 0.77 / 0.80 /
+    # 0.63 identical at n_x = 8 / 16 / 16 / 32) while the iteration statistics agree to < 1 %
+    ia, ib = float(a["iters"].float().mean()), float(b["iters"].float().mean())
+    assert frac >= 0.5 and abs(ia - ib) <= 0.02 * ib
+    # where the decisions agree the answers agree to rounding (relative to each element's own scale: the trajectories of this
+    # sweep reach 1e5)
+    for k in ("X", "U"):
+        x, y = a[k][same], b[k][same]
+        scale = y.abs().flatten(1).amax(dim=1).clamp_min(1.0)
+        err = ((x - y).abs().flatten(1).amax(dim=1) / scale)
+        print(f"   {k}: median rel err {float(err.median()):.2e}, max {float(err.max()):.2e}")
+        assert float(err.median()) < 1e-5
+        assert float((err < 1e-3).float().mean()) > 0.95
+
+
+@pytest.mark.parametrize("nx,nu", [(8, 4), (32, 8)])
+def test_lti_well_conditioned_matches_generic(monkeypatch, nx, nu):
+    """spectral radius 0.9: several genuine iLQR iterations, answers comparable element by element; fp64 so that the
+    comparison is about the algorithm, not the rounding"""
+    from tacdmpc_b200 import workloads
+    w = workloads.lti(nx, nu, B=64, T=50, seed=5, rho=0.9)
+    w["spec"]["max_iter"] = 6
+    a = _run(w, monkeypatch, generic=False, dtype=torch.float64)
+    b = _run(w, monkeypatch, generic=True, dtype=torch.float64)
+    same = (a["iters"] == b["iters"]) & (a["alpha_trace"] == b["alpha_trace"]).all(dim=1)
+    # (an element that has converged picks among candidates whose costs are equal to rounding: 1 of 64 in round 2's run)
+    assert float(same.float().mean()) >= 0.9
+    for k in a:
+        if k in ("iters", "flags", "alpha_trace"):
+            continue
+        if a[k].shape[0] == same.shape[0]:
+            x, y = a[k][same], b[k][same]
+        elif bool(same.all()):
+            x, y = a[k], b[k]
+        else:
+            continue   # batch-summed gradients include the elements that parted ways
+        scale = float(y.abs().max()) or 1.0
+        err = float((x - y).abs().max()) / scale
+        print(f"   lti {nx}x{nu} rho 0.9 fp64 {k}: {err:.2e}")
+        assert err < 1e-9, k
+
+
+def _gains(Q, rhs, reg, kkt):
+    import ctypes as C
+    from tacdmpc_b200 import _abi, _lib
+    n, nu = Q.shape[0], Q.shape[1]
+    K = torch.empty(n, nu, device="cuda")
+    k = torch.empty(n, nu, device="cuda")
+    flag = torch.empty(n, dtype=torch.uint8, device="cuda")
+    Qd, rd = Q.cuda().float().contiguous(), rhs.cuda().float().contiguous()
+    _lib.check(_lib.lib().tacd_probe_lti_gains(_abi.F32, nu, int(kkt), n, float(reg), C.c_void_p(Qd.data_ptr()), C.c_void_p(rd.data_ptr()),
+                                               C.c_void_p(K.data_ptr()), C.c_void_p(k.data_ptr()), C.c_void_p(flag.data_ptr()),
+                                               C.c_void_p(torch.cuda.current_stream().cuda_stream)), "tacd_probe_lti_gains")
+    torch.cuda.synchronize()
+    return K.cpu(), k.cpu(), flag.cpu()
+
+
+@pytest.mark.parametrize("nu", [4, 8])
+@pytest.mark.parametrize("kind", ["spd", "indefinite", "near_singular"])
+def test_gain_solve_against_lapack(nu, kind):
+    """csrc/ilqr_lti.cuh::gains (lane-distributed Cholesky / LU with partial pivoting + per-lane triangular solves) against
+    LAPACK in fp32 and fp64: the Cholesky-or-LU decision is LAPACK's (spotrf fails <=> nonpd), the solution is as accurate as
+    LAPACK's own fp32 solve of the same system (measured against the fp64 solution)."""
+    g = torch.Generator().manual_seed(nu * 7 + len(kind))
+    n, reg = 2048, 1e-6
+    M = torch.randn(n, nu, nu, generator=g, dtype=torch.float64)
+    if kind == "spd":
+        Q = M @ M.transpose(1, 2) + 0.1 * torch.eye(nu, dtype=torch.float64)
+    elif kind == "indefinite":
+        Q = 0.5 * (M + M.transpose(1, 2))
+    else:   # one eigenvalue ~1e-6 of either sign: what the unstable LTI sweep produces
+        w, V = torch.linalg.eigh(M @ M.transpose(1, 2) + 0.1 * torch.eye(nu, dtype=torch.float64))
+        w[:, 0] = 1e-6 * torch.randn(n, generator=g, dtype=torch.float64)
+        Q = V @ torch.diag_embed(w) @ V.transpose(1, 2)
+    Q = Q.float()
+    rhs = torch.randn(n, nu, 2, generator=g)
+    for kkt in (0, 1, 2, 3):     # bit 0: the KKT pass's variant; bit 1: the run-time-dimension kernels' routines (same bar)
+        K, k, flag = _gains(Q, rhs, reg, kkt)
+        reg2 = reg * 1e-8 if (kkt & 1) else reg
+        A32 = Q + reg2 * torch.eye(nu)
+        A64 = A32.double()
+        x64 = -torch.linalg.solve(A64, rhs.double())
+        x32 = -torch.linalg.solve(A32, rhs)
+        got = torch.stack([K, k], dim=2)
+        _, info = torch.linalg.cholesky_ex(A32)
+        if not (kkt & 1):
+            agree = float(((info != 0) == (flag != 0)).float().mean())
+            # (near_singular: the smallest pivot is rounding noise of either sign; two correct fp32 factorisations disagree there)
+            assert agree > (0.9 if kind == "near_singular" else 0.995), f"Cholesky success / failure differs from spotrf on {1 - agree:.4f} of the problems"
+        scale = x64.abs().amax(dim=(1, 2)).clamp_min(1e-30)
+        e_got = (got.double() - x64).abs().amax(dim=(1, 2)) / scale
+        e_lap = (x32.double() - x64).abs().amax(dim=(1, 2)) / scale
+        print(f"\nnu={nu} {kind} kkt={kkt}: nonpd {float(flag.float().mean()):.3f}  median err vs fp64: kernel {float(e_got.median()):.2e}  LAPACK fp32 {float(e_lap.median()):.2e}"
+              f"  p99: {float(e_got.quantile(0.99)):.2e} / {float(e_lap.quantile(0.99)):.2e}")
+        assert torch.isfinite(got).all()
+        assert float(e_got.median()) <= 4 * float(e_lap.median()) + 1e-6
+        assert float(e_got.quantile(0.99)) <= 8 * float(e_lap.quantile(0.99)) + 1e-5
