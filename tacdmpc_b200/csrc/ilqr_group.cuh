@@ -192,6 +192,10 @@ __host__ __device__ inline int group_stage_words(int T, int n, int cw, size_t es
 __host__ __device__ inline size_t group_xtile_words(int T, int nx) { return (size_t)T * nx * 32; }
 __host__ __device__ inline size_t group_xscratch_words(int T, int nx) { return 2 * group_xtile_words(T, nx); }
 template <typename R> TACD_DEV R ld_cg(const R* p) { return __ldcg(p); }
+// a word of the candidates' state tile: the tile is global memory (L2) or, for small batches, shared memory (generic address)
+template <typename R> TACD_DEV R ld_scr(const R* p, bool in_smem) { return in_smem ? *p : __ldcg(p); }
+// tiles per warp when the scratch lives in shared memory (the second tile only serves the restore of quirk Q4's layouts)
+__host__ __device__ inline size_t group_xscratch_smem_words(int T, int nx, bool lssep) { return (lssep ? 2 : 1) * group_xtile_words(T, nx); }
 // CTA-shared staging of the un-batched costs (+ the separate line-search cost) and the LTI matrices.
 // Running cost of step t: [C_t (n*n) | c_t (n) | pad] at stride group_cost_stride(n) (multiple of 4 words, so the
 // line search reads it with 128-bit loads); terminal cost: [C_final | c_final | pad].
@@ -500,7 +504,11 @@ __global__ void __launch_bounds__(group_max_warps<R>() * 32, 1) ilqr_forward_gro
   // buffer only at the end of step t.  K_t[m][i] lives in the U_t[m] slot of the i-th dead buffer, k_t[m] in
   // that of the NX-th one ((NX + 1) NU words needed, 5 NU there: NX <= 4); the line search reads them at the top of step t.
   // The candidates' states go to the warp's global-memory scratch tile, word w = X_{t+1}[i] of lane l at scr[(t NX + i) 32 + l].
-  R* scr0 = io.xscratch + ((size_t)blockIdx.x * (blockDim.x >> 5) + wid) * group_xscratch_words(T, NX);
+  // (small batches — few warps per CTA, the kernel lasts as long as its longest chain of iterations — keep the tiles in shared
+  // memory, behind the warps' regions: no L2 round trip per iteration; io.xscratch == nullptr)
+  const bool ssm = io.xscratch == nullptr;
+  R* scr0 = ssm ? sm + (size_t)(blockDim.x >> 5) * group_warp_words(T, NX, NU, SW) + (size_t)wid * group_xscratch_smem_words(T, NX, LSSEP)
+                : io.xscratch + ((size_t)blockIdx.x * (blockDim.x >> 5) + wid) * group_xscratch_words(T, NX);
   const size_t tileW = group_xtile_words(T, NX);
   R* myV = wreg + group_voff_words(T, NX, NU) + (size_t)e * (NX + 1) * 4;   // [e][NX+1][4]: rows of V, then v
   // Dyn<> (LTI) wants A and B separately: straight from global memory (uniform, cached)
@@ -990,7 +998,7 @@ __global__ void __launch_bounds__(group_max_warps<R>() * 32, 1) ilqr_forward_gro
         __syncwarp();                       // the candidates' inputs and states are complete and visible to the group
         if (run) {
           const R* wsx = scr + base + ai;
-          for (int w = j; w < T * NX; w += kG) xb[(NX + w) * kXS] = ld_cg<R>(wsx + w * 32);
+          for (int w = j; w < T * NX; w += kG) xb[(NX + w) * kXS] = ld_scr<R>(wsx + w * 32, ssm);
         }
         __syncwarp();
         cost_own = own_cost_rows((ai + 1) * kEPW);
@@ -1019,7 +1027,7 @@ __global__ void __launch_bounds__(group_max_warps<R>() * 32, 1) ilqr_forward_gro
           const R* wu = ub + (ai + 1) * kEPW;
           if constexpr (!LSSEP) {
             const R* wsx = scr + base + ai;
-            for (int w = j; w < T * NX; w += kG) xb[(NX + w) * kXS] = ld_cg<R>(wsx + w * 32);
+            for (int w = j; w < T * NX; w += kG) xb[(NX + w) * kXS] = ld_scr<R>(wsx + w * 32, ssm);
           }
           for (int w = j; w < UW; w += kG) ub[w * kUS] = wu[w * kUS];
           ai_prev = ai;
@@ -1028,7 +1036,7 @@ __global__ void __launch_bounds__(group_max_warps<R>() * 32, 1) ilqr_forward_gro
           // iteration's winner (the other scratch tile) or, on an element's first iteration, the hand-over trajectory io.X
           const R* src = ai_prev >= 0 ? scr0 + (size_t)(it & 1) * tileW + base + ai_prev : io.X + (size_t)b * szX + NX;
           const int st = ai_prev >= 0 ? 32 : 1;
-          for (int w = j; w < T * NX; w += kG) xb[(NX + w) * kXS] = ld_cg<R>(src + (size_t)w * st);
+          for (int w = j; w < T * NX; w += kG) xb[(NX + w) * kXS] = ld_scr<R>(src + (size_t)w * st, ssm && ai_prev >= 0);
         }
       }
       __syncwarp();   // inputs / states written by one lane are read by the whole group from here on

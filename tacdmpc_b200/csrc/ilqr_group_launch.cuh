@@ -59,7 +59,24 @@ static int run_forward_group(const tacd_problem* p, const tacd_forward_io* io, v
   const int expect = resume ? (p->B + 15) / 16 : p->B;
   const int spread = (expect + di.sms * kEPW - 1) / (di.sms * kEPW);
   if (nw > spread) nw = spread < 1 ? 1 : spread;
-  const size_t smem = cost_b + warp_b * nw;
+  // Small batches: the candidates' state tiles move from the L2-resident workspace into shared memory when the batch is at most
+  // ~1.7 waves of the warps that then fit (cart-pole T = 20 fp32: 18 KB per warp, 12 warps).  Such a launch lasts as long as its
+  // longest chain of iterations, and every iteration of the L2 variant pays two dependent L2 round trips (tile write-out, winner
+  // read-back).  Measured B = 4096 ActorMPC-shaped costs (37 iterations): 0.608 ms with L2 tiles, 0.513 ms with round 1's
+  // all-shared layout; B = 65536 keeps the L2 tiles and 16 warps (0.626 vs 0.658 ms).
+  bool ssm = false;
+  {
+    TACD_KNOB(k_ssm, "TACD_GROUP_SSM_SPREAD");
+    const int lim = env_int(k_ssm, 20);
+    const size_t warp_s = warp_b + group_xscratch_smem_words(p->T, NX, LSSEP) * sizeof(R);
+    int nws = (int)(((size_t)di.smem_optin - cost_b) / warp_s);
+    if (nws > group_max_warps<R>()) nws = group_max_warps<R>();
+    if (!resume && nws >= 1 && spread <= lim) {
+      ssm = true;
+      if (nw > nws) nw = nws;
+    }
+  }
+  const size_t smem = cost_b + (warp_b + (ssm ? group_xscratch_smem_words(p->T, NX, LSSEP) * sizeof(R) : 0)) * nw;
   if (int rc = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr")) return rc;
   int grid = (expect + nw * kEPW - 1) / (nw * kEPW);
   if (grid > di.sms) grid = di.sms;
@@ -79,7 +96,7 @@ static int run_forward_group(const tacd_problem* p, const tacd_forward_io* io, v
   f.cost = (R*)io->cost; f.cost_trace = (R*)io->cost_trace;
   f.counter = (unsigned int*)ws;
   f.order = nullptr;
-  f.xscratch = (R*)((char*)ws + wo.scratch);
+  f.xscratch = ssm ? nullptr : (R*)((char*)ws + wo.scratch);
   f.stage_words = stage;
   const DevProblem<R> dp = to_dev<R>(p);
   if (resume) {
