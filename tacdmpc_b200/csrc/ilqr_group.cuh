@@ -486,6 +486,11 @@ __global__ void __launch_bounds__(group_max_warps<R>() * 32, 1) ilqr_forward_gro
   // shared by four schedulers), and those reads were a third of its traffic.
   const bool constOwn = __syncthreads_and(same_own ? 1 : 0) != 0 && CSH;
   const bool constLs = __syncthreads_and(same_ls ? 1 : 0) != 0 && LSSEP;
+  // Trip counts (0 or 1) of the per-step cost loads, made opaque with a shuffle: written as `if (!constOwn) load`, ptxas
+  // PREDICATES the loads instead of branching around them, and a predicated-off load still takes its issue slot — 14 of ~390
+  // slots per warp-step pair with a time-invariant cost (SASS: `@!P2 LDS.128 [UR9+..]` x 8 in the line search, `@!P2 LDS` x 6 in
+  // the reverse pass).  A loop whose bound the compiler cannot see is a real (warp-uniform) branch.
+  const int ldOwn = __shfl_sync(0xffffffffu, constOwn ? 0 : 1, 0), ldLs = __shfl_sync(0xffffffffu, constLs ? 0 : 1, 0);
   // per-element costs bulk-copied into shared memory (io.stage_words > 0; never with CSH)
   const int SW = CSH ? 0 : io.stage_words;
   R* wreg = sm + (size_t)wid * group_warp_words(T, NX, NU, SW);
@@ -754,10 +759,13 @@ __global__ void __launch_bounds__(group_max_warps<R>() * 32, 1) ilqr_forward_gro
 #pragma unroll
               for (int k = 0; k < N; ++k) Crow[k] = (k == jj) ? qd : (R)0;
               cj = pcj[0];
-            } else if (!constOwn) {
+            } else {
+#pragma unroll 1
+              for (int r = 0; r < ldOwn; ++r) {
 #pragma unroll
-              for (int k = 0; k < N; ++k) Crow[k] = pCrow[k];
-              cj = pcj[0];
+                for (int k = 0; k < N; ++k) Crow[k] = pCrow[k];
+                cj = pcj[0];
+              }
             }
             R s = 0;
 #pragma unroll
@@ -914,13 +922,15 @@ __global__ void __launch_bounds__(group_max_warps<R>() * 32, 1) ilqr_forward_gro
 #pragma unroll
           for (int i = 0; i < NX; ++i) tau[i] = x[i] - px[i * kXS + kEPW];
           if constexpr (LSSEP) {
-            if (!constLs) load_cost_vec<R, N>(pCl, Cl, cl);
+#pragma unroll 1
+            for (int r = 0; r < ldLs; ++r) load_cost_vec<R, N>(pCl, Cl, cl);
             quad_terms<R, N>(Cl, cl, tau, q1, l1);
             pCl += CS;
           }
           if constexpr (!LSSEP) {   // (with a separate line-search cost the own cost is evaluated for the winner only)
             if (CSH) {
-              if (!constOwn) load_cost_vec<R, N>(pCo, Ct, ct);
+#pragma unroll 1
+              for (int r = 0; r < ldOwn; ++r) load_cost_vec<R, N>(pCo, Ct, ct);
               pCo += CS;
             } else if (DIAG) {
 #pragma unroll
