@@ -565,6 +565,15 @@ struct BwdLayout {
   static constexpr int N = NX + NU;
   static constexpr int NV = N * N + N + NX + NU;    // per step: grad_C | grad_c | grad_xref | grad_uref
   static constexpr int NVF = NX * NX + NX + NX;     // terminal: grad_Cf[:nx,:nx] | grad_cf[:nx] | grad_xref[T]
+  // Tile row of one element and step: grad_C is symmetric, so only its upper triangle goes through the tile —
+  // NS = n(n+1)/2 columns instead of n*n; with grad_c, grad_xref, grad_uref that is NP = 25 columns for n = 5 (<= 32: every
+  // column of the transposed reduction has its own lane, ONE pass of 32 row reads instead of two).  The accumulators /
+  // per-CTA partials keep the dense NV layout (reduce_shared_grads and the five-lane backward share it).
+  static constexpr int NS = N * (N + 1) / 2;
+  static constexpr int NP = NS + N + NX + NU;
+  __host__ __device__ static constexpr int pk(int i, int k) {   // packed column of entry (i, k) = (k, i)
+    return (i <= k) ? i * N - i * (i - 1) / 2 + (k - i) : k * N - k * (k - 1) / 2 + (i - k);
+  }
   static constexpr int TW = NV | 1;                 // odd tile row stride: conflict-free transposed access
   static constexpr int CW = (N * N) | 1;            // row stride of the two C_t prefetch buffers
   static constexpr int TILE = (32 * TW > 64 * CW) ? 32 * TW : 64 * CW;   // words per warp
@@ -603,6 +612,26 @@ __global__ void __launch_bounds__(256, 2) ilqr_backward_small(const DevProblem<R
   __syncthreads();
   R* mytile = tile + (size_t)wid * L::TILE;
   R* myacc = acc + (size_t)wid * NACC;
+  // packed tile column j = lane + 32 q -> its dense accumulator slot(s): (i, k) and (k, i) of grad_C, or the vector entries
+  // (dense per-element grad_C is stored straight from the tile rows: that layout keeps the full matrix in the tile)
+  const bool packC = !(io.grad_C && P.C_batched && !DIAG);
+  const int vb = packC ? L::NS : N * N;          // first column of the vector entries
+  const int ncol = vb + N + NX + NU;
+  constexpr int NCOLIT = (L::NV + 31) / 32;
+  int cd0[NCOLIT], cd1[NCOLIT];
+#pragma unroll
+  for (int q = 0; q < NCOLIT; ++q) {
+    const int j = lane + 32 * q;
+    cd0[q] = packC ? N * N + (j - L::NS) : j;
+    cd1[q] = -1;
+    if (packC && j < L::NS) {
+      int i = 0, rem = j;
+      while (rem >= N - i) { rem -= N - i; ++i; }
+      const int k = i + rem;
+      cd0[q] = i * N + k;
+      cd1[q] = (k != i) ? k * N + i : -1;
+    }
+  }
   const bool redC = reduce && io.grad_C && !P.C_batched, redc = reduce && io.grad_c && !P.C_batched;
   const bool redCf = reduce && io.grad_Cf && !P.Cf_batched, redcf = reduce && io.grad_cf && !P.Cf_batched;
   const bool redx = reduce && io.grad_xref && !P.xref_batched, redu = reduce && io.grad_uref && !P.uref_batched;
@@ -846,16 +875,23 @@ __global__ void __launch_bounds__(256, 2) ilqr_backward_small(const DevProblem<R
       // lanes write consecutive words of the [B,T,...] outputs instead of 32 scattered segments).
       {
         R* row = mytile + lane * L::TW;
+        if (packC) {
 #pragma unroll
-        for (int i = 0; i < N; ++i)
+          for (int i = 0; i < N; ++i)
 #pragma unroll
-          for (int j = 0; j < N; ++j) row[i * N + j] = live ? (R)-0.5 * (dtau[i] * tau[j] + tau[i] * dtau[j]) : (R)0;
+            for (int j = i; j < N; ++j) row[L::pk(i, j)] = live ? (R)-0.5 * (dtau[i] * tau[j] + tau[i] * dtau[j]) : (R)0;
+        } else {
 #pragma unroll
-        for (int i = 0; i < N; ++i) row[N * N + i] = live ? -dtau[i] : (R)0;
+          for (int i = 0; i < N; ++i)
 #pragma unroll
-        for (int i = 0; i < NX; ++i) row[N * N + N + i] = live ? dx[i] : (R)0;
+            for (int j = 0; j < N; ++j) row[i * N + j] = live ? (R)-0.5 * (dtau[i] * tau[j] + tau[i] * dtau[j]) : (R)0;
+        }
 #pragma unroll
-        for (int i = 0; i < NU; ++i) row[N * N + N + NX + i] = live ? du[i] : (R)0;
+        for (int i = 0; i < N; ++i) row[vb + i] = live ? -dtau[i] : (R)0;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) row[vb + N + i] = live ? dx[i] : (R)0;
+#pragma unroll
+        for (int i = 0; i < NU; ++i) row[vb + N + NX + i] = live ? du[i] : (R)0;
         if (EXACT) {   // exact: d loss / d ref_t = C_t dtau_t (tau = z - ref enters the stationarity as -C ref)
           const R* Ce = Cp + (size_t)t * (DIAG ? N : N * N);
 #pragma unroll
@@ -866,16 +902,21 @@ __global__ void __launch_bounds__(256, 2) ilqr_backward_small(const DevProblem<R
 #pragma unroll
               for (int j = 0; j < N; ++j) s += Ce[i * N + j] * dtau[j];
             }
-            row[N * N + N + i] = live ? s : (R)0;
+            row[vb + N + i] = live ? s : (R)0;
           }
         }
         __syncwarp();
         if (redC || redc || redx || redu) {   // warp-uniform
-          for (int j = lane; j < L::NV; j += 32) {
-            R sum = 0;
+#pragma unroll
+          for (int q = 0; q < NCOLIT; ++q) {
+            const int j = lane + 32 * q;
+            if (j < ncol) {
+              R sum = 0;
 #pragma unroll 8
-            for (int r = 0; r < 32; ++r) sum += mytile[r * L::TW + j];
-            myacc[t * L::NV + j] += sum;
+              for (int r = 0; r < 32; ++r) sum += mytile[r * L::TW + j];
+              myacc[t * L::NV + cd0[q]] += sum;
+              if (cd1[q] >= 0) myacc[t * L::NV + cd1[q]] += sum;
+            }
           }
         }
         const int nlive = (P.B - b0 < 32) ? (P.B - b0) : 32;
@@ -883,7 +924,7 @@ __global__ void __launch_bounds__(256, 2) ilqr_backward_small(const DevProblem<R
           R* dst = io.grad_C + ((size_t)b0 * T + t) * N;
           for (int idx = lane; idx < nlive * N; idx += 32) {
             const int r = idx / N, j = idx % N;
-            dst[(size_t)r * T * N + j] = mytile[r * L::TW + j * N + j];
+            dst[(size_t)r * T * N + j] = mytile[r * L::TW + L::pk(j, j)];
           }
         } else if (io.grad_C && P.C_batched) {
           R* dst = io.grad_C + ((size_t)b0 * T + t) * N * N;
@@ -896,21 +937,21 @@ __global__ void __launch_bounds__(256, 2) ilqr_backward_small(const DevProblem<R
           R* dst = io.grad_c + ((size_t)b0 * T + t) * N;
           for (int idx = lane; idx < nlive * N; idx += 32) {
             const int r = idx / N, j = idx % N;
-            dst[(size_t)r * T * N + j] = mytile[r * L::TW + N * N + j];
+            dst[(size_t)r * T * N + j] = mytile[r * L::TW + vb + j];
           }
         }
         if (io.grad_xref && P.xref_batched) {
           R* dst = io.grad_xref + (size_t)b0 * szX + t * NX;
           for (int idx = lane; idx < nlive * NX; idx += 32) {
             const int r = idx / NX, j = idx % NX;
-            dst[(size_t)r * szX + j] = mytile[r * L::TW + N * N + N + j];
+            dst[(size_t)r * szX + j] = mytile[r * L::TW + vb + N + j];
           }
         }
         if (io.grad_uref && P.uref_batched) {
           R* dst = io.grad_uref + (size_t)b0 * szU + t * NU;
           for (int idx = lane; idx < nlive * NU; idx += 32) {
             const int r = idx / NU, j = idx % NU;
-            dst[(size_t)r * szU + j] = mytile[r * L::TW + N * N + N + NX + j];
+            dst[(size_t)r * szU + j] = mytile[r * L::TW + vb + N + NX + j];
           }
         }
         if (live) {
