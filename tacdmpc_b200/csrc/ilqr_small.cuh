@@ -580,6 +580,23 @@ struct BwdLayout {
   __host__ __device__ static int nacc(int T) { return T * NV + NVF; }
 };
 
+// NX consecutive words of a per-element trajectory row: one 128-bit load when NX = 4 and the row is 16-byte aligned (every
+// row of a [B, T+1, 4] tensor is, if its base is), else NX scalar loads.  The backward reads four such rows per step and
+// thread at a stride of one trajectory between lanes — its LSU instruction queue was a stall reason (lg_throttle 0.64 warps
+// per issue, profiles/r2_backward_small_final).
+template <typename R, int NX>
+TACD_DEV void ld_row(const R* p, bool vec, R (&d)[NX]) {
+  if constexpr (NX == 4 && sizeof(R) == 4) {
+    if (vec) {
+      const float4 v = *reinterpret_cast<const float4*>(p);
+      d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+      return;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NX; ++i) d[i] = p[i];
+}
+
 template <typename R, int NX, int NU, int DYN, bool DIAG, bool EXACT>
 __global__ void __launch_bounds__(256, 2) ilqr_backward_small(const DevProblem<R> P, const BwdPtrs<R> io, R* partials, int reduce, int vnt) {
   constexpr int N = NX + NU;
@@ -638,6 +655,7 @@ __global__ void __launch_bounds__(256, 2) ilqr_backward_small(const DevProblem<R
 #define SK(t, i) sK[((size_t)(t) * NU * NX + (i)) * kst]
 #define Sk(t, i) sk[((size_t)(t) * NU + (i)) * kst]
   const size_t szX = (size_t)(T + 1) * NX, szU = (size_t)T * NU;
+  const bool vecX = NX == 4 && sizeof(R) == 4 && (((uintptr_t)io.X | (uintptr_t)io.gX | (uintptr_t)io.xref) & 15) == 0;
   // vnt (multiple of 32, <= NT) threads of every CTA take one element per wave, so that all CTAs — and with
   // them all SMs — carry the same load in every wave; the remaining warps of the CTA stay out of the loop
   const int stride = gridDim.x * vnt;
@@ -711,8 +729,8 @@ __global__ void __launch_bounds__(256, 2) ilqr_backward_small(const DevProblem<R
 #pragma unroll
       for (int i = 0; i < NU; ++i) { u[i] = nu_[i]; qu[i] = -ngu[i]; fixed[i] = ntg[i]; }
       if (t > 0) {   // prefetch step t-1
-#pragma unroll
-        for (int i = 0; i < NX; ++i) { nx_[i] = X[(t - 1) * NX + i]; ngx[i] = gX[(t - 1) * NX + i]; }
+        ld_row<R, NX>(X + (t - 1) * NX, vecX, nx_);
+        ld_row<R, NX>(gX + (t - 1) * NX, vecX, ngx);
 #pragma unroll
         for (int i = 0; i < NU; ++i) { nu_[i] = U[(t - 1) * NU + i]; ngu[i] = gU[(t - 1) * NU + i]; ntg[i] = tg[(t - 1) * NU + i] != 0; }
       }
@@ -855,8 +873,8 @@ __global__ void __launch_bounds__(256, 2) ilqr_backward_small(const DevProblem<R
 #pragma unroll
       for (int i = 0; i < NU; ++i) { u[i] = nu_[i]; tau[NX + i] = u[i] - nur[i]; }
       // prefetch step t+1 (X has T+1 rows; U/u_ref only T)
-#pragma unroll
-      for (int i = 0; i < NX; ++i) { nx_[i] = X[(t + 1) * NX + i]; nxr[i] = xr[(t + 1) * NX + i]; }
+      ld_row<R, NX>(X + (t + 1) * NX, vecX, nx_);
+      ld_row<R, NX>(xr + (t + 1) * NX, vecX, nxr);
       if (t + 1 < T) {
 #pragma unroll
         for (int i = 0; i < NU; ++i) { nu_[i] = U[(t + 1) * NU + i]; nur[i] = ur[(t + 1) * NU + i]; }
