@@ -924,7 +924,19 @@ __global__ void __launch_bounds__(group_max_warps<R>() * 32, 1) ilqr_forward_gro
           if constexpr (LSSEP) {
 #pragma unroll 1
             for (int r = 0; r < ldLs; ++r) load_cost_vec<R, N>(pCl, Cl, cl);
-            quad_terms<R, N>(Cl, cl, tau, q1, l1);
+            if constexpr (DIAG) {
+              // the line-search cost of a compact-diagonal problem is a diagonal too (element 0's, expanded while staging): 20
+              // instead of 35 instructions per candidate and step, bit-identical sums (quad_terms_diag).  A RUN-TIME test for
+              // "all off-diagonal entries of the staged cost are exact zeros" (the usual Q, R = diag cost) was measured too: the
+              // second code path costs more (registers, code) than the 15 instructions save — forward +1..3 % on the dense
+              // layouts, +8 % at B = 512 — so only the compile-time case takes the short form.
+              R qd[N];
+#pragma unroll
+              for (int i = 0; i < N; ++i) qd[i] = Cl[i * N + i];
+              quad_terms_diag<R, N>(qd, cl, tau, q1, l1);
+            } else {
+              quad_terms<R, N>(Cl, cl, tau, q1, l1);
+            }
             pCl += CS;
           }
           if constexpr (!LSSEP) {   // (with a separate line-search cost the own cost is evaluated for the winner only)
