@@ -413,8 +413,36 @@ __global__ void __launch_bounds__(128) ilqr_init_rollout(const DevProblem<R> P, 
 // shared line-search cost (quirk Q4), always staged.
 // DIAG (only with per-element costs, CSH = false): tacd_problem.C_diag — C, C_final (and the line-search cost)
 // are compact diagonals, the ActorMPC layout (ACMPC/actor.py:58-81); 2n instead of n*n + n words per step.
-template <typename R, int NX, int NU, int DYN, bool LSSEP, bool CSH, bool DIAG>
+// Cost mode of a shared running cost (C, c not batched), decided ON THE DEVICE by one small launch and compiled into the solve
+// kernel: 0 = general, 1 = time-invariant (C_t, c_t equal for all t: both passes keep the cost in registers), 2 = time-invariant
+// and diagonal (every off-diagonal entry an exact zero — Q, R = diag: the line search evaluates 5 instead of 25 products,
+// quad_terms_diag, bit-identical).  The launcher enqueues all three variants; each reads the mode word and the two that do not
+// match exit at once (~2 us each).  Why compiled in: every RUN-TIME form of these two tests lost — predicated-off loads that
+// still take issue slots, a second code path that costs registers — while a build with the flags forced ran the
+// forward 5 % (time-invariant) faster.
+template <typename R>
+__global__ void group_cost_mode(const R* C, const R* c, int T, int n, int* mode) {
+  __shared__ int s_same, s_diag;
+  if (threadIdx.x == 0) { s_same = 1; s_diag = 1; }
+  __syncthreads();
+  bool same = true, dg = true;
+  for (int i = threadIdx.x; i < T * n * n; i += blockDim.x) {
+    const int k = i % (n * n);
+    const R v = C[i];
+    same = same && (v == C[k]);
+    if (k / n != k % n) dg = dg && (v == (R)0);
+  }
+  for (int i = threadIdx.x; i < T * n; i += blockDim.x) same = same && (c[i] == c[i % n]);
+  if (!same) atomicAnd(&s_same, 0);
+  if (!dg) atomicAnd(&s_diag, 0);
+  __syncthreads();
+  if (threadIdx.x == 0) *mode = s_same ? (s_diag ? 2 : 1) : 0;
+}
+
+template <typename R, int NX, int NU, int DYN, bool LSSEP, bool CSH, bool DIAG, int CM = 0>
 __global__ void __launch_bounds__(group_max_warps<R>() * 32, 1) ilqr_forward_group(const DevProblem<R> P, const FwdPtrs<R> io, const R* cost0) {
+  static_assert(CM == 0 || (CSH && !LSSEP && !DIAG), "cost modes exist for a plain shared cost only");
+  if (io.cost_mode != nullptr && *io.cost_mode != CM) return;   // another variant of this launch group runs the batch
   constexpr int N = NX + NU;
   static_assert(N <= kG, "one lane per row of the Q-function");
   static_assert(NX <= 4, "value-function rows travel as one 4-word vector");
@@ -484,13 +512,13 @@ __global__ void __launch_bounds__(group_max_warps<R>() * 32, 1) ilqr_forward_gro
   // shared-memory / L1 data path (128 B/clk per SM, also carrying shuffles and global loads) is what bounds
   // this kernel (profiles/r1_forward_group_v2: 115 data-path cycles per warp-step against 380 issue slots
   // shared by four schedulers), and those reads were a third of its traffic.
-  const bool constOwn = __syncthreads_and(same_own ? 1 : 0) != 0 && CSH;
+  const bool constOwn = CM >= 1 ? true : (__syncthreads_and(same_own ? 1 : 0) != 0 && CSH);
   const bool constLs = __syncthreads_and(same_ls ? 1 : 0) != 0 && LSSEP;
   // Trip counts (0 or 1) of the per-step cost loads, made opaque with a shuffle: written as `if (!constOwn) load`, ptxas
   // PREDICATES the loads instead of branching around them, and a predicated-off load still takes its issue slot — 14 of ~390
   // slots per warp-step pair with a time-invariant cost (SASS: `@!P2 LDS.128 [UR9+..]` x 8 in the line search, `@!P2 LDS` x 6 in
   // the reverse pass).  A loop whose bound the compiler cannot see is a real (warp-uniform) branch.
-  const int ldOwn = __shfl_sync(0xffffffffu, constOwn ? 0 : 1, 0), ldLs = __shfl_sync(0xffffffffu, constLs ? 0 : 1, 0);
+  const int ldOwn = CM >= 1 ? 0 : __shfl_sync(0xffffffffu, constOwn ? 0 : 1, 0), ldLs = __shfl_sync(0xffffffffu, constLs ? 0 : 1, 0);
   // per-element costs bulk-copied into shared memory (io.stage_words > 0; never with CSH)
   const int SW = CSH ? 0 : io.stage_words;
   R* wreg = sm + (size_t)wid * group_warp_words(T, NX, NU, SW);
@@ -959,6 +987,11 @@ __global__ void __launch_bounds__(group_max_warps<R>() * 32, 1) ilqr_forward_gro
               R qd[N];
 #pragma unroll
               for (int i = 0; i < N; ++i) qd[i] = Ct[i];
+              quad_terms_diag<R, N>(qd, ct, tau, q2, l2);
+            } else if (CM == 2) {
+              R qd[N];
+#pragma unroll
+              for (int i = 0; i < N; ++i) qd[i] = Ct[i * N + i];
               quad_terms_diag<R, N>(qd, ct, tau, q2, l2);
             } else {
               quad_terms<R, N>(Ct, ct, tau, q2, l2);

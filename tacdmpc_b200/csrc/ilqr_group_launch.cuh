@@ -81,6 +81,20 @@ static int run_forward_group(const tacd_problem* p, const tacd_forward_io* io, v
   int grid = (expect + nw * kEPW - 1) / (nw * kEPW);
   if (grid > di.sms) grid = di.sms;
   if (grid < 1) grid = 1;
+  // cost-mode variants (ilqr_group.cuh::group_cost_mode): a plain shared cost, full solves of more than one wave — there the
+  // mode is decided on the helper stream, off the critical path, and the two variants that exit cost ~5 us against ~6 % of the
+  // forward (0.640 -> 0.602 ms at B = 65536); a single-wave launch (B <= 14 k) would pay the three extra launches in line
+  // (measured +4 us at B = 1024)
+  constexpr bool kModes = CSH && !LSSEP && !DIAG;
+  TACD_KNOB(k_nomodes, "TACD_NO_COST_MODES");
+  TACD_KNOB(k_forcemodes, "TACD_FORCE_COST_MODES");   // tests: the variants on single-wave launches too
+  const bool modes = kModes && !resume && ((long)p->B > (long)grid * nw * kEPW || env_set(k_forcemodes)) && !env_set(k_nomodes);
+  if constexpr (kModes) {
+    if (modes) {
+      if (int rc = check_cuda(cudaFuncSetAttribute(ilqr_forward_group<R, NX, NU, DYN, LSSEP, CSH, DIAG, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr")) return rc;
+      if (int rc = check_cuda(cudaFuncSetAttribute(ilqr_forward_group<R, NX, NU, DYN, LSSEP, CSH, DIAG, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr")) return rc;
+    }
+  }
   const GroupWs wo = group_ws<R>(p);
   const size_t scratch_bytes = (size_t)grid * nw * group_xscratch_words(p->T, NX) * sizeof(R);
   if (ws_bytes < wo.end || wo.scratch + scratch_bytes > wo.list) { set_error("forward workspace too small for the initial costs / state tiles"); return TACD_EWORKSPACE; }
@@ -98,6 +112,7 @@ static int run_forward_group(const tacd_problem* p, const tacd_forward_io* io, v
   f.order = nullptr;
   f.xscratch = ssm ? nullptr : (R*)((char*)ws + wo.scratch);
   f.stage_words = stage;
+  f.cost_mode = modes ? (const int*)((char*)ws + 32) : nullptr;
   const DevProblem<R> dp = to_dev<R>(p);
   if (resume) {
     // the nominal trajectories, costs, iteration counts and flags of the handed-over solves are where the first phase left
@@ -125,6 +140,10 @@ static int run_forward_group(const tacd_problem* p, const tacd_forward_io* io, v
     if (int rc = check_cuda(cudaEventRecord(ss.fork, s), "fork record")) return rc;
     if (int rc = check_cuda(cudaStreamWaitEvent(ss.stream, ss.fork, 0), "fork wait")) return rc;
     s2 = ss.stream;
+  }
+  if (modes) {   // on the helper stream when there is one: off the critical path, next to the queue ordering
+    group_cost_mode<R><<<1, 256, 0, s2>>>((const R*)io->C, (const R*)io->c, p->T, NX + NU, (int*)((char*)ws + 32));
+    note_launches(1);
   }
   if (!lpt) {
     queue_init<<<1, 1, 0, s>>>(f.counter, 0u);
@@ -172,6 +191,13 @@ static int run_forward_group(const tacd_problem* p, const tacd_forward_io* io, v
   if (fork) {
     if (int rc = check_cuda(cudaEventRecord(ss.join, ss.stream), "join record")) return rc;
     if (int rc = check_cuda(cudaStreamWaitEvent(s, ss.join, 0), "join wait")) return rc;
+  }
+  if constexpr (kModes) {
+    if (modes) {   // the two variants whose mode does not match exit at once
+      ilqr_forward_group<R, NX, NU, DYN, LSSEP, CSH, DIAG, 2><<<grid, nw * 32, smem, s>>>(dp, f, cost0);
+      ilqr_forward_group<R, NX, NU, DYN, LSSEP, CSH, DIAG, 1><<<grid, nw * 32, smem, s>>>(dp, f, cost0);
+      note_launches(2);
+    }
   }
   kernel<<<grid, nw * 32, smem, s>>>(dp, f, cost0);
   note_launches(1);

@@ -46,6 +46,7 @@ struct FwdPtrs {
   R* resume_cost;                // thread kernel: best cost of every handed-over element, [B]
   const unsigned int* n_dev;     // five-lane kernel: number of queue entries, read on the device (nullable = P.B)
   int resume;                    // five-lane kernel: elements continue from (io.X, io.Uinit, cost0, io.iters, io.flags)
+  const int* cost_mode;          // five-lane kernel, shared costs: the mode group_cost_mode wrote (nullable); a variant whose CM differs exits
 };
 
 // ---------------------------------------------------------------------------
