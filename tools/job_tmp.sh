@@ -1,10 +1,6 @@
-python bench.py > gpurun_out/r2_bench_4.json 2> gpurun_out/r2_bench_4.err; tail -c 300 gpurun_out/r2_bench_4.err
-for lay in per_element diag; do python bench.py --no-extra --no-cpu-baseline --layout $lay > gpurun_out/r2_bench_4_$lay.json 2>/dev/null; done
-python - <<'PY'
-import json
-for f in ("r2_bench_4","r2_bench_4_per_element","r2_bench_4_diag"):
-    l=json.loads(open(f"gpurun_out/{f}.json").read().strip().splitlines()[-1]); t=l['timing']
-    print(f, 'value %.2fM fwd %.4f bwd %.4f e2e %.2fM frac %.3f'%(l['value']/1e6,t['fwd_ms'],t['bwd_ms'],l['e2e']['value']/1e6,l['roofline']['frac']))
-    for e in l.get("extra_configs") or []: print("   ", e["config"], '%.3gM fwd %.3f bwd %.3f iters %.2f'%(e["solves_per_s"]/1e6,e["fwd_ms"],e["bwd_ms"],e["mean_iters"]))
-PY
-python bench.py --impl reference --steps 3 --warmup 1 | cut -c1-400
+export TACD_BENCH_NO_GRAPH=1
+B="python bench.py --steps 2 --warmup 3 --no-extra --no-cpu-baseline"
+$B > gpurun_out/prof_plain_cm.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:ilqr_forward_group -s 9 -c 3 -f -o gpurun_out/r2h_fwd_group_cm $B > gpurun_out/prof_ncu_cm.log 2>&1; tail -3 gpurun_out/prof_ncu_cm.log | cut -c1-150
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2h_launches_shared.csv $B > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:ilqr_backward_small -s 3 -c 1 -f -o gpurun_out/r2h_bwd_small $B > gpurun_out/prof_ncu_bwd.log 2>&1; tail -2 gpurun_out/prof_ncu_bwd.log | cut -c1-150
