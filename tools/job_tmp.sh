@@ -1,6 +1,6 @@
-export TACD_BENCH_NO_GRAPH=1
-B="python bench.py --steps 2 --warmup 3 --no-extra --no-cpu-baseline"
-$B > gpurun_out/prof_plain_cm.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:ilqr_forward_group -s 9 -c 3 -f -o gpurun_out/r2h_fwd_group_cm $B > gpurun_out/prof_ncu_cm.log 2>&1; tail -3 gpurun_out/prof_ncu_cm.log | cut -c1-150
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2h_launches_shared.csv $B > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:ilqr_backward_small -s 3 -c 1 -f -o gpurun_out/r2h_bwd_small $B > gpurun_out/prof_ncu_bwd.log 2>&1; tail -2 gpurun_out/prof_ncu_bwd.log | cut -c1-150
+run() { python bench.py --no-extra --no-cpu-baseline "$@" 2>/dev/null | python -c "import json,sys; l=json.loads(sys.stdin.read()); t=l['timing']; print('value %.2fM fwd %.4f bwd %.4f e2e %.2fM iters %.3f launches %s'%(l['value']/1e6,t['fwd_ms'],t['bwd_ms'],l['e2e']['value']/1e6,l['roofline']['mean_iters'],l['gpu_launches']))"; }
+timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/r2_tests_24.log 2>&1; grep -E "passed|failed" gpurun_out/r2_tests_24.log | tail -2; grep -E "^FAILED|^E  " gpurun_out/r2_tests_24.log | head -20
+echo "== new diag"; run --layout diag; echo "== prev diag"; TACD_LIB=$PWD/tacdmpc_b200/variants/prev.so run --layout diag
+echo "== new"; timeout 300 python tools/bench_configs.py ppo512 ppo4096 2>&1 | grep "diag"
+echo "== prev"; TACD_LIB=$PWD/tacdmpc_b200/variants/prev.so timeout 300 python tools/bench_configs.py ppo512 ppo4096 2>&1 | grep "diag"
+echo "== new"; timeout 300 python tools/bench_configs.py ppo512 ppo4096 2>&1 | grep "diag"
