@@ -774,14 +774,26 @@ __global__ void __launch_bounds__(group_max_warps<R>() * 32, 1) ilqr_forward_gro
             for (int m = 0; m < NJ; ++m) jc[m] = 0;
           }
           s_in_blk = (s_in_blk == kG - 1) ? 0 : s_in_blk + 1;
+          // row jj of C_t, l_j = C_t[j,:] tau + c_t[j]
+          R Qrow[N], qj;
+          if constexpr (CM == 2) {
+            // time-invariant DIAGONAL cost (cost mode 2): row jj of C has one entry, so this lane needs its OWN tau_jj only —
+            // 2 shared-memory loads and 2 arithmetic instructions instead of 10 and 10.  The dense sum adds exact zeros to the same
+            // product (a non-finite tau_k, k != jj, would make it NaN there: such a nominal trajectory is never improved on —
+            // NaN / inf candidate costs do not pass `new < best` — and l only feeds k_t and v, not Q_uu or the flags).
+            const R* pa = (jj < NX) ? px + jj * kXS : pu + (jj - NX) * kUS + nomo;   // the word of z_t = [X_t; U_t] this lane's row meets
+            const R tj = pa[0] - pa[(jj < NX) ? kEPW : kURef];
+#pragma unroll
+            for (int k = 0; k < N; ++k) Qrow[k] = Crow[k];
+            R s = 0;
+            s += pick<N, R>(Crow, jj) * tj;
+            qj = s + cj;
+          } else {
           R tau[N];
 #pragma unroll
           for (int i = 0; i < NX; ++i) tau[i] = px[i * kXS] - px[i * kXS + kEPW];
 #pragma unroll
           for (int i = 0; i < NU; ++i) tau[NX + i] = pu[i * kUS + nomo] - pu[i * kUS + kURef];
-          // row jj of C_t, l_j = C_t[j,:] tau + c_t[j]
-          R Qrow[N], qj;
-          {
             if (DIAG) {
               const R qd = pCrow[0];
 #pragma unroll
