@@ -867,8 +867,18 @@ __global__ void __launch_bounds__(256, 2) ilqr_backward_small(const DevProblem<R
     for (int i = 0; i < NX; ++i) { nx_[i] = X[i]; nxr[i] = xr[i]; }
 #pragma unroll
     for (int i = 0; i < NU; ++i) { nu_[i] = U[i]; nur[i] = ur[i]; }
+    // the gains of step t come from the workspace column (L2) one step ahead of use, like the other per-step inputs
+    R nK[NU * NX], nk[NU];
+#pragma unroll
+    for (int i = 0; i < NU * NX; ++i) nK[i] = SK(0, i);
+#pragma unroll
+    for (int i = 0; i < NU; ++i) nk[i] = Sk(0, i);
     for (int t = 0; t < T; ++t) {
-      R x[NX], u[NU], tau[N], dtau[N], du[NU];
+      R x[NX], u[NU], tau[N], dtau[N], du[NU], Kt[NU * NX], kt[NU];
+#pragma unroll
+      for (int i = 0; i < NU * NX; ++i) Kt[i] = nK[i];
+#pragma unroll
+      for (int i = 0; i < NU; ++i) kt[i] = nk[i];
 #pragma unroll
       for (int i = 0; i < NX; ++i) { x[i] = nx_[i]; tau[i] = x[i] - nxr[i]; dtau[i] = dx[i]; }
 #pragma unroll
@@ -879,13 +889,17 @@ __global__ void __launch_bounds__(256, 2) ilqr_backward_small(const DevProblem<R
       if (t + 1 < T) {
 #pragma unroll
         for (int i = 0; i < NU; ++i) { nu_[i] = U[(t + 1) * NU + i]; nur[i] = ur[(t + 1) * NU + i]; }
+#pragma unroll
+        for (int i = 0; i < NU * NX; ++i) nK[i] = SK(t + 1, i);
+#pragma unroll
+        for (int i = 0; i < NU; ++i) nk[i] = Sk(t + 1, i);
       }
 #pragma unroll
       for (int i = 0; i < NU; ++i) {
         R s = 0;
 #pragma unroll
-        for (int j = 0; j < NX; ++j) s += SK(t, i * NX + j) * dx[j];
-        du[i] = s + Sk(t, i);
+        for (int j = 0; j < NX; ++j) s += Kt[i * NX + j] * dx[j];
+        du[i] = s + kt[i];
         dtau[NX + i] = du[i];
       }
       // grad_C = -1/2 (dtau (x) tau + tau (x) dtau), grad_c = -dtau, grad_xref[t] = dx, grad_uref[t] = du.
