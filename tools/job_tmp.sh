@@ -1,2 +1,8 @@
-timeout 900 python -m pytest tests -m gpu -q > gpurun_out/r2_tests_26.log 2>&1; grep -E "passed|failed" gpurun_out/r2_tests_26.log | tail -2; grep -E "^FAILED|^E  " gpurun_out/r2_tests_26.log | head -20
-timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2_smoke_2.log 2>&1; tail -24 gpurun_out/r2_smoke_2.log
+python bench.py > gpurun_out/r2_bench_5.json 2> gpurun_out/r2_bench_5.err
+python - <<'PY'
+import json
+l=json.loads(open("gpurun_out/r2_bench_5.json").read().strip().splitlines()[-1]); t=l['timing']
+print('value %.2fM fwd %.4f bwd %.4f e2e %.2fM frac %.3f launches %s'%(l['value']/1e6,t['fwd_ms'],t['bwd_ms'],l['e2e']['value']/1e6,l['roofline']['frac'], l['gpu_launches']))
+print(json.dumps(l['roofline'])[:900]); print(l['cpu_baseline']); print(l['clocks'])
+for e in l.get("extra_configs") or []: print("   ", e["config"], '%.3gM fwd %.3f bwd %.3f iters %.2f'%(e["solves_per_s"]/1e6,e["fwd_ms"],e["bwd_ms"],e["mean_iters"]))
+PY
