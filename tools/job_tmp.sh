@@ -1,8 +1,5 @@
-python bench.py > gpurun_out/r2_bench_5.json 2> gpurun_out/r2_bench_5.err
-python - <<'PY'
-import json
-l=json.loads(open("gpurun_out/r2_bench_5.json").read().strip().splitlines()[-1]); t=l['timing']
-print('value %.2fM fwd %.4f bwd %.4f e2e %.2fM frac %.3f launches %s'%(l['value']/1e6,t['fwd_ms'],t['bwd_ms'],l['e2e']['value']/1e6,l['roofline']['frac'], l['gpu_launches']))
-print(json.dumps(l['roofline'])[:900]); print(l['cpu_baseline']); print(l['clocks'])
-for e in l.get("extra_configs") or []: print("   ", e["config"], '%.3gM fwd %.3f bwd %.3f iters %.2f'%(e["solves_per_s"]/1e6,e["fwd_ms"],e["bwd_ms"],e["mean_iters"]))
-PY
+run() { python bench.py --no-extra --no-cpu-baseline "$@" 2>/dev/null | python -c "import json,sys; l=json.loads(sys.stdin.read()); t=l['timing']; print('value %.2fM fwd %.4f bwd %.4f e2e %.2fM iters %.3f launches %s'%(l['value']/1e6,t['fwd_ms'],t['bwd_ms'],l['e2e']['value']/1e6,l['roofline']['mean_iters'],l['gpu_launches']))"; }
+timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/r2_tests_27.log 2>&1; grep -E "passed|failed" gpurun_out/r2_tests_27.log | tail -2; grep -E "^FAILED|^E  " gpurun_out/r2_tests_27.log | head -20
+echo "== new diag"; run --layout diag; echo "== prev diag"; TACD_LIB=$PWD/tacdmpc_b200/variants/prev.so run --layout diag
+echo "== new"; timeout 300 python tools/bench_configs.py ppo512 ppo4096 2>&1 | grep "diag"
+echo "== prev"; TACD_LIB=$PWD/tacdmpc_b200/variants/prev.so timeout 300 python tools/bench_configs.py ppo512 ppo4096 2>&1 | grep "diag"
