@@ -246,26 +246,6 @@ struct LtiWarp {
     };
     load_row();
     bool chol = false;
-#ifdef TACD_LTI_OLD_CHOL
-    if (!KKT) {
-      R Lf[NU * NU];
-#pragma unroll
-      for (int i = 0; i < NU * NU; i += 4) {
-        R t4[4];
-        ldv<4>(t4, Quu() + i);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) Lf[i + e] = t4[e] + (((i + e) / NU == (i + e) % NU) ? reg2 : (R)0);
-      }
-      chol = gen_chol_reg<R, NU>(Lf);
-      if (chol) {
-#pragma unroll
-        for (int i = 0; i < NU; ++i)
-#pragma unroll
-          for (int k = 0; k < NU; ++k)
-            if (i == m) { Ls[i * NU + k] = (k <= i) ? Lf[i * NU + k] : (R)0; LTs[k * NU + i] = (k <= i) ? Lf[i * NU + k] : (R)0; }
-      }
-    }
-#else
     if (!KKT) {
       bool ok = true;
       R lrow[NU];
@@ -290,7 +270,6 @@ struct LtiWarp {
         for (int k = 0; k < NU; ++k) LTs[k * NU + m] = lrow[k];
       }
     }
-#endif
     if (!chol) {
       if (!KKT) load_row();
       int rowid = m;
@@ -454,47 +433,10 @@ struct LtiWarp {
       for (int e = 0; e < UQ; ++e) Quu()[m * NU + mq + e] = c.quu[e] + (auu[e] + ((m == mq + e) ? P.reg : (R)0));   // + reg I (:554)
     }
     __syncwarp();
-#ifdef TACD_LTI_GAINS_V1
-    // ---- gains: every lane factorises, lane i solves column i of [Q_ux | q_u]
-    bool nonpd = false;
-    const int li = lane < NX ? lane : NX - 1;
-    R Kc[NU], kt[NU], Qxi[NU], qu[NU];
-    {
-      R L[NU * NU];
-      int piv[NU];
-      const R reg2 = KKT ? (R)1e-8 * P.reg : P.reg;
-      auto loadL = [&]() {
-#pragma unroll
-        for (int i = 0; i < NU * NU; i += 4) {
-          R t4[4];
-          ldv<4>(t4, Quu() + i);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) L[i + e] = t4[e] + (((i + e) / NU == (i + e) % NU) ? reg2 : (R)0);
-        }
-      };
-      loadL();
-      bool chol = false;
-      if (!KKT) chol = gen_chol_reg<R, NU>(L);
-      if (!chol) {
-        if (!KKT) { nonpd = true; loadL(); }
-        gen_lu_reg<R, NU>(L, piv);
-      }
-#pragma unroll
-      for (int mm = 0; mm < NU; ++mm) { Qxi[mm] = Qux()[mm * NX + li]; Kc[mm] = Qxi[mm]; }
-      ldv<NU>(qu, qv() + NX);
-#pragma unroll
-      for (int mm = 0; mm < NU; ++mm) kt[mm] = qu[mm];
-      if (chol) { gen_chol_solve_col_reg<R, NU>(L, Kc, 1, 0); gen_chol_solve_col_reg<R, NU>(L, kt, 1, 0); }
-      else { gen_lu_solve_col_reg<R, NU>(L, piv, Kc, 1, 0); gen_lu_solve_col_reg<R, NU>(L, piv, kt, 1, 0); }
-#pragma unroll
-      for (int mm = 0; mm < NU; ++mm) { Kc[mm] = -Kc[mm]; kt[mm] = -kt[mm]; }
-    }
-#else
     // ---- gains: K_t, k_t = -(Q_uu + reg I)^-1 [Q_ux | q_u]  (:557-566)
     const int li = li_();
     R Kc[NU], kt[NU], Qxi[NU], qu[NU];
     const bool nonpd = gains<KKT>(P, Kc, kt, Qxi, qu);
-#endif
     {
       // Q_uu K (column li), Q_uu k, the new v_li (:574)
       R QKc[NU], Qk[NU];
