@@ -743,6 +743,9 @@ __global__ void __launch_bounds__(group_max_warps<R>() * 32, 1) ilqr_forward_gro
         const R* pCrow = CSH ? sC + (size_t)(T - 1) * CS + jj * N : DIAG ? Cp + (size_t)(T - 1) * N + jj : Cp + ((size_t)(T - 1) * N + jj) * N;
         const R* pcj = CSH ? sC + (size_t)(T - 1) * CS + N * N + jj : cp + (size_t)(T - 1) * N + jj;
         R Crow[N], cj;        // row jj of C_t and c_t[jj]; loaded once when the running cost is time-invariant
+        constexpr bool kRowPF = !CSH && !DIAG;   // dense per-element costs (global memory): prefetched one step ahead
+        R nCrow[kRowPF ? N : 1], ncj = 0;
+        (void)nCrow; (void)ncj;
         if (DIAG) {
           const R qd = pCrow[0];
 #pragma unroll
@@ -799,6 +802,14 @@ __global__ void __launch_bounds__(group_max_warps<R>() * 32, 1) ilqr_forward_gro
 #pragma unroll
               for (int k = 0; k < N; ++k) Crow[k] = (k == jj) ? qd : (R)0;
               cj = pcj[0];
+            } else if constexpr (kRowPF) {
+              // per-element dense costs read through L2: row jj of C_{t-1} is requested now and consumed one step later (the
+              // ~200 instructions of this step hide the L2 round trip that a load-and-use paid at the top of every step)
+              if (t > 0) {
+#pragma unroll
+                for (int k = 0; k < N; ++k) nCrow[k] = (pCrow - CW)[k];
+                ncj = (pcj - N)[0];
+              }
             } else {
 #pragma unroll 1
               for (int r = 0; r < ldOwn; ++r) {
@@ -915,6 +926,11 @@ __global__ void __launch_bounds__(group_max_warps<R>() * 32, 1) ilqr_forward_gro
           __syncwarp();
           px -= NX * kXS; pu -= NU * kUS;
           pCrow -= CSH ? CS : CW; pcj -= CSH ? CS : N;
+          if constexpr (kRowPF) {
+#pragma unroll
+            for (int k = 0; k < N; ++k) Crow[k] = nCrow[k];
+            cj = ncj;
+          }
         }
         if constexpr (kOwnInit) {
           if (__ballot_sync(FULL, fresh) != 0u) {   // some group of this warp is on the first iteration of a new element
