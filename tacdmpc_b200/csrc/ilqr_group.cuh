@@ -439,7 +439,11 @@ __global__ void group_cost_mode(const R* C, const R* c, int T, int n, int* mode)
   if (threadIdx.x == 0) *mode = s_same ? (s_diag ? 2 : 1) : 0;
 }
 
-template <typename R, int NX, int NU, int DYN, bool LSSEP, bool CSH, bool DIAG, int CM = 0>
+// SSM: the candidates' state tiles live in shared memory (small batches) instead of the L2-resident workspace.  A template
+// parameter, not a run-time flag: with `ssm = io.xscratch == nullptr` the tile stores of the line search became generic stores
+// and the read-back a select of two loads, and the B = 65536 forward paid 3 % (shared cost) to 13 % (compact diagonal) for a
+// feature it does not use (measured with the flag forced at compile time: 0.593 -> 0.572 ms, 0.868 -> 0.752 ms).
+template <typename R, int NX, int NU, int DYN, bool LSSEP, bool CSH, bool DIAG, int CM = 0, bool SSM = false>
 __global__ void __launch_bounds__(group_max_warps<R>() * 32, 1) ilqr_forward_group(const DevProblem<R> P, const FwdPtrs<R> io, const R* cost0) {
   static_assert(CM == 0 || (CSH && !LSSEP && !DIAG), "cost modes exist for a plain shared cost only");
   if (io.cost_mode != nullptr && *io.cost_mode != CM) return;   // another variant of this launch group runs the batch
@@ -539,7 +543,7 @@ __global__ void __launch_bounds__(group_max_warps<R>() * 32, 1) ilqr_forward_gro
   // The candidates' states go to the warp's global-memory scratch tile, word w = X_{t+1}[i] of lane l at scr[(t NX + i) 32 + l].
   // (small batches — few warps per CTA, the kernel lasts as long as its longest chain of iterations — keep the tiles in shared
   // memory, behind the warps' regions: no L2 round trip per iteration; io.xscratch == nullptr)
-  const bool ssm = io.xscratch == nullptr;
+  constexpr bool ssm = SSM;
   R* scr0 = ssm ? sm + (size_t)(blockDim.x >> 5) * group_warp_words(T, NX, NU, SW) + (size_t)wid * group_xscratch_smem_words(T, NX, LSSEP)
                 : io.xscratch + ((size_t)blockIdx.x * (blockDim.x >> 5) + wid) * group_xscratch_words(T, NX);
   const size_t tileW = group_xtile_words(T, NX);

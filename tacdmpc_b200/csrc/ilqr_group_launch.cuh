@@ -28,7 +28,7 @@ static GroupWs group_ws(const tacd_problem* p) {
 // resume = the second phase of the two-phase solve: the queue holds the solves the thread-per-element kernel handed over
 template <typename R, int NX, int NU, int DYN, bool LSSEP, bool CSH, bool DIAG>
 static int run_forward_group(const tacd_problem* p, const tacd_forward_io* io, void* ws, size_t ws_bytes, cudaStream_t s, bool resume = false) {
-  auto kernel = ilqr_forward_group<R, NX, NU, DYN, LSSEP, CSH, DIAG>;
+  using KFn = void (*)(const DevProblem<R>, const FwdPtrs<R>, const R*);
   const DeviceInfo di = device_info();
   const size_t cost_b = (size_t)group_cost_words(p->T, NX, NU, p->C_batched, p->Cf_batched, LSSEP ? 1 : 0, DYN == TACD_DYN_LTI) * sizeof(R);
   // Per-element costs are staged in shared memory by bulk asynchronous copies when the blocks are 16-byte aligned AND the staged
@@ -77,6 +77,7 @@ static int run_forward_group(const tacd_problem* p, const tacd_forward_io* io, v
     }
   }
   const size_t smem = cost_b + (warp_b + (ssm ? group_xscratch_smem_words(p->T, NX, LSSEP) * sizeof(R) : 0)) * nw;
+  const KFn kernel = ssm ? (KFn)ilqr_forward_group<R, NX, NU, DYN, LSSEP, CSH, DIAG, 0, true> : (KFn)ilqr_forward_group<R, NX, NU, DYN, LSSEP, CSH, DIAG, 0, false>;
   if (int rc = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr")) return rc;
   int grid = (expect + nw * kEPW - 1) / (nw * kEPW);
   if (grid > di.sms) grid = di.sms;
@@ -91,8 +92,10 @@ static int run_forward_group(const tacd_problem* p, const tacd_forward_io* io, v
   const bool modes = kModes && !resume && ((long)p->B > (long)grid * nw * kEPW || env_set(k_forcemodes)) && !env_set(k_nomodes);
   if constexpr (kModes) {
     if (modes) {
-      if (int rc = check_cuda(cudaFuncSetAttribute(ilqr_forward_group<R, NX, NU, DYN, LSSEP, CSH, DIAG, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr")) return rc;
-      if (int rc = check_cuda(cudaFuncSetAttribute(ilqr_forward_group<R, NX, NU, DYN, LSSEP, CSH, DIAG, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr")) return rc;
+      const KFn k1 = ssm ? (KFn)ilqr_forward_group<R, NX, NU, DYN, LSSEP, CSH, DIAG, 1, true> : (KFn)ilqr_forward_group<R, NX, NU, DYN, LSSEP, CSH, DIAG, 1, false>;
+      const KFn k2 = ssm ? (KFn)ilqr_forward_group<R, NX, NU, DYN, LSSEP, CSH, DIAG, 2, true> : (KFn)ilqr_forward_group<R, NX, NU, DYN, LSSEP, CSH, DIAG, 2, false>;
+      if (int rc = check_cuda(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr")) return rc;
+      if (int rc = check_cuda(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr")) return rc;
     }
   }
   const GroupWs wo = group_ws<R>(p);
@@ -194,8 +197,10 @@ static int run_forward_group(const tacd_problem* p, const tacd_forward_io* io, v
   }
   if constexpr (kModes) {
     if (modes) {   // the two variants whose mode does not match exit at once
-      ilqr_forward_group<R, NX, NU, DYN, LSSEP, CSH, DIAG, 2><<<grid, nw * 32, smem, s>>>(dp, f, cost0);
-      ilqr_forward_group<R, NX, NU, DYN, LSSEP, CSH, DIAG, 1><<<grid, nw * 32, smem, s>>>(dp, f, cost0);
+      const KFn k1 = ssm ? (KFn)ilqr_forward_group<R, NX, NU, DYN, LSSEP, CSH, DIAG, 1, true> : (KFn)ilqr_forward_group<R, NX, NU, DYN, LSSEP, CSH, DIAG, 1, false>;
+      const KFn k2 = ssm ? (KFn)ilqr_forward_group<R, NX, NU, DYN, LSSEP, CSH, DIAG, 2, true> : (KFn)ilqr_forward_group<R, NX, NU, DYN, LSSEP, CSH, DIAG, 2, false>;
+      k2<<<grid, nw * 32, smem, s>>>(dp, f, cost0);
+      k1<<<grid, nw * 32, smem, s>>>(dp, f, cost0);
       note_launches(2);
     }
   }
