@@ -628,6 +628,20 @@ __global__ void __launch_bounds__(group_max_warps<R>() * 32, 1) ilqr_forward_gro
   // staged cost block) and ilqr_init_rollout only rolls the initial inputs out: a thread per element walking its own 2.4 KB of
   // costs took 176 us of the 1.06 ms forward at B = 65536 (profiles/r2_launches_per_element.csv)
   constexpr bool kOwnInit = LSSEP && !CSH;
+  // States X_1..X_T of one candidate (word w at src[w st]) -> the nominal state trajectory, the group's lanes taking every
+  // kG-th word.  Four loads are issued before their four stores: with the tile in shared memory a load-store-load-store loop
+  // is one dependent chain (the stores may alias the next load), 17 shared-memory round trips per lane and iteration.
+  auto fetch_states = [&](const R* src, size_t st, bool in_smem) {
+    const int nwd = T * NX;
+    for (int w = j; w < nwd; w += 4 * kG) {
+      R v4[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) v4[q] = (w + q * kG < nwd) ? ld_scr<R>(src + (size_t)(w + q * kG) * st, in_smem) : (R)0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (w + q * kG < nwd) xb[(NX + w + q * kG) * kXS] = v4[q];
+    }
+  };
 
   while (true) {
     // ------------------------------------------------------------------ refill (queue pop by the group leader)
@@ -1085,7 +1099,7 @@ __global__ void __launch_bounds__(group_max_warps<R>() * 32, 1) ilqr_forward_gro
         __syncwarp();                       // the candidates' inputs and states are complete and visible to the group
         if (run) {
           const R* wsx = scr + base + ai;
-          for (int w = j; w < T * NX; w += kG) xb[(NX + w) * kXS] = ld_scr<R>(wsx + w * 32, ssm);
+          fetch_states(wsx, 32, ssm);
         }
         __syncwarp();
         cost_own = own_cost_rows((ai + 1) * kEPW);
@@ -1114,7 +1128,7 @@ __global__ void __launch_bounds__(group_max_warps<R>() * 32, 1) ilqr_forward_gro
           const R* wu = ub + (ai + 1) * kEPW;
           if constexpr (!LSSEP) {
             const R* wsx = scr + base + ai;
-            for (int w = j; w < T * NX; w += kG) xb[(NX + w) * kXS] = ld_scr<R>(wsx + w * 32, ssm);
+            fetch_states(wsx, 32, ssm);
           }
           for (int w = j; w < UW; w += kG) ub[w * kUS] = wu[w * kUS];
           ai_prev = ai;
@@ -1123,7 +1137,7 @@ __global__ void __launch_bounds__(group_max_warps<R>() * 32, 1) ilqr_forward_gro
           // iteration's winner (the other scratch tile) or, on an element's first iteration, the hand-over trajectory io.X
           const R* src = ai_prev >= 0 ? scr0 + (size_t)(it & 1) * tileW + base + ai_prev : io.X + (size_t)b * szX + NX;
           const int st = ai_prev >= 0 ? 32 : 1;
-          for (int w = j; w < T * NX; w += kG) xb[(NX + w) * kXS] = ld_scr<R>(src + (size_t)w * st, ssm && ai_prev >= 0);
+          fetch_states(src, (size_t)st, ssm && ai_prev >= 0);
         }
       }
       __syncwarp();   // inputs / states written by one lane are read by the whole group from here on
